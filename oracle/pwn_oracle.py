@@ -1,0 +1,426 @@
+"""ctypes wrapper around oracle/pwn_oracle.c (CPU restatement of pwn_core).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/pwn_oracle.h.  May be imported from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, nowhere else.
+PARITY UNPINNED: the reference cannot be built here and ships no golden vectors.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    """(Re)build the oracle shared objects with `make` (gcc is in the image)."""
+    so = os.path.join(_HERE, "build", "liboracle.so")
+    so2 = os.path.join(_HERE, "build", "liboracle_fast.so")
+    src = os.path.join(_HERE, "pwn_oracle.c")
+    stale = (not os.path.exists(so) or not os.path.exists(so2)
+             or os.path.getmtime(so) < os.path.getmtime(src))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+class StatsParams(C.Structure):
+    _fields_ = [("worldRadius", C.c_float), ("minImageRadius", C.c_int), ("maxImageRadius", C.c_int),
+                ("minPoints", C.c_int), ("curvatureThreshold", C.c_float),
+                ("omegaCurvatureThreshold", C.c_float),
+                ("flatOmegaP", C.c_float * 3), ("nonFlatOmegaP", C.c_float * 3),
+                ("flatOmegaN", C.c_float * 3), ("nonFlatOmegaN", C.c_float * 3)]
+
+
+class CorrParams(C.Structure):
+    _fields_ = [("inlierDistanceThreshold", C.c_float), ("inlierNormalAngularThreshold", C.c_float),
+                ("flatCurvatureThreshold", C.c_float), ("inlierCurvatureRatioThreshold", C.c_float)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("kind", C.c_int), ("mean", C.c_float * 16), ("refInv", C.c_float * 16),
+                ("info", C.c_float * 36)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("outerIterations", C.c_int), ("innerIterations", C.c_int), ("K", C.c_float * 9),
+                ("rows", C.c_int), ("cols", C.c_int), ("minD", C.c_float), ("maxD", C.c_float),
+                ("refSensorOffset", C.c_float * 16), ("curSensorOffset", C.c_float * 16),
+                ("initialGuess", C.c_float * 16), ("corr", CorrParams), ("inlierMaxChi2", C.c_float),
+                ("robustKernel", C.c_int), ("numThreads", C.c_int), ("numPriors", C.c_int),
+                ("priors", C.POINTER(Prior))]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("H", C.c_float * 36), ("b", C.c_float * 6), ("error", C.c_float),
+                ("inliers", C.c_int), ("numCorrespondences", C.c_int), ("omega", C.c_float * 36),
+                ("mean", C.c_float * 6), ("translationalRatio", C.c_float), ("rotationalRatio", C.c_float)]
+
+
+TRACE_STRIDE = 61
+
+
+def lib(fast=False):
+    key = "fast" if fast else "verify"
+    if key not in _LIBS:
+        build()
+        name = "liboracle_fast.so" if fast else "liboracle.so"
+        _LIBS[key] = C.CDLL(os.path.join(_HERE, "build", name))
+    return _LIBS[key]
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _fp(a):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def colmajor(M):
+    """numpy (r,c) matrix -> flat column-major float32 (the ABI's matrix convention)."""
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float32).T).reshape(-1)
+
+
+def from_colmajor(v, n):
+    return np.asarray(v, dtype=np.float32).reshape(n, n).T.copy()
+
+
+def default_stats_params(**kw):
+    """ctor defaults: statscalculatorintegralimage.cpp:6-12, informationmatrixcalculator.h:107-109,142-144"""
+    p = StatsParams()
+    p.worldRadius = 0.1
+    p.minImageRadius = 10
+    p.maxImageRadius = 30
+    p.minPoints = 50
+    p.curvatureThreshold = 0.02
+    p.omegaCurvatureThreshold = 0.02
+    p.flatOmegaP[:] = [1000.0, 1.0, 1.0]
+    p.nonFlatOmegaP[:] = [1.0, 1.0, 1.0]
+    p.flatOmegaN[:] = [100.0, 100.0, 100.0]
+    p.nonFlatOmegaN[:] = [1.0, 1.0, 1.0]
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_corr_params(**kw):
+    """ctor defaults: correspondencefinder.cpp:9-18"""
+    p = CorrParams()
+    p.inlierDistanceThreshold = 0.5
+    p.inlierNormalAngularThreshold = float(np.cos(np.pi / 6))
+    p.flatCurvatureThreshold = 0.02
+    p.inlierCurvatureRatioThreshold = 1.3
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Cloud:
+    """Host cloud in the oracle's layout (full 4x4 stats / information matrices)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.points = np.zeros((n, 4), np.float32)
+        self.normals = np.zeros((n, 4), np.float32)
+        self.statsM = np.zeros((n, 16), np.float32)
+        self.eigvals = np.zeros((n, 3), np.float32)
+        self.statsN = np.zeros(n, np.int32)
+        self.curvature = np.zeros(n, np.float32)
+        self.omegaP = np.zeros((n, 16), np.float32)
+        self.omegaN = np.zeros((n, 16), np.float32)
+
+    def truncated(self, n):
+        c = Cloud(0)
+        c.n = n
+        for k in ("points", "normals", "statsM", "eigvals", "statsN", "curvature", "omegaP", "omegaN"):
+            setattr(c, k, np.ascontiguousarray(getattr(self, k)[:n]))
+        return c
+
+    def omegaP6(self):
+        return sym6(self.omegaP)
+
+    def omegaN6(self):
+        return sym6(self.omegaN)
+
+
+def sym6(om16):
+    """(n,16) column-major 4x4 -> (n,6) upper triangle xx,xy,xz,yy,yz,zz (row<=col entries)."""
+    o = om16.reshape(-1, 4, 4)  # o[i, c, r]
+    return np.ascontiguousarray(np.stack([o[:, 0, 0], o[:, 1, 0], o[:, 2, 0], o[:, 1, 1], o[:, 2, 1], o[:, 2, 2]], axis=1))
+
+
+def depth_u16_to_f32(raw, scale=0.001, fast=False):
+    raw = np.ascontiguousarray(raw, dtype=np.uint16)
+    out = np.empty(raw.shape, np.float32)
+    lib(fast).orc_depth_u16_to_f32(raw.ctypes.data_as(C.POINTER(C.c_uint16)), raw.size, C.c_float(scale), _fp(out))
+    return out
+
+
+def depth_scale(depth, step, max_depth_cov=0.01, fast=False):
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    out = np.zeros((rows // step, cols // step), np.float32)
+    lib(fast).orc_depth_scale(dp, rows, cols, step, C.c_float(max_depth_cov), _fp(out))
+    return out
+
+
+def v2t(v):
+    v, vp = _f(v)
+    T = np.zeros(16, np.float32)
+    lib().orc_v2t(vp, _fp(T))
+    return from_colmajor(T, 4)
+
+
+def t2v(T):
+    Tc, tp = _f(colmajor(T))
+    v = np.zeros(6, np.float32)
+    lib().orc_t2v(tp, _fp(v))
+    return v
+
+
+def update_matrices(K, T):
+    Kc, kp = _f(colmajor(K))
+    Tc, tp = _f(colmajor(T))
+    KRt = np.zeros(16, np.float32)
+    iKRt = np.zeros(16, np.float32)
+    lib().orc_update_matrices(kp, tp, _fp(KRt), _fp(iKRt))
+    return from_colmajor(KRt, 4), from_colmajor(iKRt, 4)
+
+
+def unproject(depth, K, T, minD, maxD, fast=False):
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    _, iKRt = update_matrices(K, T)
+    ik, ikp = _f(colmajor(iKRt))
+    pts = np.zeros((rows * cols, 4), np.float32)
+    idx = np.zeros((rows, cols), np.int32)
+    n = lib(fast).orc_unproject(dp, rows, cols, ikp, C.c_float(minD), C.c_float(maxD), _fp(pts), _ip(idx))
+    return np.ascontiguousarray(pts[:n]), idx
+
+
+def project_intervals(depth, K, minD, maxD, world_radius, fast=False):
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    Kc, kp = _f(colmajor(K))
+    out = np.zeros((rows, cols), np.int32)
+    lib(fast).orc_project_intervals(dp, rows, cols, kp, C.c_float(minD), C.c_float(maxD), C.c_float(world_radius), _ip(out))
+    return out
+
+
+def project(points, rows, cols, K, T, minD, maxD, fast=False):
+    """PinholePointProjector::project with projector transform T (sensor pose)."""
+    KRt, _ = update_matrices(K, T)
+    return project_KRt(points, rows, cols, KRt, minD, maxD, fast)
+
+
+def project_KRt(points, rows, cols, KRt, minD, maxD, fast=False):
+    pts, pp = _f(points)
+    kr, krp = _f(colmajor(KRt))
+    idx = np.zeros((rows, cols), np.int32)
+    dep = np.zeros((rows, cols), np.float32)
+    lib(fast).orc_project(pp, pts.shape[0], rows, cols, krp, C.c_float(minD), C.c_float(maxD), _ip(idx), _fp(dep))
+    return idx, dep
+
+
+def integral_image(index, points, fast=False):
+    index, ip = _i(index)
+    pts, pp = _f(points)
+    rows, cols = index.shape
+    out = np.zeros((rows, cols, 10), np.float32)
+    lib(fast).orc_integral_image(ip, pp, rows, cols, _fp(out))
+    return out
+
+
+def eigen3(Cm):
+    c, cp = _f(colmajor(Cm))
+    ev = np.zeros(3, np.float32)
+    U = np.zeros(9, np.float32)
+    lib().orc_eigen3(cp, _fp(ev), _fp(U))
+    return ev, from_colmajor(U, 3)
+
+
+def depth_to_cloud(depth, K, minD, maxD, sp, sensor_offset=None, fast=False, want_aux=False):
+    """DepthImageConverterIntegralImage::compute -> (Cloud, index image[, interval, integral])."""
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    Kc, kp = _f(colmajor(K))
+    so, sop = _f(colmajor(np.eye(4) if sensor_offset is None else sensor_offset))
+    cl = Cloud(rows * cols)
+    idx = np.zeros((rows, cols), np.int32)
+    itv = np.zeros((rows, cols), np.int32)
+    integ = np.zeros((rows, cols, 10), np.float32)
+    n = lib(fast).orc_depth_to_cloud(dp, rows, cols, kp, C.c_float(minD), C.c_float(maxD), C.byref(sp), sop,
+                                     _fp(cl.points), _fp(cl.normals), _fp(cl.statsM), _fp(cl.eigvals),
+                                     _ip(cl.statsN), _fp(cl.curvature), _fp(cl.omegaP), _fp(cl.omegaN),
+                                     _ip(idx), _ip(itv), _fp(integ))
+    cl = cl.truncated(n)
+    if want_aux:
+        return cl, idx, itv, integ
+    return cl, idx
+
+
+def correspond(ref_index, cur_index, ref, cur, T, cp, num_threads=8, fast=False):
+    """CorrespondenceFinder::compute(ref, cur, T) -> (corr (n,2), corr image of ref indices)."""
+    ri, rip = _i(ref_index)
+    ci, cip = _i(cur_index)
+    rows, cols = ri.shape
+    Tc, tp = _f(colmajor(T))
+    corr = np.full((rows * cols, 2), -1, np.int32)
+    cimg = np.full((rows, cols), -1, np.int32)
+    n = lib(fast).orc_correspond(rip, cip, rows, cols, _fp(ref.points), _fp(ref.normals), _fp(ref.curvature),
+                                 _fp(cur.points), _fp(cur.normals), _fp(cur.curvature), tp, C.byref(cp),
+                                 num_threads, _ip(corr), _ip(cimg))
+    return np.ascontiguousarray(corr[:n]), cimg
+
+
+def linearize(corr, ref, cur, T, max_chi2=9e3, robust=True, num_threads=8, fast=False):
+    corr, cp = _i(corr)
+    Tc, tp = _f(colmajor(T))
+    H = np.zeros(36, np.float32)
+    b = np.zeros(6, np.float32)
+    err = C.c_float(0)
+    inl = C.c_int(0)
+    lib(fast).orc_linearize(cp, corr.shape[0], _fp(ref.points), _fp(ref.normals), _fp(cur.points), _fp(cur.normals),
+                            _fp(cur.omegaP), _fp(cur.omegaN), tp, C.c_float(max_chi2), int(robust), num_threads,
+                            _fp(H), _fp(b), C.byref(err), C.byref(inl))
+    return from_colmajor(H, 6), b, err.value, inl.value
+
+
+def linearize_f64(corr, ref, cur, T, max_chi2=9e3, robust=True):
+    corr, cp = _i(corr)
+    Tc, tp = _f(colmajor(T))
+    H = np.zeros(36, np.float64)
+    b = np.zeros(6, np.float64)
+    err = C.c_double(0)
+    inl = C.c_int(0)
+    dptr = C.POINTER(C.c_double)
+    lib().orc_linearize_f64(cp, corr.shape[0], _fp(ref.points), _fp(ref.normals), _fp(cur.points), _fp(cur.normals),
+                            _fp(cur.omegaP), _fp(cur.omegaN), tp, C.c_float(max_chi2), int(robust),
+                            H.ctypes.data_as(dptr), b.ctypes.data_as(dptr), C.byref(err), C.byref(inl))
+    return H.reshape(6, 6).T.copy(), b, err.value, inl.value
+
+
+def ldlt_solve6(H, b):
+    Hc, hp = _f(colmajor(H))
+    bb, bp = _f(b)
+    x = np.zeros(6, np.float32)
+    lib().orc_ldlt_solve6(hp, bp, _fp(x))
+    return x
+
+
+def make_prior(kind, mean, info, reference=None):
+    p = Prior()
+    p.kind = kind
+    p.mean[:] = colmajor(mean).tolist()
+    ri = np.eye(4, dtype=np.float32)
+    if reference is not None:
+        ref = np.asarray(reference, np.float32)
+        ri = np.eye(4, dtype=np.float32)
+        ri[:3, :3] = ref[:3, :3].T
+        ri[:3, 3] = -(ref[:3, :3].T @ ref[:3, 3])
+    p.refInv[:] = colmajor(ri).tolist()
+    p.info[:] = colmajor(info).tolist()
+    return p
+
+
+def make_align_params(K, rows, cols, minD, maxD, cp, outer=10, inner=1, guess=None, ref_offset=None,
+                      cur_offset=None, max_chi2=9e3, robust=True, num_threads=8, priors=()):
+    p = AlignParams()
+    p.outerIterations = outer
+    p.innerIterations = inner
+    p.K[:] = colmajor(K).tolist()
+    p.rows, p.cols = rows, cols
+    p.minD, p.maxD = minD, maxD
+    eye = np.eye(4, dtype=np.float32)
+    p.refSensorOffset[:] = colmajor(eye if ref_offset is None else ref_offset).tolist()
+    p.curSensorOffset[:] = colmajor(eye if cur_offset is None else cur_offset).tolist()
+    p.initialGuess[:] = colmajor(eye if guess is None else guess).tolist()
+    p.corr = cp
+    p.inlierMaxChi2 = max_chi2
+    p.robustKernel = int(robust)
+    p.numThreads = num_threads
+    p.numPriors = len(priors)
+    if priors:
+        arr = (Prior * len(priors))(*priors)
+        p._keep = arr
+        p.priors = C.cast(arr, C.POINTER(Prior))
+    return p
+
+
+class AlignOutput:
+    pass
+
+
+def align(ref, cur, ap, fast=False, want_trace=True):
+    """Aligner::align() on two oracle clouds."""
+    rows, cols = ap.rows, ap.cols
+    res = AlignResult()
+    out = AlignOutput()
+    out.refIndex = np.zeros((rows, cols), np.int32)
+    out.refDepth = np.zeros((rows, cols), np.float32)
+    out.curIndex = np.zeros((rows, cols), np.int32)
+    out.curDepth = np.zeros((rows, cols), np.float32)
+    corr = np.full((rows * cols, 2), -1, np.int32)
+    trace = np.zeros((max(ap.outerIterations, 1), TRACE_STRIDE), np.float32)
+    lib(fast).orc_align(ref.n, _fp(ref.points), _fp(ref.normals), _fp(ref.curvature),
+                        cur.n, _fp(cur.points), _fp(cur.normals), _fp(cur.curvature),
+                        _fp(cur.omegaP), _fp(cur.omegaN), C.byref(ap), C.byref(res),
+                        _ip(out.refIndex), _fp(out.refDepth), _ip(out.curIndex), _fp(out.curDepth), _ip(corr),
+                        _fp(trace) if want_trace else None)
+    out.T = from_colmajor(np.array(res.T[:], np.float32), 4)
+    out.H = from_colmajor(np.array(res.H[:], np.float32), 6)
+    out.b = np.array(res.b[:], np.float32)
+    out.error = res.error
+    out.inliers = res.inliers
+    out.numCorrespondences = res.numCorrespondences
+    out.corr = np.ascontiguousarray(corr[:res.numCorrespondences])
+    out.omega = from_colmajor(np.array(res.omega[:], np.float32), 6)
+    out.mean = np.array(res.mean[:], np.float32)
+    out.translationalRatio = res.translationalRatio
+    out.rotationalRatio = res.rotationalRatio
+    out.trace_T = [from_colmajor(trace[i, :16], 4) for i in range(ap.outerIterations)]
+    out.trace_H = [from_colmajor(trace[i, 16:52], 6) for i in range(ap.outerIterations)]
+    out.trace_b = [trace[i, 52:58].copy() for i in range(ap.outerIterations)]
+    out.trace_err = trace[:, 58].copy()
+    out.trace_inliers = trace[:, 59].astype(np.int64)
+    out.trace_ncorr = trace[:, 60].astype(np.int64)
+    return out
+
+
+def image_stats(cur_depth, ref_depth, thr=50.0):
+    c, cp = _f(cur_depth)
+    r, rp = _f(ref_depth)
+    nz, inl, outl = C.c_int(0), C.c_int(0), C.c_int(0)
+    rd = C.c_float(0)
+    lib().orc_image_stats(cp, rp, c.size, C.c_float(thr), C.byref(nz), C.byref(inl), C.byref(outl), C.byref(rd))
+    return nz.value, inl.value, outl.value, rd.value
+
+
+# restype declarations that are not int
+def _declare():
+    for fast in (False, True):
+        l = lib(fast)
+        for name in ("orc_unproject", "orc_depth_to_cloud", "orc_correspond"):
+            getattr(l, name).restype = C.c_int
+        for name in ("orc_depth_u16_to_f32", "orc_depth_scale", "orc_v2t", "orc_t2v", "orc_update_matrices",
+                     "orc_project_intervals", "orc_project", "orc_integral_image", "orc_eigen3", "orc_linearize",
+                     "orc_linearize_f64", "orc_ldlt_solve6", "orc_align", "orc_image_stats"):
+            getattr(l, name).restype = None
+
+
+_declare()
