@@ -1,0 +1,413 @@
+"""ctypes binding of the C-ABI in include/nicp_b200.h (the CUDA library built from csrc/).
+
+This is the thin Python face used by tests/, bench.py and __graft_entry__.py.  It never falls
+back to a CPU implementation: if the shared library is missing, or no CUDA device works,
+calls raise.  (The C++ host classes mirroring pwn:: live in include/pwn/.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+
+NICP_OK = 0
+
+# every symbol include/nicp_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "nicp_create", "nicp_destroy", "nicp_last_error", "nicp_synchronize", "nicp_is_verification_build",
+    "nicp_launch_count", "nicp_stream",
+    "nicp_cloud_create", "nicp_cloud_destroy", "nicp_cloud_size", "nicp_cloud_upload", "nicp_cloud_download",
+    "nicp_cloud_download_stats", "nicp_cloud_transform",
+    "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
+    "nicp_raw_depth_to_cloud", "nicp_last_integral_image", "nicp_last_interval_image",
+    "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
+    "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch",
+]
+
+
+class Projector(C.Structure):
+    _fields_ = [("K", C.c_float * 9), ("rows", C.c_int), ("cols", C.c_int),
+                ("min_distance", C.c_float), ("max_distance", C.c_float)]
+
+
+class StatsParams(C.Structure):
+    _fields_ = [("world_radius", C.c_float), ("min_image_radius", C.c_int), ("max_image_radius", C.c_int),
+                ("min_points", C.c_int), ("curvature_threshold", C.c_float),
+                ("omega_curvature_threshold", C.c_float), ("flat_omega_p", C.c_float * 3),
+                ("flat_omega_n", C.c_float * 3), ("nonflat_omega_n", C.c_float * 3)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("inlier_distance_threshold", C.c_float), ("inlier_normal_angular_threshold", C.c_float),
+                ("flat_curvature_threshold", C.c_float), ("inlier_curvature_ratio_threshold", C.c_float),
+                ("inlier_max_chi2", C.c_float), ("robust_kernel", C.c_int), ("outer_iterations", C.c_int),
+                ("inner_iterations", C.c_int)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("kind", C.c_int), ("mean", C.c_float * 16), ("reference", C.c_float * 16),
+                ("information", C.c_float * 36)]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("omega", C.c_float * 36), ("error", C.c_float), ("inliers", C.c_int),
+                ("num_correspondences", C.c_int), ("image_non_zeros", C.c_int), ("image_inliers", C.c_int),
+                ("image_outliers", C.c_int), ("image_reprojection_distance", C.c_float), ("status", C.c_int),
+                ("translational_eigen_ratio", C.c_float), ("rotational_eigen_ratio", C.c_float),
+                ("reserved", C.c_float * 2)]
+
+
+assert C.sizeof(AlignResult) == 256
+
+RESULT_DTYPE = np.dtype([("T", np.float32, 16), ("omega", np.float32, 36), ("error", np.float32),
+                         ("inliers", np.int32), ("num_correspondences", np.int32), ("image_non_zeros", np.int32),
+                         ("image_inliers", np.int32), ("image_outliers", np.int32),
+                         ("image_reprojection_distance", np.float32), ("status", np.int32),
+                         ("translational_eigen_ratio", np.float32), ("rotational_eigen_ratio", np.float32),
+                         ("reserved", np.float32, 2)])
+assert RESULT_DTYPE.itemsize == 256
+
+
+def lib_path(verify=False):
+    return os.path.join(LIB_DIR, "libnicp_b200_verify.so" if verify else "libnicp_b200.so")
+
+
+_LIBS = {}
+
+
+def load(verify=False):
+    """dlopen the CUDA library; raises if it has not been built (no fallback)."""
+    key = bool(verify)
+    if key in _LIBS:
+        return _LIBS[key]
+    path = lib_path(verify)
+    if not os.path.exists(path):
+        raise RuntimeError("%s is missing: build it with `make -C g2o_frontend_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    L.nicp_last_error.restype = C.c_char_p
+    L.nicp_launch_count.restype = C.c_longlong
+    L.nicp_stream.restype = C.c_void_p
+    L.nicp_destroy.restype = None
+    L.nicp_cloud_destroy.restype = None
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:
+            pass
+    _LIBS[key] = L
+    return L
+
+
+class NicpError(RuntimeError):
+    pass
+
+
+def _check(L, rc):
+    if rc != NICP_OK:
+        raise NicpError("nicp error %d: %s" % (rc, L.nicp_last_error().decode()))
+
+
+def colmajor(M):
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float32).T).reshape(-1)
+
+
+def from_colmajor(v, n):
+    return np.asarray(v, dtype=np.float32).reshape(n, n).T.copy()
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def make_projector(K, rows, cols, min_distance=0.01, max_distance=6.0):
+    p = Projector()
+    p.K[:] = colmajor(K).tolist()
+    p.rows, p.cols = int(rows), int(cols)
+    p.min_distance, p.max_distance = min_distance, max_distance
+    return p
+
+
+def make_stats_params(world_radius=0.1, min_image_radius=10, max_image_radius=30, min_points=50,
+                      curvature_threshold=0.02, omega_curvature_threshold=0.02,
+                      flat_omega_p=(1000.0, 1.0, 1.0), flat_omega_n=(100.0, 100.0, 100.0),
+                      nonflat_omega_n=(1.0, 1.0, 1.0)):
+    s = StatsParams()
+    s.world_radius = world_radius
+    s.min_image_radius, s.max_image_radius, s.min_points = min_image_radius, max_image_radius, min_points
+    s.curvature_threshold, s.omega_curvature_threshold = curvature_threshold, omega_curvature_threshold
+    s.flat_omega_p[:] = list(flat_omega_p)
+    s.flat_omega_n[:] = list(flat_omega_n)
+    s.nonflat_omega_n[:] = list(nonflat_omega_n)
+    return s
+
+
+def make_align_params(inlier_distance_threshold=0.5, inlier_normal_angular_threshold=float(np.cos(np.pi / 6)),
+                      flat_curvature_threshold=0.02, inlier_curvature_ratio_threshold=1.3, inlier_max_chi2=9e3,
+                      robust_kernel=True, outer_iterations=10, inner_iterations=1):
+    a = AlignParams()
+    a.inlier_distance_threshold = inlier_distance_threshold
+    a.inlier_normal_angular_threshold = inlier_normal_angular_threshold
+    a.flat_curvature_threshold = flat_curvature_threshold
+    a.inlier_curvature_ratio_threshold = inlier_curvature_ratio_threshold
+    a.inlier_max_chi2 = inlier_max_chi2
+    a.robust_kernel = int(robust_kernel)
+    a.outer_iterations, a.inner_iterations = outer_iterations, inner_iterations
+    return a
+
+
+class Cloud:
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        self.capacity = int(capacity)
+        self.handle = C.c_void_p()
+        _check(ctx.L, ctx.L.nicp_cloud_create(ctx.handle, self.capacity, C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.ctx.L.nicp_cloud_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return self.ctx.L.nicp_cloud_size(self.handle)
+
+    def upload(self, points4, normals4=None, curvature=None, omega_p6=None, omega_n6=None):
+        pts = np.ascontiguousarray(points4, np.float32)
+        n = pts.shape[0]
+        keep = [pts]
+
+        def opt(a, w):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            assert a.size == n * w
+            keep.append(a)
+            return _fptr(a)
+
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_upload(self.ctx.handle, self.handle, n, _fptr(pts), opt(normals4, 4),
+                                                         opt(curvature, 1), opt(omega_p6, 6), opt(omega_n6, 6)))
+        return self
+
+    def download(self):
+        n = self.size()
+        out = {"points": np.zeros((n, 4), np.float32), "normals": np.zeros((n, 4), np.float32),
+               "curvature": np.zeros(n, np.float32), "omega_p": np.zeros((n, 6), np.float32),
+               "omega_n": np.zeros((n, 6), np.float32)}
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_download(self.ctx.handle, self.handle, _fptr(out["points"]),
+                                                           _fptr(out["normals"]), _fptr(out["curvature"]),
+                                                           _fptr(out["omega_p"]), _fptr(out["omega_n"])))
+        return out
+
+    def download_stats(self):
+        n = self.size()
+        s16 = np.zeros((n, 16), np.float32)
+        ev = np.zeros((n, 3), np.float32)
+        cnt = np.zeros(n, np.int32)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_download_stats(self.ctx.handle, self.handle, _fptr(s16), _fptr(ev),
+                                                                 _iptr(cnt)))
+        return s16, ev, cnt
+
+    def transform(self, T):
+        t = colmajor(T)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_transform(self.ctx.handle, self.handle, _fptr(t)))
+
+
+class Context:
+    """One nicp_context (one GPU, one stream)."""
+
+    def __init__(self, device=0, verify=False):
+        self.L = load(verify)
+        self.verify = verify
+        self.handle = C.c_void_p()
+        _check(self.L, self.L.nicp_create(int(device), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.L.nicp_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self.L, self.L.nicp_synchronize(self.handle))
+
+    def launch_count(self):
+        return int(self.L.nicp_launch_count(self.handle))
+
+    def stream(self):
+        return self.L.nicp_stream(self.handle)
+
+    def new_cloud(self, capacity):
+        return Cloud(self, capacity)
+
+    # ---- depth helpers
+    def depth_prepare(self, raw, depth_scale=0.001, step=1, max_depth_cov=0.01):
+        raw = np.ascontiguousarray(raw, np.uint16)
+        rows, cols = raw.shape
+        out = np.zeros((rows // max(step, 1), cols // max(step, 1)), np.float32)
+        _check(self.L, self.L.nicp_depth_prepare(self.handle, raw.ctypes.data_as(C.POINTER(C.c_uint16)), rows, cols,
+                                                 C.c_float(depth_scale), int(step), C.c_float(max_depth_cov), _fptr(out)))
+        return out
+
+    # ---- frame preparation
+    def unproject(self, depth, iKRt, min_distance, max_distance, cloud=None):
+        depth = np.ascontiguousarray(depth, np.float32)
+        rows, cols = depth.shape
+        cloud = cloud or self.new_cloud(rows * cols)
+        index = np.zeros((rows, cols), np.int32)
+        m = colmajor(iKRt)
+        _check(self.L, self.L.nicp_unproject(self.handle, _fptr(depth), rows, cols, _fptr(m), C.c_float(min_distance),
+                                             C.c_float(max_distance), cloud.handle, _iptr(index)))
+        return cloud, index
+
+    def project_intervals(self, depth, proj, world_radius):
+        depth = np.ascontiguousarray(depth, np.float32)
+        out = np.zeros(depth.shape, np.int32)
+        _check(self.L, self.L.nicp_project_intervals(self.handle, _fptr(depth), C.byref(proj), C.c_float(world_radius),
+                                                     _iptr(out)))
+        return out
+
+    def depth_to_cloud(self, depth, proj, sp, sensor_offset=None, keep_stats=False, cloud=None, want_index=True):
+        depth = np.ascontiguousarray(depth, np.float32)
+        assert depth.shape == (proj.rows, proj.cols)
+        cloud = cloud or self.new_cloud(proj.rows * proj.cols)
+        index = np.zeros(depth.shape, np.int32) if want_index else None
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        _check(self.L, self.L.nicp_depth_to_cloud(self.handle, _fptr(depth), C.byref(proj), C.byref(sp), _fptr(so),
+                                                  int(keep_stats), cloud.handle,
+                                                  _iptr(index) if want_index else None))
+        return cloud, index
+
+    def raw_depth_to_cloud(self, raw, proj, sp, depth_scale=0.001, step=1, max_depth_cov=0.01, sensor_offset=None,
+                           keep_stats=False, cloud=None, want_index=False):
+        """raw may be a numpy uint16 array or an integer host address (pinned buffer) with raw_shape."""
+        raw = np.ascontiguousarray(raw, np.uint16)
+        rows, cols = raw.shape
+        cloud = cloud or self.new_cloud(proj.rows * proj.cols)
+        index = np.zeros((proj.rows, proj.cols), np.int32) if want_index else None
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        _check(self.L, self.L.nicp_raw_depth_to_cloud(self.handle, raw.ctypes.data_as(C.POINTER(C.c_uint16)), rows, cols,
+                                                      C.c_float(depth_scale), int(step), C.c_float(max_depth_cov),
+                                                      C.byref(proj), C.byref(sp), _fptr(so), int(keep_stats),
+                                                      cloud.handle, _iptr(index) if want_index else None))
+        return cloud, index
+
+    def last_integral_image(self, rows, cols):
+        out = np.zeros((rows, cols, 10), np.float32)
+        _check(self.L, self.L.nicp_last_integral_image(self.handle, _fptr(out)))
+        return out
+
+    def last_interval_image(self, rows, cols):
+        out = np.zeros((rows, cols), np.int32)
+        _check(self.L, self.L.nicp_last_interval_image(self.handle, _iptr(out)))
+        return out
+
+    # ---- projection
+    def project(self, cloud, KRt, rows, cols, min_distance, max_distance):
+        index = np.zeros((rows, cols), np.int32)
+        depth = np.zeros((rows, cols), np.float32)
+        m = colmajor(KRt)
+        _check(self.L, self.L.nicp_project(self.handle, cloud.handle, _fptr(m), rows, cols, C.c_float(min_distance),
+                                           C.c_float(max_distance), _iptr(index), _fptr(depth)))
+        return index, depth
+
+    # ---- stage-level finder + lineariser
+    def correspond_linearize(self, ref, cur, ref_index, cur_index, T, ap):
+        ri = np.ascontiguousarray(ref_index, np.int32)
+        ci = np.ascontiguousarray(cur_index, np.int32)
+        rows, cols = ri.shape
+        t = colmajor(T)
+        H = np.zeros(36, np.float32)
+        b = np.zeros(6, np.float32)
+        err, inl, nc = C.c_float(0), C.c_int(0), C.c_int(0)
+        cimg = np.zeros((rows, cols), np.int32)
+        _check(self.L, self.L.nicp_correspond_linearize(self.handle, ref.handle, cur.handle, _iptr(ri), _iptr(ci), rows,
+                                                        cols, _fptr(t), C.byref(ap), _fptr(H), _fptr(b), C.byref(err),
+                                                        C.byref(inl), C.byref(nc), _iptr(cimg)))
+        return from_colmajor(H, 6), b, err.value, inl.value, nc.value, cimg
+
+    def linearize(self, ref, cur, corr, T, ap):
+        corr = np.ascontiguousarray(corr, np.int32)
+        t = colmajor(T)
+        H = np.zeros(36, np.float32)
+        b = np.zeros(6, np.float32)
+        err, inl = C.c_float(0), C.c_int(0)
+        _check(self.L, self.L.nicp_linearize(self.handle, ref.handle, cur.handle, _iptr(corr), corr.shape[0], _fptr(t),
+                                             C.byref(ap), _fptr(H), _fptr(b), C.byref(err), C.byref(inl)))
+        return from_colmajor(H, 6), b, err.value, inl.value
+
+    # ---- alignment
+    def align(self, ref, cur, proj, ap, ref_offset=None, cur_offset=None, guess=None, img_threshold=50.0):
+        eye = np.eye(4, dtype=np.float32)
+        ro = colmajor(eye if ref_offset is None else ref_offset)
+        co = colmajor(eye if cur_offset is None else cur_offset)
+        g = colmajor(eye if guess is None else guess)
+        res = AlignResult()
+        _check(self.L, self.L.nicp_align(self.handle, ref.handle, cur.handle, C.byref(proj), C.byref(ap), _fptr(ro),
+                                         _fptr(co), _fptr(g), None, 0, C.c_float(img_threshold), C.byref(res)))
+        return res
+
+    def align_state(self, rows, cols, max_corr=None):
+        ri = np.zeros((rows, cols), np.int32)
+        rd = np.zeros((rows, cols), np.float32)
+        ci = np.zeros((rows, cols), np.int32)
+        cd = np.zeros((rows, cols), np.float32)
+        corr = np.full((rows * cols, 2), -1, np.int32)
+        H = np.zeros(36, np.float32)
+        b = np.zeros(6, np.float32)
+        _check(self.L, self.L.nicp_align_get_state(self.handle, _iptr(ri), _fptr(rd), _iptr(ci), _fptr(cd), _iptr(corr),
+                                                   _fptr(H), _fptr(b)))
+        n = int((corr[:, 0] >= 0).sum())
+        return {"ref_index": ri, "ref_depth": rd, "cur_index": ci, "cur_depth": cd, "corr": corr[:n],
+                "H": from_colmajor(H, 6), "b": b}
+
+    def align_trace(self, iters):
+        tr = np.zeros((iters, 61), np.float32)
+        _check(self.L, self.L.nicp_align_get_trace(self.handle, _fptr(tr), iters))
+        return tr
+
+    def align_batch(self, refs, curs, proj, ap, guesses=None, ref_offset=None, cur_offset=None, img_threshold=50.0,
+                    results=None):
+        """refs/curs: sequences of Cloud.  guesses: (n,4,4) row/col matrices or None.  Returns a
+        numpy structured array (RESULT_DTYPE) of n 256-byte records."""
+        n = len(refs)
+        assert len(curs) == n
+        eye = np.eye(4, dtype=np.float32)
+        ro = colmajor(eye if ref_offset is None else ref_offset)
+        co = colmajor(eye if cur_offset is None else cur_offset)
+        if guesses is None:
+            g = np.tile(colmajor(eye), (n, 1))
+        else:
+            g = np.ascontiguousarray(np.asarray(guesses, np.float32).transpose(0, 2, 1)).reshape(n, 16)
+        g = np.ascontiguousarray(g, np.float32)
+        RA = (C.c_void_p * n)(*[r.handle for r in refs])
+        CA = (C.c_void_p * n)(*[c.handle for c in curs])
+        if results is None:
+            results = np.zeros(n, RESULT_DTYPE)
+        _check(self.L, self.L.nicp_align_batch(self.handle, n, RA, CA, C.byref(proj), C.byref(ap), _fptr(ro), _fptr(co),
+                                               _fptr(g), C.c_float(img_threshold),
+                                               results.ctypes.data_as(C.POINTER(AlignResult))))
+        return results
+
+
+def result_T(res):
+    return from_colmajor(np.array(res.T[:], np.float32), 4)
+
+
+def result_omega(res):
+    return from_colmajor(np.array(res.omega[:], np.float32), 6)

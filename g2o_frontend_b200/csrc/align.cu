@@ -1,0 +1,505 @@
+// align.cu -- the NICP alignment loop on the device.
+//
+// Replaces, for a batch of independent (reference, current) cloud pairs processed in lock step:
+//   PinholePointProjector::project      pinholepointprojector.cpp:33-66   -> k_project
+//   CorrespondenceFinder::compute       correspondencefinder.cpp:20-118  \  k_corr_lin<0> (fused)
+//   Linearizer::update                  linearizer.cpp:17-115            /  k_corr_lin<1> (from the stored correspondences)
+//   Aligner::align loop body            aligner.cpp:66-118                -> k_reduce_solve
+//   PwnMatcherBase::matchClouds stats   pwn_tracker2/pwn_matcher_base.cpp:167-196 -> folded into k_corr_lin<1>
+//
+// z-buffer: one 64-bit word per pixel, (float_bits(depth) << 32) | pointIndex, filled with
+// atomicMin.  depth > 0 so unsigned order == float order: the nearest point wins and, on equal
+// depth, the lowest point index wins -- exactly the outcome of the reference's sequential scatter
+// with its strict `otherDistance > d` test.  Empty = all ones (index decodes to -1).
+//
+// Reduction: every thread accumulates 30 float sums over its pixels (21 unique H entries, 6 b,
+// chi2, inliers, correspondences), a transposing warp butterfly leaves component j in lane j
+// (31 shuffles instead of 160), the 8 warps of a CTA are added in fixed order, and one partial
+// row per CTA goes to global memory.  k_reduce_solve adds the rows in fixed order, so H, b and
+// the pose are bit-reproducible run to run (no float atomics anywhere).
+#include "nicp_internal.cuh"
+
+namespace nicp {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PairState *st = desc[i].state;
+  float T[16], tmp[16];
+  for (int k = 0; k < 16; k++) T[k] = desc[i].guess[k];
+  fix_last_row(T);
+  for (int k = 0; k < 16; k++) st->T[k] = T[k];
+  iso_inverse(T, tmp);
+  for (int k = 0; k < 16; k++) st->invT[k] = tmp[k];
+  iso_mul(T, ac.refOffset, tmp);
+  float KRt[16];
+  compute_KRt(ac.K, tmp, KRt);
+  for (int k = 0; k < 16; k++) st->KRt[k] = KRt[k];
+  for (int k = 0; k < 36; k++) { st->H[k] = 0.f; st->statH[k] = 0.f; }
+  for (int k = 0; k < 6; k++) { st->b[k] = 0.f; st->statb[k] = 0.f; }
+  st->error = 0.f;
+  st->inliers = 0;
+  st->ncorr = 0;
+  st->img_nonzeros = 0;
+  st->img_inliers = 0;
+  st->img_sum = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// _project (pinholepointprojector.h:224-233) + the z-test of project (pinholepointprojector.cpp:52-64)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i, int rows, int cols, float minD,
+                                              float maxD, unsigned long long *__restrict__ z) {
+  float ix, iy, d;
+  xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
+  if (d < minD || d > maxD) return;
+  float s = fdiv(1.0f, d);
+  float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
+  if (!(fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows)) return;
+  int x = (int)fx, y = (int)fy;
+  unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
+  atomicMin(&z[(size_t)y * cols + x], key);
+}
+
+// which: 0/1 = reference cloud into refZ[which] with the pair's KRt; 2 = current cloud into curZ
+// with the (shared) current-sensor KRt, only for the pair that owns that buffer.
+__global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ desc, int which, Affine curKRt, int rows,
+                                                 int cols, float minD, float maxD, const int *__restrict__ ownsCur) {
+  const PairDesc &D = desc[blockIdx.y];
+  const float4 *pts;
+  unsigned long long *z;
+  int n;
+  Affine KRt;
+  if (which == 2) {
+    if (!ownsCur[blockIdx.y]) return;
+    pts = D.curPoints;
+    n = *D.curN;
+    z = D.curZ;
+    KRt = curKRt;
+  } else {
+    pts = D.refPoints;
+    n = *D.refN;
+    z = D.refZ[which];
+    KRt = affine_from(D.state->KRt);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+}
+
+__global__ void __launch_bounds__(256) k_project_single(const float4 *__restrict__ pts, const int *__restrict__ nPtr,
+                                                        Affine KRt, int rows, int cols, float minD, float maxD,
+                                                        unsigned long long *__restrict__ z) {
+  int n = *nPtr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+}
+
+__global__ void k_decode_z(const unsigned long long *__restrict__ z, int n, int *__restrict__ index,
+                           float *__restrict__ depth) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long v = z[i];
+  int idx = (int)(unsigned int)(v & 0xFFFFFFFFull);
+  if (index) index[i] = idx;
+  if (depth) depth[i] = (v == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(v >> 32));
+}
+
+__global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int *__restrict__ ownsCur) {
+  if (!ownsCur[blockIdx.y]) return;
+  const PairDesc &D = desc[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+    D.curIndex[i] = (int)(unsigned int)(D.curZ[i] & 0xFFFFFFFFull);
+}
+
+int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
+                          float minD, float maxD, unsigned long long *d_z) {
+  NICP_CUDA(cudaMemsetAsync(d_z, 0xFF, (size_t)rows * cols * sizeof(unsigned long long), ctx->stream));
+  int blocks = (cloud->capacity + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  k_project_single<<<blocks, 256, 0, ctx->stream>>>(cloud->points, cloud->d_n, affine_from(KRt), rows, cols, minD, maxD,
+                                                    d_z);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth) {
+  k_decode_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_z, n, d_index, d_depth);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transposing warp reduction of 32 values: afterwards lane j holds the warp total of v[j] in v[0]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[kAccum], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      float mine = upper ? v[i + off] : v[i];
+      float send = upper ? v[i] : v[i + off];
+      v[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// one correspondence's contribution (linearizer.cpp:56-89); ordinary operators: may be contracted
+// into FMAs in the default build, never in the --fmad=false build.
+__device__ __forceinline__ void accumulate_term(float (&acc)[kAccum], float rpx, float rpy, float rpz, float rnx,
+                                                float rny, float rnz, float4 cp, float4 cn, float4 o0, float4 o1,
+                                                float4 o2, float maxChi2, int robust) {
+  // Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l]
+  const float a = o0.x, b = o0.y, c = o0.z, d = o0.w, e = o1.x, f = o1.y;
+  const float g = o1.z, h = o1.w, i = o2.x, j = o2.y, k = o2.z, l = o2.w;
+  const float pe0 = rpx - cp.x, pe1 = rpy - cp.y, pe2 = rpz - cp.z;
+  const float ne0 = rnx - cn.x, ne1 = rny - cn.y, ne2 = rnz - cn.z;
+  const float ep0 = (a * pe0 + b * pe1) + c * pe2;
+  const float ep1 = (b * pe0 + d * pe1) + e * pe2;
+  const float ep2 = (c * pe0 + e * pe1) + f * pe2;
+  const float en0 = (g * ne0 + h * ne1) + i * ne2;
+  const float en1 = (h * ne0 + j * ne1) + k * ne2;
+  const float en2 = (i * ne0 + k * ne1) + l * ne2;
+  const float chi = ((pe0 * ep0 + pe1 * ep1) + pe2 * ep2) + ((ne0 * en0 + ne1 * en1) + ne2 * en2);
+  float ks = 1.0f;
+  if (chi > maxChi2) {
+    if (!robust) return;
+    ks = sqrtf(maxChi2 / chi);
+  }
+  acc[A_INL] += 1.0f;
+  acc[A_ERR] += ks * chi;
+  // skew(v) = -2 [v]x (bm_se3.h:54-66): columns s0=(0,-tz,ty) s1=(tz,0,-tx) s2=(-ty,tx,0)
+  const float px = 2.0f * rpx, py = 2.0f * rpy, pz = 2.0f * rpz;
+  const float qx = 2.0f * rnx, qy = 2.0f * rny, qz = 2.0f * rnz;
+  // M = Omega_P * Sp
+  const float m00 = c * py - b * pz, m01 = a * pz - c * px, m02 = b * px - a * py;
+  const float m10 = e * py - d * pz, m11 = b * pz - e * px, m12 = d * px - b * py;
+  const float m20 = f * py - e * pz, m21 = c * pz - f * px, m22 = e * px - c * py;
+  // N = Omega_N * Sn
+  const float n00 = i * qy - h * qz, n01 = g * qz - i * qx, n02 = h * qx - g * qy;
+  const float n10 = k * qy - j * qz, n11 = h * qz - k * qx, n12 = j * qx - h * qy;
+  const float n20 = l * qy - k * qz, n21 = i * qz - l * qx, n22 = k * qx - i * qy;
+  acc[A_HTT + 0] += a; acc[A_HTT + 1] += b; acc[A_HTT + 2] += c;
+  acc[A_HTT + 3] += d; acc[A_HTT + 4] += e; acc[A_HTT + 5] += f;
+  acc[A_HTR + 0] += m00; acc[A_HTR + 1] += m01; acc[A_HTR + 2] += m02;
+  acc[A_HTR + 3] += m10; acc[A_HTR + 4] += m11; acc[A_HTR + 5] += m12;
+  acc[A_HTR + 6] += m20; acc[A_HTR + 7] += m21; acc[A_HTR + 8] += m22;
+  // Hrr = Sp^T M + Sn^T N, upper triangle; S^T row0 = (0,-tz,ty), row1 = (tz,0,-tx), row2 = (-ty,tx,0)
+  acc[A_HRR + 0] += (py * m20 - pz * m10) + (qy * n20 - qz * n10);
+  acc[A_HRR + 1] += (py * m21 - pz * m11) + (qy * n21 - qz * n11);
+  acc[A_HRR + 2] += (py * m22 - pz * m12) + (qy * n22 - qz * n12);
+  acc[A_HRR + 3] += (pz * m01 - px * m21) + (qz * n01 - qx * n21);
+  acc[A_HRR + 4] += (pz * m02 - px * m22) + (qz * n02 - qx * n22);
+  acc[A_HRR + 5] += (px * m12 - py * m02) + (qx * n12 - qy * n02);
+  acc[A_BT + 0] += ks * ep0; acc[A_BT + 1] += ks * ep1; acc[A_BT + 2] += ks * ep2;
+  acc[A_BR + 0] += ks * ((py * ep2 - pz * ep1) + (qy * en2 - qz * en1));
+  acc[A_BR + 1] += ks * ((pz * ep0 - px * ep2) + (qz * en0 - qx * en2));
+  acc[A_BR + 2] += ks * ((px * ep1 - py * ep0) + (qx * en1 - qy * en0));
+}
+
+// MODE 0: correspondence gates + linearise at state->invT; writes the correspondence image and
+//         resets the other reference z-buffer for the next iteration's projection.
+// MODE 1: linearise at state->invT over the stored correspondence image (inner iterations > 0,
+//         _computeStatistics) and, if imgStats, accumulate the matchClouds image statistics
+//         (slots 29,30,31 = reprojection sum, nonZeros, inliers).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_corr_lin(const PairDesc *__restrict__ desc, int parity, AlignConsts ac,
+                                                  int numPixels, int pixelsPerBlock, int imgStats, float imgThreshold) {
+  const PairDesc &D = desc[blockIdx.y];
+  const Affine T = affine_from(D.state->invT);
+  const float4 *__restrict__ refPoints = D.refPoints;
+  const float4 *__restrict__ refNormals = D.refNormals;
+  const float4 *__restrict__ curPoints = D.curPoints;
+  const float4 *__restrict__ curNormals = D.curNormals;
+  const float4 *__restrict__ curOmega = D.curOmega;
+  const int *__restrict__ curIndex = D.curIndex;
+  int *__restrict__ corrImage = D.corrImage;
+  const unsigned long long *__restrict__ zref = D.refZ[parity];
+  unsigned long long *__restrict__ znext = D.refZ[parity ^ 1];
+  const unsigned long long *__restrict__ zcur = D.curZ;
+
+  float acc[kAccum];
+#pragma unroll
+  for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
+
+  const int begin = blockIdx.x * pixelsPerBlock;
+  const int end = min(begin + pixelsPerBlock, numPixels);
+  for (int pix = begin + threadIdx.x; pix < end; pix += blockDim.x) {
+    int ri, ci = curIndex[pix];
+    if (MODE == 0) {
+      unsigned long long zr = zref[pix];
+      znext[pix] = kEmptyZ;
+      ri = (int)(unsigned int)(zr & 0xFFFFFFFFull);
+    } else {
+      ri = corrImage[pix];
+      if (imgStats) {
+        // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
+        unsigned long long zc = zcur[pix], zr = zref[pix];
+        float dc = (zc == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zc >> 32));
+        float dr = (zr == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zr >> 32));
+        unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
+        unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
+        if (c16 > 0 && r16 > 0) {
+          float df = fabsf(fsub((float)c16, (float)r16));
+          float dm = __uint_as_float(__float_as_uint(df) & 0x437F0000u);
+          acc[30] += 1.0f;
+          if (dm < imgThreshold) acc[31] += 1.0f;
+          acc[29] += dm;
+        }
+      }
+    }
+    if (ri < 0 || ci < 0) {
+      if (MODE == 0) corrImage[pix] = -1;
+      continue;
+    }
+    const float4 cn = curNormals[ci];
+    const float4 rn0 = refNormals[ri];
+    const float4 cp = curPoints[ci];
+    const float4 rp0 = refPoints[ri];
+    float rpx, rpy, rpz, rnx, rny, rnz;
+    xform_point(T, rp0.x, rp0.y, rp0.z, rpx, rpy, rpz);
+    xform_normal(T, rn0.x, rn0.y, rn0.z, rnx, rny, rnz);
+    if (MODE == 0) {
+      bool ok = true;
+      // correspondencefinder.cpp:69: zero normals are skipped
+      if (dot3(cn.x, cn.y, cn.z, cn.x, cn.y, cn.z) == 0.0f || dot3(rn0.x, rn0.y, rn0.z, rn0.x, rn0.y, rn0.z) == 0.0f)
+        ok = false;
+      // :78 normal angle
+      if (ok && dot3(cn.x, cn.y, cn.z, rnx, rny, rnz) < ac.normalThreshold) ok = false;
+      // :84 point distance
+      if (ok) {
+        float dx = fsub(cp.x, rpx), dy = fsub(cp.y, rpy), dz = fsub(cp.z, rpz);
+        if (dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold) ok = false;
+      }
+      // :87-99 curvature ratio, evaluated in double like the reference's (float + 1e-5) / (float + 1e-5)
+      if (ok) {
+        float rc = rn0.w, cc = cn.w;
+        if (rc < ac.flatCurvature) rc = ac.flatCurvature;
+        if (cc < ac.flatCurvature) cc = ac.flatCurvature;
+        float ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
+        if (ratio < ac.minRatio || ratio > ac.maxRatio) ok = false;
+      }
+      corrImage[pix] = ok ? ri : -1;
+      if (!ok) continue;
+      acc[A_NCORR] += 1.0f;
+    }
+    const float4 o0 = curOmega[3 * (size_t)ci], o1 = curOmega[3 * (size_t)ci + 1], o2 = curOmega[3 * (size_t)ci + 2];
+    accumulate_term(acc, rpx, rpy, rpz, rnx, rny, rnz, cp, cn, o0, o1, o2, ac.maxChi2, ac.robust);
+  }
+
+  __shared__ float red[8][kAccum];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float tot = warp_transpose_reduce(acc, lane);
+  red[warp][lane] = tot;
+  __syncthreads();
+  if (warp == 0) {
+    float s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; w++) s += red[w][lane];
+    D.partials[(size_t)blockIdx.x * kAccum + lane] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sum the per-CTA partial rows in fixed order, assemble H/b (linearizer.cpp:109-114), then:
+//  mode 0: one Gauss-Newton step of Aligner::align (aligner.cpp:84-118): H += I + 1000 I,
+//          dx = LDLT(H)^-1 (-b), invT = v2t(dx) invT; if lastInner: T = invT^-1, T = v2t(t2v(T)),
+//          and the matrices of the next iteration (invT = T^-1, KRt for the next projection).
+//  mode 1: _computeStatistics' linearisation: store H/b + image statistics, write the result record.
+//  mode 2: stage-level call: store H/b/error/inliers/ncorr only.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict__ desc, int numBlocks, int mode,
+                                                      int lastInner, int firstInner, int iter, AlignConsts ac) {
+  const PairDesc &D = desc[blockIdx.x];
+  __shared__ float red[8][kAccum];
+  __shared__ float tot[kAccum];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s = 0.0f;
+  for (int bi = warp; bi < numBlocks; bi += 8) s += D.partials[(size_t)bi * kAccum + lane];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; w++) t += red[w][lane];
+    tot[lane] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+
+  PairState *st = D.state;
+  float H[36], b[6];
+  // Htt / Hrr upper triangles mirrored, Htr full
+  const int ut[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      NM6(H, r, c) = tot[A_HTT + ut[r][c]];
+      NM6(H, r + 3, c + 3) = tot[A_HRR + ut[r][c]];
+      NM6(H, r, c + 3) = tot[A_HTR + r * 3 + c];
+      NM6(H, c + 3, r) = tot[A_HTR + r * 3 + c];
+    }
+  for (int r = 0; r < 3; r++) { b[r] = tot[A_BT + r]; b[r + 3] = tot[A_BR + r]; }
+
+  if (mode == 1) {
+    for (int k = 0; k < 36; k++) st->statH[k] = H[k];
+    for (int k = 0; k < 6; k++) st->statb[k] = b[k];
+    st->img_sum = tot[29];
+    st->img_nonzeros = (int)tot[30];
+    st->img_inliers = (int)tot[31];
+    nicp_align_result *res = D.result;
+    if (res) {
+      for (int k = 0; k < 16; k++) res->T[k] = st->T[k];
+      res->error = st->error;
+      res->inliers = st->inliers;
+      res->num_correspondences = st->ncorr;
+      res->image_non_zeros = st->img_nonzeros;
+      res->image_inliers = st->img_inliers;
+      res->image_outliers = st->img_nonzeros - st->img_inliers;
+      res->image_reprojection_distance = fdiv(st->img_sum, (float)st->img_nonzeros);
+      res->status = NICP_OK;
+    }
+    return;
+  }
+
+  for (int k = 0; k < 36; k++) st->H[k] = H[k];
+  for (int k = 0; k < 6; k++) st->b[k] = b[k];
+  st->error = tot[A_ERR];
+  st->inliers = (int)tot[A_INL];
+  if (firstInner) st->ncorr = (int)tot[A_NCORR];
+  if (mode == 2) return;
+
+  if (D.trace && firstInner) {
+    float *tr = D.trace + 61 * iter;
+    for (int k = 0; k < 16; k++) tr[k] = st->T[k];
+    for (int k = 0; k < 36; k++) tr[16 + k] = H[k];
+    for (int k = 0; k < 6; k++) tr[52 + k] = b[k];
+    tr[58] = st->error;
+    tr[59] = (float)st->inliers;
+    tr[60] = (float)st->ncorr;
+  }
+
+  // aligner.cpp:92-94: H = H_lin + I; H += 1000 I
+  for (int d = 0; d < 6; d++) NM6(H, d, d) = fadd(fadd(NM6(H, d, d), 1.0f), 1000.0f);
+  float nb[6], dx[6], dT[16], invT[16];
+  for (int k = 0; k < 6; k++) nb[k] = -b[k];
+  ldlt_solve6(H, nb, dx);
+  v2t(dx, dT);
+  for (int k = 0; k < 16; k++) invT[k] = st->invT[k];
+  iso_mul(dT, invT, invT);
+  if (!lastInner) {
+    fix_last_row(invT);
+    for (int k = 0; k < 16; k++) st->invT[k] = invT[k];
+    return;
+  }
+  // aligner.cpp:115-117
+  float T[16], v[6], tmp[16], KRt[16];
+  iso_inverse(invT, T);
+  t2v(T, v);
+  v2t(v, T);
+  fix_last_row(T);
+  for (int k = 0; k < 16; k++) st->T[k] = T[k];
+  iso_inverse(T, invT);
+  fix_last_row(invT);
+  for (int k = 0; k < 16; k++) st->invT[k] = invT[k];
+  iso_mul(T, ac.refOffset, tmp);
+  compute_KRt(ac.K, tmp, KRt);
+  for (int k = 0; k < 16; k++) st->KRt[k] = KRt[k];
+}
+
+__global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *__restrict__ statHb) {
+  int i = blockIdx.x;
+  const PairState *st = desc[i].state;
+  for (int k = threadIdx.x; k < 42; k += blockDim.x) statHb[(size_t)i * 42 + k] = k < 36 ? st->statH[k] : st->statb[k - 36];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+static int pixels_per_block(const nicp_context *ctx, int P) {
+  int ppb = (P + ctx->blocksPerPair - 1) / ctx->blocksPerPair;
+  return ppb < 256 ? 256 : ppb;
+}
+static int num_blocks_for(const nicp_context *ctx, int P) {
+  int ppb = pixels_per_block(ctx, P);
+  return (P + ppb - 1) / ppb;
+}
+
+// runs Aligner::align for the nPairs descriptors staged in ctx->h_desc (one lock-step chunk).
+// ownsCur: per pair, 1 if the pair's curZ/curIndex buffers must be produced by it.
+int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const float curKRt[16], int outerIters,
+                    int innerIters, float imgThreshold, int /*nUniqueCur*/, const int *h_ownsCur, bool /*wantTrace*/,
+                    int resultOffset) {
+  cudaStream_t st = ctx->stream;
+  const int P = ac.rows * ac.cols;
+  const int ppb = pixels_per_block(ctx, P);
+  const int nb = num_blocks_for(ctx, P);
+  // descriptors + ownership flags (flags live right after the descriptors in the staging buffer)
+  int *h_flags = reinterpret_cast<int *>(ctx->h_desc + ctx->slots);
+  int *d_flags = reinterpret_cast<int *>(ctx->d_desc + ctx->slots);
+  for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * nPairs, cudaMemcpyHostToDevice, st));
+  // reference z-buffer 0 and the current z-buffers start empty (all ones)
+  // (slot buffers are contiguous: refZ is laid out [2][slots][slotPixels], curZ [slots][slotPixels])
+  NICP_CUDA(cudaMemsetAsync(ctx->d_refZ, 0xFF, sizeof(unsigned long long) * ctx->slotPixels * nPairs, st));
+  NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, sizeof(unsigned long long) * ctx->slotPixels * nPairs, st));
+  k_init_pairs<<<(nPairs + 63) / 64, 64, 0, st>>>(ctx->d_desc, nPairs, ac);
+  NICP_CHECK_LAUNCH(ctx);
+  const int projBlocks = (P + 1023) / 1024;  // grid-stride: 4 points per thread at full density
+  dim3 pg(projBlocks, nPairs);
+  k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, affine_from(curKRt), ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+  NICP_CHECK_LAUNCH(ctx);
+  k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags);
+  NICP_CHECK_LAUNCH(ctx);
+  Affine dummy = affine_from(curKRt);
+  dim3 cg(nb, nPairs);
+  int parity = 0;
+  for (int it = 0; it < outerIters; it++) {
+    parity = it & 1;
+    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+    NICP_CHECK_LAUNCH(ctx);
+    for (int k = 0; k < innerIters; k++) {
+      if (k == 0)
+        k_corr_lin<0><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
+      else
+        k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
+      NICP_CHECK_LAUNCH(ctx);
+      k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
+      NICP_CHECK_LAUNCH(ctx);
+    }
+  }
+  if (outerIters <= 0 || innerIters <= 0) {
+    // no loop linearisation happened: the correspondence image must still be defined (all -1)
+    for (int i = 0; i < nPairs; i++)
+      NICP_CUDA(cudaMemsetAsync(ctx->h_desc[i].corrImage, 0xFF, sizeof(int) * P, st));
+  }
+  // _computeStatistics linearisation at the final T over the last correspondences + image statistics
+  k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 1, imgThreshold);
+  NICP_CHECK_LAUNCH(ctx);
+  k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
+  NICP_CHECK_LAUNCH(ctx);
+  k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
+  NICP_CHECK_LAUNCH(ctx);
+  ctx->lastAlignParity = parity;
+  return NICP_OK;
+}
+
+// stage-level: slot's refZ[0]/curIndex (or corrImage when fromCorrImage) already staged, state->invT set.
+int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int numPixels) {
+  cudaStream_t st = ctx->stream;
+  const int ppb = pixels_per_block(ctx, numPixels);
+  const int nb = (numPixels + ppb - 1) / ppb;
+  dim3 cg(nb, 1);
+  if (fromCorrImage)
+    k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, 0, ac, numPixels, ppb, 0, 0.0f);
+  else
+    k_corr_lin<0><<<cg, 256, 0, st>>>(ctx->d_desc, 0, ac, numPixels, ppb, 0, 0.0f);
+  NICP_CHECK_LAUNCH(ctx);
+  k_reduce_solve<<<1, 256, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+}  // namespace nicp

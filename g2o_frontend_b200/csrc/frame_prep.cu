@@ -1,0 +1,639 @@
+// frame_prep.cu -- depth image -> point/normal/curvature/information-matrix cloud.
+//
+// Replaces DepthImageConverterIntegralImage::compute (depthimageconverterintegralimage.cpp:15-55)
+// and the pieces it calls:
+//   PinholePointProjector::unProject / projectIntervals   pinholepointprojector.cpp:68-147
+//   PointIntegralImage::compute / getRegion                 pointintegralimage.cpp:7-66
+//   StatsCalculatorIntegralImage::compute                   statscalculatorintegralimage.cpp:14-82
+//   Point/NormalInformationMatrixCalculator::compute        informationmatrixcalculator.cpp:9-58
+//   Cloud::transformInPlace                                 cloud.cpp:173-186
+//   DepthImage_convert_16UC1_to_32FC1 / DepthImage_scale    pwn_static.cpp:5-68
+//
+// Three kernels per frame:
+//   k_integral_rows   one CTA per image row: unproject in registers, stage the 10 accumulator
+//                     channels of the row in shared memory, scan them SEQUENTIALLY along image-x
+//                     (the reference's float32 summation order is part of the result -- SURVEY.md
+//                     section 7 hard part 1), write back coalesced (planar [10][rows][cols]).
+//   k_integral_cols   one thread per (channel, column): sequential scan along image-y, coalesced
+//                     across the warp, loads software-prefetched 16 rows ahead.
+//   k_stats           one thread per pixel: compacted index straight from channel 0 of the
+//                     integral image (no separate compaction pass), 4-corner region, covariance,
+//                     closed-form 3x3 eigen-decomposition, normal / curvature / Omega_P / Omega_N,
+//                     sensor-offset transform fused into the writes.
+#include "nicp_internal.cuh"
+
+namespace nicp {
+
+// ---------------------------------------------------------------------------------------------
+// DepthImage_convert_16UC1_to_32FC1 (pwn_static.cpp:54-68) + DepthImage_scale (:5-36)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_depth_convert(const uint16_t *__restrict__ raw, int rows, int cols, float scale, int step,
+                                float maxCov, float *__restrict__ out) {
+  int drows = rows / step, dcols = cols / step;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= drows * dcols) return;
+  int r = i / dcols, c = i - r * dcols;
+  if (step <= 1) {
+    uint16_t v = raw[i];
+    out[i] = v ? fmul(scale, (float)v) : 0.0f;
+    return;
+  }
+  float acc = 0.f, acc2 = 0.f;
+  int np = 0;
+  int sr = r * step, sc = c * step;
+  for (int a = 0; a < step; a++)
+    for (int b = 0; b < step; b++) {
+      if (sr + a < rows && sc + b < cols) {
+        uint16_t v = raw[(size_t)(sr + a) * cols + sc + b];
+        float f = v ? fmul(scale, (float)v) : 0.0f;
+        acc = fadd(acc, f);
+        acc2 = fadd(acc2, fmul(f, f));
+        np += f > 0;
+      }
+    }
+  float res = 0.0f;
+  if (np) {
+    float mu = fdiv(acc, (float)np);
+    float sigma = fsub(fdiv(acc2, (float)np), fmul(mu, mu));
+    if (!(sigma > maxCov)) res = mu;
+  }
+  out[i] = res;
+}
+
+int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int cols, float scale, int step,
+                         float maxCov, float *d_out) {
+  if (step < 1) step = 1;
+  int n = (rows / step) * (cols / step);
+  k_depth_convert<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_raw, rows, cols, scale, step, maxCov, d_out);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PointIntegralImage::compute, pass 1 (scatter + prefix along image-x)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_integral_rows(const float *__restrict__ depth, int rows, int cols, Affine iKRt,
+                                                       float minD, float maxD, float *__restrict__ I) {
+  extern __shared__ float sm[];  // [10][stride]
+  const int stride = cols + 1;   // +1: the 10 scanning lanes hit 10 different banks
+  const int r = blockIdx.x;
+  const float *drow = depth + (size_t)r * cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float d = drow[c];
+    float ch[kIntegralCh];
+    if (d < minD || d > maxD) {
+#pragma unroll
+      for (int k = 0; k < kIntegralCh; k++) ch[k] = 0.0f;
+    } else {
+      float x, y, z;
+      xform_point(iKRt, fmul((float)c, d), fmul((float)r, d), d, x, y, z);
+      ch[0] = 1.0f; ch[1] = x; ch[2] = y; ch[3] = z;
+      ch[4] = fmul(x, x); ch[5] = fmul(x, y); ch[6] = fmul(x, z);
+      ch[7] = fmul(y, y); ch[8] = fmul(y, z); ch[9] = fmul(z, z);
+    }
+#pragma unroll
+    for (int k = 0; k < kIntegralCh; k++) sm[k * stride + c] = ch[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kIntegralCh) {
+    float *p = sm + threadIdx.x * stride;
+    float v = p[0];
+    int c = 1;
+    for (; c + 8 <= cols; c += 8) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t[u] = p[c + u];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { v = fadd(t[u], v); p[c + u] = v; }
+    }
+    for (; c < cols; c++) { v = fadd(p[c], v); p[c] = v; }
+  }
+  __syncthreads();
+  const size_t plane = (size_t)rows * cols;
+  for (int k = 0; k < kIntegralCh; k++) {
+    float *orow = I + k * plane + (size_t)r * cols;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) orow[c] = sm[k * stride + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PointIntegralImage::compute, pass 2 (prefix along image-y)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_integral_cols(int rows, int cols, float *__restrict__ I) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= cols) return;
+  float *p = I + (size_t)blockIdx.y * rows * cols + x;
+  float v = p[0];
+  int y = 1;
+  constexpr int U = 16;
+  for (; y + U <= rows; y += U) {
+    float t[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) t[u] = p[(size_t)(y + u) * cols];
+#pragma unroll
+    for (int u = 0; u < U; u++) { v = fadd(t[u], v); p[(size_t)(y + u) * cols] = v; }
+  }
+  for (; y < rows; y++) { v = fadd(p[(size_t)y * cols], v); p[(size_t)y * cols] = v; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eigen::SelfAdjointEigenSolver<Matrix3f>::computeDirect (Eigen 3.2.x),
+// called at statscalculatorintegralimage.cpp:56-57.  C symmetric (6 unique), evals ascending,
+// U column-major.  atan2/cos/sin are evaluated in float64 and rounded to float32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
+  o[0] = fsub(fmul(a[1], b[2]), fmul(a[2], b[1]));
+  o[1] = fsub(fmul(a[2], b[0]), fmul(a[0], b[2]));
+  o[2] = fsub(fmul(a[0], b[1]), fmul(a[1], b[0]));
+}
+__device__ __forceinline__ float sqnorm3(const float *a) {
+  return fadd(fadd(fmul(a[0], a[0]), fmul(a[1], a[1])), fmul(a[2], a[2]));
+}
+__device__ __forceinline__ void unit_orthogonal(const float *s, float *o) {
+  const float prec = 1e-5f;
+  if (!(fabsf(s[0]) <= fmul(fabsf(s[2]), prec)) || !(fabsf(s[1]) <= fmul(fabsf(s[2]), prec))) {
+    float invnm = fdiv(1.0f, fsqrt(fadd(fmul(s[0], s[0]), fmul(s[1], s[1]))));
+    o[0] = fmul(-s[1], invnm); o[1] = fmul(s[0], invnm); o[2] = 0.0f;
+  } else {
+    float invnm = fdiv(1.0f, fsqrt(fadd(fmul(s[1], s[1]), fmul(s[2], s[2]))));
+    o[0] = 0.0f; o[1] = fmul(-s[2], invnm); o[2] = fmul(s[1], invnm);
+  }
+}
+__device__ __forceinline__ void set_col(float *U, int col, const float *v) {
+  // static-index friendly
+  if (col == 0) { U[0] = v[0]; U[1] = v[1]; U[2] = v[2]; }
+  else if (col == 1) { U[3] = v[0]; U[4] = v[1]; U[5] = v[2]; }
+  else { U[6] = v[0]; U[7] = v[1]; U[8] = v[2]; }
+}
+__device__ void eigen3(float c00, float c10, float c20, float c11, float c21, float c22, float *evals, float *U) {
+  const float eps = FLT_EPSILON;
+  float scale = fmaxf(fmaxf(fmaxf(fabsf(c00), fabsf(c10)), fmaxf(fabsf(c20), fabsf(c11))), fmaxf(fabsf(c21), fabsf(c22)));
+  float m00 = fdiv(c00, scale), m10 = fdiv(c10, scale), m20 = fdiv(c20, scale);
+  float m11 = fdiv(c11, scale), m21 = fdiv(c21, scale), m22 = fdiv(c22, scale);
+  const float s_inv3 = 1.0f / 3.0f;
+  const float s_sqrt3 = 1.7320508075688772f;  // sqrtf(3.0f)
+  float c0 = fsub(fsub(fsub(fadd(fmul(fmul(m00, m11), m22), fmul(fmul(fmul(2.0f, m10), m20), m21)),
+                            fmul(fmul(m00, m21), m21)),
+                       fmul(fmul(m11, m20), m20)),
+                  fmul(fmul(m22, m10), m10));
+  float c1 = fsub(fadd(fsub(fadd(fsub(fmul(m00, m11), fmul(m10, m10)), fmul(m00, m22)), fmul(m20, m20)), fmul(m11, m22)),
+                  fmul(m21, m21));
+  float c2 = fadd(fadd(m00, m11), m22);
+  float c2_over_3 = fmul(c2, s_inv3);
+  float a_over_3 = fmul(fsub(c1, fmul(c2, c2_over_3)), s_inv3);
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  float half_b = fmul(0.5f, fadd(c0, fmul(c2_over_3, fsub(fmul(fmul(2.0f, c2_over_3), c2_over_3), c1))));
+  float q = fadd(fmul(half_b, half_b), fmul(fmul(a_over_3, a_over_3), a_over_3));
+  if (q > 0.0f) q = 0.0f;
+  float rho = fsqrt(-a_over_3);
+  float theta = fmul((float)atan2((double)fsqrt(-q), (double)half_b), s_inv3);
+  float cos_theta = (float)cos((double)theta);
+  float sin_theta = (float)sin((double)theta);
+  float r0 = fadd(c2_over_3, fmul(fmul(2.0f, rho), cos_theta));
+  float r1 = fsub(c2_over_3, fmul(rho, fadd(cos_theta, fmul(s_sqrt3, sin_theta))));
+  float r2 = fsub(c2_over_3, fmul(rho, fsub(cos_theta, fmul(s_sqrt3, sin_theta))));
+  float tsw;
+  if (r0 >= r1) { tsw = r0; r0 = r1; r1 = tsw; }
+  if (r1 >= r2) {
+    tsw = r1; r1 = r2; r2 = tsw;
+    if (r0 >= r1) { tsw = r0; r0 = r1; r1 = tsw; }
+  }
+  evals[0] = fmul(r0, scale); evals[1] = fmul(r1, scale); evals[2] = fmul(r2, scale);
+  const float safeNorm2 = eps * eps;
+  U[0] = 1.f; U[1] = 0.f; U[2] = 0.f; U[3] = 0.f; U[4] = 1.f; U[5] = 0.f; U[6] = 0.f; U[7] = 0.f; U[8] = 1.f;
+  if (fsub(r2, r0) <= eps) return;
+  float d0 = fsub(r2, r1), d1 = fsub(r1, r0);
+  int k = d0 > d1 ? 2 : 0;
+  float evk = d0 > d1 ? r2 : r0;
+  d0 = d0 > d1 ? d1 : d0;
+  float row0[3] = {fsub(m00, evk), m10, m20};
+  float row1[3] = {m10, fsub(m11, evk), m21};
+  float row2[3] = {m20, m21, fsub(m22, evk)};
+  float cr[3], n, uk[3], u1[3], ul[3];
+  cross3(row0, row1, cr);
+  n = sqnorm3(cr);
+  if (!(n > safeNorm2)) {
+    cross3(row0, row2, cr);
+    n = sqnorm3(cr);
+    if (!(n > safeNorm2)) {
+      cross3(row1, row2, cr);
+      n = sqnorm3(cr);
+      if (!(n > safeNorm2)) return;  // NumericalIssue: identity eigenvectors (oracle's definition)
+    }
+  }
+  { float sn = fsqrt(n); uk[0] = fdiv(cr[0], sn); uk[1] = fdiv(cr[1], sn); uk[2] = fdiv(cr[2], sn); }
+  if (d0 <= eps) {
+    unit_orthogonal(uk, u1);
+  } else {
+    float r0v[3] = {fsub(m00, r1), m10, m20};
+    float r1v[3] = {m10, fsub(m11, r1), m21};
+    float r2v[3] = {m20, m21, fsub(m22, r1)};
+    float nr0 = fsqrt(sqnorm3(r0v));
+    float r0n[3] = {fdiv(r0v[0], nr0), fdiv(r0v[1], nr0), fdiv(r0v[2], nr0)};
+    bool have = true;
+    cross3(uk, r0n, cr);
+    n = sqnorm3(cr);
+    if (!(n > safeNorm2)) {
+      cross3(uk, r1v, cr);
+      n = sqnorm3(cr);
+      if (!(n > safeNorm2)) {
+        cross3(uk, r2v, cr);
+        n = sqnorm3(cr);
+        if (!(n > safeNorm2)) { unit_orthogonal(uk, u1); have = false; }
+      }
+    }
+    if (have) { float sn = fsqrt(n); u1[0] = fdiv(cr[0], sn); u1[1] = fdiv(cr[1], sn); u1[2] = fdiv(cr[2], sn); }
+    float t1[3], t2[3];
+    cross3(u1, uk, t1);
+    cross3(uk, t1, t2);
+    float sn = fsqrt(sqnorm3(t2));
+    u1[0] = fdiv(t2[0], sn); u1[1] = fdiv(t2[1], sn); u1[2] = fdiv(t2[2], sn);
+  }
+  {
+    float t[3];
+    cross3(uk, u1, t);
+    float sn = fsqrt(sqnorm3(t));
+    ul[0] = fdiv(t[0], sn); ul[1] = fdiv(t[1], sn); ul[2] = fdiv(t[2], sn);
+  }
+  set_col(U, k, uk);
+  set_col(U, 1, u1);
+  set_col(U, k == 2 ? 0 : 2, ul);
+}
+
+struct StatsConsts {
+  Affine iKRt;      // unProject matrix with the projector at identity
+  float minD, maxD;
+  float ivx, ivy;   // K * (worldRadius, worldRadius, 0), rows 0 and 1 (projectIntervals)
+  int minR, maxR, minPoints;
+  float curvThr, omegaCurvThr;
+  float flatP[3], flatN[3], nonflatN[3];
+  int applyOffset;
+  float M[16];      // sensor offset (last row fixed)
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// R * Om * R^T for the 3x3 blocks (InformationMatrixVector::transformInPlace, informationmatrix.h:111-121)
+__device__ __forceinline__ void rotate_sym(const float *M, const float *Om /*3x3 col-major*/, float *out) {
+  float t[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++)
+      NM3(t, r, c) = dot3(NM4(M, r, 0), NM4(M, r, 1), NM4(M, r, 2), NM3(Om, 0, c), NM3(Om, 1, c), NM3(Om, 2, c));
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++)
+      NM3(out, r, c) = dot3(NM3(t, r, 0), NM3(t, r, 1), NM3(t, r, 2), NM4(M, c, 0), NM4(M, c, 1), NM4(M, c, 2));
+}
+
+__global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, const float *__restrict__ I, int rows,
+                                               int cols, StatsConsts sc, float4 *__restrict__ points,
+                                               float4 *__restrict__ normals, float4 *__restrict__ omega,
+                                               int *__restrict__ index, int *__restrict__ interval,
+                                               float *__restrict__ stats16, float *__restrict__ eigvalsOut,
+                                               int *__restrict__ statsN, int *__restrict__ countOut) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= cols || r >= rows) return;
+  const size_t plane = (size_t)rows * cols;
+  const size_t pix = (size_t)r * cols + c;
+  if (r == rows - 1 && c == cols - 1) *countOut = (int)I[pix];
+  const float d = depth[pix];
+  if (d < sc.minD || d > sc.maxD) {
+    index[pix] = -1;
+    interval[pix] = -1;
+    return;
+  }
+  // compacted raster-order index from channel 0 (exact integer counts in float32)
+  float above = r > 0 ? I[(size_t)(r - 1) * cols + cols - 1] : 0.0f;
+  float upto = I[pix] - (r > 0 ? I[pix - cols] : 0.0f);
+  const int idx = (int)above + (int)upto - 1;
+  index[pix] = idx;
+
+  float px, py, pz;
+  xform_point(sc.iKRt, fmul((float)c, d), fmul((float)r, d), d, px, py, pz);
+
+  // _projectInterval (pinholepointprojector.h:264-274)
+  float invd = fdiv(1.0f, d);
+  float ia = fmul(sc.ivx, invd), ib = fmul(sc.ivy, invd);
+  int k = (ia > ib) ? (int)ia : (int)ib;
+  interval[pix] = k;
+
+  float nx = 0.f, ny = 0.f, nz = 0.f, curv = 0.f;
+  float OP[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float ON[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float U[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float ev[3] = {0, 0, 0};
+  float mu[3] = {0, 0, 0};
+  int npts = 0;
+  bool computed = false;
+
+  if (k >= 0) {
+    k = clampi(k, sc.minR, sc.maxR);
+    // getRegion(c-k, c+k, r-k, r+k) (pointintegralimage.cpp:53-66)
+    int x0 = clampi(c - k - 1, 0, cols - 1), x1 = clampi(c + k - 1, 0, cols - 1);
+    int y0 = clampi(r - k - 1, 0, rows - 1), y1 = clampi(r + k - 1, 0, rows - 1);
+    size_t o11 = (size_t)y1 * cols + x1, o00 = (size_t)y0 * cols + x0;
+    size_t o10 = (size_t)y1 * cols + x0, o01 = (size_t)y0 * cols + x1;
+    float acc[kIntegralCh];
+#pragma unroll
+    for (int ch = 0; ch < kIntegralCh; ch++) {
+      const float *P = I + ch * plane;
+      acc[ch] = fsub(fsub(fadd(P[o11], P[o00]), P[o10]), P[o01]);
+    }
+    if ((int)acc[0] >= sc.minPoints) {
+      computed = true;
+      npts = (int)acc[0];
+      float dd = fdiv(1.0f, acc[0]);
+      mu[0] = fmul(acc[1], dd); mu[1] = fmul(acc[2], dd); mu[2] = fmul(acc[3], dd);
+      float c00 = fsub(fmul(acc[4], dd), fmul(mu[0], mu[0]));
+      float c10 = fsub(fmul(acc[5], dd), fmul(mu[0], mu[1]));
+      float c20 = fsub(fmul(acc[6], dd), fmul(mu[0], mu[2]));
+      float c11 = fsub(fmul(acc[7], dd), fmul(mu[1], mu[1]));
+      float c21 = fsub(fmul(acc[8], dd), fmul(mu[1], mu[2]));
+      float c22 = fsub(fmul(acc[9], dd), fmul(mu[2], mu[2]));
+      eigen3(c00, c10, c20, c11, c21, c22, ev, U);
+      if (ev[0] < 0.0f) ev[0] = 0.0f;
+      // Stats::curvature (stats.h:98-103): float sum, double divide
+      curv = (float)((double)ev[0] / ((double)fadd(fadd(ev[0], ev[1]), ev[2]) + 1e-9));
+      nx = U[0]; ny = U[1]; nz = U[2];
+      if (curv < sc.curvThr) {
+        if (dot4(nx, ny, nz, 0.0f, px, py, pz, 1.0f) > 0) { nx = -nx; ny = -ny; nz = -nz; }
+      } else {
+        nx = ny = nz = 0.0f;
+      }
+      // information matrices (informationmatrixcalculator.cpp:17-35, 46-57)
+      float sq = fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz));
+      if (sq > 0) {
+        bool flat = curv < sc.omegaCurvThr;
+        float dg[3];
+        if (flat) { dg[0] = sc.flatP[0]; dg[1] = sc.flatP[1]; dg[2] = sc.flatP[2]; }
+        else { dg[0] = fdiv(1.0f, ev[0]); dg[1] = fdiv(1.0f, ev[1]); dg[2] = fdiv(1.0f, ev[2]); }
+        float UD[9];
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++) NM3(UD, rr, cc) = fmul(NM3(U, rr, cc), dg[cc]);
+        for (int rr = 0; rr < 3; rr++)
+          for (int cc = 0; cc < 3; cc++)
+            NM3(OP, rr, cc) = dot3(NM3(UD, rr, 0), NM3(UD, rr, 1), NM3(UD, rr, 2), NM3(U, cc, 0), NM3(U, cc, 1), NM3(U, cc, 2));
+        const float *dn = flat ? sc.flatN : sc.nonflatN;
+        ON[0] = dn[0]; ON[4] = dn[1]; ON[8] = dn[2];
+      }
+    }
+  }
+
+  float S[16];
+  if (stats16) {
+    for (int i = 0; i < 16; i++) S[i] = 0.0f;
+    for (int rr = 0; rr < 3; rr++)
+      for (int cc = 0; cc < 3; cc++) NM4(S, rr, cc) = NM3(U, rr, cc);
+    if (computed) { NM4(S, 0, 3) = mu[0]; NM4(S, 1, 3) = mu[1]; NM4(S, 2, 3) = mu[2]; }
+    NM4(S, 3, 3) = 1.0f;
+  }
+
+  if (sc.applyOffset) {
+    // Cloud::transformInPlace (cloud.cpp:173-186)
+    Affine M = affine_from(sc.M);
+    float tx, ty, tz;
+    xform_point(M, px, py, pz, tx, ty, tz);
+    px = tx; py = ty; pz = tz;
+    xform_normal(M, nx, ny, nz, tx, ty, tz);
+    nx = tx; ny = ty; nz = tz;
+    float t9[9];
+    rotate_sym(sc.M, OP, t9);
+    for (int i = 0; i < 9; i++) OP[i] = t9[i];
+    rotate_sym(sc.M, ON, t9);
+    for (int i = 0; i < 9; i++) ON[i] = t9[i];
+    if (stats16) {
+      float o[16];
+      for (int cc = 0; cc < 4; cc++)
+        for (int rr = 0; rr < 4; rr++)
+          NM4(o, rr, cc) = dot4(NM4(sc.M, rr, 0), NM4(sc.M, rr, 1), NM4(sc.M, rr, 2), NM4(sc.M, rr, 3), NM4(S, 0, cc),
+                                NM4(S, 1, cc), NM4(S, 2, cc), NM4(S, 3, cc));
+      for (int i = 0; i < 16; i++) S[i] = o[i];
+    }
+  }
+
+  points[idx] = make_float4(px, py, pz, 1.0f);
+  normals[idx] = make_float4(nx, ny, nz, curv);
+  omega[3 * (size_t)idx + 0] = make_float4(NM3(OP, 0, 0), NM3(OP, 0, 1), NM3(OP, 0, 2), NM3(OP, 1, 1));
+  omega[3 * (size_t)idx + 1] = make_float4(NM3(OP, 1, 2), NM3(OP, 2, 2), NM3(ON, 0, 0), NM3(ON, 0, 1));
+  omega[3 * (size_t)idx + 2] = make_float4(NM3(ON, 0, 2), NM3(ON, 1, 1), NM3(ON, 1, 2), NM3(ON, 2, 2));
+  if (stats16) {
+    float4 *so = reinterpret_cast<float4 *>(stats16 + 16 * (size_t)idx);
+    so[0] = make_float4(S[0], S[1], S[2], S[3]);
+    so[1] = make_float4(S[4], S[5], S[6], S[7]);
+    so[2] = make_float4(S[8], S[9], S[10], S[11]);
+    so[3] = make_float4(S[12], S[13], S[14], S[15]);
+    eigvalsOut[3 * (size_t)idx + 0] = ev[0];
+    eigvalsOut[3 * (size_t)idx + 1] = ev[1];
+    eigvalsOut[3 * (size_t)idx + 2] = ev[2];
+    statsN[idx] = npts;
+  }
+}
+
+static bool is_identity16(const float *m) {
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++)
+      if (NM4(m, r, c) != (r == c ? 1.0f : 0.0f)) return false;
+  return true;
+}
+
+int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
+                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index) {
+  const int rows = proj->rows, cols = proj->cols;
+  float I4[16], iKRt[16];
+  mat4_identity(I4);
+  compute_iKRt(proj->K, I4, iKRt);
+  Affine a = affine_from(iKRt);
+  size_t smem = (size_t)kIntegralCh * (cols + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    NICP_CUDA(cudaFuncSetAttribute(k_integral_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  k_integral_rows<<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
+                                                    ctx->d_integral);
+  NICP_CHECK_LAUNCH(ctx);
+  dim3 gc((cols + 63) / 64, kIntegralCh);
+  k_integral_cols<<<gc, 64, 0, ctx->stream>>>(rows, cols, ctx->d_integral);
+  NICP_CHECK_LAUNCH(ctx);
+
+  StatsConsts sc;
+  sc.iKRt = a;
+  sc.minD = proj->min_distance;
+  sc.maxD = proj->max_distance;
+  const float *K = proj->K;
+  sc.ivx = dot3(NM3(K, 0, 0), NM3(K, 0, 1), NM3(K, 0, 2), sp->world_radius, sp->world_radius, 0.0f);
+  sc.ivy = dot3(NM3(K, 1, 0), NM3(K, 1, 1), NM3(K, 1, 2), sp->world_radius, sp->world_radius, 0.0f);
+  sc.minR = sp->min_image_radius;
+  sc.maxR = sp->max_image_radius;
+  sc.minPoints = sp->min_points;
+  sc.curvThr = sp->curvature_threshold;
+  sc.omegaCurvThr = sp->omega_curvature_threshold;
+  for (int i = 0; i < 3; i++) {
+    sc.flatP[i] = sp->flat_omega_p[i];
+    sc.flatN[i] = sp->flat_omega_n[i];
+    sc.nonflatN[i] = sp->nonflat_omega_n[i];
+  }
+  for (int i = 0; i < 16; i++) sc.M[i] = sensorOffset[i];
+  fix_last_row(sc.M);
+  sc.applyOffset = is_identity16(sc.M) ? 0 : 1;
+  dim3 bs(32, 8);
+  dim3 gs((cols + 31) / 32, (rows + 7) / 8);
+  bool ks = keepStats && cloud->stats16;
+  k_stats<<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, cloud->points, cloud->normals,
+                                      cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
+                                      ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
+  NICP_CHECK_LAUNCH(ctx);
+  cloud->n_known = false;
+  cloud->has_stats = ks;
+  ctx->lastRows = rows;
+  ctx->lastCols = cols;
+  return NICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PinholePointProjector::unProject stand-alone (arbitrary projector pose): row counts, then
+// one CTA per row writes its points at (valid pixels in earlier rows) + (rank inside the row).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_row_counts(const float *__restrict__ depth, int rows, int cols, float minD, float maxD,
+                             int *__restrict__ rowCount) {
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  int r = blockIdx.x, cnt = 0;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float d = depth[(size_t)r * cols + c];
+    cnt += !(d < minD || d > maxD);
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) rowCount[r] = s;
+}
+
+__global__ void __launch_bounds__(256) k_unproject_rows(const float *__restrict__ depth, int rows, int cols, Affine iKRt,
+                                                        float minD, float maxD, const int *__restrict__ rowCount,
+                                                        float4 *__restrict__ points, int *__restrict__ index,
+                                                        int *__restrict__ countOut) {
+  __shared__ int sbase;
+  __shared__ int warpTot[8];
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) sbase = 0;
+  __syncthreads();
+  int part = 0;
+  for (int i = threadIdx.x; i < r; i += blockDim.x) part += rowCount[i];
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0 && part) atomicAdd(&sbase, part);
+  __syncthreads();
+  int base = sbase;
+  if (r == rows - 1 && threadIdx.x == 0) *countOut = base + rowCount[r];
+  for (int c0 = 0; c0 < cols; c0 += blockDim.x) {
+    int c = c0 + threadIdx.x;
+    float d = c < cols ? depth[(size_t)r * cols + c] : -1.0f;
+    bool valid = c < cols && !(d < minD || d > maxD);
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) warpTot[warp] = __popc(m);
+    __syncthreads();
+    int off = base + __popc(m & ((1u << lane) - 1));
+    int tot = 0;
+    for (int w = 0; w < 8; w++) {
+      if (w < warp) off += warpTot[w];
+      tot += warpTot[w];
+    }
+    if (c < cols) {
+      if (valid) {
+        float x, y, z;
+        xform_point(iKRt, fmul((float)c, d), fmul((float)r, d), d, x, y, z);
+        points[off] = make_float4(x, y, z, 1.0f);
+        if (index) index[(size_t)r * cols + c] = off;
+      } else if (index) {
+        index[(size_t)r * cols + c] = -1;
+      }
+    }
+    base += tot;
+    __syncthreads();
+  }
+}
+
+int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
+                     float maxD, nicp_cloud *cloud, int *d_index) {
+  int *rowCount = ctx->d_interval;  // scratch (rows ints)
+  k_row_counts<<<rows, 256, 0, ctx->stream>>>(d_depth, rows, cols, minD, maxD, rowCount);
+  NICP_CHECK_LAUNCH(ctx);
+  k_unproject_rows<<<rows, 256, 0, ctx->stream>>>(d_depth, rows, cols, affine_from(iKRt), minD, maxD, rowCount,
+                                                  cloud->points, d_index, cloud->d_n);
+  NICP_CHECK_LAUNCH(ctx);
+  cloud->n_known = false;
+  cloud->has_stats = false;
+  return NICP_OK;
+}
+
+__global__ void k_intervals(const float *__restrict__ depth, int n, float minD, float maxD, float ivx, float ivy,
+                            int *__restrict__ interval) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = depth[i];
+  if (d < minD || d > maxD) { interval[i] = -1; return; }
+  float invd = fdiv(1.0f, d);
+  float a = fmul(ivx, invd), b = fmul(ivy, invd);
+  interval[i] = (a > b) ? (int)a : (int)b;
+}
+
+int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius,
+                     int *d_interval) {
+  const float *K = proj->K;
+  float ivx = dot3(NM3(K, 0, 0), NM3(K, 0, 1), NM3(K, 0, 2), worldRadius, worldRadius, 0.0f);
+  float ivy = dot3(NM3(K, 1, 0), NM3(K, 1, 1), NM3(K, 1, 2), worldRadius, worldRadius, 0.0f);
+  int n = proj->rows * proj->cols;
+  k_intervals<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_depth, n, proj->min_distance, proj->max_distance, ivx, ivy,
+                                                        d_interval);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+// Cloud::transformInPlace on an existing device cloud
+__global__ void k_cloud_transform(int capacity, const int *__restrict__ nPtr, Affine M, float4 *__restrict__ points,
+                                  float4 *__restrict__ normals, float4 *__restrict__ omega, float *__restrict__ stats16) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *nPtr || i >= capacity) return;
+  float M16[16];
+  mat4_identity(M16);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 4; c++) NM4(M16, r, c) = M.r[r][c];
+  float4 p = points[i], nn = normals[i];
+  float x, y, z;
+  xform_point(M, p.x, p.y, p.z, x, y, z);
+  points[i] = make_float4(x, y, z, 1.0f);
+  xform_normal(M, nn.x, nn.y, nn.z, x, y, z);
+  normals[i] = make_float4(x, y, z, nn.w);
+  float4 o0 = omega[3 * (size_t)i], o1 = omega[3 * (size_t)i + 1], o2 = omega[3 * (size_t)i + 2];
+  float OP[9] = {o0.x, o0.y, o0.z, o0.y, o0.w, o1.x, o0.z, o1.x, o1.y};
+  float ON[9] = {o1.z, o1.w, o2.x, o1.w, o2.y, o2.z, o2.x, o2.z, o2.w};
+  float tp[9], tn[9];
+  rotate_sym(M16, OP, tp);
+  rotate_sym(M16, ON, tn);
+  omega[3 * (size_t)i + 0] = make_float4(NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1));
+  omega[3 * (size_t)i + 1] = make_float4(NM3(tp, 1, 2), NM3(tp, 2, 2), NM3(tn, 0, 0), NM3(tn, 0, 1));
+  omega[3 * (size_t)i + 2] = make_float4(NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2));
+  if (stats16) {
+    float *S = stats16 + 16 * (size_t)i;
+    float o[16];
+    for (int cc = 0; cc < 4; cc++)
+      for (int rr = 0; rr < 4; rr++)
+        NM4(o, rr, cc) = dot4(NM4(M16, rr, 0), NM4(M16, rr, 1), NM4(M16, rr, 2), NM4(M16, rr, 3), NM4(S, 0, cc),
+                              NM4(S, 1, cc), NM4(S, 2, cc), NM4(S, 3, cc));
+    for (int k = 0; k < 16; k++) S[k] = o[k];
+  }
+}
+
+int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]) {
+  float m[16];
+  for (int i = 0; i < 16; i++) m[i] = T[i];
+  fix_last_row(m);
+  if (is_identity16(m)) return NICP_OK;
+  k_cloud_transform<<<(cloud->capacity + 255) / 256, 256, 0, ctx->stream>>>(
+      cloud->capacity, cloud->d_n, affine_from(m), cloud->points, cloud->normals, cloud->omega,
+      cloud->has_stats ? cloud->stats16 : nullptr);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+}  // namespace nicp

@@ -1,0 +1,921 @@
+// nicp_capi.cu -- the extern "C" boundary declared in include/nicp_b200.h.
+// Host-side orchestration only: scratch management, H2D/D2H, kernel sequencing, and the tiny
+// dense statistics of Aligner::_computeStatistics (aligner.cpp:152-199).  No CPU fallback: every
+// compute entry point launches CUDA kernels or fails.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "nicp_internal.cuh"
+
+namespace nicp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+static int env_int(const char *name, int def) {
+  const char *v = getenv(name);
+  if (!v || !*v) return def;
+  int x = atoi(v);
+  return x > 0 ? x : def;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return NICP_ERR_ALLOC;
+  }
+  *p = reinterpret_cast<T *>(q);
+  return NICP_OK;
+}
+template <typename T>
+static void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static int ensure_prep(nicp_context *ctx, size_t pixels) {
+  if (pixels <= ctx->prepPixels) return NICP_OK;
+  dev_free(ctx->d_depth);
+  dev_free(ctx->d_integral);
+  dev_free(ctx->d_interval);
+  dev_free(ctx->d_index);
+  ctx->prepPixels = 0;
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_depth, pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_integral, pixels * kIntegralCh))) return rc;
+  if ((rc = dev_alloc(&ctx->d_interval, pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_index, pixels))) return rc;
+  ctx->prepPixels = pixels;
+  return NICP_OK;
+}
+static int ensure_raw(nicp_context *ctx, size_t pixels) {
+  if (pixels <= ctx->rawPixels) return NICP_OK;
+  dev_free(ctx->d_raw);
+  ctx->rawPixels = 0;
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_raw, pixels))) return rc;
+  ctx->rawPixels = pixels;
+  return NICP_OK;
+}
+
+static void free_align(nicp_context *ctx) {
+  dev_free(ctx->d_refZ);
+  dev_free(ctx->d_curZ);
+  dev_free(ctx->d_curIndex);
+  dev_free(ctx->d_corrImage);
+  dev_free(ctx->d_partials);
+  dev_free(ctx->d_state);
+  dev_free(ctx->d_desc);
+  if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+  ctx->h_desc = nullptr;
+  ctx->slots = 0;
+  ctx->slotPixels = 0;
+}
+static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
+  if (slots <= ctx->slots && pixels <= ctx->slotPixels) return NICP_OK;
+  if (slots < ctx->slots) slots = ctx->slots;
+  if (pixels < ctx->slotPixels) pixels = ctx->slotPixels;
+  free_align(ctx);
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_refZ, 2 * (size_t)slots * pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_curZ, (size_t)slots * pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_curIndex, (size_t)slots * pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_corrImage, (size_t)slots * pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->blocksPerPair * kAccum))) return rc;
+  if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
+  // descriptors followed by one int flag per slot
+  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
+  void *p = nullptr;
+  NICP_CUDA(cudaMalloc(&p, descBytes));
+  ctx->d_desc = reinterpret_cast<PairDesc *>(p);
+  NICP_CUDA(cudaMallocHost(&p, descBytes));
+  ctx->h_desc = reinterpret_cast<PairDesc *>(p);
+  ctx->slots = slots;
+  ctx->slotPixels = pixels;
+  return NICP_OK;
+}
+static int ensure_results(nicp_context *ctx, int n) {
+  if (n <= ctx->resultCap) return NICP_OK;
+  dev_free(ctx->d_results);
+  dev_free(ctx->d_statHb);
+  if (ctx->h_results) cudaFreeHost(ctx->h_results);
+  if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
+  ctx->h_results = nullptr;
+  ctx->h_statHb = nullptr;
+  ctx->resultCap = 0;
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_results, (size_t)n))) return rc;
+  if ((rc = dev_alloc(&ctx->d_statHb, (size_t)n * 42))) return rc;
+  void *p = nullptr;
+  NICP_CUDA(cudaMallocHost(&p, sizeof(nicp_align_result) * n));
+  ctx->h_results = reinterpret_cast<nicp_align_result *>(p);
+  NICP_CUDA(cudaMallocHost(&p, sizeof(float) * 42 * n));
+  ctx->h_statHb = reinterpret_cast<float *>(p);
+  ctx->resultCap = n;
+  return NICP_OK;
+}
+static int ensure_trace(nicp_context *ctx, int iters) {
+  if (iters <= ctx->traceIters) return NICP_OK;
+  dev_free(ctx->d_trace);
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_trace, (size_t)iters * 61))) return rc;
+  ctx->traceIters = iters;
+  return NICP_OK;
+}
+
+static int cloud_sync_n(nicp_context *ctx, const nicp_cloud *cloud) {
+  nicp_cloud *c = const_cast<nicp_cloud *>(cloud);
+  if (c->n_known) return NICP_OK;
+  NICP_CUDA(cudaMemcpyAsync(&c->n_host, c->d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  c->n_known = true;
+  return NICP_OK;
+}
+
+static int ensure_stats(nicp_cloud *cloud) {
+  if (cloud->stats16) return NICP_OK;
+  int rc;
+  if ((rc = dev_alloc(&cloud->stats16, (size_t)cloud->capacity * 16))) return rc;
+  if ((rc = dev_alloc(&cloud->eigvals, (size_t)cloud->capacity * 3))) return rc;
+  if ((rc = dev_alloc(&cloud->statsN, (size_t)cloud->capacity))) return rc;
+  return NICP_OK;
+}
+
+static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset) {
+  AlignConsts ac;
+  memset(&ac, 0, sizeof ac);
+  for (int i = 0; i < 9; i++) ac.K[i] = proj->K[i];
+  if (refOffset) {
+    for (int i = 0; i < 16; i++) ac.refOffset[i] = refOffset[i];
+    fix_last_row(ac.refOffset);
+  } else {
+    mat4_identity(ac.refOffset);
+  }
+  ac.rows = proj->rows;
+  ac.cols = proj->cols;
+  ac.minD = proj->min_distance;
+  ac.maxD = proj->max_distance;
+  // correspondencefinder.h:63-70 (_squaredThreshold), correspondencefinder.cpp:28-29
+  ac.squaredThreshold = ap->inlier_distance_threshold * ap->inlier_distance_threshold;
+  ac.normalThreshold = ap->inlier_normal_angular_threshold;
+  ac.flatCurvature = ap->flat_curvature_threshold;
+  ac.minRatio = 1.0f / ap->inlier_curvature_ratio_threshold;
+  ac.maxRatio = ap->inlier_curvature_ratio_threshold;
+  ac.maxChi2 = ap->inlier_max_chi2;
+  ac.robust = ap->robust_kernel;
+  return ac;
+}
+
+static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud *ref, const nicp_cloud *cur,
+                      const float *guess, nicp_align_result *d_result, float *d_trace) {
+  PairDesc &D = ctx->h_desc[slot];
+  const size_t P = ctx->slotPixels;
+  D.refPoints = ref->points;
+  D.refNormals = ref->normals;
+  D.refN = ref->d_n;
+  D.curPoints = cur->points;
+  D.curNormals = cur->normals;
+  D.curOmega = cur->omega;
+  D.curN = cur->d_n;
+  D.refZ[0] = ctx->d_refZ + (size_t)slot * P;
+  D.refZ[1] = ctx->d_refZ + ((size_t)ctx->slots + slot) * P;
+  D.curZ = ctx->d_curZ + (size_t)curSlot * P;
+  D.curIndex = ctx->d_curIndex + (size_t)curSlot * P;
+  D.corrImage = ctx->d_corrImage + (size_t)slot * P;
+  D.partials = ctx->d_partials + (size_t)slot * ctx->blocksPerPair * kAccum;
+  D.state = ctx->d_state + slot;
+  D.trace = d_trace;
+  D.result = d_result;
+  if (guess) {
+    for (int i = 0; i < 16; i++) D.guess[i] = guess[i];
+  } else {
+    mat4_identity(D.guess);
+  }
+}
+
+// ---- Aligner::_computeStatistics tail (aligner.cpp:172-198, unscented.h:23-65), host, tiny ----
+static void jacobi_sym(int n, double *A, double *V, double *w) {
+  for (int i = 0; i < n * n; i++) V[i] = 0;
+  for (int i = 0; i < n; i++) V[i * n + i] = 1;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += A[q * n + p] * A[q * n + p];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = A[q * n + p];
+        if (fabs(apq) < 1e-300) continue;
+        double app = A[p * n + p], aqq = A[q * n + q];
+        double tau = (aqq - app) / (2 * apq);
+        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1 + tau * tau));
+        double c = 1 / sqrt(1 + t * t), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = A[p * n + k], akq = A[q * n + k];
+          A[p * n + k] = c * akp - s * akq;
+          A[q * n + k] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = A[k * n + p], aqk = A[k * n + q];
+          A[k * n + p] = c * apk - s * aqk;
+          A[k * n + q] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double vkp = V[p * n + k], vkq = V[q * n + k];
+          V[p * n + k] = c * vkp - s * vkq;
+          V[q * n + k] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; i++) w[i] = A[i * n + i];
+}
+static void sym_pinv6(const float *H, float *Hi) {
+  double A[36], V[36], w[6];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) A[c * 6 + r] = 0.5 * ((double)NM6(H, r, c) + (double)NM6(H, c, r));
+  jacobi_sym(6, A, V, w);
+  double wmax = 0;
+  for (int i = 0; i < 6; i++)
+    if (fabs(w[i]) > wmax) wmax = fabs(w[i]);
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      double s = 0;
+      for (int k = 0; k < 6; k++)
+        if (fabs(w[k]) > wmax * 6 * (double)FLT_EPSILON) s += V[k * 6 + r] * V[k * 6 + c] / w[k];
+      NM6(Hi, r, c) = (float)s;
+    }
+}
+static void mat6_inverse(const float *A, float *Ai) {
+  double a[6][12];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      a[r][c] = NM6(A, r, c);
+      a[r][c + 6] = (r == c);
+    }
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++)
+      if (fabs(a[r][k]) > fabs(a[piv][k])) piv = r;
+    if (piv != k)
+      for (int c = 0; c < 12; c++) { double t = a[k][c]; a[k][c] = a[piv][c]; a[piv][c] = t; }
+    double d = a[k][k];
+    for (int c = 0; c < 12; c++) a[k][c] /= d;
+    for (int r = 0; r < 6; r++)
+      if (r != k) {
+        double f = a[r][k];
+        if (f != 0.0)
+          for (int c = 0; c < 12; c++) a[r][c] -= f * a[k][c];
+      }
+  }
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) NM6(Ai, r, c) = (float)a[r][c + 6];
+}
+static float sym_eig_ratio3(const float *O, int off) {
+  double A[9], V[9], w[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) A[c * 3 + r] = 0.5 * ((double)NM6(O, off + r, off + c) + (double)NM6(O, off + c, off + r));
+  jacobi_sym(3, A, V, w);
+  double mx = 0, mn = 1e300;
+  for (int i = 0; i < 3; i++) {
+    double a = fabs(w[i]);
+    if (a > mx) mx = a;
+    if (a < mn) mn = a;
+  }
+  return (float)(mx / mn);
+}
+static void compute_statistics(const float *H_lin, const float *T, float *Omega, float *tr, float *rr) {
+  float H[36], Sigma[36];
+  memcpy(H, H_lin, sizeof H);
+  for (int i = 0; i < 6; i++) NM6(H, i, i) += 1.0f;
+  sym_pinv6(H, Sigma);
+  const int dim = 6;
+  const double alpha = 1e-3, beta = 2.;
+  const double lambda = alpha * alpha * dim;
+  const double wi = 1. / (2. * (dim + lambda));
+  double wm[13], wc[13];
+  float samples[13][6];
+  memset(samples, 0, sizeof samples);
+  wm[0] = lambda / (dim + lambda);
+  wc[0] = lambda / (dim + lambda) + (1. - alpha * alpha + beta);
+  float A[36], L[36];
+  memset(L, 0, sizeof L);
+  float sc = (float)(dim + lambda);
+  for (int i = 0; i < 36; i++) A[i] = Sigma[i] * sc;
+  for (int j = 0; j < 6; j++) {
+    float s = NM6(A, j, j);
+    for (int k = 0; k < j; k++) s -= NM6(L, j, k) * NM6(L, j, k);
+    float d = sqrtf(s);
+    NM6(L, j, j) = d;
+    for (int i = j + 1; i < 6; i++) {
+      float t = NM6(A, i, j);
+      for (int k = 0; k < j; k++) t -= NM6(L, i, k) * NM6(L, j, k);
+      NM6(L, i, j) = t / d;
+    }
+  }
+  int k = 1;
+  for (int i = 0; i < dim; i++) {
+    for (int r = 0; r < 6; r++) {
+      samples[k][r] = NM6(L, r, i);
+      samples[k + 1][r] = -NM6(L, r, i);
+    }
+    wm[k] = wc[k] = wi;
+    wm[k + 1] = wc[k + 1] = wi;
+    k += 2;
+  }
+  for (int i = 0; i < 13; i++) {
+    float X[16], Xi[16], Y[16];
+    v2t(samples[i], X);
+    iso_inverse(X, Xi);
+    iso_mul(T, Xi, Y);
+    t2v(Y, samples[i]);
+  }
+  float mean[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 13; i++)
+    for (int r = 0; r < 6; r++) mean[r] += (float)(wm[i] * (double)samples[i][r]);
+  float cov[36];
+  memset(cov, 0, sizeof cov);
+  for (int i = 0; i < 13; i++) {
+    float dl[6];
+    for (int r = 0; r < 6; r++) dl[r] = samples[i][r] - mean[r];
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 6; c++) NM6(cov, r, c) += (float)(wc[i] * (double)(dl[r] * dl[c]));
+  }
+  mat6_inverse(cov, Omega);
+  *tr = sym_eig_ratio3(Omega, 0);
+  *rr = sym_eig_ratio3(Omega, 3);
+}
+
+static void finish_results(nicp_context *ctx, int n, nicp_align_result *out) {
+  for (int i = 0; i < n; i++) {
+    nicp_align_result r = ctx->h_results[i];
+    const float *Hb = ctx->h_statHb + (size_t)i * 42;
+    compute_statistics(Hb, r.T, r.omega, &r.translational_eigen_ratio, &r.rotational_eigen_ratio);
+    r.reserved[0] = r.reserved[1] = 0.0f;
+    out[i] = r;
+  }
+}
+
+}  // namespace nicp
+
+using namespace nicp;
+
+// =============================================================================================
+extern "C" {
+
+const char *nicp_last_error(void) { return g_err; }
+
+int nicp_is_verification_build(void) {
+#ifdef NICP_VERIFY_BUILD
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+int nicp_create(int device, nicp_context **out) {
+  if (!out) return NICP_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return NICP_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device %d out of range (0..%d)", device, count - 1);
+    return NICP_ERR_INVALID;
+  }
+  NICP_CUDA(cudaSetDevice(device));
+  nicp_context *ctx = new nicp_context();
+  memset(ctx, 0, sizeof *ctx);
+  ctx->device = device;
+  NICP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  NICP_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->smCount = prop.multiProcessorCount;
+  // fixed so that H/b of a pair do not depend on batch size or GPU count (2 CTAs per SM on a B200)
+  ctx->blocksPerPair = env_int("NICP_BLOCKS_PER_PAIR", 296);
+  *out = ctx;
+  return NICP_OK;
+}
+
+void nicp_destroy(nicp_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx->d_depth);
+  dev_free(ctx->d_raw);
+  dev_free(ctx->d_integral);
+  dev_free(ctx->d_interval);
+  dev_free(ctx->d_index);
+  free_align(ctx);
+  dev_free(ctx->d_trace);
+  dev_free(ctx->d_results);
+  dev_free(ctx->d_statHb);
+  if (ctx->h_results) cudaFreeHost(ctx->h_results);
+  if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int nicp_synchronize(nicp_context *ctx) {
+  if (!ctx) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+long long nicp_launch_count(const nicp_context *ctx) { return ctx ? ctx->launches : 0; }
+void *nicp_stream(nicp_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ---- clouds ----------------------------------------------------------------------------------
+int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **out) {
+  if (!ctx || !out || capacity <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  nicp_cloud *c = new nicp_cloud();
+  memset(c, 0, sizeof *c);
+  c->ctx = ctx;
+  c->capacity = capacity;
+  int rc;
+  if ((rc = dev_alloc(&c->points, (size_t)capacity)) || (rc = dev_alloc(&c->normals, (size_t)capacity)) ||
+      (rc = dev_alloc(&c->omega, (size_t)capacity * 3)) || (rc = dev_alloc(&c->d_n, 1))) {
+    nicp_cloud_destroy(c);
+    return rc;
+  }
+  NICP_CUDA(cudaMemsetAsync(c->d_n, 0, sizeof(int), ctx->stream));
+  c->n_host = 0;
+  c->n_known = true;
+  *out = c;
+  return NICP_OK;
+}
+
+void nicp_cloud_destroy(nicp_cloud *c) {
+  if (!c) return;
+  if (c->ctx) {
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+  }
+  dev_free(c->points);
+  dev_free(c->normals);
+  dev_free(c->omega);
+  dev_free(c->stats16);
+  dev_free(c->eigvals);
+  dev_free(c->statsN);
+  dev_free(c->d_n);
+  delete c;
+}
+
+int nicp_cloud_size(const nicp_cloud *c) {
+  if (!c) return -1;
+  if (cloud_sync_n(c->ctx, c) != NICP_OK) return -1;
+  return c->n_host;
+}
+
+int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *points4, const float *normals4,
+                      const float *curvature, const float *omega_p6, const float *omega_n6) {
+  if (!ctx || !c || n < 0 || !points4) return NICP_ERR_INVALID;
+  if (n > c->capacity) {
+    set_error("cloud upload of %d points exceeds capacity %d", n, c->capacity);
+    return NICP_ERR_INVALID;
+  }
+  std::vector<float> nrm((size_t)n * 4, 0.0f), om((size_t)n * 12, 0.0f);
+  for (int i = 0; i < n; i++) {
+    if (normals4) { nrm[4 * i] = normals4[4 * i]; nrm[4 * i + 1] = normals4[4 * i + 1]; nrm[4 * i + 2] = normals4[4 * i + 2]; }
+    nrm[4 * i + 3] = curvature ? curvature[i] : 0.0f;
+    if (omega_p6)
+      for (int k = 0; k < 6; k++) om[12 * (size_t)i + k] = omega_p6[6 * (size_t)i + k];
+    if (omega_n6)
+      for (int k = 0; k < 6; k++) om[12 * (size_t)i + 6 + k] = omega_n6[6 * (size_t)i + k];
+  }
+  NICP_CUDA(cudaMemcpyAsync(c->points, points4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(c->normals, nrm.data(), sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(c->omega, om.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(c->d_n, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  c->n_host = n;
+  c->n_known = true;
+  c->has_stats = false;
+  return NICP_OK;
+}
+
+int nicp_cloud_download(nicp_context *ctx, const nicp_cloud *c, float *points4, float *normals4, float *curvature,
+                        float *omega_p6, float *omega_n6) {
+  if (!ctx || !c) return NICP_ERR_INVALID;
+  int rc = cloud_sync_n(ctx, c);
+  if (rc) return rc;
+  const int n = c->n_host;
+  if (n == 0) return NICP_OK;
+  if (points4) NICP_CUDA(cudaMemcpyAsync(points4, c->points, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<float> nrm, om;
+  if (normals4 || curvature) {
+    nrm.resize((size_t)n * 4);
+    NICP_CUDA(cudaMemcpyAsync(nrm.data(), c->normals, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (omega_p6 || omega_n6) {
+    om.resize((size_t)n * 12);
+    NICP_CUDA(cudaMemcpyAsync(om.data(), c->omega, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    if (normals4) {
+      normals4[4 * i] = nrm[4 * i]; normals4[4 * i + 1] = nrm[4 * i + 1]; normals4[4 * i + 2] = nrm[4 * i + 2];
+      normals4[4 * i + 3] = 0.0f;
+    }
+    if (curvature) curvature[i] = nrm[4 * i + 3];
+    if (omega_p6)
+      for (int k = 0; k < 6; k++) omega_p6[6 * (size_t)i + k] = om[12 * (size_t)i + k];
+    if (omega_n6)
+      for (int k = 0; k < 6; k++) omega_n6[6 * (size_t)i + k] = om[12 * (size_t)i + 6 + k];
+  }
+  return NICP_OK;
+}
+
+int nicp_cloud_download_stats(nicp_context *ctx, const nicp_cloud *c, float *stats16, float *eigenvalues3, int *n_points) {
+  if (!ctx || !c) return NICP_ERR_INVALID;
+  if (!c->has_stats) {
+    set_error("cloud was built without keep_stats");
+    return NICP_ERR_INVALID;
+  }
+  int rc = cloud_sync_n(ctx, c);
+  if (rc) return rc;
+  const int n = c->n_host;
+  if (stats16) NICP_CUDA(cudaMemcpyAsync(stats16, c->stats16, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (eigenvalues3) NICP_CUDA(cudaMemcpyAsync(eigenvalues3, c->eigvals, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_points) NICP_CUDA(cudaMemcpyAsync(n_points, c->statsN, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *c, const float T[16]) {
+  if (!ctx || !c || !T) return NICP_ERR_INVALID;
+  return launch_cloud_transform(ctx, c, T);
+}
+
+// ---- depth helpers ---------------------------------------------------------------------------
+int nicp_depth_prepare(nicp_context *ctx, const uint16_t *raw, int rows, int cols, float depth_scale, int step,
+                       float max_depth_cov, float *out) {
+  if (!ctx || !raw || !out || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  if (step < 1) step = 1;
+  int rc;
+  size_t px = (size_t)rows * cols;
+  if ((rc = ensure_raw(ctx, px))) return rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_raw, raw, px * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_depth_convert(ctx, ctx->d_raw, rows, cols, depth_scale, step, max_depth_cov, ctx->d_depth))) return rc;
+  size_t opx = (size_t)(rows / step) * (cols / step);
+  NICP_CUDA(cudaMemcpyAsync(out, ctx->d_depth, opx * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+// ---- frame preparation -------------------------------------------------------------------------
+int nicp_unproject(nicp_context *ctx, const float *depth, int rows, int cols, const float iKRt[16], float min_distance,
+                   float max_distance, nicp_cloud *cloud, int *index) {
+  if (!ctx || !depth || !iKRt || !cloud || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)rows * cols;
+  if ((size_t)cloud->capacity < px) {
+    set_error("cloud capacity %d smaller than the image (%zu pixels)", cloud->capacity, px);
+    return NICP_ERR_INVALID;
+  }
+  int rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_depth, depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_unproject(ctx, ctx->d_depth, rows, cols, iKRt, min_distance, max_distance, cloud, ctx->d_index))) return rc;
+  // a points-only cloud: normals / information matrices are zero
+  NICP_CUDA(cudaMemsetAsync(cloud->normals, 0, sizeof(float4) * px, ctx->stream));
+  NICP_CUDA(cudaMemsetAsync(cloud->omega, 0, sizeof(float4) * 3 * px, ctx->stream));
+  if (index) NICP_CUDA(cudaMemcpyAsync(index, ctx->d_index, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+int nicp_project_intervals(nicp_context *ctx, const float *depth, const nicp_projector *proj, float world_radius,
+                           int *interval) {
+  if (!ctx || !depth || !proj || !interval || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)proj->rows * proj->cols;
+  int rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_depth, depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_intervals(ctx, ctx->d_depth, proj, world_radius, ctx->d_interval))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(interval, ctx->d_interval, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+static int depth_to_cloud_device(nicp_context *ctx, const nicp_projector *proj, const nicp_stats_params *sp,
+                                 const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
+  size_t px = (size_t)proj->rows * proj->cols;
+  int rc;
+  if (keep_stats && (rc = ensure_stats(cloud))) return rc;
+  float eye[16];
+  mat4_identity(eye);
+  if ((rc = launch_frame_prep(ctx, ctx->d_depth, proj, sp, sensor_offset ? sensor_offset : eye, keep_stats, cloud,
+                              ctx->d_index)))
+    return rc;
+  if (index) {
+    NICP_CUDA(cudaMemcpyAsync(index, ctx->d_index, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return NICP_OK;
+}
+
+int nicp_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_projector *proj, const nicp_stats_params *sp,
+                        const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
+  if (!ctx || !depth || !proj || !sp || !cloud || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)proj->rows * proj->cols;
+  if ((size_t)cloud->capacity < px) {
+    set_error("cloud capacity %d smaller than the image (%zu pixels)", cloud->capacity, px);
+    return NICP_ERR_INVALID;
+  }
+  int rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_depth, depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return depth_to_cloud_device(ctx, proj, sp, sensor_offset, keep_stats, cloud, index);
+}
+
+int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows, int raw_cols, float depth_scale, int step,
+                            float max_depth_cov, const nicp_projector *proj, const nicp_stats_params *sp,
+                            const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
+  if (!ctx || !raw || !proj || !sp || !cloud || raw_rows <= 0 || raw_cols <= 0) return NICP_ERR_INVALID;
+  if (step < 1) step = 1;
+  if (proj->rows != raw_rows / step || proj->cols != raw_cols / step) {
+    set_error("projector image size %dx%d does not match the scaled raw image %dx%d", proj->rows, proj->cols,
+              raw_rows / step, raw_cols / step);
+    return NICP_ERR_INVALID;
+  }
+  size_t rpx = (size_t)raw_rows * raw_cols, px = (size_t)proj->rows * proj->cols;
+  if ((size_t)cloud->capacity < px) {
+    set_error("cloud capacity %d smaller than the image (%zu pixels)", cloud->capacity, px);
+    return NICP_ERR_INVALID;
+  }
+  int rc;
+  if ((rc = ensure_raw(ctx, rpx))) return rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_raw, raw, rpx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_depth_convert(ctx, ctx->d_raw, raw_rows, raw_cols, depth_scale, step, max_depth_cov, ctx->d_depth)))
+    return rc;
+  return depth_to_cloud_device(ctx, proj, sp, sensor_offset, keep_stats, cloud, index);
+}
+
+int nicp_last_integral_image(nicp_context *ctx, float *integral10) {
+  if (!ctx || !integral10 || ctx->lastRows <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)ctx->lastRows * ctx->lastCols;
+  std::vector<float> planar(px * kIntegralCh);
+  NICP_CUDA(cudaMemcpyAsync(planar.data(), ctx->d_integral, planar.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (size_t p = 0; p < px; p++)
+    for (int k = 0; k < kIntegralCh; k++) integral10[p * kIntegralCh + k] = planar[k * px + p];
+  return NICP_OK;
+}
+
+int nicp_last_interval_image(nicp_context *ctx, int *interval) {
+  if (!ctx || !interval || ctx->lastRows <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)ctx->lastRows * ctx->lastCols;
+  NICP_CUDA(cudaMemcpyAsync(interval, ctx->d_interval, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+// ---- projection --------------------------------------------------------------------------------
+int nicp_project(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols, float min_distance,
+                 float max_distance, int *index, float *depth) {
+  if (!ctx || !cloud || !KRt || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  size_t px = (size_t)rows * cols;
+  int rc;
+  if ((rc = ensure_align(ctx, 1, px))) return rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  unsigned long long *z = ctx->d_curZ;
+  if ((rc = launch_project_single(ctx, cloud, KRt, rows, cols, min_distance, max_distance, z))) return rc;
+  if ((rc = launch_decode_z(ctx, z, (int)px, ctx->d_index, ctx->d_depth))) return rc;
+  if (index) NICP_CUDA(cudaMemcpyAsync(index, ctx->d_index, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth) NICP_CUDA(cudaMemcpyAsync(depth, ctx->d_depth, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->lastAlignValid = false;
+  return NICP_OK;
+}
+
+// ---- stage-level correspondence + linearisation ------------------------------------------------------
+static int fetch_stage_result(nicp_context *ctx, float H[36], float b[6], float *error, int *inliers, int *ncorr) {
+  PairState st;
+  NICP_CUDA(cudaMemcpyAsync(&st, ctx->d_state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (H) memcpy(H, st.H, sizeof st.H);
+  if (b) memcpy(b, st.b, sizeof st.b);
+  if (error) *error = st.error;
+  if (inliers) *inliers = st.inliers;
+  if (ncorr) *ncorr = st.ncorr;
+  return NICP_OK;
+}
+
+static int stage_set_T(nicp_context *ctx, const float T[16]) {
+  float invT[16];
+  for (int i = 0; i < 16; i++) invT[i] = T[i];
+  fix_last_row(invT);
+  NICP_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->d_state) + offsetof(PairState, invT), invT, sizeof invT,
+                            cudaMemcpyHostToDevice, ctx->stream));
+  return NICP_OK;
+}
+
+int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current,
+                              const int *reference_index, const int *current_index, int rows, int cols, const float T[16],
+                              const nicp_align_params *ap, float H[36], float b[6], float *error, int *inliers,
+                              int *num_correspondences, int *corr_image) {
+  if (!ctx || !reference || !current || !reference_index || !current_index || !T || !ap || rows <= 0 || cols <= 0)
+    return NICP_ERR_INVALID;
+  size_t px = (size_t)rows * cols;
+  int rc;
+  if ((rc = ensure_align(ctx, 1, px))) return rc;
+  nicp_projector proj;
+  memset(&proj, 0, sizeof proj);
+  proj.rows = rows;
+  proj.cols = cols;
+  AlignConsts ac = make_consts(&proj, ap, nullptr);
+  fill_desc(ctx, 0, 0, reference, current, nullptr, nullptr, nullptr);
+  std::vector<unsigned long long> z(px);
+  for (size_t i = 0; i < px; i++) z[i] = reference_index[i] < 0 ? kEmptyZ : (unsigned long long)(unsigned int)reference_index[i];
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].refZ[0], z.data(), px * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, current_index, px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = stage_set_T(ctx, T))) return rc;
+  if ((rc = run_correspond_linearize(ctx, ac, false, (int)px))) return rc;
+  if (corr_image)
+    NICP_CUDA(cudaMemcpyAsync(corr_image, ctx->h_desc[0].corrImage, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->lastAlignValid = false;
+  return fetch_stage_result(ctx, H, b, error, inliers, num_correspondences);
+}
+
+int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current, const int *correspondences,
+                   int n, const float T[16], const nicp_align_params *ap, float H[36], float b[6], float *error,
+                   int *inliers) {
+  if (!ctx || !reference || !current || (!correspondences && n > 0) || n < 0 || !T || !ap) return NICP_ERR_INVALID;
+  size_t px = n > 0 ? (size_t)n : 1;
+  int rc;
+  if ((rc = ensure_align(ctx, 1, px))) return rc;
+  nicp_projector proj;
+  memset(&proj, 0, sizeof proj);
+  proj.rows = 1;
+  proj.cols = (int)px;
+  AlignConsts ac = make_consts(&proj, ap, nullptr);
+  fill_desc(ctx, 0, 0, reference, current, nullptr, nullptr, nullptr);
+  std::vector<int> ri(px, -1), ci(px, -1);
+  for (int i = 0; i < n; i++) {
+    ri[i] = correspondences[2 * i];
+    ci[i] = correspondences[2 * i + 1];
+  }
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].corrImage, ri.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, ci.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = stage_set_T(ctx, T))) return rc;
+  if ((rc = run_correspond_linearize(ctx, ac, true, (int)px))) return rc;
+  ctx->lastAlignValid = false;
+  return fetch_stage_result(ctx, H, b, error, inliers, nullptr);
+}
+
+// ---- alignment -----------------------------------------------------------------------------------
+static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs, const nicp_cloud *const *curs,
+                        const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset,
+                        const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
+                        bool single) {
+  const size_t P = (size_t)proj->rows * proj->cols;
+  int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 64);
+  if (maxSlots > n) maxSlots = n;
+  int rc;
+  if ((rc = ensure_align(ctx, maxSlots, P))) return rc;
+  if ((rc = ensure_results(ctx, n))) return rc;
+  if (single && (rc = ensure_trace(ctx, ap->outer_iterations > 0 ? ap->outer_iterations : 1))) return rc;
+  AlignConsts ac = make_consts(proj, ap, refOffset);
+  float eye[16], co[16], curKRt[16];
+  mat4_identity(eye);
+  for (int i = 0; i < 16; i++) co[i] = curOffset ? curOffset[i] : eye[i];
+  fix_last_row(co);
+  compute_KRt(proj->K, co, curKRt);  // aligner.cpp:60: projector->setTransform(_currentSensorOffset)
+  const int slots = ctx->slots;
+  std::vector<int> owns(slots);
+  for (int base = 0; base < n; base += maxSlots) {
+    int m = n - base < maxSlots ? n - base : maxSlots;
+    if (base > 0) {
+      // the staging buffer of the previous chunk must have been consumed by its H2D copy
+      NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    std::map<const nicp_cloud *, int> curSlot;
+    for (int i = 0; i < m; i++) {
+      const nicp_cloud *r = refs[base + i], *c = curs[base + i];
+      if (!r || !c) {
+        set_error("null cloud in pair %d", base + i);
+        return NICP_ERR_INVALID;
+      }
+      auto it = curSlot.find(c);
+      int cs;
+      if (it == curSlot.end()) {
+        cs = i;
+        curSlot[c] = i;
+        owns[i] = 1;
+      } else {
+        cs = it->second;
+        owns[i] = 0;
+      }
+      fill_desc(ctx, i, cs, r, c, guesses ? guesses + 16 * (size_t)(base + i) : nullptr, ctx->d_results + base + i,
+                single ? ctx->d_trace : nullptr);
+    }
+    if ((rc = run_align_chunk(ctx, m, ac, curKRt, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+                              owns.data(), single, base)))
+      return rc;
+  }
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(nicp_align_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb, ctx->d_statHb, sizeof(float) * 42 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  finish_results(ctx, n, results);
+  ctx->lastAlignRows = proj->rows;
+  ctx->lastAlignCols = proj->cols;
+  ctx->lastAlignIters = ap->outer_iterations;
+  ctx->lastAlignValid = single;
+  return NICP_OK;
+}
+
+int nicp_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current, const nicp_projector *proj,
+               const nicp_align_params *ap, const float reference_sensor_offset[16], const float current_sensor_offset[16],
+               const float initial_guess[16], const nicp_prior *priors, int num_priors, float frame_inlier_depth_threshold,
+               nicp_align_result *result) {
+  if (!ctx || !reference || !current || !proj || !ap || !result || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  if (num_priors > 0 || priors) {
+    set_error("SE3 priors are not implemented on the device path yet");
+    return NICP_ERR_INVALID;
+  }
+  return align_common(ctx, 1, &reference, &current, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guess,
+                      frame_inlier_depth_threshold, result, true);
+}
+
+int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *references, const nicp_cloud *const *currents,
+                     const nicp_projector *proj, const nicp_align_params *ap, const float reference_sensor_offset[16],
+                     const float current_sensor_offset[16], const float *initial_guesses, float frame_inlier_depth_threshold,
+                     nicp_align_result *results) {
+  if (!ctx || n < 0 || !proj || !ap || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  if (n == 0) return NICP_OK;
+  if (!references || !currents || !results) return NICP_ERR_INVALID;
+  return align_common(ctx, n, references, currents, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guesses,
+                      frame_inlier_depth_threshold, results, false);
+}
+
+int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *reference_depth, int *current_index,
+                         float *current_depth, int *correspondences, float H[36], float b[6]) {
+  if (!ctx || !ctx->lastAlignValid) {
+    set_error("no single nicp_align state available on this context");
+    return NICP_ERR_INVALID;
+  }
+  const size_t P = (size_t)ctx->lastAlignRows * ctx->lastAlignCols;
+  int rc;
+  if ((rc = ensure_prep(ctx, P))) return rc;
+  const PairDesc &D = ctx->h_desc[0];
+  std::vector<int> ci, corrImg;
+  if (reference_index || reference_depth) {
+    if ((rc = launch_decode_z(ctx, D.refZ[ctx->lastAlignParity], (int)P, ctx->d_index, ctx->d_depth))) return rc;
+    if (reference_index) NICP_CUDA(cudaMemcpyAsync(reference_index, ctx->d_index, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reference_depth) NICP_CUDA(cudaMemcpyAsync(reference_depth, ctx->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (current_index || current_depth) {
+    if ((rc = launch_decode_z(ctx, D.curZ, (int)P, ctx->d_index, ctx->d_depth))) return rc;
+    if (current_index) NICP_CUDA(cudaMemcpyAsync(current_index, ctx->d_index, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (current_depth) NICP_CUDA(cudaMemcpyAsync(current_depth, ctx->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (correspondences) {
+    ci.resize(P);
+    corrImg.resize(P);
+    NICP_CUDA(cudaMemcpyAsync(ci.data(), D.curIndex, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaMemcpyAsync(corrImg.data(), D.corrImage, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+    size_t k = 0;  // raster-order compaction, the order of correspondencefinder.cpp:108-113
+    for (size_t p = 0; p < P; p++)
+      if (corrImg[p] >= 0) {
+        correspondences[2 * k] = corrImg[p];
+        correspondences[2 * k + 1] = ci[p];
+        k++;
+      }
+  }
+  if (H) memcpy(H, ctx->h_statHb, sizeof(float) * 36);
+  if (b) memcpy(b, ctx->h_statHb + 36, sizeof(float) * 6);
+  return NICP_OK;
+}
+
+int nicp_align_get_trace(nicp_context *ctx, float *trace61, int max_iterations) {
+  if (!ctx || !trace61 || !ctx->lastAlignValid) return NICP_ERR_INVALID;
+  int it = ctx->lastAlignIters < max_iterations ? ctx->lastAlignIters : max_iterations;
+  if (it <= 0) return NICP_OK;
+  NICP_CUDA(cudaMemcpyAsync(trace61, ctx->d_trace, sizeof(float) * 61 * it, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+}  // extern "C"

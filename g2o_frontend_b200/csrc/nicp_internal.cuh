@@ -1,0 +1,175 @@
+// nicp_internal.cuh -- internal structures shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/nicp_b200.h"
+#include "nicp_math.cuh"
+
+namespace nicp {
+
+void set_error(const char *fmt, ...);
+
+#define NICP_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ::nicp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NICP_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+#define NICP_CHECK_LAUNCH(ctx)                                                                   \
+  do {                                                                                           \
+    (ctx)->launches++;                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess) {                                                                     \
+      ::nicp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NICP_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
+constexpr int kIntegralCh = 10;   // n,x,y,z,xx,xy,xz,yy,yz,zz
+constexpr unsigned long long kEmptyZ = 0xFFFFFFFFFFFFFFFFull;
+
+// accumulator slot layout of the fused correspondence+linearise reduction
+enum {
+  A_HTT = 0,   // 6: xx xy xz yy yz zz
+  A_HTR = 6,   // 9: row-major (r*3+c)
+  A_HRR = 15,  // 6: upper triangle
+  A_BT = 21,   // 3
+  A_BR = 24,   // 3
+  A_ERR = 27,
+  A_INL = 28,
+  A_NCORR = 29
+};
+
+// per-pair pose / linear-system state, lives in device memory
+struct PairState {
+  float T[16];     // current estimate (reference <- current)
+  float invT[16];  // working inverse used by the finder and the lineariser
+  float KRt[16];   // K * (T * referenceSensorOffset)^-1 for the next reference projection
+  float H[36];     // last assembled H (column-major 6x6, without damping)
+  float b[6];
+  float error;     // from the last LOOP linearisation (Aligner::error())
+  int inliers;
+  int ncorr;
+  float statH[36]; // linearisation of _computeStatistics at the final T
+  float statb[6];
+  int img_nonzeros, img_inliers;
+  float img_sum;
+  int pad;
+};
+
+// per-pair descriptor for the batched kernels (device memory, filled by the host per chunk)
+struct PairDesc {
+  const float4 *refPoints;
+  const float4 *refNormals;  // w = curvature
+  const int *refN;
+  const float4 *curPoints;
+  const float4 *curNormals;  // w = curvature
+  const float4 *curOmega;    // 3 float4 per point: (Pxx,Pxy,Pxz,Pyy) (Pyz,Pzz,Nxx,Nxy) (Nxz,Nyy,Nyz,Nzz)
+  const int *curN;
+  unsigned long long *refZ[2];  // double-buffered reference z-buffer (packed depth|index)
+  unsigned long long *curZ;     // current z-buffer (shared by pairs with the same current cloud)
+  int *curIndex;                // decoded current index image
+  int *corrImage;               // accepted reference index per pixel or -1
+  float *partials;              // [blocksPerPair][kAccum]
+  PairState *state;
+  float *trace;                 // may be null
+  nicp_align_result *result;
+  float guess[16];
+};
+
+struct AlignConsts {
+  float K[9];
+  float refOffset[16];
+  int rows, cols;
+  float minD, maxD;
+  float squaredThreshold, normalThreshold, flatCurvature, minRatio, maxRatio;
+  float maxChi2;
+  int robust;
+};
+
+}  // namespace nicp
+
+struct nicp_cloud {
+  nicp_context *ctx;
+  int capacity;
+  float4 *points;
+  float4 *normals;  // w = curvature
+  float4 *omega;    // 3 per point
+  float *stats16;   // optional
+  float *eigvals;
+  int *statsN;
+  int *d_n;         // device-side point count
+  int n_host;       // host mirror (valid if n_known)
+  bool n_known;
+  bool has_stats;
+};
+
+struct nicp_context {
+  int device;
+  cudaStream_t stream;
+  long long launches;
+  int smCount;
+
+  // frame-prep scratch
+  size_t prepPixels;
+  float *d_depth;
+  uint16_t *d_raw;
+  size_t rawPixels;
+  float *d_integral;  // planar [10][rows][cols]
+  int *d_interval;
+  int *d_index;
+  int lastRows, lastCols;
+  void *h_stage;      // pinned staging
+  size_t stageBytes;
+
+  // align scratch
+  int slots;          // allocated slots
+  size_t slotPixels;  // pixels per slot
+  int blocksPerPair;
+  unsigned long long *d_refZ;   // [slots][2][P]
+  unsigned long long *d_curZ;   // [slots][P]
+  int *d_curIndex;              // [slots][P]
+  int *d_corrImage;             // [slots][P]
+  float *d_partials;            // [slots][blocksPerPair][kAccum]
+  nicp::PairState *d_state;     // [slots]
+  nicp::PairDesc *d_desc;       // [slots]
+  nicp::PairDesc *h_desc;       // pinned
+  float *d_trace;               // [maxIter][61] for slot 0 (single align)
+  int traceIters;
+  nicp_align_result *d_results; // [resultCap]
+  int resultCap;
+  nicp_align_result *h_results; // pinned
+  float *d_statHb;              // [resultCap][42]
+  float *h_statHb;              // pinned
+
+  // last single-align bookkeeping
+  int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;
+  bool lastAlignValid;
+};
+
+namespace nicp {
+// frame_prep.cu
+int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int cols, float scale, int step,
+                         float maxCov, float *d_out);
+int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
+                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index);
+int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
+                     float maxD, nicp_cloud *cloud, int *d_index);
+int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius, int *d_interval);
+int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]);
+// align.cu
+int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
+                          float minD, float maxD, unsigned long long *d_z);
+int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth);
+int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const float curKRt[16], int outerIters,
+                    int innerIters, float imgThreshold, int nUniqueCur, const int *curSlotOfPair, bool wantTrace,
+                    int resultOffset);
+int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);
+}  // namespace nicp

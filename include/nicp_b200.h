@@ -1,0 +1,214 @@
+/*
+ * nicp_b200.h -- C-ABI of the B200-native NICP registration hot path.
+ *
+ * Drop-in boundary for g2o_frontend's pwn_core (reference paths below are relative to
+ * /root/reference/g2o_frontend/pwn_core/).  The reference's seam is the C++ class API of
+ * namespace pwn; its only GPU precedent is the flat function API of
+ * pwn_cuda/cudaaligner.h:59-80 (createContext / initComputation / simpleIteration / getHb with
+ * raw float* / int*, column-major 4x4, status return).  This header is the same kind of seam:
+ * extern "C", plain pointers and sizes, int status codes, no exceptions, no torch types.
+ * include/pwn/ holds the C++ pwn:: classes (same names, setters and defaults as the reference)
+ * implemented over these entry points.
+ *
+ * Conventions
+ *   - matrices: column-major float32 (Eigen default).  4x4 isometries as float[16], K as float[9].
+ *   - images: row-major rows x cols (cv::Mat_).  Index images int32 (-1 = empty), depth float32
+ *     metres (empty z-buffer pixel = FLT_MAX, pinholepointprojector.cpp:41).
+ *   - points/normals on the host side: 4 floats per element (x,y,z,w), w=1 / w=0
+ *     (homogeneousvector4f.h:17-83).  Information matrices: 6 floats per point, the upper
+ *     triangle xx,xy,xz,yy,yz,zz of the 3x3 block (informationmatrix.h:13-84 stores a 4x4 whose
+ *     last row/column are zero; the reference's U*D*U^T is symmetric up to float rounding, the
+ *     device keeps the row<=col entries).
+ *   - every host pointer may be pageable or pinned memory; calls are synchronous unless stated.
+ *   - there is NO CPU fallback: every entry point fails with NICP_ERR_CUDA when no device works.
+ */
+#ifndef NICP_B200_H
+#define NICP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NICP_OK 0
+#define NICP_ERR_INVALID 1   /* bad argument (null handle, zero-sized image, capacity exceeded) */
+#define NICP_ERR_CUDA 2      /* a CUDA runtime call or kernel failed; see nicp_last_error() */
+#define NICP_ERR_ALLOC 3
+
+typedef struct nicp_context nicp_context; /* one per host thread / GPU (not thread-safe, like pwn_core) */
+typedef struct nicp_cloud nicp_cloud;     /* device-resident pwn::Cloud (cloud.h:20-187) */
+
+/* PointProjector + PinholePointProjector state (pointprojector.cpp:6-13, pinholepointprojector.cpp:5-13) */
+typedef struct {
+  float K[9];          /* camera matrix, column-major */
+  int rows, cols;      /* image size */
+  float min_distance;  /* default 0.01 */
+  float max_distance;  /* default 6.0 */
+} nicp_projector;
+
+/* StatsCalculatorIntegralImage (statscalculatorintegralimage.cpp:6-12) +
+ * Point/NormalInformationMatrixCalculator (informationmatrixcalculator.h:100-150) */
+typedef struct {
+  float world_radius;               /* 0.1 */
+  int min_image_radius;             /* 10 */
+  int max_image_radius;             /* 30 */
+  int min_points;                   /* 50 */
+  float curvature_threshold;        /* 0.02  (stats) */
+  float omega_curvature_threshold;  /* 0.02  (information matrices) */
+  float flat_omega_p[3];            /* diag(1000,1,1) */
+  float flat_omega_n[3];            /* diag(100,100,100) */
+  float nonflat_omega_n[3];         /* diag(1,1,1); non-flat Omega_P is U diag(1/eigenvalues) U^T */
+} nicp_stats_params;
+
+/* CorrespondenceFinder (correspondencefinder.cpp:9-18), Linearizer (linearizer.cpp:9-15),
+ * Aligner (aligner.cpp:13-32) */
+typedef struct {
+  float inlier_distance_threshold;         /* 0.5 */
+  float inlier_normal_angular_threshold;   /* cos(pi/6) */
+  float flat_curvature_threshold;          /* 0.02 */
+  float inlier_curvature_ratio_threshold;  /* 1.3 */
+  float inlier_max_chi2;                   /* 9e3 */
+  int robust_kernel;                       /* 1 */
+  int outer_iterations;                    /* 10 */
+  int inner_iterations;                    /* 1 */
+} nicp_align_params;
+
+/* SE3Prior (se3_prior.h / se3_prior.cpp:8-71) as added by Aligner::addRelativePrior / addAbsolutePrior */
+typedef struct {
+  int kind;                  /* 0 = SE3RelativePrior, 1 = SE3AbsolutePrior */
+  float mean[16];
+  float reference[16];       /* reference transform (absolute prior only) */
+  float information[36];     /* column-major 6x6 */
+} nicp_prior;
+
+/* Fixed 256-byte result record of one alignment: what Aligner exposes after align()
+ * (aligner.h:115,314-332) plus PwnMatcherBase::matchClouds' image statistics
+ * (pwn_tracker2/pwn_matcher_base.cpp:167-196).  This is also the record the batched /
+ * multi-GPU path gathers. */
+typedef struct {
+  float T[16];                  /* Aligner::T() */
+  float omega[36];              /* Aligner::omega() */
+  float error;                  /* Aligner::error(): chi2 of the last loop linearisation */
+  int inliers;                  /* Aligner::inliers() */
+  int num_correspondences;      /* CorrespondenceFinder::numCorrespondences() of the last iteration */
+  int image_non_zeros;          /* MatcherResult::image_nonZeros */
+  int image_inliers;
+  int image_outliers;
+  float image_reprojection_distance;
+  int status;                   /* NICP_OK or an error code for this pair */
+  float translational_eigen_ratio;
+  float rotational_eigen_ratio;
+  float reserved[2];
+} nicp_align_result;
+
+/* ---- context -------------------------------------------------------------------------- */
+int nicp_create(int device, nicp_context **ctx);
+void nicp_destroy(nicp_context *ctx);
+const char *nicp_last_error(void);
+int nicp_synchronize(nicp_context *ctx);
+/* 1 if the library was built with --fmad=false (verification build), else 0 */
+int nicp_is_verification_build(void);
+/* number of kernel launches issued by this context since creation */
+long long nicp_launch_count(const nicp_context *ctx);
+/* the CUDA stream (cudaStream_t) this context launches on, for event timing by the caller */
+void *nicp_stream(nicp_context *ctx);
+
+/* ---- clouds (cloud.h) ------------------------------------------------------------------- */
+int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **cloud);
+void nicp_cloud_destroy(nicp_cloud *cloud);
+int nicp_cloud_size(const nicp_cloud *cloud);
+/* host -> device.  normals4/curvature/omega_p6/omega_n6 may be NULL (zero-filled). */
+int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *cloud, int n, const float *points4,
+                      const float *normals4, const float *curvature, const float *omega_p6,
+                      const float *omega_n6);
+/* device -> host; any output may be NULL */
+int nicp_cloud_download(nicp_context *ctx, const nicp_cloud *cloud, float *points4, float *normals4,
+                        float *curvature, float *omega_p6, float *omega_n6);
+/* Stats (stats.h:13-121) if the cloud was built with keep_stats: 4x4 column-major per point
+ * (eigenvectors + mean), eigenvalues (3), n.  Returns NICP_ERR_INVALID if not materialised. */
+int nicp_cloud_download_stats(nicp_context *ctx, const nicp_cloud *cloud, float *stats16,
+                              float *eigenvalues3, int *n_points);
+/* Cloud::transformInPlace (cloud.cpp:173-186) */
+int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]);
+
+/* ---- depth image helpers (pwn_static.cpp:5-68) ----------------------------------------------- */
+/* DepthImage_convert_16UC1_to_32FC1 followed by DepthImage_scale(step) on the device.
+ * out has (rows/step) x (cols/step) floats.  step <= 1 skips the scaling. */
+int nicp_depth_prepare(nicp_context *ctx, const uint16_t *raw, int rows, int cols, float depth_scale,
+                       int step, float max_depth_cov, float *out);
+
+/* ---- frame preparation --------------------------------------------------------------------- */
+/* PinholePointProjector::unProject (pinholepointprojector.cpp:68-91): points only, compacted in
+ * raster order.  iKRt from PinholePointProjector::_updateMatrices.  index may be NULL. */
+int nicp_unproject(nicp_context *ctx, const float *depth, int rows, int cols, const float iKRt[16],
+                   float min_distance, float max_distance, nicp_cloud *cloud, int *index);
+/* PinholePointProjector::projectIntervals (pinholepointprojector.cpp:135-147) */
+int nicp_project_intervals(nicp_context *ctx, const float *depth, const nicp_projector *proj,
+                           float world_radius, int *interval);
+/* DepthImageConverterIntegralImage::compute (depthimageconverterintegralimage.cpp:15-55):
+ * unProject + projectIntervals + PointIntegralImage + StatsCalculatorIntegralImage +
+ * Point/NormalInformationMatrixCalculator + Cloud::transformInPlace(sensor_offset).
+ * index (rows*cols) may be NULL.  keep_stats != 0 also materialises pwn::Stats. */
+int nicp_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_projector *proj,
+                        const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
+                        nicp_cloud *cloud, int *index);
+/* same, from a raw 16-bit image: convert (depth_scale) + DepthImage_scale(step) + the above;
+ * proj describes the camera AFTER scaling (PwnMatcherBase::makeCloud, pwn_matcher_base.cpp:46-75). */
+int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows, int raw_cols,
+                            float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
+                            const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
+                            nicp_cloud *cloud, int *index);
+/* PointIntegralImage::compute (pointintegralimage.cpp:7-44) of the last nicp_depth_to_cloud call:
+ * 10 channels per pixel, interleaved [rows][cols][10] = n,x,y,z,xx,xy,xz,yy,yz,zz (test hook) */
+int nicp_last_integral_image(nicp_context *ctx, float *integral10);
+int nicp_last_interval_image(nicp_context *ctx, int *interval);
+
+/* ---- projection ---------------------------------------------------------------------------- */
+/* PinholePointProjector::project (pinholepointprojector.cpp:33-66).  KRt from _updateMatrices. */
+int nicp_project(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
+                 float min_distance, float max_distance, int *index, float *depth);
+
+/* ---- correspondence + linearisation (stage level) ----------------------------------------- */
+/* CorrespondenceFinder::compute (correspondencefinder.cpp:20-118) fused with Linearizer::update
+ * (linearizer.cpp:17-115) for the same T, given the two index images (host).  corr_image
+ * (rows*cols, may be NULL) receives the accepted reference index per pixel or -1; H column-major. */
+int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current,
+                              const int *reference_index, const int *current_index, int rows, int cols,
+                              const float T[16], const nicp_align_params *ap, float H[36], float b[6],
+                              float *error, int *inliers, int *num_correspondences, int *corr_image);
+/* Linearizer::update over an explicit correspondence list (n pairs of (referenceIndex, currentIndex)) */
+int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current,
+                   const int *correspondences, int n, const float T[16], const nicp_align_params *ap,
+                   float H[36], float b[6], float *error, int *inliers);
+
+/* ---- alignment ------------------------------------------------------------------------------ */
+/* Aligner::align() (aligner.cpp:49-150): all iterations on the device, one synchronisation at the end. */
+int nicp_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current,
+               const nicp_projector *proj, const nicp_align_params *ap,
+               const float reference_sensor_offset[16], const float current_sensor_offset[16],
+               const float initial_guess[16], const nicp_prior *priors, int num_priors,
+               float frame_inlier_depth_threshold, nicp_align_result *result);
+/* state of the last nicp_align on this context (what CorrespondenceFinder / Linearizer expose after
+ * align(), pwn_matcher_base.cpp:156-171): any pointer may be NULL.  correspondences receives
+ * num_correspondences (referenceIndex, currentIndex) pairs in raster order; H/b are the
+ * linearisation of _computeStatistics at the final T. */
+int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *reference_depth,
+                         int *current_index, float *current_depth, int *correspondences,
+                         float H[36], float b[6]);
+/* per-iteration trace of the last nicp_align: T at the start of each outer iteration (16), H (36),
+ * b (6), error, inliers, numCorrespondences = 61 floats per iteration (test hook) */
+int nicp_align_get_trace(nicp_context *ctx, float *trace61, int max_iterations);
+
+/* Batched alignment of n independent pairs (loop-closure candidate verification,
+ * pwn_tracker2/pwn_closer.cpp:83-182).  initial_guesses = n x 16 floats.  Results of pair i are
+ * identical to nicp_align on pair i.  No priors. */
+int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *references,
+                     const nicp_cloud *const *currents, const nicp_projector *proj,
+                     const nicp_align_params *ap, const float reference_sensor_offset[16],
+                     const float current_sensor_offset[16], const float *initial_guesses,
+                     float frame_inlier_depth_threshold, nicp_align_result *results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

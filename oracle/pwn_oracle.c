@@ -1102,6 +1102,28 @@ static void compute_statistics(const float *H_lin, const float *T, float *mean, 
 /* ------------------------------------------------------------------------------------------
  * Aligner::align, aligner.cpp:49-150
  * ---------------------------------------------------------------------------------------- */
+/* test knob: accumulate the Linearizer sums of orc_align in float64 (same float32 terms, exact
+   summation) -- the yardstick that separates the GPU's error from the reference's own float32
+   summation noise.  0 = reference behaviour. */
+static int g_accumulate_f64 = 0;
+void orc_set_accumulate_f64(int on) { g_accumulate_f64 = on; }
+static void align_linearize(const int *corr, int numCorr, const float *refPoints, const float *refNormals,
+                            const float *curPoints, const float *curNormals, const float *curOmegaP,
+                            const float *curOmegaN, const float *invT, const orc_align_params *p, float *H, float *b,
+                            float *err, int *inl) {
+  if (!g_accumulate_f64) {
+    orc_linearize(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN, invT,
+                  p->inlierMaxChi2, p->robustKernel, p->numThreads, H, b, err, inl);
+    return;
+  }
+  double Hd[36], bd[6], ed;
+  orc_linearize_f64(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN, invT,
+                    p->inlierMaxChi2, p->robustKernel, Hd, bd, &ed, inl);
+  for (int i = 0; i < 36; i++) H[i] = (float)Hd[i];
+  for (int i = 0; i < 6; i++) b[i] = (float)bd[i];
+  *err = (float)ed;
+}
+
 void orc_align(int nRef, const float *refPoints, const float *refNormals, const float *refCurv,
                int nCur, const float *curPoints, const float *curNormals, const float *curCurv,
                const float *curOmegaP, const float *curOmegaN,
@@ -1127,8 +1149,8 @@ void orc_align(int nRef, const float *refPoints, const float *refNormals, const 
     if (trace) memcpy(trace + ORC_TRACE_STRIDE * i, T, 16 * sizeof(float));
     for (int k = 0; k < p->innerIterations; k++) {
       fix_last_row(invT);
-      orc_linearize(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN,
-                    invT, p->inlierMaxChi2, p->robustKernel, p->numThreads, H, b, &err, &inl);
+      align_linearize(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN, invT, p, H, b,
+                      &err, &inl);
       if (trace && k == 0) {
         float *tr = trace + ORC_TRACE_STRIDE * i;
         memcpy(tr + 16, H, 36 * sizeof(float));
@@ -1159,8 +1181,8 @@ void orc_align(int nRef, const float *refPoints, const float *refNormals, const 
   /* _computeStatistics: one more linearisation at the final T with the last correspondences */
   orc_iso_inverse(T, invT);
   fix_last_row(invT);
-  orc_linearize(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN,
-                invT, p->inlierMaxChi2, p->robustKernel, p->numThreads, H, b, &err, &inl);
+  align_linearize(corr, numCorr, refPoints, refNormals, curPoints, curNormals, curOmegaP, curOmegaN, invT, p, H, b,
+                  &err, &inl);
   memcpy(res->H, H, sizeof res->H);
   memcpy(res->b, b, sizeof res->b);
   compute_statistics(H, T, res->mean, res->omega, &res->translationalRatio, &res->rotationalRatio);

@@ -147,6 +147,9 @@ void orc_align(int nRef, const float *refPoints, const float *refNormals, const 
                int *refIndex, float *refDepth, int *curIndex, float *curDepth, int *corr,
                float *trace);
 
+/* test knob: float64 accumulation of the Linearizer sums inside orc_align (0 = reference behaviour) */
+void orc_set_accumulate_f64(int on);
+
 /* PwnMatcherBase::matchClouds image statistics (pwn_tracker2/pwn_matcher_base.cpp:156-196) */
 void orc_image_stats(const float *curDepth, const float *refDepth, int n, float inlierDepthThreshold,
                      int *nonZeros, int *inliers, int *outliers, float *reprojectionDistance);

@@ -366,8 +366,10 @@ class AlignOutput:
     pass
 
 
-def align(ref, cur, ap, fast=False, want_trace=True):
-    """Aligner::align() on two oracle clouds."""
+def align(ref, cur, ap, fast=False, want_trace=True, accumulate_f64=False):
+    """Aligner::align() on two oracle clouds.  accumulate_f64: sum the Linearizer terms exactly
+    (float64) instead of the reference's float32 partial sums -- a yardstick, not the reference."""
+    lib(fast).orc_set_accumulate_f64(int(accumulate_f64))
     rows, cols = ap.rows, ap.cols
     res = AlignResult()
     out = AlignOutput()

@@ -1,0 +1,367 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, include/nicp_b200.h) against the CPU oracle
+on the same seeded inputs.  Stage-isolated / teacher-forced protocol of SURVEY.md Appendix C:
+every stage is fed the ORACLE's inputs for that stage.
+
+Tolerances (BASELINE.json north_star): index / correspondence images bit-exact in the
+--fmad=false build, >= 99.9 % correspondence agreement in the default build, H and b within 1e-4
+relative, final transform within 1e-4 rad / 1e-4 m.
+"""
+import numpy as np
+import pytest
+
+from conftest import get_scene
+
+pytestmark = pytest.mark.gpu
+
+H_RTOL = 1e-4     # ||dH||_F / ||H||_F
+T_ROT_TOL = 1e-4  # rad
+T_TRA_TOL = 1e-4  # m
+
+
+@pytest.fixture(scope="module", params=["verify", "default"])
+def ctx(request):
+    from g2o_frontend_b200 import capi
+    c = capi.Context(0, verify=(request.param == "verify"))
+    assert bool(c.L.nicp_is_verification_build()) == (request.param == "verify")
+    yield c
+    c.close()
+
+
+def upload(ctx, oc):
+    """oracle cloud -> device cloud"""
+    cl = ctx.new_cloud(max(oc.n, 1))
+    cl.upload(oc.points, oc.normals, oc.curvature, oc.omegaP6(), oc.omegaN6())
+    return cl
+
+
+def rot_angle(Ra, Rb):
+    """angle of Ra^T Rb from its antisymmetric part (arccos of the trace loses everything below
+    sqrt(eps_float32) ~ 3e-4 rad when the matrices are float32)"""
+    R = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    return float(np.arcsin(min(1.0, np.linalg.norm(w))))
+
+
+def frob_rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("step", [4, 1])
+def test_unproject_bit_exact(ctx, step):
+    from oracle import pwn_oracle as O
+    s = get_scene(step)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.1, -0.2, 0.05]
+    _, iKRt = O.update_matrices(s.K, T)
+    pts_o, idx_o = O.unproject(s.depthA, s.K, T, s.conf["minD"], s.conf["maxD"])
+    cl, idx = ctx.unproject(s.depthA, iKRt, s.conf["minD"], s.conf["maxD"])
+    assert cl.size() == pts_o.shape[0]
+    assert np.array_equal(idx, idx_o)
+    got = cl.download()["points"]
+    assert np.array_equal(got.view(np.uint32), pts_o.view(np.uint32))
+
+
+@pytest.mark.parametrize("step,seed,dropout", [(4, None, 0.0), (4, 0, 0.05), (1, None, 0.0), (1, 1, 0.05)])
+def test_integral_image_bit_exact(ctx, step, seed, dropout):
+    """all 10 channels, every pixel, in BOTH builds (the float32 scan order is part of the result)"""
+    s = get_scene(step, seed, dropout)
+    cl, idx = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params())
+    I = ctx.last_integral_image(s.rows, s.cols)
+    assert np.array_equal(idx, s.indexA)
+    assert np.array_equal(I.view(np.uint32), s.integralA.view(np.uint32))
+    assert np.array_equal(ctx.last_interval_image(s.rows, s.cols), s.intervalA)
+
+
+@pytest.mark.parametrize("step,seed,dropout,offset", [(4, None, 0.0, False), (4, 0, 0.05, True), (1, None, 0.0, False),
+                                                       (1, 2, 0.05, True)])
+def test_depth_to_cloud(ctx, step, seed, dropout, offset):
+    s = get_scene(step, seed, dropout, offset)
+    cl, idx = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params(), s.sensor_offset, keep_stats=True)
+    oc = s.cloudA
+    assert cl.size() == oc.n
+    assert np.array_equal(idx, s.indexA)
+    d = cl.download()
+    # points: no transcendental involved -> bit exact
+    assert np.array_equal(d["points"].view(np.uint32), oc.points.view(np.uint32))
+    # which points got a normal must agree except at the curvature-threshold boundary
+    has_o = np.abs(oc.normals[:, :3]).sum(1) > 0
+    has_g = np.abs(d["normals"][:, :3]).sum(1) > 0
+    assert (has_o != has_g).mean() < 1e-4
+    both = has_o & has_g
+    # normals: angle <= 1e-3 rad where the two smallest eigenvalues are separated
+    ev = oc.eigvals
+    well = both & ((ev[:, 1] - ev[:, 0]) > 1e-4 * ev[:, 2])
+    dots = np.clip((d["normals"][well, :3].astype(np.float64) * oc.normals[well, :3]).sum(1), -1, 1)
+    ang = np.arccos(dots)
+    assert well.sum() > 0.5 * oc.n
+    assert np.quantile(ang, 0.999) <= 1e-3, np.quantile(ang, [0.5, 0.99, 0.999, 1.0])
+    # curvature rel 1e-4 (absolute floor for ~0 curvatures)
+    cerr = np.abs(d["curvature"][both] - oc.curvature[both]) / np.maximum(np.abs(oc.curvature[both]), 1e-3)
+    assert np.quantile(cerr, 0.999) <= 1e-4, np.quantile(cerr, [0.5, 0.99, 0.999, 1.0])
+    # information matrices rel 1e-4 of the matrix norm
+    for got, ref in ((d["omega_p"], oc.omegaP6()), (d["omega_n"], oc.omegaN6())):
+        fin = both & np.isfinite(ref).all(1) & np.isfinite(got).all(1)
+        num = np.linalg.norm(got[fin].astype(np.float64) - ref[fin], axis=1)
+        den = np.maximum(np.linalg.norm(ref[fin].astype(np.float64), axis=1), 1e-12)
+        assert np.quantile(num / den, 0.999) <= 2e-3, np.quantile(num / den, [0.5, 0.99, 0.999, 1.0])
+        assert np.median(num / den) <= 1e-4
+    # fraction of bit-identical normals is reported, not required: atan2/cos/sin differ in ulps
+    same = (d["normals"][both, :3].view(np.uint32) == oc.normals[both, :3].view(np.uint32)).all(1).mean()
+    print("bit-identical normals: %.4f" % same)
+    # Stats (eigenvectors / mean / eigenvalues / n)
+    s16, evg, cnt = cl.download_stats()
+    assert np.array_equal(cnt, oc.statsN)
+    assert np.allclose(s16[both][:, 12:15], oc.statsM[both][:, 12:15], rtol=1e-5, atol=1e-6)
+    assert np.quantile(np.abs(evg[both] - oc.eigvals[both]) / np.maximum(oc.eigvals[both].max(1, keepdims=True), 1e-12),
+                       0.999) < 1e-4
+
+
+@pytest.mark.parametrize("step", [4, 1])
+def test_project_bit_exact(ctx, step):
+    """index image + depth image for 3 poses, given the oracle's cloud"""
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    s = get_scene(step)
+    cl = upload(ctx, s.cloudA)
+    poses = [np.eye(4), synth.POSE_B, synth.make_pose((-0.2, 0.1, -0.3), (1.0, 0.2, 0.1), 8.0)]
+    for T in poses:
+        KRt, _ = O.update_matrices(s.K, T.astype(np.float32))
+        io, do = O.project_KRt(s.cloudA.points, s.rows, s.cols, KRt, s.conf["minD"], s.conf["maxD"])
+        ig, dg = ctx.project(cl, KRt, s.rows, s.cols, s.conf["minD"], s.conf["maxD"])
+        assert np.array_equal(ig, io)
+        assert np.array_equal(dg.view(np.uint32), do.view(np.uint32))
+        assert (io >= 0).sum() > 0.3 * s.rows * s.cols
+
+
+@pytest.mark.parametrize("step,seed,dropout", [(4, None, 0.0), (4, 0, 0.05), (1, None, 0.0), (1, 1, 0.05)])
+def test_correspondence_and_linearize(ctx, step, seed, dropout):
+    """correspondence image bit-exact and H/b within 1e-4 given the ORACLE's clouds, index images and T"""
+    from oracle import pwn_oracle as O
+    s = get_scene(step, seed, dropout)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    c = s.conf
+    ap = s.oracle_align_params()
+    for guess in (np.eye(4, dtype=np.float32), s.gt):
+        KRt, _ = O.update_matrices(s.K, guess)
+        ri, _ = O.project_KRt(s.cloudA.points, s.rows, s.cols, KRt, c["minD"], c["maxD"])
+        KRtc, _ = O.update_matrices(s.K, np.eye(4, dtype=np.float32))
+        ci, _ = O.project_KRt(s.cloudB.points, s.rows, s.cols, KRtc, c["minD"], c["maxD"])
+        invT = np.linalg.inv(guess.astype(np.float64)).astype(np.float32)
+        corr_o, cimg_o = O.correspond(ri, ci, s.cloudA, s.cloudB, invT, s.cp, num_threads=8)
+        H, b, err, inl, nc, cimg = ctx.correspond_linearize(ref, cur, ri, ci, invT, s.align_params())
+        assert np.array_equal(cimg, cimg_o)
+        assert nc == corr_o.shape[0]
+        assert nc > 0.2 * s.rows * s.cols
+        H64, b64, err64, inl64 = O.linearize_f64(corr_o, s.cloudA, s.cloudB, invT, c["inlierMaxChi2"], True)
+        assert inl == inl64
+        # against the exact (float64-accumulated) sums of the same float32 terms: the 1e-4 bar
+        assert frob_rel(H, H64) <= H_RTOL and frob_rel(b, b64) <= H_RTOL
+        # against the reference's own float32 accumulation (8 OpenMP partial sums, then a serial
+        # reduce; linearizer.cpp:32-107).  Its sequential float32 sums carry their own rounding noise
+        # (up to a few 1e-4 at 640x480), so the bar is 1e-4 or that noise floor, whichever is larger.
+        for nt in (8, 1):
+            Ho, bo, erro, inlo = O.linearize(corr_o, s.cloudA, s.cloudB, invT, c["inlierMaxChi2"], True, num_threads=nt)
+            floorH = 2 * frob_rel(Ho, H64) + (8.0 / max(nc, 1) if nt > 1 else 0.0)
+            floorb = 2 * frob_rel(bo, b64) + (8.0 / max(nc, 1) if nt > 1 else 0.0)
+            assert frob_rel(H, Ho) <= max(H_RTOL, floorH), (nt, frob_rel(H, Ho), floorH)
+            assert frob_rel(b, bo) <= max(H_RTOL, floorb), (nt, frob_rel(b, bo), floorb)
+            print("H vs oracle(f32,%d threads): %.2e  oracle vs f64: %.2e  gpu vs f64: %.2e" %
+                  (nt, frob_rel(H, Ho), frob_rel(Ho, H64), frob_rel(H, H64)))
+        assert abs(err - err64) <= 1e-4 * abs(err64)
+        # explicit-list API gives the same sums
+        H2, b2, err2, inl2 = ctx.linearize(ref, cur, corr_o, invT, s.align_params())
+        assert inl2 == inl
+        assert frob_rel(H2, H64) <= H_RTOL and frob_rel(b2, b64) <= H_RTOL
+        # symmetric
+        assert np.array_equal(H, H.T)
+
+
+@pytest.mark.parametrize("step,seed,dropout,offset", [(4, None, 0.0, False), (4, 0, 0.05, True), (1, None, 0.0, False),
+                                                       (1, 2, 0.05, False)])
+def test_align_end_to_end(ctx, step, seed, dropout, offset):
+    """free-running 10-iteration align on the oracle's clouds: final T within 1e-4 rad / 1e-4 m of the
+    oracle, correspondence agreement >= 99.9 %, and recovery of the known transform."""
+    from g2o_frontend_b200 import capi
+    from oracle import pwn_oracle as O
+    s = get_scene(step, seed, dropout, offset)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    out = O.align(s.cloudA, s.cloudB, s.oracle_align_params(num_threads=8))
+    res = ctx.align(ref, cur, s.projector(), s.align_params(), s.sensor_offset, s.sensor_offset)
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], out.T[:3, :3]) <= T_ROT_TOL
+    assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
+    # ground truth (the sensor offset is the same on both sides so T is conjugated by it)
+    so = s.sensor_offset.astype(np.float64)
+    gt = so @ s.gt.astype(np.float64) @ np.linalg.inv(so)
+    assert rot_angle(T[:3, :3], gt[:3, :3]) <= 5e-3
+    assert np.abs(T[:3, 3] - gt[:3, 3]).max() <= 1e-2
+    st = ctx.align_state(s.rows, s.cols)
+    # z-buffers of the last iteration and the current frame
+    agree_idx = (st["ref_index"] == out.refIndex).mean()
+    assert agree_idx >= 0.999
+    assert np.array_equal(st["cur_index"], out.curIndex)
+    assert np.array_equal(st["cur_depth"].view(np.uint32), out.curDepth.view(np.uint32))
+    # correspondences of the last iteration (raster order on both sides)
+    a = set(map(tuple, st["corr"].tolist()))
+    o = set(map(tuple, out.corr.tolist()))
+    agree = len(a & o) / max(len(a | o), 1)
+    assert agree >= 0.999, agree
+    assert abs(res.num_correspondences - out.numCorrespondences) <= 1e-3 * out.numCorrespondences
+    # inliers: the oracle (8 threads) drops numCorr % 8 correspondences (linearizer.cpp:32-39)
+    assert abs(res.inliers - out.inliers) <= 1e-3 * out.inliers + 8
+    assert abs(res.error - out.error) <= 2e-3 * abs(out.error)
+    assert frob_rel(st["H"], out.H) <= 1e-3
+    # per-iteration trace: T at the start of every iteration
+    tr = ctx.align_trace(10)
+    for i in range(10):
+        Ti = capi.from_colmajor(tr[i, :16], 4)
+        assert rot_angle(Ti[:3, :3], out.trace_T[i][:3, :3]) <= T_ROT_TOL
+        assert np.abs(Ti[:3, 3] - out.trace_T[i][:3, 3]).max() <= T_TRA_TOL
+    # Aligner::omega(): tolerance-level (float64 Jacobi stands in for JacobiSVD on both sides)
+    om = capi.result_omega(res)
+    assert frob_rel(om, out.omega) <= 2e-2
+    # matchClouds image statistics
+    nz, inl, outl, rd = O.image_stats(out.curDepth, st["ref_depth"])
+    assert res.image_non_zeros == nz and res.image_inliers == inl and res.image_outliers == outl
+    assert abs(res.image_reprojection_distance - rd) <= 1e-4 * abs(rd) + 1e-6
+
+
+def test_align_teacher_forced_iterations(ctx):
+    """every iteration restarted from the ORACLE's T: index + correspondence images bit-exact"""
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    out = O.align(s.cloudA, s.cloudB, s.oracle_align_params(num_threads=8))
+    c = s.conf
+    for i in (0, 3, 9):
+        Ti = out.trace_T[i]
+        o1 = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=1, guess=Ti, num_threads=1))
+        r1 = ctx.align(ref, cur, s.projector(), s.align_params(outer=1), guess=Ti)
+        st = ctx.align_state(s.rows, s.cols)
+        assert np.array_equal(st["ref_index"], o1.refIndex)
+        assert np.array_equal(st["ref_depth"].view(np.uint32), o1.refDepth.view(np.uint32))
+        assert np.array_equal(st["corr"], o1.corr)
+        assert r1.num_correspondences == o1.numCorrespondences
+        tr = ctx.align_trace(1)
+        from g2o_frontend_b200 import capi
+        assert frob_rel(capi.from_colmajor(tr[0, 16:52], 6), o1.trace_H[0]) <= H_RTOL
+        assert frob_rel(tr[0, 52:58], o1.trace_b[0]) <= H_RTOL
+        assert int(tr[0, 59]) == o1.trace_inliers[0]
+
+
+def test_inner_iterations(ctx):
+    from g2o_frontend_b200 import capi
+    from oracle import pwn_oracle as O
+    s = get_scene(4)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    out = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=4, inner=3, num_threads=1))
+    res = ctx.align(ref, cur, s.projector(), s.align_params(outer=4, inner=3))
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], out.T[:3, :3]) <= T_ROT_TOL
+    assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
+
+
+def test_determinism_and_batch_identity(ctx):
+    """two runs are bit-identical; a pair gives the same bits alone or inside a batch"""
+    s = get_scene(4, 0, 0.05)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    rng = np.random.default_rng(0)
+    from g2o_frontend_b200 import synth
+    guesses = np.stack([synth.perturbed_pose(rng, np.eye(4), 0.03, 1.5) for _ in range(5)]).astype(np.float32)
+    singles = []
+    for g in guesses:
+        r = ctx.align(ref, cur, s.projector(), s.align_params(), guess=g)
+        r2 = ctx.align(ref, cur, s.projector(), s.align_params(), guess=g)
+        assert bytes(r) == bytes(r2)
+        singles.append(bytes(r))
+    # batch: mixed (ref,cur) and (cur,ref) pairs so that current clouds are both shared and distinct
+    refs = [ref, ref, cur, ref, ref]
+    curs = [cur, cur, ref, cur, cur]
+    batch = ctx.align_batch(refs, curs, s.projector(), s.align_params(), guesses)
+    for i in (0, 1, 3, 4):
+        assert batch[i].tobytes() == singles[i]
+    r = ctx.align(cur, ref, s.projector(), s.align_params(), guess=guesses[2])
+    assert batch[2].tobytes() == bytes(r)
+    assert (batch["status"] == 0).all()
+
+
+def test_depth_prepare_bit_exact(ctx):
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05)
+    for step in (1, 2, 4):
+        ref = O.depth_u16_to_f32(s.rawA)
+        if step > 1:
+            ref = O.depth_scale(ref, step)
+        got = ctx.depth_prepare(s.rawA, 0.001, step)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_raw_depth_to_cloud_matches_two_step(ctx):
+    s = get_scene(4, 0, 0.05)
+    c1, _ = ctx.raw_depth_to_cloud(s.rawA, s.projector(), s.stats_params(), step=4)
+    c2, _ = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params())
+    a, b = c1.download(), c2.download()
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+
+
+# ---- edge cases -----------------------------------------------------------------------------------
+def test_empty_depth_image(ctx):
+    s = get_scene(4)
+    z = np.zeros((s.rows, s.cols), np.float32)
+    cl, idx = ctx.depth_to_cloud(z, s.projector(), s.stats_params())
+    assert cl.size() == 0
+    assert (idx == -1).all()
+    # aligning an empty cloud against a real one: no correspondences, T stays at the guess
+    ref = upload(ctx, s.cloudA)
+    from g2o_frontend_b200 import capi
+    r = ctx.align(ref, cl, s.projector(), s.align_params())
+    assert r.inliers == 0 and r.num_correspondences == 0
+    assert np.allclose(capi.result_T(r), np.eye(4), atol=1e-6)
+    r = ctx.align(cl, ref, s.projector(), s.align_params())
+    assert r.inliers == 0 and r.num_correspondences == 0
+
+
+def test_ragged_and_tiny_images(ctx):
+    """non multiple-of-32 sizes, a single row, a single pixel"""
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import capi
+    s = get_scene(4)
+    for rows, cols in ((37, 53), (1, 160), (120, 1), (1, 1)):
+        d = np.ascontiguousarray(s.depthA[:rows, :cols])
+        oc, oi, oitv, ointeg = O.depth_to_cloud(d, s.K, 0.5, 4.5, s.sp, want_aux=True)
+        proj = capi.make_projector(s.K, rows, cols, 0.5, 4.5)
+        cl, idx = ctx.depth_to_cloud(d, proj, s.stats_params())
+        assert cl.size() == oc.n
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(ctx.last_integral_image(rows, cols).view(np.uint32), ointeg.view(np.uint32))
+        if oc.n:
+            assert np.array_equal(cl.download()["points"].view(np.uint32), oc.points.view(np.uint32))
+
+
+def test_distance_limits_and_ties(ctx):
+    """points exactly at min/max distance are kept; equal depths at one pixel keep the lowest index"""
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import capi
+    K = np.array([[100, 0, 8], [0, 100, 6], [0, 0, 1]], np.float32)
+    rows, cols = 12, 16
+    pts = np.array([[0, 0, 0.5, 1], [0, 0, 0.5, 1], [0.01, 0, 4.5, 1], [0, 0, 4.5000005, 1], [0, 0, 0.49999997, 1],
+                    [0.001, 0.001, 0.5, 1], [5, 5, 1, 1], [-5, 0, 1, 1], [0, 0, -1, 1]], np.float32)
+    KRt, _ = O.update_matrices(K, np.eye(4, dtype=np.float32))
+    io, do = O.project_KRt(pts, rows, cols, KRt, 0.5, 4.5)
+    cl = ctx.new_cloud(16)
+    cl.upload(pts)
+    ig, dg = ctx.project(cl, KRt, rows, cols, 0.5, 4.5)
+    assert np.array_equal(ig, io) and np.array_equal(dg.view(np.uint32), do.view(np.uint32))
+    assert io[6, 8] == 0  # the tie at depth 0.5 goes to the lowest index
+
+
+def test_no_gpu_fallback_symbols(ctx):
+    # the python binding resolves every entry point from the CUDA library (no pure-python substitute)
+    from g2o_frontend_b200 import capi
+    for name in capi.SYMBOLS:
+        assert hasattr(ctx.L, name)
+    assert ctx.launch_count() >= 0

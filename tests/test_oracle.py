@@ -1,0 +1,272 @@
+"""CPU tests of the oracle itself (oracle/pwn_oracle.c), the checker of every GPU parity test.
+
+The reference has no tests, golden vectors or fixtures for this path and cannot be built here
+ => "parity unpinned".  What CAN be pinned is pinned here:
+  * independent float64 / numpy restatements of each stage (eigen-solver, integral image, z-buffer,
+    Gauss-Newton terms via the Jacobian of octave/pwn/pwn_jacobian.m, LDLT, SE(3) helpers),
+  * recovery of a known transform on synthetic frames,
+  * the committed fixtures under tests/golden/ (made by tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, get_scene
+from oracle import pwn_oracle as O
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_golden_small_pair_reproduced():
+    g = np.load(os.path.join(GOLD, "small_pair.npz"))
+    K = g["K"]
+    sp = O.default_stats_params(minImageRadius=3, maxImageRadius=6, minPoints=10, curvatureThreshold=0.2)
+    cA, iA, itvA, integA = O.depth_to_cloud(g["depthA"], K, 0.5, 4.5, sp, want_aux=True)
+    cB, iB = O.depth_to_cloud(g["depthB"], K, 0.5, 4.5, sp)
+    assert np.array_equal(iA, g["indexA"]) and np.array_equal(itvA, g["intervalA"])
+    assert np.array_equal(integA, g["integralA"])
+    assert np.array_equal(cA.points, g["pointsA"]) and np.array_equal(cB.points, g["pointsB"])
+    # normals involve libm's atan2f/cosf/sinf: allow ulp-level differences between glibc builds
+    assert np.allclose(cA.normals, g["normalsA"], atol=2e-5)
+    assert np.allclose(cA.curvature, g["curvatureA"], rtol=1e-3, atol=1e-6)
+    rows, cols = g["depthA"].shape
+    cp = O.default_corr_params(inlierDistanceThreshold=0.5, inlierNormalAngularThreshold=0.95)
+    out = O.align(cA, cB, O.make_align_params(K, rows, cols, 0.5, 4.5, cp, num_threads=1))
+    assert np.allclose(out.T, g["T"], atol=1e-5)
+    assert abs(out.numCorrespondences - int(g["numCorr"])) <= 2
+    assert np.array_equal(out.curIndex, g["curIndex"])
+
+
+def test_golden_eigen3():
+    g = np.load(os.path.join(GOLD, "eigen3.npz"))
+    for Cm, ev, U in zip(g["C"], g["evals"], g["evecs"]):
+        e2, U2 = O.eigen3(Cm)
+        assert np.allclose(e2, ev, rtol=1e-5, atol=1e-7 * np.abs(ev).max())
+        assert np.allclose(np.abs((U2 * U).sum(0)), 1.0, atol=1e-4)
+
+
+def test_eigen3_against_numpy_eigh():
+    rng = np.random.default_rng(0)
+    for i in range(200):
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        lam = np.sort(rng.uniform(0.01, 1.0, 3)) * 10.0 ** rng.integers(-5, 1)
+        if i % 3 == 0:
+            lam[0] *= 1e-3  # planar patch
+        Cm = (Q @ np.diag(lam) @ Q.T)
+        Cm = ((Cm + Cm.T) / 2).astype(np.float32)
+        ev, U = O.eigen3(Cm)
+        w, V = np.linalg.eigh(Cm.astype(np.float64))
+        assert np.all(np.diff(ev) >= 0)
+        # the closed form loses ~sqrt(eps) when eigenvalues cluster (documented for computeDirect)
+        sep = min(w[1] - w[0], w[2] - w[1]) / w[2]
+        assert np.allclose(ev, w, atol=(2e-5 if sep > 0.1 else 1e-3) * w[-1])
+        # orthonormal, and the smallest-eigenvalue direction (the NICP normal) matches when separated
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-4)
+        if (w[1] - w[0]) > 1e-2 * w[2]:
+            assert abs(float(U[:, 0] @ V[:, 0])) > 1 - 1e-4
+
+
+def test_integral_image_against_float64_cumsum():
+    s = get_scene(4)
+    I = s.integralA.astype(np.float64)
+    pts = np.zeros((s.rows, s.cols, 4))
+    valid = s.indexA >= 0
+    # undo the (identity) sensor offset: cloud points are the unprojected points
+    pts[valid] = s.cloudA.points[s.indexA[valid]]
+    ch = [valid.astype(np.float64), pts[..., 0], pts[..., 1], pts[..., 2], pts[..., 0] ** 2, pts[..., 0] * pts[..., 1],
+          pts[..., 0] * pts[..., 2], pts[..., 1] ** 2, pts[..., 1] * pts[..., 2], pts[..., 2] ** 2]
+    for k, c in enumerate(ch):
+        ref = np.cumsum(np.cumsum(c, axis=1), axis=0)
+        if k == 0:
+            assert np.array_equal(I[..., 0], ref)  # counts are exact in float32
+        else:
+            assert np.abs(I[..., k] - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1.0)
+    # compacted index = raster rank of the valid pixels
+    assert np.array_equal(s.indexA[valid], np.arange(valid.sum()))
+
+
+def test_project_against_python_zbuffer():
+    s = get_scene(4)
+    pts = s.cloudA.points[::7]
+    KRt, _ = O.update_matrices(s.K, s.gt)
+    idx, dep = O.project_KRt(pts, s.rows, s.cols, KRt, 0.5, 4.5)
+    KR = KRt.astype(np.float32)
+    ref_idx = np.full((s.rows, s.cols), -1, np.int32)
+    ref_dep = np.full((s.rows, s.cols), np.finfo(np.float32).max, np.float32)
+    f32 = np.float32
+    for i, p in enumerate(pts):
+        ip = [f32(f32(f32(f32(KR[r, 0] * p[0]) + f32(KR[r, 1] * p[1])) + f32(KR[r, 2] * p[2])) + f32(KR[r, 3] * p[3]))
+              for r in range(3)]
+        d = ip[2]
+        if d < f32(0.5) or d > f32(4.5):
+            continue
+        inv = f32(1.0) / d
+        x = float(f32(ip[0] * inv))
+        y = float(f32(ip[1] * inv))
+        x = int(np.floor(abs(x) + 0.5) * np.sign(x))
+        y = int(np.floor(abs(y) + 0.5) * np.sign(y))
+        if x < 0 or x >= s.cols or y < 0 or y >= s.rows:
+            continue
+        if ref_dep[y, x] > d:
+            ref_dep[y, x] = d
+            ref_idx[y, x] = i
+    assert np.array_equal(idx, ref_idx)
+    assert np.array_equal(dep, ref_dep)
+
+
+def skew(v):
+    """bm_se3.h:54-66: S = -2 [v]x"""
+    tx, ty, tz = 2 * v
+    return np.array([[0, tz, -ty], [-tz, 0, tx], [ty, -tx, 0]])
+
+
+def test_linearize_against_jacobian_model():
+    """H = sum J^T Omega J, b = sum J^T Omega e with J = [I, S(Tp); 0, S(Tn)] -- the Jacobian of
+    octave/pwn/pwn_jacobian.m / linearizer.cpp:78-87, restated in float64 numpy."""
+    s = get_scene(4)
+    c = s.conf
+    KRt, _ = O.update_matrices(s.K, np.eye(4, dtype=np.float32))
+    ri, _ = O.project_KRt(s.cloudA.points, s.rows, s.cols, KRt, c["minD"], c["maxD"])
+    ci, _ = O.project_KRt(s.cloudB.points, s.rows, s.cols, KRt, c["minD"], c["maxD"])
+    T = np.eye(4, dtype=np.float32)
+    corr, cimg = O.correspond(ri, ci, s.cloudA, s.cloudB, T, s.cp, num_threads=1)
+    assert corr.shape[0] > 1000
+    sub = corr[::37]
+    H, b, err, inl = O.linearize(sub, s.cloudA, s.cloudB, T, 9e3, True, num_threads=1)
+    Hn = np.zeros((6, 6))
+    bn = np.zeros(6)
+    en = 0.0
+    for r, cidx in sub:
+        p, n = s.cloudA.points[r, :3].astype(np.float64), s.cloudA.normals[r, :3].astype(np.float64)
+        q, m = s.cloudB.points[cidx, :3].astype(np.float64), s.cloudB.normals[cidx, :3].astype(np.float64)
+        OP = s.cloudB.omegaP[cidx].reshape(4, 4).T[:3, :3].astype(np.float64)
+        ON = s.cloudB.omegaN[cidx].reshape(4, 4).T[:3, :3].astype(np.float64)
+        ep, enn = p - q, n - m
+        chi = ep @ OP @ ep + enn @ ON @ enn
+        k = np.sqrt(9e3 / chi) if chi > 9e3 else 1.0
+        Jp = np.hstack([np.eye(3), skew(p)])
+        Jn = np.hstack([np.zeros((3, 3)), skew(n)])
+        Hn += Jp.T @ OP @ Jp + Jn.T @ ON @ Jn
+        bn += k * (Jp.T @ OP @ ep + Jn.T @ ON @ enn)
+        en += k * chi
+    assert np.linalg.norm(H - Hn) <= 1e-4 * np.linalg.norm(Hn)
+    assert np.linalg.norm(b - bn) <= 1e-4 * np.linalg.norm(bn)
+    assert abs(err - en) <= 1e-4 * en
+    assert inl == sub.shape[0]
+    H64, b64, e64, i64 = O.linearize_f64(sub, s.cloudA, s.cloudB, T, 9e3, True)
+    assert np.linalg.norm(H64 - Hn) <= 1e-5 * np.linalg.norm(Hn)
+
+
+def test_linearize_thread_truncation():
+    """linearizer.cpp:32-39 drops numCorrespondences % numThreads correspondences"""
+    s = get_scene(4)
+    corr = np.stack([np.arange(21), np.arange(21)], 1).astype(np.int32)
+    T = np.eye(4, dtype=np.float32)
+    _, _, _, inl8 = O.linearize(corr, s.cloudA, s.cloudA, T, 9e3, True, num_threads=8)
+    _, _, _, inl1 = O.linearize(corr, s.cloudA, s.cloudA, T, 9e3, True, num_threads=1)
+    assert inl8 == 16 and inl1 == 21
+
+
+def test_ldlt_solve_against_numpy():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        A = rng.standard_normal((6, 6))
+        H = (A @ A.T * 100 + 1001 * np.eye(6)).astype(np.float32)
+        b = rng.standard_normal(6).astype(np.float32) * 50
+        x = O.ldlt_solve6(H, b)
+        ref = np.linalg.solve(H.astype(np.float64), b.astype(np.float64))
+        assert np.allclose(x, ref, rtol=1e-4, atol=1e-6)
+
+
+def test_se3_helpers():
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        v = np.concatenate([rng.uniform(-1, 1, 3), rng.uniform(-0.4, 0.4, 3)]).astype(np.float32)
+        T = O.v2t(v)
+        R = T[:3, :3].astype(np.float64)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-5) and abs(np.linalg.det(R) - 1) < 1e-5
+        assert np.allclose(O.t2v(T), v, atol=2e-6)
+    # quaternion branch with negative trace (rotation by ~170 deg)
+    from g2o_frontend_b200 import synth
+    T = synth.make_pose((0.1, 0.2, 0.3), (0.2, 1.0, 0.1), 170.0).astype(np.float32)
+    v = O.t2v(T)
+    assert np.allclose(O.v2t(v), T, atol=1e-5)
+
+
+def test_update_matrices():
+    from g2o_frontend_b200 import synth
+    s = get_scene(4)
+    T = synth.POSE_B.astype(np.float32)
+    KRt, iKRt = O.update_matrices(s.K, T)
+    K4 = np.eye(4)
+    K4[:3, :3] = s.K
+    assert np.allclose(KRt, K4 @ np.linalg.inv(T.astype(np.float64)), rtol=1e-5, atol=1e-4)
+    assert np.allclose(iKRt[:3, :3], T[:3, :3].astype(np.float64) @ np.linalg.inv(s.K.astype(np.float64)), rtol=1e-5,
+                       atol=1e-7)
+    assert np.allclose(iKRt[:3, 3], T[:3, 3])
+
+
+def test_unproject_project_round_trip():
+    """unProject followed by project with the same pose reproduces the index image (size-independent)"""
+    s = get_scene(1)
+    pts, idx = O.unproject(s.depthA, s.K, np.eye(4), 0.5, 4.5)
+    idx2, dep2 = O.project(pts, s.rows, s.cols, s.K, np.eye(4), 0.5, 4.5)
+    valid = idx >= 0
+    assert (idx2[valid] == idx[valid]).mean() > 0.9999
+    assert np.allclose(dep2[valid], s.depthA[valid], rtol=1e-6)
+
+
+def test_depth_scale_and_convert():
+    s = get_scene(4, 0, 0.05)
+    d = O.depth_u16_to_f32(s.rawA)
+    assert np.array_equal(d == 0, s.rawA == 0)
+    assert np.allclose(d, s.rawA * 0.001, rtol=1e-6)
+    sc = O.depth_scale(d, 4)
+    assert sc.shape == (120, 160)
+    blk = d.reshape(120, 4, 160, 4).transpose(0, 2, 1, 3).reshape(120, 160, 16).astype(np.float64)
+    npos = (blk > 0).sum(-1)
+    mu = np.divide(blk.sum(-1), npos, out=np.zeros((120, 160)), where=npos > 0)
+    var = np.divide((blk ** 2).sum(-1), npos, out=np.zeros((120, 160)), where=npos > 0) - mu ** 2
+    keep = (npos > 0) & (var <= 0.01 - 1e-6)
+    assert np.allclose(sc[keep], mu[keep], rtol=1e-5)
+    assert (sc[npos == 0] == 0).all()
+
+
+@pytest.mark.parametrize("step", [4, 1])
+def test_known_transform_recovery(step):
+    """ground truth B = A o delta is recovered by 10 iterations (ransac/alignment_test.cpp style check)"""
+    s = get_scene(step)
+    out = O.align(s.cloudA, s.cloudB, s.oracle_align_params())
+    R = out.T[:3, :3].astype(np.float64).T @ s.gt[:3, :3]
+    ang = np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))
+    assert ang < 3e-3
+    assert np.abs(out.T[:3, 3] - s.gt[:3, 3]).max() < 5e-3
+    assert out.inliers > 0.3 * s.rows * s.cols
+    # monotone growth of the correspondence set as the pose converges
+    assert out.trace_ncorr[-1] > out.trace_ncorr[0]
+
+
+def test_priors_pull_towards_mean():
+    """SE3RelativePrior (se3_prior.cpp:54-60) with a strong information matrix dominates the step"""
+    s = get_scene(4)
+    from g2o_frontend_b200 import synth
+    mean = synth.make_pose((0.2, 0, 0), (0, 1, 0), 0).astype(np.float32)
+    pr = O.make_prior(0, mean, np.eye(6, dtype=np.float32) * 1e9)
+    ap = O.make_align_params(s.K, s.rows, s.cols, 0.5, 4.5, s.cp, outer=10, priors=[pr])
+    out = O.align(s.cloudA, s.cloudB, ap)
+    # error(invT) = t2v(invT * mean) -> 0  =>  T -> mean
+    assert np.abs(out.T[:3, 3] - mean[:3, 3]).max() < 2e-2
+
+
+def test_image_stats_bit_trick():
+    """abs(cur-ref) & mask is a bitwise AND with 255.0f's bit pattern (pwn_matcher_base.cpp:177-181)"""
+    cur = np.array([1.0, 1.0, 2.0, 3.4e38, 0.0], np.float32)
+    ref = np.array([1.0, 1.1, 1.0, 1.0, 1.0], np.float32)
+    nz, inl, outl, rd = O.image_stats(cur, ref, 50.0)
+    assert nz == 3
+    # diffs in mm: 0, 100, 1000 -> after & 0x437F0000 (255.0f): 0.0, 50.0, 3.90625
+    m = (np.array([0.0, 100.0, 1000.0], np.float32).view(np.uint32) & np.uint32(0x437F0000)).view(np.float32)
+    assert m.tolist() == [0.0, 50.0, 3.90625]
+    assert inl == int((m < 50.0).sum()) == 2 and outl == 1
+    assert abs(rd - m.sum() / 3) < 1e-4
