@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- NICP 640x480 alignments/s on 1/2/4/8 B200 (BASELINE.json metric).
+
+Workload (config 4 of BASELINE.json, the one the metric's multi-GPU numbers are quoted on):
+batched loop-closure candidate verification -- every rank aligns PAIRS = 1024 independent
+640x480 frame pairs per step (16 "current" frames x 64 candidate "reference" frames, guesses
+perturbed by U(+-5 cm, +-3 deg), 10 outer iterations, parameters of pwn_core/conf/pwn_aligner_1_1.conf).
+At 8 GPUs that is exactly the 8192 pairs of config 4; scaling is weak (per-GPU work fixed).
+
+One JSON line on rank 0:
+  value     whole-job alignments/s with the clouds already resident in HBM (device-timed, CUDA events
+            on the library's stream, max over ranks)
+  e2e       the same metric through the C-ABI with HOST buffers: every step uploads the 80 raw
+            16-bit depth frames from pinned memory, builds the 80 clouds, aligns the 1024 pairs and
+            reads the 256-byte result records back
+  roofline  the fused correspondence+linearise kernel: algorithmic bytes / live CUDA-event time
+  cpu_baseline  the CPU oracle (restatement of pwn_core; the reference itself cannot be built here)
+            timed on this box's host cores on a bounded sample of the same workload
+
+`--impl reference` times the CPU path only (rank 0), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS = 480, 640
+CONF = dict(minD=0.5, maxD=4.5, minImageRadius=10, maxImageRadius=30, minPoints=50, curvatureThreshold=0.2,
+            worldRadius=0.1, omegaCurvatureThreshold=0.02, inlierDistanceThreshold=1.0,
+            inlierNormalAngularThreshold=0.95, inlierCurvatureRatioThreshold=1.3, flatCurvatureThreshold=0.02,
+            inlierMaxChi2=9000.0, outerIterations=10, innerIterations=1)
+METRIC = "nicp_640x480_alignments_per_s"
+UNIT = "alignments/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--currents", type=int, default=16)
+    ap.add_argument("--candidates", type=int, default=64)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_workload(n_cur, n_cand, rank):
+    """poses + raw frames + pair list + guesses (deterministic, different per rank)"""
+    from g2o_frontend_b200 import synth
+    rng = np.random.default_rng(1000 + rank)
+    cur_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cur)]
+    cand_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cand)]
+    raws_cur = [synth.render_depth_u16(p, ROWS, COLS, seed=10 * rank + i) for i, p in enumerate(cur_poses)]
+    raws_cand = [synth.render_depth_u16(p, ROWS, COLS, seed=5000 + 10 * rank + i) for i, p in enumerate(cand_poses)]
+    pairs, guesses = [], []
+    for ci, cp in enumerate(cur_poses):
+        for ri, rp in enumerate(cand_poses):
+            T_true = np.linalg.inv(rp) @ cp  # reference <- current
+            guesses.append(synth.perturbed_pose(rng, T_true, 0.05, 3.0))
+            pairs.append((ri, ci))
+    return raws_cur, raws_cand, np.array(pairs), np.stack(guesses).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_pairs, n_threads=None):
+    """The reference arm: the CPU restatement of pwn_core (oracle, performance build: the reference's
+    own flags + OpenMP) on this box's host cores.  Each step = 1 cloud build from a raw frame +
+    `sample_pairs` alignments (the workload's ratio of 80 cloud builds per 1024 alignments)."""
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import synth
+    cores = n_threads or os.cpu_count() or 1
+    # the finder drops rows % numThreads (correspondencefinder.cpp:38): use a divisor of 480
+    while ROWS % cores:
+        cores -= 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    raws_cur, raws_cand, pairs, guesses = make_workload(1, sample_pairs, 0)
+    K = synth.K_KINECT
+    sp = O.default_stats_params(minImageRadius=CONF["minImageRadius"], maxImageRadius=CONF["maxImageRadius"],
+                                minPoints=CONF["minPoints"], curvatureThreshold=CONF["curvatureThreshold"],
+                                worldRadius=CONF["worldRadius"], omegaCurvatureThreshold=CONF["omegaCurvatureThreshold"])
+    cp = O.default_corr_params(inlierDistanceThreshold=CONF["inlierDistanceThreshold"],
+                               inlierNormalAngularThreshold=CONF["inlierNormalAngularThreshold"],
+                               flatCurvatureThreshold=CONF["flatCurvatureThreshold"],
+                               inlierCurvatureRatioThreshold=CONF["inlierCurvatureRatioThreshold"])
+
+    def build(raw):
+        d = O.depth_u16_to_f32(raw, fast=True)
+        return O.depth_to_cloud(d, K, CONF["minD"], CONF["maxD"], sp, fast=True)[0]
+
+    cur = build(raws_cur[0])
+    cands = [build(r) for r in raws_cand]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        cur = build(raws_cur[0])  # the step's share of cloud building
+        for j, (ri, ci) in enumerate(pairs):
+            ap = O.make_align_params(K, ROWS, COLS, CONF["minD"], CONF["maxD"], cp, guess=guesses[j],
+                                     max_chi2=CONF["inlierMaxChi2"], num_threads=cores)
+            O.align(cands[ri], cur, ap, fast=True, want_trace=False)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = sample_pairs * len(times) / total
+    return value, cores, total / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_sample_pairs
+    value, cores, ms = cpu_reference_run(args.steps, args.warmup, n)
+    sample = ("per step: 1 cloud build from a raw 640x480 frame + %d alignments (10 iterations) of the "
+              "loop-closure workload, CPU oracle performance build (-O3 -march=x86-64-v3 -fopenmp)" % n)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batched loop-closure candidate verification, 640x480, 10 iters (bounded CPU sample)",
+                       "pairs_per_step": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from g2o_frontend_b200 import capi, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the NICP path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_cur, n_cand = args.currents, args.candidates
+    n_pairs = n_cur * n_cand
+    raws_cur, raws_cand, pairs, guesses = make_workload(n_cur, n_cand, rank)
+    n_frames = n_cur + n_cand
+    # pinned host staging of the raw frames (what a tracker would hand over)
+    pinned = torch.empty((n_frames, ROWS, COLS), dtype=torch.int16).pin_memory()
+    host_raw = pinned.numpy().view(np.uint16)
+    for i, r in enumerate(raws_cur + raws_cand):
+        host_raw[i] = r
+
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    proj = capi.make_projector(synth.K_KINECT, ROWS, COLS, CONF["minD"], CONF["maxD"])
+    sp = capi.make_stats_params(CONF["worldRadius"], CONF["minImageRadius"], CONF["maxImageRadius"], CONF["minPoints"],
+                                CONF["curvatureThreshold"], CONF["omegaCurvatureThreshold"])
+    ap = capi.make_align_params(CONF["inlierDistanceThreshold"], CONF["inlierNormalAngularThreshold"],
+                                CONF["flatCurvatureThreshold"], CONF["inlierCurvatureRatioThreshold"],
+                                CONF["inlierMaxChi2"], True, CONF["outerIterations"], CONF["innerIterations"])
+    clouds = [ctx.new_cloud(ROWS * COLS) for _ in range(n_frames)]
+
+    def build_clouds():
+        for i in range(n_frames):
+            ctx.raw_depth_to_cloud(host_raw[i], proj, sp, cloud=clouds[i])
+
+    refs = [clouds[n_cur + ri] for ri, ci in pairs]
+    curs = [clouds[ci] for ri, ci in pairs]
+    results = np.zeros(n_pairs, capi.RESULT_DTYPE)
+
+    def align_step():
+        ctx.align_batch(refs, curs, proj, ap, guesses, results=results)
+        if world > 1:
+            return sharding.gather_records(results, n_pairs * world, device=dev)
+        return results
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: clouds resident in HBM ---------------------------------------------------------
+    build_clouds()
+    ctx.synchronize()
+    for _ in range(args.warmup):
+        align_step()
+    ctx.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sumMidx = sumMacc = 0.0
+    for _ in range(args.steps):
+        allrec = align_step()
+        sumMidx += float(results["reserved"][:, 0].sum())
+        sumMacc += float(results["reserved"][:, 1].sum())
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    kt = ctx.kernel_timing()
+    ctx.set_kernel_timing(False)
+    value = world * n_pairs * args.steps / (dev_ms * 1e-3)
+    ok_pairs = int((allrec["status"] == 0).sum())
+    mean_inliers = float(results["inliers"].mean())
+
+    # roofline of the fused correspondence+linearise kernel (SURVEY.md 8d algorithmic bytes)
+    P = ROWS * COLS
+    n_launch = max(kt["corr_lin_launches"], 1)
+    bytes_total = 8.0 * P * n_pairs * args.steps * CONF["outerIterations"] + 56.0 * sumMidx + 48.0 * sumMacc
+    achieved = bytes_total / (kt["corr_lin_ms"] * 1e-3) / 1e9 if kt["corr_lin_ms"] > 0 else 0.0
+    peak, peak_src = measured_peak()
+    roofline = {"kernel": "k_corr_lin<0> (CorrespondenceFinder::compute + Linearizer::update fused)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "avg_launch_ms": kt["corr_lin_ms"] / n_launch, "launches_timed": kt["corr_lin_launches"],
+                "algorithmic_bytes_per_launch": bytes_total / n_launch,
+                "project_avg_launch_ms": kt["project_ms"] / max(kt["project_launches"], 1),
+                "share_of_step": kt["corr_lin_ms"] / dev_ms if dev_ms > 0 else None}
+
+    # ---- e2e: host buffers in, records out, every step -------------------------------------------
+    def e2e_step():
+        build_clouds()
+        return align_step()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall_ms))
+    e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
+    h2d = n_frames * ROWS * COLS * 2 + n_pairs * 64 + n_pairs * 0
+    d2h = n_pairs * 256 + n_pairs * 42 * 4
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/GPU/step = "
+                                       "%d current x %d candidate 640x480 frames, 10 outer iterations, "
+                                       "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
+                           "pairs_per_gpu_per_step": n_pairs, "rows": ROWS, "cols": COLS,
+                           "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per step)" %
+                                        (n_frames * P * 80 / 1e9, 64 * P * 32 / 1e9),
+                           "parallelism": "pair-sharded x%d" % world},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms / args.steps},
+                "roofline": roofline,
+                "checks": {"pairs_ok": ok_pairs, "pairs_total": int(world * n_pairs), "mean_inliers": mean_inliers}}
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, ms = cpu_reference_run(1, 1, args.cpu_sample_pairs)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 cloud build + %d alignments (10 iterations) of the same workload, CPU "
+                                              "oracle performance build, 1 warm-up + 1 timed pass" % args.cpu_sample_pairs}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@ NICP_OK = 0
 # every symbol include/nicp_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "nicp_create", "nicp_destroy", "nicp_last_error", "nicp_synchronize", "nicp_is_verification_build",
-    "nicp_launch_count", "nicp_stream",
+    "nicp_launch_count", "nicp_stream", "nicp_set_kernel_timing", "nicp_get_kernel_timing",
     "nicp_cloud_create", "nicp_cloud_destroy", "nicp_cloud_size", "nicp_cloud_upload", "nicp_cloud_download",
     "nicp_cloud_download_stats", "nicp_cloud_transform",
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
@@ -251,6 +251,17 @@ class Context:
 
     def stream(self):
         return self.L.nicp_stream(self.handle)
+
+    def set_kernel_timing(self, enable=True):
+        _check(self.L, self.L.nicp_set_kernel_timing(self.handle, int(enable)))
+
+    def kernel_timing(self):
+        """{'corr_lin_ms', 'corr_lin_launches', 'project_ms', 'project_launches'} since the last enable"""
+        a, b = C.c_double(0), C.c_double(0)
+        na, nb = C.c_longlong(0), C.c_longlong(0)
+        _check(self.L, self.L.nicp_get_kernel_timing(self.handle, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return {"corr_lin_ms": a.value, "corr_lin_launches": na.value, "project_ms": b.value,
+                "project_launches": nb.value}
 
     def new_cloud(self, capacity):
         return Cloud(self, capacity)

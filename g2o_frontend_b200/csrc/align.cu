@@ -44,6 +44,8 @@ __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
   st->img_nonzeros = 0;
   st->img_inliers = 0;
   st->img_sum = 0.f;
+  st->sumMidx = 0.f;
+  st->sumMacc = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(256) k_corr_lin(const PairDesc *__restrict__ d
       if (MODE == 0) corrImage[pix] = -1;
       continue;
     }
+    if (MODE == 0) acc[A_MIDX] += 1.0f;
     const float4 cn = curNormals[ci];
     const float4 rn0 = refNormals[ri];
     const float4 cp = curPoints[ci];
@@ -359,6 +362,8 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
       res->image_outliers = st->img_nonzeros - st->img_inliers;
       res->image_reprojection_distance = fdiv(st->img_sum, (float)st->img_nonzeros);
       res->status = NICP_OK;
+      res->reserved[0] = st->sumMidx;
+      res->reserved[1] = st->sumMacc;
     }
     return;
   }
@@ -367,7 +372,11 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
   for (int k = 0; k < 6; k++) st->b[k] = b[k];
   st->error = tot[A_ERR];
   st->inliers = (int)tot[A_INL];
-  if (firstInner) st->ncorr = (int)tot[A_NCORR];
+  if (firstInner) {
+    st->ncorr = (int)tot[A_NCORR];
+    st->sumMidx += tot[A_MIDX];
+    st->sumMacc += tot[A_NCORR];
+  }
   if (mode == 2) return;
 
   if (D.trace && firstInner) {
@@ -426,6 +435,19 @@ static int num_blocks_for(const nicp_context *ctx, int P) {
   return (P + ppb - 1) / ppb;
 }
 
+static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used) {
+  if (used == pool->size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool->push_back(e);
+  }
+  return (*pool)[used++];
+}
+#define NICP_TIME_BEGIN(pool, used) \
+  if (ctx->timing) cudaEventRecord(next_event(ctx->pool, ctx->used), st)
+#define NICP_TIME_END(pool, used) \
+  if (ctx->timing) cudaEventRecord(next_event(ctx->pool, ctx->used), st)
+
 // runs Aligner::align for the nPairs descriptors staged in ctx->h_desc (one lock-step chunk).
 // ownsCur: per pair, 1 if the pair's curZ/curIndex buffers must be produced by it.
 int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const float curKRt[16], int outerIters,
@@ -458,13 +480,18 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   int parity = 0;
   for (int it = 0; it < outerIters; it++) {
     parity = it & 1;
+    NICP_TIME_BEGIN(evProj, evProjUsed);
     k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+    NICP_TIME_END(evProj, evProjUsed);
     NICP_CHECK_LAUNCH(ctx);
     for (int k = 0; k < innerIters; k++) {
-      if (k == 0)
+      if (k == 0) {
+        NICP_TIME_BEGIN(evCorr, evCorrUsed);
         k_corr_lin<0><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
-      else
+        NICP_TIME_END(evCorr, evCorrUsed);
+      } else {
         k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
+      }
       NICP_CHECK_LAUNCH(ctx);
       k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
       NICP_CHECK_LAUNCH(ctx);

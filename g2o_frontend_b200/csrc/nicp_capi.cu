@@ -356,12 +356,31 @@ static void compute_statistics(const float *H_lin, const float *T, float *Omega,
   *rr = sym_eig_ratio3(Omega, 3);
 }
 
+// after a stream synchronisation: fold the recorded event pairs into the running totals
+static void collect_timing(nicp_context *ctx) {
+  if (!ctx->timing) return;
+  for (size_t i = 0; i + 1 < ctx->evCorrUsed; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, (*ctx->evCorr)[i], (*ctx->evCorr)[i + 1]) == cudaSuccess) {
+      ctx->msCorr += ms;
+      ctx->nCorr++;
+    }
+  }
+  for (size_t i = 0; i + 1 < ctx->evProjUsed; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, (*ctx->evProj)[i], (*ctx->evProj)[i + 1]) == cudaSuccess) {
+      ctx->msProj += ms;
+      ctx->nProj++;
+    }
+  }
+  ctx->evCorrUsed = ctx->evProjUsed = 0;
+}
+
 static void finish_results(nicp_context *ctx, int n, nicp_align_result *out) {
   for (int i = 0; i < n; i++) {
     nicp_align_result r = ctx->h_results[i];
     const float *Hb = ctx->h_statHb + (size_t)i * 42;
     compute_statistics(Hb, r.T, r.omega, &r.translational_eigen_ratio, &r.rotational_eigen_ratio);
-    r.reserved[0] = r.reserved[1] = 0.0f;
     out[i] = r;
   }
 }
@@ -407,6 +426,8 @@ int nicp_create(int device, nicp_context **out) {
   ctx->smCount = prop.multiProcessorCount;
   // fixed so that H/b of a pair do not depend on batch size or GPU count (2 CTAs per SM on a B200)
   ctx->blocksPerPair = env_int("NICP_BLOCKS_PER_PAIR", 296);
+  ctx->evCorr = new std::vector<cudaEvent_t>();
+  ctx->evProj = new std::vector<cudaEvent_t>();
   *out = ctx;
   return NICP_OK;
 }
@@ -426,6 +447,10 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
   if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
+  for (cudaEvent_t e : *ctx->evCorr) cudaEventDestroy(e);
+  for (cudaEvent_t e : *ctx->evProj) cudaEventDestroy(e);
+  delete ctx->evCorr;
+  delete ctx->evProj;
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -437,6 +462,25 @@ int nicp_synchronize(nicp_context *ctx) {
 }
 
 long long nicp_launch_count(const nicp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int nicp_set_kernel_timing(nicp_context *ctx, int enable) {
+  if (!ctx) return NICP_ERR_INVALID;
+  ctx->timing = enable != 0;
+  ctx->msCorr = ctx->msProj = 0.0;
+  ctx->nCorr = ctx->nProj = 0;
+  ctx->evCorrUsed = ctx->evProjUsed = 0;
+  return NICP_OK;
+}
+
+int nicp_get_kernel_timing(const nicp_context *ctx, double *corr_lin_ms, long long *corr_lin_launches, double *project_ms,
+                           long long *project_launches) {
+  if (!ctx) return NICP_ERR_INVALID;
+  if (corr_lin_ms) *corr_lin_ms = ctx->msCorr;
+  if (corr_lin_launches) *corr_lin_launches = ctx->nCorr;
+  if (project_ms) *project_ms = ctx->msProj;
+  if (project_launches) *project_launches = ctx->nProj;
+  return NICP_OK;
+}
 void *nicp_stream(nicp_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 // ---- clouds ----------------------------------------------------------------------------------
@@ -446,6 +490,7 @@ int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **out) {
   nicp_cloud *c = new nicp_cloud();
   memset(c, 0, sizeof *c);
   c->ctx = ctx;
+  c->device = ctx->device;
   c->capacity = capacity;
   int rc;
   if ((rc = dev_alloc(&c->points, (size_t)capacity)) || (rc = dev_alloc(&c->normals, (size_t)capacity)) ||
@@ -462,10 +507,8 @@ int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **out) {
 
 void nicp_cloud_destroy(nicp_cloud *c) {
   if (!c) return;
-  if (c->ctx) {
-    cudaSetDevice(c->ctx->device);
-    cudaStreamSynchronize(c->ctx->stream);
-  }
+  // the owning context may already be gone: cudaFree synchronises the device by itself
+  cudaSetDevice(c->device);
   dev_free(c->points);
   dev_free(c->normals);
   dev_free(c->omega);
@@ -807,6 +850,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     if (base > 0) {
       // the staging buffer of the previous chunk must have been consumed by its H2D copy
       NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+      collect_timing(ctx);
     }
     std::map<const nicp_cloud *, int> curSlot;
     for (int i = 0; i < m; i++) {
@@ -835,6 +879,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   NICP_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(nicp_align_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb, ctx->d_statHb, sizeof(float) * 42 * n, cudaMemcpyDeviceToHost, ctx->stream));
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  collect_timing(ctx);
   finish_results(ctx, n, results);
   ctx->lastAlignRows = proj->rows;
   ctx->lastAlignCols = proj->cols;

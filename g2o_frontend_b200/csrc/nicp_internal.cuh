@@ -44,7 +44,8 @@ enum {
   A_BR = 24,   // 3
   A_ERR = 27,
   A_INL = 28,
-  A_NCORR = 29
+  A_NCORR = 29,
+  A_MIDX = 30   // MODE 0 only: pixels where both index images are valid
 };
 
 // per-pair pose / linear-system state, lives in device memory
@@ -61,6 +62,8 @@ struct PairState {
   float statb[6];
   int img_nonzeros, img_inliers;
   float img_sum;
+  float sumMidx;   // sum over outer iterations of pixels with both indices valid (roofline accounting)
+  float sumMacc;   // sum over outer iterations of accepted correspondences
   int pad;
 };
 
@@ -98,6 +101,7 @@ struct AlignConsts {
 
 struct nicp_cloud {
   nicp_context *ctx;
+  int device;
   int capacity;
   float4 *points;
   float4 *normals;  // w = curvature
@@ -148,6 +152,15 @@ struct nicp_context {
   nicp_align_result *h_results; // pinned
   float *d_statHb;              // [resultCap][42]
   float *h_statHb;              // pinned
+
+  // optional per-kernel timing (nicp_set_kernel_timing): CUDA events around the k_corr_lin<0>
+  // and k_project launches of every chunk, accumulated after the final synchronisation
+  bool timing;
+  std::vector<cudaEvent_t> *evCorr;  // pairs (start, stop)
+  std::vector<cudaEvent_t> *evProj;
+  size_t evCorrUsed, evProjUsed;
+  double msCorr, msProj;
+  long long nCorr, nProj;
 
   // last single-align bookkeeping
   int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;

@@ -98,7 +98,8 @@ typedef struct {
   int status;                   /* NICP_OK or an error code for this pair */
   float translational_eigen_ratio;
   float rotational_eigen_ratio;
-  float reserved[2];
+  float reserved[2];            /* roofline accounting: sums over the outer iterations of [0] pixels
+                                   whose two index images are both valid, [1] accepted correspondences */
 } nicp_align_result;
 
 /* ---- context -------------------------------------------------------------------------- */
@@ -110,6 +111,12 @@ int nicp_synchronize(nicp_context *ctx);
 int nicp_is_verification_build(void);
 /* number of kernel launches issued by this context since creation */
 long long nicp_launch_count(const nicp_context *ctx);
+/* Optional live kernel timing for the roofline report: when enabled, CUDA events are recorded on the
+ * context's stream around every fused correspondence+linearise launch and every reference projection
+ * launch of nicp_align / nicp_align_batch; totals (ms, launch count) since the last enable. */
+int nicp_set_kernel_timing(nicp_context *ctx, int enable);
+int nicp_get_kernel_timing(const nicp_context *ctx, double *corr_lin_ms, long long *corr_lin_launches,
+                           double *project_ms, long long *project_launches);
 /* the CUDA stream (cudaStream_t) this context launches on, for event timing by the caller */
 void *nicp_stream(nicp_context *ctx);
 
