@@ -18,6 +18,7 @@ NICP_OK = 0
 SYMBOLS = [
     "nicp_create", "nicp_destroy", "nicp_last_error", "nicp_synchronize", "nicp_is_verification_build",
     "nicp_launch_count", "nicp_stream", "nicp_set_kernel_timing", "nicp_get_kernel_timing",
+    "nicp_update_matrices", "nicp_v2t", "nicp_t2v",
     "nicp_cloud_create", "nicp_cloud_destroy", "nicp_cloud_size", "nicp_cloud_upload", "nicp_cloud_download",
     "nicp_cloud_download_stats", "nicp_cloud_transform",
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
@@ -92,6 +93,9 @@ def load(verify=False):
     L.nicp_stream.restype = C.c_void_p
     L.nicp_destroy.restype = None
     L.nicp_cloud_destroy.restype = None
+    L.nicp_update_matrices.restype = None
+    L.nicp_v2t.restype = None
+    L.nicp_t2v.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:
@@ -414,6 +418,15 @@ class Context:
                                                _fptr(g), C.c_float(img_threshold),
                                                results.ctypes.data_as(C.POINTER(AlignResult))))
         return results
+
+
+def update_matrices(K, T, verify=False):
+    """PinholePointProjector::_updateMatrices through the library (host-side, no GPU needed)."""
+    L = load(verify)
+    k, t = colmajor(K), colmajor(T)
+    KRt, iKRt = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    L.nicp_update_matrices(_fptr(k), _fptr(t), _fptr(KRt), _fptr(iKRt))
+    return from_colmajor(KRt, 4), from_colmajor(iKRt, 4)
 
 
 def result_T(res):

@@ -483,6 +483,13 @@ int nicp_get_kernel_timing(const nicp_context *ctx, double *corr_lin_ms, long lo
 }
 void *nicp_stream(nicp_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+void nicp_update_matrices(const float K[9], const float T[16], float KRt[16], float iKRt[16]) {
+  if (KRt) compute_KRt(K, T, KRt);
+  if (iKRt) compute_iKRt(K, T, iKRt);
+}
+void nicp_v2t(const float v[6], float T[16]) { v2t(v, T); }
+void nicp_t2v(const float T[16], float v[6]) { t2v(T, v); }
+
 // ---- clouds ----------------------------------------------------------------------------------
 int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **out) {
   if (!ctx || !out || capacity <= 0) return NICP_ERR_INVALID;

@@ -1,0 +1,168 @@
+// pwn_simple_aligner -- the reference's CLI odometry driver (g2o_frontend/pwn_core/pwn_simple_aligner.cpp:28-269)
+// re-expressed over the pwn:: classes of include/pwn/pwn.h, i.e. over the B200 library.
+//
+//   pwn_simple_aligner <config.conf> <out.jsonl> <depth0.pgm> <depth1.pgm> ...
+//
+// Reads a `key value` configuration (same keys as pwn_core/conf/pwn_aligner_1_1.conf), 16-bit binary PGM depth
+// images in millimetres (the format of PlaneEx_gui/test_images/*.pgm), aligns every frame to the previous one and
+// writes one JSON line per frame: the relative transform, the accumulated global transform (as t2v), inliers,
+// error, correspondences and the image statistics of PwnMatcherBase::matchClouds.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+
+#include "pwn/pwn.h"
+
+using namespace pwn;
+
+static std::map<std::string, float> readConfig(const char *path) {  // pwn_simple_aligner.cpp:190-212
+  std::map<std::string, float> m;
+  std::ifstream is(path);
+  std::string line;
+  while (std::getline(is, line)) {
+    if (line.empty() || line[0] == '#' || line[0] == '/') continue;
+    std::istringstream ls(line);
+    std::string key;
+    float v;
+    if (ls >> key >> v) m[key] = v;
+  }
+  return m;
+}
+
+static float get(const std::map<std::string, float> &m, const char *k, float def) {
+  std::map<std::string, float>::const_iterator it = m.find(k);
+  return it == m.end() ? def : it->second;
+}
+
+static bool readPgm16(const char *path, RawDepthImage &img) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return false;
+  char magic[3] = {0, 0, 0};
+  int w = 0, h = 0, maxv = 0;
+  if (fscanf(f, "%2s", magic) != 1 || std::string(magic) != "P5") { fclose(f); return false; }
+  int c = fgetc(f);
+  while (c == '#' || c == '\n' || c == ' ' || c == '\r') {
+    if (c == '#') while (c != '\n' && c != EOF) c = fgetc(f);
+    c = fgetc(f);
+  }
+  ungetc(c, f);
+  if (fscanf(f, "%d %d %d", &w, &h, &maxv) != 3) { fclose(f); return false; }
+  fgetc(f);
+  img.create(h, w);
+  std::vector<unsigned char> buf((size_t)w * h * 2);
+  size_t got = fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (got != buf.size()) return false;
+  for (size_t i = 0; i < (size_t)w * h; i++) img.buf[i] = (uint16_t)((buf[2 * i] << 8) | buf[2 * i + 1]);  // big-endian
+  return true;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 5) {
+    fprintf(stderr, "usage: %s config.conf out.jsonl depth0.pgm depth1.pgm ...\n", argv[0]);
+    return 2;
+  }
+  try {
+    std::map<std::string, float> cfg = readConfig(argv[1]);
+    // setInputParameters, pwn_simple_aligner.cpp:214-269
+    const int imageScale = (int)get(cfg, "imageScale", 1);
+    const float depthScale = get(cfg, "depthScale", 0.001f);
+    Matrix3f K;
+    K.setIdentity();
+    K(0, 0) = get(cfg, "fx", 525.0f); K(1, 1) = get(cfg, "fy", 525.0f);
+    K(0, 2) = get(cfg, "cx", 319.5f); K(1, 2) = get(cfg, "cy", 239.5f);
+    Isometry3f sensorOffset;
+    {
+      Vector6f v;
+      v(0) = get(cfg, "tx", 0); v(1) = get(cfg, "ty", 0); v(2) = get(cfg, "tz", 0);
+      v(3) = get(cfg, "qx", 0); v(4) = get(cfg, "qy", 0); v(5) = get(cfg, "qz", 0);
+      sensorOffset = v2t(v);
+    }
+    PinholePointProjector projector;
+    projector.setMinDistance(get(cfg, "minDistance", 0.5f));
+    projector.setMaxDistance(get(cfg, "maxDistance", 4.5f));
+    projector.setCameraMatrix(K);
+
+    StatsCalculatorIntegralImage statsCalculator;
+    statsCalculator.setMinImageRadius((int)get(cfg, "minImageRadius", 10));
+    statsCalculator.setMaxImageRadius((int)get(cfg, "maxImageRadius", 30));
+    statsCalculator.setMinPoints((int)get(cfg, "minPoints", 50));
+    statsCalculator.setCurvatureThreshold(get(cfg, "curvatureThreshold", 0.2f));
+    statsCalculator.setWorldRadius(get(cfg, "worldRadius", 0.1f));
+    PointInformationMatrixCalculator pointInformationMatrixCalculator;
+    NormalInformationMatrixCalculator normalInformationMatrixCalculator;
+    pointInformationMatrixCalculator.setCurvatureThreshold(get(cfg, "informationMatrixCurvatureThreshold", 0.02f));
+    normalInformationMatrixCalculator.setCurvatureThreshold(get(cfg, "informationMatrixCurvatureThreshold", 0.02f));
+    DepthImageConverterIntegralImage converter(&projector, &statsCalculator, &pointInformationMatrixCalculator,
+                                               &normalInformationMatrixCalculator);
+
+    CorrespondenceFinder correspondenceFinder;
+    correspondenceFinder.setInlierDistanceThreshold(get(cfg, "inlierDistanceThreshold", 1.0f));
+    correspondenceFinder.setInlierNormalAngularThreshold(get(cfg, "inlierNormalAngularThreshold", 0.95f));
+    correspondenceFinder.setInlierCurvatureRatioThreshold(get(cfg, "inlierCurvatureRatioThreshold", 1.3f));
+    correspondenceFinder.setFlatCurvatureThreshold(get(cfg, "flatCurvatureThreshold", 0.02f));
+    Linearizer linearizer;
+    linearizer.setInlierMaxChi2(get(cfg, "inlierMaxChi2", 9e3f));
+    linearizer.setRobustKernel(get(cfg, "robustKernel", 1) != 0);
+    Aligner aligner;
+    aligner.setProjector(&projector);
+    aligner.setLinearizer(&linearizer);
+    aligner.setCorrespondenceFinder(&correspondenceFinder);
+    aligner.setOuterIterations((int)get(cfg, "outerIterations", 10));
+    aligner.setInnerIterations((int)get(cfg, "innerIterations", 1));
+    aligner.setMinInliers((int)get(cfg, "minInliers", 100));
+    aligner.setSensorOffset(sensorOffset);
+
+    FILE *out = fopen(argv[2], "w");
+    if (!out) throw std::runtime_error("cannot open output file");
+    Cloud *previous = 0;
+    Isometry3f globalT;
+    for (int a = 3; a < argc; a++) {
+      RawDepthImage raw;
+      if (!readPgm16(argv[a], raw)) throw std::runtime_error(std::string("cannot read ") + argv[a]);
+      DepthImage depth;
+      DepthImage_convertAndScale(depth, raw, imageScale, depthScale);
+      // projector->scale(1/imageScale): pinholepointprojector.cpp:149-154
+      projector.setCameraMatrix(K);
+      projector.setImageSize(raw.rows, raw.cols);
+      projector.scale(1.0f / imageScale);
+      Cloud *current = new Cloud();
+      converter.compute(*current, depth, sensorOffset);
+      if (previous) {
+        projector.setCameraMatrix(K);
+        projector.setImageSize(raw.rows, raw.cols);
+        projector.scale(1.0f / imageScale);
+        correspondenceFinder.setImageSize(projector.imageRows(), projector.imageCols());
+        aligner.setReferenceCloud(previous);
+        aligner.setCurrentCloud(current);
+        aligner.setInitialGuess(Isometry3f::Identity());
+        aligner.align();
+        globalT = globalT * aligner.T();
+        Vector6f g = t2v(globalT);
+        const nicp_align_result &r = aligner.lastResult();
+        fprintf(out, "{\"frame\": %d, \"points\": %zu, \"T\": [", a - 3, current->size());
+        for (int i = 0; i < 16; i++) fprintf(out, "%s%.9g", i ? ", " : "", aligner.T().data()[i]);
+        fprintf(out, "], \"global\": [");
+        for (int i = 0; i < 6; i++) fprintf(out, "%s%.9g", i ? ", " : "", g(i));
+        fprintf(out, "], \"inliers\": %d, \"error\": %.9g, \"correspondences\": %d, \"image_nonZeros\": %d, "
+                     "\"image_inliers\": %d, \"Hsum\": %.9g, \"time_ms\": %.3f}\n",
+                aligner.inliers(), aligner.error(), correspondenceFinder.numCorrespondences(), r.image_non_zeros,
+                r.image_inliers, linearizer.H()(0, 0) + linearizer.H()(5, 5), aligner.totalTime());
+        delete previous;
+      } else {
+        fprintf(out, "{\"frame\": 0, \"points\": %zu}\n", current->size());
+      }
+      previous = current;
+    }
+    delete previous;
+    fclose(out);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "pwn_simple_aligner: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

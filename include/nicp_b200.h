@@ -120,6 +120,14 @@ int nicp_get_kernel_timing(const nicp_context *ctx, double *corr_lin_ms, long lo
 /* the CUDA stream (cudaStream_t) this context launches on, for event timing by the caller */
 void *nicp_stream(nicp_context *ctx);
 
+/* ---- host-side helpers shared by the pwn:: classes (same bits as the device code) ------------ */
+/* PinholePointProjector::_updateMatrices (pinholepointprojector.cpp:17-31): KRt = [K R^-1, K t_inv],
+ * iKRt = [R K^-1, t] for a projector with camera matrix K and pose T.  Either output may be NULL. */
+void nicp_update_matrices(const float K[9], const float T[16], float KRt[16], float iKRt[16]);
+/* v2t / t2v (bm_se3.h:36-52): 6-vector (t, qx, qy, qz) <-> isometry */
+void nicp_v2t(const float v[6], float T[16]);
+void nicp_t2v(const float T[16], float v[6]);
+
 /* ---- clouds (cloud.h) ------------------------------------------------------------------- */
 int nicp_cloud_create(nicp_context *ctx, int capacity, nicp_cloud **cloud);
 void nicp_cloud_destroy(nicp_cloud *cloud);

