@@ -306,6 +306,236 @@ __global__ void __launch_bounds__(256) k_corr_lin(const PairDesc *__restrict__ d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tiled variant of the fused kernel (the default): one CTA of NT threads owns a tile of NT*TK pixels.
+//   stage 1  every thread loads the z-buffer word / current index of its TK pixels, then issues the
+//            4*TK gathers (float4 each) back to back -- 5*TK independent loads in flight per thread
+//            instead of 3 dependent round trips per pixel -- transforms the reference point/normal,
+//            applies the gates and writes the correspondence image.
+//   compact  accepted correspondences get a slot in shared memory through a ballot/prefix compaction
+//            whose order is fixed (pixel slot, warp, lane).  The transformed reference point/normal and
+//            the current point/normal are parked there (12 floats), and the 48 bytes of Omega_P/Omega_N
+//            of the current point are fetched straight into shared memory with cp.async (LDGSTS): the
+//            whole tile's Omega traffic is in flight at once and costs no registers.
+//   stage 2  all threads walk the compacted list (full warps even when only a third of the pixels is
+//            accepted): shared-memory reads + the Linearizer term, 30 sums in registers.
+//   stage 3  transposing warp butterfly + fixed-order CTA reduction -> one partial row.
+// The accumulators only become live in stage 2, so stage 1 can spend the registers on loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int NT, int TK>
+struct TileSmem {
+  static constexpr int CAP = NT * TK;
+  float f[12][CAP];    // rp(3) rn(3) cp(3) cn(3) of the accepted correspondences
+  float4 om[3][CAP];   // Omega_P / Omega_N of the current point
+  int cnt[TK * (NT / 32)];
+  int off[TK * (NT / 32)];
+  int total;
+  float red[NT / 32][kAccum];
+};
+
+template <int MODE, int NT, int TK, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, AlignConsts ac,
+                                                             int numPixels, int imgStats, float imgThreshold) {
+  constexpr int NW = NT / 32;
+  constexpr int TILE = NT * TK;
+  static_assert(TK * NW <= 32, "prefix scan is done by one warp");
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  TileSmem<NT, TK> &S = *reinterpret_cast<TileSmem<NT, TK> *>(smemRaw);
+
+  const PairDesc &D = desc[blockIdx.y];
+  const Affine T = affine_from(D.state->invT);
+  const float4 *__restrict__ refPoints = D.refPoints;
+  const float4 *__restrict__ refNormals = D.refNormals;
+  const float4 *__restrict__ curPoints = D.curPoints;
+  const float4 *__restrict__ curNormals = D.curNormals;
+  const float4 *__restrict__ curOmega = D.curOmega;
+  const int *__restrict__ curIndex = D.curIndex;
+  int *__restrict__ corrImage = D.corrImage;
+  const unsigned long long *__restrict__ zref = D.refZ[parity];
+  unsigned long long *__restrict__ znext = D.refZ[parity ^ 1];
+  const unsigned long long *__restrict__ zcur = D.curZ;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = blockIdx.x * TILE;
+  float midx = 0.0f, imgSum = 0.0f, imgNz = 0.0f, imgInl = 0.0f;
+
+  // ---- stage 1: loads ----
+  int ri[TK], ci[TK];
+  bool ok[TK];
+#pragma unroll
+  for (int k = 0; k < TK; k++) {
+    const int pix = base + k * NT + threadIdx.x;
+    ri[k] = -1;
+    ci[k] = -1;
+    if (pix < numPixels) {
+      ci[k] = curIndex[pix];
+      if (MODE == 0) {
+        unsigned long long zr = zref[pix];
+        ri[k] = (int)(unsigned int)(zr & 0xFFFFFFFFull);
+      } else {
+        ri[k] = corrImage[pix];
+      }
+    }
+  }
+  float4 cn[TK], rn0[TK], cp[TK], rp0[TK];
+#pragma unroll
+  for (int k = 0; k < TK; k++) {
+    ok[k] = ri[k] >= 0 && ci[k] >= 0;
+    if (ok[k]) {
+      cn[k] = curNormals[ci[k]];
+      rn0[k] = refNormals[ri[k]];
+      cp[k] = curPoints[ci[k]];
+      rp0[k] = refPoints[ri[k]];
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      const int pix = base + k * NT + threadIdx.x;
+      if (pix < numPixels) znext[pix] = kEmptyZ;
+    }
+  } else if (imgStats) {
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      const int pix = base + k * NT + threadIdx.x;
+      if (pix < numPixels) {
+        // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
+        unsigned long long zc = zcur[pix], zr = zref[pix];
+        float dc = (zc == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zc >> 32));
+        float dr = (zr == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zr >> 32));
+        unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
+        unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
+        if (c16 > 0 && r16 > 0) {
+          float df = fabsf(fsub((float)c16, (float)r16));
+          float dm = __uint_as_float(__float_as_uint(df) & 0x437F0000u);
+          imgNz += 1.0f;
+          if (dm < imgThreshold) imgInl += 1.0f;
+          imgSum += dm;
+        }
+      }
+    }
+  }
+
+  // ---- stage 1: transform + gates (results overwrite rp0 / rn0) ----
+#pragma unroll
+  for (int k = 0; k < TK; k++) {
+    bool good = ok[k];
+    if (good) {
+      float rpx, rpy, rpz, rnx, rny, rnz;
+      xform_point(T, rp0[k].x, rp0[k].y, rp0[k].z, rpx, rpy, rpz);
+      xform_normal(T, rn0[k].x, rn0[k].y, rn0[k].z, rnx, rny, rnz);
+      if (MODE == 0) {
+        midx += 1.0f;
+        // correspondencefinder.cpp:69 zero normals, :78 normal angle, :84 distance, :87-99 curvature ratio
+        if (dot3(cn[k].x, cn[k].y, cn[k].z, cn[k].x, cn[k].y, cn[k].z) == 0.0f ||
+            dot3(rn0[k].x, rn0[k].y, rn0[k].z, rn0[k].x, rn0[k].y, rn0[k].z) == 0.0f)
+          good = false;
+        if (good && dot3(cn[k].x, cn[k].y, cn[k].z, rnx, rny, rnz) < ac.normalThreshold) good = false;
+        if (good) {
+          float dx = fsub(cp[k].x, rpx), dy = fsub(cp[k].y, rpy), dz = fsub(cp[k].z, rpz);
+          if (dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold) good = false;
+        }
+        if (good) {
+          float rc = rn0[k].w, cc = cn[k].w;
+          if (rc < ac.flatCurvature) rc = ac.flatCurvature;
+          if (cc < ac.flatCurvature) cc = ac.flatCurvature;
+          // (rc + 1e-5) / (cc + 1e-5) in double, rounded to float; identical operands give exactly 1
+          float ratio = 1.0f;
+          if (rc != cc) ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
+          if (ratio < ac.minRatio || ratio > ac.maxRatio) good = false;
+        }
+      }
+      rp0[k].x = rpx; rp0[k].y = rpy; rp0[k].z = rpz;
+      rn0[k].x = rnx; rn0[k].y = rny; rn0[k].z = rnz;
+    }
+    ok[k] = good;
+    if (MODE == 0) {
+      const int pix = base + k * NT + threadIdx.x;
+      if (pix < numPixels) corrImage[pix] = good ? ri[k] : -1;
+    }
+  }
+
+  // ---- compaction (fixed order: pixel slot k, then warp, then lane) ----
+  unsigned int bal[TK];
+#pragma unroll
+  for (int k = 0; k < TK; k++) {
+    bal[k] = __ballot_sync(0xffffffffu, ok[k]);
+    if (lane == 0) S.cnt[k * NW + warp] = __popc(bal[k]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int c = lane < TK * NW ? S.cnt[lane] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane < TK * NW) S.off[lane] = incl - c;
+    if (lane == 31) S.total = incl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < TK; k++) {
+    if (ok[k]) {
+      const int pos = S.off[k * NW + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+      const float4 *om = curOmega + 3 * (size_t)ci[k];
+      cp_async16(&S.om[0][pos], om);
+      cp_async16(&S.om[1][pos], om + 1);
+      cp_async16(&S.om[2][pos], om + 2);
+      S.f[0][pos] = rp0[k].x; S.f[1][pos] = rp0[k].y; S.f[2][pos] = rp0[k].z;
+      S.f[3][pos] = rn0[k].x; S.f[4][pos] = rn0[k].y; S.f[5][pos] = rn0[k].z;
+      S.f[6][pos] = cp[k].x; S.f[7][pos] = cp[k].y; S.f[8][pos] = cp[k].z;
+      S.f[9][pos] = cn[k].x; S.f[10][pos] = cn[k].y; S.f[11][pos] = cn[k].z;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int nAcc = S.total;
+
+  // ---- stage 2 ----
+  float acc[kAccum];
+#pragma unroll
+  for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
+  for (int e = threadIdx.x; e < nAcc; e += NT) {
+    const float4 o0 = S.om[0][e], o1 = S.om[1][e], o2 = S.om[2][e];
+    const float4 cpv = make_float4(S.f[6][e], S.f[7][e], S.f[8][e], 1.0f);
+    const float4 cnv = make_float4(S.f[9][e], S.f[10][e], S.f[11][e], 0.0f);
+    accumulate_term(acc, S.f[0][e], S.f[1][e], S.f[2][e], S.f[3][e], S.f[4][e], S.f[5][e], cpv, cnv, o0, o1, o2, ac.maxChi2,
+                    ac.robust);
+  }
+  if (MODE == 0) {
+    acc[A_MIDX] = midx;
+    float nc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < TK; k++) nc += ok[k] ? 1.0f : 0.0f;
+    acc[A_NCORR] = nc;
+  } else {
+    acc[29] = imgSum;
+    acc[30] = imgNz;
+    acc[31] = imgInl;
+  }
+
+  // ---- stage 3 ----
+  float tot = warp_transpose_reduce(acc, lane);
+  S.red[warp][lane] = tot;
+  __syncthreads();
+  if (warp == 0) {
+    float s = S.red[0][lane];
+#pragma unroll
+    for (int w = 1; w < NW; w++) s += S.red[w][lane];
+    D.partials[(size_t)blockIdx.x * kAccum + lane] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sum the per-CTA partial rows in fixed order, assemble H/b (linearizer.cpp:109-114), then:
 //  mode 0: one Gauss-Newton step of Aligner::align (aligner.cpp:84-118): H += I + 1000 I,
 //          dx = LDLT(H)^-1 (-b), invT = v2t(dx) invT; if lastInner: T = invT^-1, T = v2t(t2v(T)),
@@ -426,13 +656,61 @@ __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *_
 // ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
+// tiled-kernel configurations (NICP_TILE_CONFIG): threads per CTA, pixels per thread, min CTAs per SM
+struct TileCfg { int nt, tk; };
+// (measured on a B200, 64 pairs x 640x480 per launch: {64,2} 371 us, {128,2} 381 us, {128,2}@88 regs 423 us,
+//  {256,4} 519 us; see profiles/r1_corr_lin_tuning.md)
+static const TileCfg kTileCfgs[] = {{64, 2}, {128, 2}, {256, 4}};
+static int tile_px(const nicp_context *ctx) { return kTileCfgs[ctx->tileConfig].nt * kTileCfgs[ctx->tileConfig].tk; }
+
 static int pixels_per_block(const nicp_context *ctx, int P) {
+  if (ctx->corrVariant == 1) return tile_px(ctx);
   int ppb = (P + ctx->blocksPerPair - 1) / ctx->blocksPerPair;
   return ppb < 256 ? 256 : ppb;
 }
 static int num_blocks_for(const nicp_context *ctx, int P) {
   int ppb = pixels_per_block(ctx, P);
-  return (P + ppb - 1) / ppb;
+  int nb = (P + ppb - 1) / ppb;
+  return nb < 1 ? 1 : nb;
+}
+int partial_rows_for(const nicp_context *ctx, size_t pixels) {
+  int a = (int)((pixels + 63) / 64);  // smallest tile of any configuration
+  return a > ctx->blocksPerPair ? a : ctx->blocksPerPair;
+}
+
+template <int MODE, int NT, int TK, int MINB>
+static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, const AlignConsts &ac, int P, int imgStats, float imgThr) {
+  size_t smem = sizeof(TileSmem<NT, TK>);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  k_corr_lin_tiled<MODE, NT, TK, MINB><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, ac, P, imgStats, imgThr);
+}
+template <int MODE>
+static void launch_tiled_cfg(nicp_context *ctx, dim3 grid, int parity, const AlignConsts &ac, int P, int imgStats, float imgThr) {
+  switch (ctx->tileConfig) {
+    case 1: launch_tiled<MODE, 128, 2, 6>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
+    case 2: launch_tiled<MODE, 256, 4, 2>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
+    default: launch_tiled<MODE, 64, 2, 12>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
+  }
+}
+// MODE 0 / 1 launch of the fused kernel in the context's variant
+static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, const AlignConsts &ac, int P, int ppb,
+                            int imgStats, float imgThr) {
+  cudaStream_t st = ctx->stream;
+  if (ctx->corrVariant == 1) {
+    if (mode == 0)
+      launch_tiled_cfg<0>(ctx, grid, parity, ac, P, imgStats, imgThr);
+    else
+      launch_tiled_cfg<1>(ctx, grid, parity, ac, P, imgStats, imgThr);
+  } else {
+    if (mode == 0)
+      k_corr_lin<0><<<grid, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, imgStats, imgThr);
+    else
+      k_corr_lin<1><<<grid, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, imgStats, imgThr);
+  }
 }
 
 static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used) {
@@ -487,10 +765,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     for (int k = 0; k < innerIters; k++) {
       if (k == 0) {
         NICP_TIME_BEGIN(evCorr, evCorrUsed);
-        k_corr_lin<0><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
+        launch_corr_lin(ctx, 0, cg, parity, ac, P, ppb, 0, 0.0f);
         NICP_TIME_END(evCorr, evCorrUsed);
       } else {
-        k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 0, 0.0f);
+        launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 0, 0.0f);
       }
       NICP_CHECK_LAUNCH(ctx);
       k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
@@ -503,7 +781,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
       NICP_CUDA(cudaMemsetAsync(ctx->h_desc[i].corrImage, 0xFF, sizeof(int) * P, st));
   }
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
-  k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, 1, imgThreshold);
+  launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 1, imgThreshold);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
@@ -519,10 +797,7 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   const int ppb = pixels_per_block(ctx, numPixels);
   const int nb = (numPixels + ppb - 1) / ppb;
   dim3 cg(nb, 1);
-  if (fromCorrImage)
-    k_corr_lin<1><<<cg, 256, 0, st>>>(ctx->d_desc, 0, ac, numPixels, ppb, 0, 0.0f);
-  else
-    k_corr_lin<0><<<cg, 256, 0, st>>>(ctx->d_desc, 0, ac, numPixels, ppb, 0, 0.0f);
+  launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, ac, numPixels, ppb, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<<<1, 256, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
   NICP_CHECK_LAUNCH(ctx);

@@ -92,7 +92,8 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_curZ, (size_t)slots * pixels))) return rc;
   if ((rc = dev_alloc(&ctx->d_curIndex, (size_t)slots * pixels))) return rc;
   if ((rc = dev_alloc(&ctx->d_corrImage, (size_t)slots * pixels))) return rc;
-  if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->blocksPerPair * kAccum))) return rc;
+  ctx->partialRows = partial_rows_for(ctx, pixels);
+  if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->partialRows * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   // descriptors followed by one int flag per slot
   size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
@@ -193,7 +194,7 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   D.curZ = ctx->d_curZ + (size_t)curSlot * P;
   D.curIndex = ctx->d_curIndex + (size_t)curSlot * P;
   D.corrImage = ctx->d_corrImage + (size_t)slot * P;
-  D.partials = ctx->d_partials + (size_t)slot * ctx->blocksPerPair * kAccum;
+  D.partials = ctx->d_partials + (size_t)slot * ctx->partialRows * kAccum;
   D.state = ctx->d_state + slot;
   D.trace = d_trace;
   D.result = d_result;
@@ -426,6 +427,13 @@ int nicp_create(int device, nicp_context **out) {
   ctx->smCount = prop.multiProcessorCount;
   // fixed so that H/b of a pair do not depend on batch size or GPU count (2 CTAs per SM on a B200)
   ctx->blocksPerPair = env_int("NICP_BLOCKS_PER_PAIR", 296);
+  {
+    const char *v = getenv("NICP_CORR_VARIANT");
+    ctx->corrVariant = (v && v[0] == '0') ? 0 : 1;
+    // fixed per build (not per batch) so that a pair's H/b never depend on batch size or GPU count
+    ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
+    if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
+  }
   ctx->evCorr = new std::vector<cudaEvent_t>();
   ctx->evProj = new std::vector<cudaEvent_t>();
   *out = ctx;

@@ -136,7 +136,10 @@ struct nicp_context {
   // align scratch
   int slots;          // allocated slots
   size_t slotPixels;  // pixels per slot
-  int blocksPerPair;
+  int blocksPerPair;            // CTAs per pair of the per-pixel variant (NICP_CORR_VARIANT=0)
+  int corrVariant;              // 1 = tiled fused kernel (default), 0 = per-pixel fused kernel (A/B only)
+  int tileConfig;               // index into the tiled kernel's (threads, pixels/thread) table
+  int partialRows;              // rows of d_partials per slot
   unsigned long long *d_refZ;   // [slots][2][P]
   unsigned long long *d_curZ;   // [slots][P]
   int *d_curIndex;              // [slots][P]
@@ -185,4 +188,5 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
                     int innerIters, float imgThreshold, int nUniqueCur, const int *curSlotOfPair, bool wantTrace,
                     int resultOffset);
 int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);
+int partial_rows_for(const nicp_context *ctx, size_t pixels);
 }  // namespace nicp
