@@ -151,6 +151,16 @@ def make_stats_params(world_radius=0.1, min_image_radius=10, max_image_radius=30
     return s
 
 
+def make_prior(kind, mean, information, reference=None):
+    """kind 0 = SE3RelativePrior(mean, information), 1 = SE3AbsolutePrior(reference, mean, information)"""
+    p = Prior()
+    p.kind = int(kind)
+    p.mean[:] = colmajor(mean).tolist()
+    p.reference[:] = colmajor(np.eye(4) if reference is None else reference).tolist()
+    p.information[:] = colmajor(information).tolist()
+    return p
+
+
 def make_align_params(inlier_distance_threshold=0.5, inlier_normal_angular_threshold=float(np.cos(np.pi / 6)),
                       flat_curvature_threshold=0.02, inlier_curvature_ratio_threshold=1.3, inlier_max_chi2=9e3,
                       robust_kernel=True, outer_iterations=10, inner_iterations=1):
@@ -367,14 +377,16 @@ class Context:
         return from_colmajor(H, 6), b, err.value, inl.value
 
     # ---- alignment
-    def align(self, ref, cur, proj, ap, ref_offset=None, cur_offset=None, guess=None, img_threshold=50.0):
+    def align(self, ref, cur, proj, ap, ref_offset=None, cur_offset=None, guess=None, img_threshold=50.0, priors=()):
+        """priors: sequence of Prior (make_prior) -- Aligner::addRelativePrior / addAbsolutePrior"""
         eye = np.eye(4, dtype=np.float32)
         ro = colmajor(eye if ref_offset is None else ref_offset)
         co = colmajor(eye if cur_offset is None else cur_offset)
         g = colmajor(eye if guess is None else guess)
         res = AlignResult()
+        parr = (Prior * len(priors))(*priors) if len(priors) else None
         _check(self.L, self.L.nicp_align(self.handle, ref.handle, cur.handle, C.byref(proj), C.byref(ap), _fptr(ro),
-                                         _fptr(co), _fptr(g), None, 0, C.c_float(img_threshold), C.byref(res)))
+                                         _fptr(co), _fptr(g), parr, len(priors), C.c_float(img_threshold), C.byref(res)))
         return res
 
     def align_state(self, rows, cols, max_corr=None):

@@ -536,6 +536,113 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
 }
 
 // ---------------------------------------------------------------------------------------------
+// SE3Prior / SE3RelativePrior / SE3AbsolutePrior (se3_prior.cpp:8-71) and their use in the
+// Gauss-Newton step (aligner.cpp:97-108), evaluated by the solving thread.  Numeric Jacobians with
+// eps = 1e-3 exactly as the reference; the 6x6 inverse of Jz (Eigen's general inverse) is a
+// Gauss-Jordan elimination with partial pivoting in float64 (tolerance-level parity, like the oracle).
+// ---------------------------------------------------------------------------------------------
+struct DevPrior {
+  int kind;
+  float mean[16];
+  float refInv[16];
+  float info[36];
+};
+
+__device__ void prior_error(const DevPrior &pr, const float *mean, const float *invT, float *e) {
+  float t[16];
+  if (pr.kind == 0) {
+    iso_mul(invT, mean, t);
+  } else {
+    float u[16];
+    iso_mul(invT, pr.refInv, u);
+    iso_mul(u, mean, t);
+  }
+  t2v(t, e);
+}
+__device__ void mat6_mul(const float *A, const float *B, float *C) {
+  float t[36];
+  for (int c = 0; c < 6; c++)
+    for (int r = 0; r < 6; r++) {
+      float s = 0.0f;
+      for (int k = 0; k < 6; k++) s = fadd(s, fmul(NM6(A, r, k), NM6(B, k, c)));
+      NM6(t, r, c) = s;
+    }
+  for (int i = 0; i < 36; i++) C[i] = t[i];
+}
+__device__ void mat6_transpose(const float *A, float *At) {
+  float t[36];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) NM6(t, r, c) = NM6(A, c, r);
+  for (int i = 0; i < 36; i++) At[i] = t[i];
+}
+__device__ void mat6_inverse(const float *A, float *Ai) {
+  double a[6][12];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      a[r][c] = NM6(A, r, c);
+      a[r][c + 6] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++)
+      if (fabs(a[r][k]) > fabs(a[piv][k])) piv = r;
+    if (piv != k)
+      for (int c = 0; c < 12; c++) { double t = a[k][c]; a[k][c] = a[piv][c]; a[piv][c] = t; }
+    double d = a[k][k];
+    for (int c = 0; c < 12; c++) a[k][c] = __ddiv_rn(a[k][c], d);
+    for (int r = 0; r < 6; r++)
+      if (r != k) {
+        double f = a[r][k];
+        if (f != 0.0)
+          for (int c = 0; c < 12; c++) a[r][c] = __dsub_rn(a[r][c], __dmul_rn(f, a[k][c]));
+      }
+  }
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) NM6(Ai, r, c) = (float)a[r][c + 6];
+}
+__device__ void add_priors(const DevPrior *priors, int numPriors, const float *invT, float *H, float *b) {
+  const float epsilon = 1e-3f, iEps = fdiv(0.5f, epsilon);
+  for (int j = 0; j < numPriors; j++) {
+    const DevPrior &pr = priors[j];
+    float e[6], J[36], Jz[36];
+    prior_error(pr, pr.mean, invT, e);
+    for (int i = 0; i < 6; i++) {
+      float up[6] = {0, 0, 0, 0, 0, 0}, dn[6] = {0, 0, 0, 0, 0, 0}, Tu[16], Td[16], A[16], eu[6], ed[6];
+      up[i] = epsilon;
+      dn[i] = -epsilon;
+      v2t(up, Tu);
+      v2t(dn, Td);
+      // SE3Prior::jacobian: perturb the estimate on the left
+      iso_mul(Tu, invT, A);
+      prior_error(pr, pr.mean, A, eu);
+      iso_mul(Td, invT, A);
+      prior_error(pr, pr.mean, A, ed);
+      for (int r = 0; r < 6; r++) NM6(J, r, i) = fmul(iEps, fsub(eu[r], ed[r]));
+      // SE3Prior::jacobianZ: perturb the prior mean on the right
+      iso_mul(pr.mean, Tu, A);
+      prior_error(pr, A, invT, eu);
+      iso_mul(pr.mean, Td, A);
+      prior_error(pr, A, invT, ed);
+      for (int r = 0; r < 6; r++) NM6(Jz, r, i) = fmul(iEps, fsub(eu[r], ed[r]));
+    }
+    float iJz[36], iJzT[36], info[36], Jt[36], A[36], Hp[36];
+    mat6_inverse(Jz, iJz);
+    mat6_transpose(iJz, iJzT);
+    mat6_mul(iJzT, pr.info, A);
+    mat6_mul(A, iJz, info);
+    mat6_transpose(J, Jt);
+    mat6_mul(Jt, info, A);
+    mat6_mul(A, J, Hp);
+    for (int i = 0; i < 36; i++) H[i] = fadd(H[i], Hp[i]);
+    for (int r = 0; r < 6; r++) {
+      float s = 0.0f;
+      for (int k = 0; k < 6; k++) s = fadd(s, fmul(NM6(A, r, k), e[k]));
+      b[r] = fadd(b[r], s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sum the per-CTA partial rows in fixed order, assemble H/b (linearizer.cpp:109-114), then:
 //  mode 0: one Gauss-Newton step of Aligner::align (aligner.cpp:84-118): H += I + 1000 I,
 //          dx = LDLT(H)^-1 (-b), invT = v2t(dx) invT; if lastInner: T = invT^-1, T = v2t(t2v(T)),
@@ -622,10 +729,11 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
   // aligner.cpp:92-94: H = H_lin + I; H += 1000 I
   for (int d = 0; d < 6; d++) NM6(H, d, d) = fadd(fadd(NM6(H, d, d), 1.0f), 1000.0f);
   float nb[6], dx[6], dT[16], invT[16];
+  for (int k = 0; k < 16; k++) invT[k] = st->invT[k];
+  if (D.numPriors > 0) add_priors(reinterpret_cast<const DevPrior *>(D.priors), D.numPriors, invT, H, b);
   for (int k = 0; k < 6; k++) nb[k] = -b[k];
   ldlt_solve6(H, nb, dx);
   v2t(dx, dT);
-  for (int k = 0; k < 16; k++) invT[k] = st->invT[k];
   iso_mul(dT, invT, invT);
   if (!lastInner) {
     fix_last_row(invT);

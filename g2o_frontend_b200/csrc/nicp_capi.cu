@@ -76,8 +76,10 @@ static void free_align(nicp_context *ctx) {
   dev_free(ctx->d_corrImage);
   dev_free(ctx->d_partials);
   dev_free(ctx->d_state);
-  dev_free(ctx->d_desc);
-  if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+  dev_free(ctx->d_descBase);
+  if (ctx->h_descBase) cudaFreeHost(ctx->h_descBase);
+  ctx->h_descBase = nullptr;
+  ctx->d_desc = nullptr;
   ctx->h_desc = nullptr;
   ctx->slots = 0;
   ctx->slotPixels = 0;
@@ -95,13 +97,17 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   ctx->partialRows = partial_rows_for(ctx, pixels);
   if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->partialRows * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
-  // descriptors followed by one int flag per slot
+  // two sets of: descriptors followed by one int flag per slot
   size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
+  descBytes = (descBytes + 255) & ~(size_t)255;
   void *p = nullptr;
-  NICP_CUDA(cudaMalloc(&p, descBytes));
-  ctx->d_desc = reinterpret_cast<PairDesc *>(p);
-  NICP_CUDA(cudaMallocHost(&p, descBytes));
-  ctx->h_desc = reinterpret_cast<PairDesc *>(p);
+  NICP_CUDA(cudaMalloc(&p, 2 * descBytes));
+  ctx->d_descBase = reinterpret_cast<unsigned char *>(p);
+  NICP_CUDA(cudaMallocHost(&p, 2 * descBytes));
+  ctx->h_descBase = reinterpret_cast<unsigned char *>(p);
+  ctx->descStride = descBytes;
+  ctx->d_desc = reinterpret_cast<PairDesc *>(ctx->d_descBase);
+  ctx->h_desc = reinterpret_cast<PairDesc *>(ctx->h_descBase);
   ctx->slots = slots;
   ctx->slotPixels = pixels;
   return NICP_OK;
@@ -198,6 +204,8 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   D.state = ctx->d_state + slot;
   D.trace = d_trace;
   D.result = d_result;
+  D.priors = nullptr;
+  D.numPriors = 0;
   if (guess) {
     for (int i = 0; i < 16; i++) D.guess[i] = guess[i];
   } else {
@@ -377,8 +385,13 @@ static void collect_timing(nicp_context *ctx) {
   ctx->evCorrUsed = ctx->evProjUsed = 0;
 }
 
-static void finish_results(nicp_context *ctx, int n, nicp_align_result *out) {
-  for (int i = 0; i < n; i++) {
+static void select_desc_set(nicp_context *ctx, int set) {
+  ctx->d_desc = reinterpret_cast<PairDesc *>(ctx->d_descBase + (size_t)set * ctx->descStride);
+  ctx->h_desc = reinterpret_cast<PairDesc *>(ctx->h_descBase + (size_t)set * ctx->descStride);
+}
+
+static void finish_results(nicp_context *ctx, int base, int n, nicp_align_result *out) {
+  for (int i = base; i < base + n; i++) {
     nicp_align_result r = ctx->h_results[i];
     const float *Hb = ctx->h_statHb + (size_t)i * 42;
     compute_statistics(Hb, r.T, r.omega, &r.translational_eigen_ratio, &r.rotational_eigen_ratio);
@@ -434,6 +447,8 @@ int nicp_create(int device, nicp_context **out) {
     ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
     if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
   }
+  NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming));
+  NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming));
   ctx->evCorr = new std::vector<cudaEvent_t>();
   ctx->evProj = new std::vector<cudaEvent_t>();
   *out = ctx;
@@ -451,6 +466,7 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_index);
   free_align(ctx);
   dev_free(ctx->d_trace);
+  if (ctx->d_priors) cudaFree(ctx->d_priors);
   dev_free(ctx->d_results);
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -459,6 +475,8 @@ void nicp_destroy(nicp_context *ctx) {
   for (cudaEvent_t e : *ctx->evProj) cudaEventDestroy(e);
   delete ctx->evCorr;
   delete ctx->evProj;
+  cudaEventDestroy(ctx->evChunk[0]);
+  cudaEventDestroy(ctx->evChunk[1]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -841,10 +859,18 @@ int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cl
 }
 
 // ---- alignment -----------------------------------------------------------------------------------
+// host mirror of align.cu's DevPrior
+struct HostPrior {
+  int kind;
+  float mean[16];
+  float refInv[16];
+  float info[36];
+};
+
 static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs, const nicp_cloud *const *curs,
                         const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset,
                         const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
-                        bool single) {
+                        bool single, const nicp_prior *priors = nullptr, int numPriors = 0) {
   const size_t P = (size_t)proj->rows * proj->cols;
   int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 64);
   if (maxSlots > n) maxSlots = n;
@@ -852,6 +878,26 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   if ((rc = ensure_align(ctx, maxSlots, P))) return rc;
   if ((rc = ensure_results(ctx, n))) return rc;
   if (single && (rc = ensure_trace(ctx, ap->outer_iterations > 0 ? ap->outer_iterations : 1))) return rc;
+  if (numPriors > 0) {
+    // SE3AbsolutePrior keeps the inverse of its reference transform (se3_prior.h setReferenceTransform)
+    std::vector<HostPrior> hp(numPriors);
+    for (int j = 0; j < numPriors; j++) {
+      hp[j].kind = priors[j].kind;
+      float m[16], r[16];
+      for (int i = 0; i < 16; i++) { m[i] = priors[j].mean[i]; r[i] = priors[j].reference[i]; }
+      for (int i = 0; i < 16; i++) hp[j].mean[i] = m[i];
+      iso_inverse(r, hp[j].refInv);
+      for (int i = 0; i < 36; i++) hp[j].info[i] = priors[j].information[i];
+    }
+    if (numPriors > ctx->priorCap) {
+      if (ctx->d_priors) cudaFree(ctx->d_priors);
+      ctx->d_priors = nullptr;
+      NICP_CUDA(cudaMalloc(&ctx->d_priors, sizeof(HostPrior) * numPriors));
+      ctx->priorCap = numPriors;
+    }
+    NICP_CUDA(cudaMemcpyAsync(ctx->d_priors, hp.data(), sizeof(HostPrior) * numPriors, cudaMemcpyHostToDevice, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   AlignConsts ac = make_consts(proj, ap, refOffset);
   float eye[16], co[16], curKRt[16];
   mat4_identity(eye);
@@ -860,13 +906,12 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   compute_KRt(proj->K, co, curKRt);  // aligner.cpp:60: projector->setTransform(_currentSensorOffset)
   const int slots = ctx->slots;
   std::vector<int> owns(slots);
-  for (int base = 0; base < n; base += maxSlots) {
+  int chunk = 0, prevBase = 0, prevM = 0;
+  for (int base = 0; base < n; base += maxSlots, chunk++) {
     int m = n - base < maxSlots ? n - base : maxSlots;
-    if (base > 0) {
-      // the staging buffer of the previous chunk must have been consumed by its H2D copy
-      NICP_CUDA(cudaStreamSynchronize(ctx->stream));
-      collect_timing(ctx);
-    }
+    // chunk c stages into descriptor set c&1; the event of chunk c-2 (same set) was waited for when the
+    // host post-processed that chunk, so the set is free
+    select_desc_set(ctx, chunk & 1);
     std::map<const nicp_cloud *, int> curSlot;
     for (int i = 0; i < m; i++) {
       const nicp_cloud *r = refs[base + i], *c = curs[base + i];
@@ -886,16 +931,30 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       }
       fill_desc(ctx, i, cs, r, c, guesses ? guesses + 16 * (size_t)(base + i) : nullptr, ctx->d_results + base + i,
                 single ? ctx->d_trace : nullptr);
+      if (numPriors > 0) {
+        ctx->h_desc[i].priors = ctx->d_priors;
+        ctx->h_desc[i].numPriors = numPriors;
+      }
     }
     if ((rc = run_align_chunk(ctx, m, ac, curKRt, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
                               owns.data(), single, base)))
       return rc;
+    NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb + (size_t)base * 42, ctx->d_statHb + (size_t)base * 42, sizeof(float) * 42 * m,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    NICP_CUDA(cudaEventRecord(ctx->evChunk[chunk & 1], ctx->stream));
+    // while this chunk runs on the GPU, finish the previous one on the host (Aligner::_computeStatistics tail)
+    if (chunk > 0) {
+      NICP_CUDA(cudaEventSynchronize(ctx->evChunk[(chunk - 1) & 1]));
+      finish_results(ctx, prevBase, prevM, results);
+    }
+    prevBase = base;
+    prevM = m;
   }
-  NICP_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(nicp_align_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb, ctx->d_statHb, sizeof(float) * 42 * n, cudaMemcpyDeviceToHost, ctx->stream));
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   collect_timing(ctx);
-  finish_results(ctx, n, results);
+  finish_results(ctx, prevBase, prevM, results);
   ctx->lastAlignRows = proj->rows;
   ctx->lastAlignCols = proj->cols;
   ctx->lastAlignIters = ap->outer_iterations;
@@ -908,12 +967,9 @@ int nicp_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud 
                const float initial_guess[16], const nicp_prior *priors, int num_priors, float frame_inlier_depth_threshold,
                nicp_align_result *result) {
   if (!ctx || !reference || !current || !proj || !ap || !result || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
-  if (num_priors > 0 || priors) {
-    set_error("SE3 priors are not implemented on the device path yet");
-    return NICP_ERR_INVALID;
-  }
+  if (num_priors < 0 || (num_priors > 0 && !priors)) return NICP_ERR_INVALID;
   return align_common(ctx, 1, &reference, &current, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guess,
-                      frame_inlier_depth_threshold, result, true);
+                      frame_inlier_depth_threshold, result, true, priors, num_priors);
 }
 
 int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *references, const nicp_cloud *const *currents,

@@ -84,6 +84,8 @@ struct PairDesc {
   PairState *state;
   float *trace;                 // may be null
   nicp_align_result *result;
+  const void *priors;           // DevPrior[numPriors] (device) or null
+  int numPriors;
   float guess[16];
 };
 
@@ -146,8 +148,15 @@ struct nicp_context {
   int *d_corrImage;             // [slots][P]
   float *d_partials;            // [slots][blocksPerPair][kAccum]
   nicp::PairState *d_state;     // [slots]
-  nicp::PairDesc *d_desc;       // [slots]
+  // descriptor staging is double buffered so that the host can fill chunk c+1 (and post-process chunk
+  // c-1) while chunk c runs; d_desc / h_desc point at the set of the chunk being issued
+  nicp::PairDesc *d_desc;       // [slots] + one int flag per slot
   nicp::PairDesc *h_desc;       // pinned
+  unsigned char *d_descBase, *h_descBase;
+  size_t descStride;
+  cudaEvent_t evChunk[2];
+  void *d_priors;               // device copy of the priors of the last nicp_align
+  int priorCap;
   float *d_trace;               // [maxIter][61] for slot 0 (single align)
   int traceIters;
   nicp_align_result *d_results; // [resultCap]

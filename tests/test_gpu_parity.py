@@ -270,6 +270,31 @@ def test_inner_iterations(ctx):
     assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
 
 
+def test_priors(ctx):
+    """Aligner::addRelativePrior / addAbsolutePrior (se3_prior.cpp) on the device path vs the oracle"""
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    s = get_scene(4)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    mean = synth.make_pose((0.05, -0.03, 0.08), (0.1, 1.0, 0.3), 3.0).astype(np.float32)
+    refT = synth.make_pose((0.2, 0.1, -0.1), (1.0, 0.2, 0.1), 5.0).astype(np.float32)
+    info = (np.diag([2e5, 1e5, 3e5, 5e6, 4e6, 6e6]) + 1e3).astype(np.float32)
+    cases = [[(0, mean, info, None)], [(1, mean, info, refT)], [(0, mean, info, None), (1, mean, info * 0.5, refT)]]
+    base = capi.result_T(ctx.align(ref, cur, s.projector(), s.align_params()))
+    for case in cases:
+        opri = [O.make_prior(k, m, i, r) for k, m, i, r in case]
+        gpri = [capi.make_prior(k, m, i, r) for k, m, i, r in case]
+        ap = O.make_align_params(s.K, s.rows, s.cols, s.conf["minD"], s.conf["maxD"], s.cp, max_chi2=s.conf["inlierMaxChi2"],
+                                 num_threads=1, priors=opri)
+        out = O.align(s.cloudA, s.cloudB, ap)
+        res = ctx.align(ref, cur, s.projector(), s.align_params(), priors=gpri)
+        T = capi.result_T(res)
+        assert rot_angle(T[:3, :3], out.T[:3, :3]) <= 2e-4
+        assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= 2e-4
+        # the prior really changed the solution
+        assert np.abs(T - base).max() > 1e-3
+
+
 def test_determinism_and_batch_identity(ctx):
     """two runs are bit-identical; a pair gives the same bits alone or inside a batch"""
     s = get_scene(4, 0, 0.05)
