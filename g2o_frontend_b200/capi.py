@@ -25,12 +25,21 @@ SYMBOLS = [
     "nicp_raw_depth_to_cloud", "nicp_last_integral_image", "nicp_last_interval_image",
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
     "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch",
+    "nicp_multi_image_size", "nicp_multi_depth_to_cloud", "nicp_multi_project", "nicp_multi_align",
 ]
 
 
 class Projector(C.Structure):
     _fields_ = [("K", C.c_float * 9), ("rows", C.c_int), ("cols", C.c_int),
                 ("min_distance", C.c_float), ("max_distance", C.c_float)]
+
+
+MAX_CAMERAS = 8
+
+
+class MultiProjector(C.Structure):
+    _fields_ = [("num_cameras", C.c_int), ("camera", Projector * MAX_CAMERAS),
+                ("sensor_offset", (C.c_float * 16) * MAX_CAMERAS)]
 
 
 class StatsParams(C.Structure):
@@ -96,6 +105,7 @@ def load(verify=False):
     L.nicp_update_matrices.restype = None
     L.nicp_v2t.restype = None
     L.nicp_t2v.restype = None
+    L.nicp_multi_image_size.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:
@@ -135,6 +145,22 @@ def make_projector(K, rows, cols, min_distance=0.01, max_distance=6.0):
     p.rows, p.cols = int(rows), int(cols)
     p.min_distance, p.max_distance = min_distance, max_distance
     return p
+
+
+def make_multi_projector(cameras):
+    """cameras: list of dicts {K, width, height, minD, maxD, offset} (addPointProjector(p, offset, width, height))"""
+    m = MultiProjector()
+    m.num_cameras = len(cameras)
+    for i, c in enumerate(cameras):
+        m.camera[i] = make_projector(c["K"], c["width"], c["height"], c["minD"], c["maxD"])
+        m.sensor_offset[i][:] = colmajor(c["offset"]).tolist()
+    return m
+
+
+def multi_image_size(mp, verify=False):
+    r, c = C.c_int(0), C.c_int(0)
+    load(verify).nicp_multi_image_size(C.byref(mp), C.byref(r), C.byref(c))
+    return r.value, c.value
 
 
 def make_stats_params(world_radius=0.1, min_image_radius=10, max_image_radius=30, min_points=50,
@@ -387,6 +413,37 @@ class Context:
         parr = (Prior * len(priors))(*priors) if len(priors) else None
         _check(self.L, self.L.nicp_align(self.handle, ref.handle, cur.handle, C.byref(proj), C.byref(ap), _fptr(ro),
                                          _fptr(co), _fptr(g), parr, len(priors), C.c_float(img_threshold), C.byref(res)))
+        return res
+
+    # ---- MultiPointProjector
+    def multi_depth_to_cloud(self, depth, mp, sp, sensor_offset=None, keep_stats=False, cloud=None):
+        depth = np.ascontiguousarray(depth, np.float32)
+        rows, cols = multi_image_size(mp, self.verify)
+        assert depth.shape == (rows, cols)
+        cloud = cloud or self.new_cloud(rows * cols)
+        index = np.zeros((rows, cols), np.int32)
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        _check(self.L, self.L.nicp_multi_depth_to_cloud(self.handle, _fptr(depth), C.byref(mp), C.byref(sp), _fptr(so),
+                                                        int(keep_stats), cloud.handle, _iptr(index)))
+        return cloud, index
+
+    def multi_project(self, cloud, mp, T):
+        rows, cols = multi_image_size(mp, self.verify)
+        index = np.zeros((rows, cols), np.int32)
+        depth = np.zeros((rows, cols), np.float32)
+        t = colmajor(T)
+        _check(self.L, self.L.nicp_multi_project(self.handle, cloud.handle, C.byref(mp), _fptr(t), _iptr(index), _fptr(depth)))
+        return index, depth
+
+    def multi_align(self, ref, cur, mp, ap, ref_offset=None, cur_offset=None, guess=None, img_threshold=50.0, priors=()):
+        eye = np.eye(4, dtype=np.float32)
+        ro = colmajor(eye if ref_offset is None else ref_offset)
+        co = colmajor(eye if cur_offset is None else cur_offset)
+        g = colmajor(eye if guess is None else guess)
+        res = AlignResult()
+        parr = (Prior * len(priors))(*priors) if len(priors) else None
+        _check(self.L, self.L.nicp_multi_align(self.handle, ref.handle, cur.handle, C.byref(mp), C.byref(ap), _fptr(ro),
+                                               _fptr(co), _fptr(g), parr, len(priors), C.c_float(img_threshold), C.byref(res)))
         return res
 
     def align_state(self, rows, cols, max_corr=None):

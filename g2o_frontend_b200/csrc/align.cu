@@ -21,6 +21,17 @@
 
 namespace nicp {
 
+// KRt of every camera for the projector pose `pose` (PinholePointProjector::_updateMatrices after
+// MultiPointProjector::setTransform(pose): child pose = pose * offset_i, multipointprojector.cpp:207-215)
+__device__ void store_cam_KRt(const CamSet *cams, const float *pose, PairState *st) {
+  for (int i = 0; i < cams->n; i++) {
+    float Tc[16], KRt[16];
+    iso_mul(pose, cams->offset[i], Tc);
+    compute_KRt(cams->K[i], Tc, KRt);
+    for (int k = 0; k < 16; k++) st->KRt[i][k] = KRt[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,9 +44,7 @@ __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
   iso_inverse(T, tmp);
   for (int k = 0; k < 16; k++) st->invT[k] = tmp[k];
   iso_mul(T, ac.refOffset, tmp);
-  float KRt[16];
-  compute_KRt(ac.K, tmp, KRt);
-  for (int k = 0; k < 16; k++) st->KRt[k] = KRt[k];
+  store_cam_KRt(ac.cams, tmp, st);
   for (int k = 0; k < 36; k++) { st->H[k] = 0.f; st->statH[k] = 0.f; }
   for (int k = 0; k < 6; k++) { st->b[k] = 0.f; st->statb[k] = 0.f; }
   st->error = 0.f;
@@ -64,6 +73,48 @@ __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i
   atomicMin(&z[(size_t)y * cols + x], key);
 }
 
+CamGeom geom_of(const CamSet &c) {
+  CamGeom g;
+  g.n = c.n;
+  g.multi = c.multi;
+  for (int i = 0; i < kMaxCams; i++) {
+    g.width[i] = c.width[i]; g.height[i] = c.height[i]; g.colOff[i] = c.colOff[i];
+    g.minD[i] = c.minD[i]; g.maxD[i] = c.maxD[i];
+  }
+  return g;
+}
+
+// MultiPointProjector::project per point (multipointprojector.cpp:157-205) under the base-class z-buffer
+// (pointprojector.cpp:17-40): the first camera whose pinhole projection lands inside its
+// [0,width) x [0,height) wins; composite pixel = (row u, col v + colOff).
+template <typename MatSrc>
+__device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatSrc &mats, float4 p, int i, int rows,
+                                                    int cols, unsigned long long *__restrict__ z) {
+  for (int c = 0; c < g.n; c++) {
+    const Affine KRt = mats(c);
+    float ix, iy, d;
+    xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
+    if (d < g.minD[c] || d > g.maxD[c]) continue;
+    float s = fdiv(1.0f, d);
+    float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
+    if (d < 0.0f || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
+    int X = (int)fx, Y = (int)fy + g.colOff[c];
+    if (X < rows && Y < cols) {
+      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
+      atomicMin(&z[(size_t)X * cols + Y], key);
+    }
+    return;
+  }
+}
+struct MatsFromState {
+  const PairState *st;
+  __device__ __forceinline__ Affine operator()(int c) const { return affine_from(st->KRt[c]); }
+};
+struct MatsFromParam {
+  const CamMats *m;
+  __device__ __forceinline__ Affine operator()(int c) const { return m->M[c]; }
+};
+
 // which: 0/1 = reference cloud into refZ[which] with the pair's KRt; 2 = current cloud into curZ
 // with the (shared) current-sensor KRt, only for the pair that owns that buffer.
 __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ desc, int which, Affine curKRt, int rows,
@@ -83,10 +134,29 @@ __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ de
     pts = D.refPoints;
     n = *D.refN;
     z = D.refZ[which];
-    KRt = affine_from(D.state->KRt);
+    KRt = affine_from(D.state->KRt[0]);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+}
+
+// the same for a MultiPointProjector camera set
+__global__ void __launch_bounds__(256) k_project_multi(const PairDesc *__restrict__ desc, int which, CamGeom g,
+                                                       const CamMats *__restrict__ curMats, int rows, int cols,
+                                                       const int *__restrict__ ownsCur) {
+  const PairDesc &D = desc[blockIdx.y];
+  if (which == 2) {
+    if (!ownsCur[blockIdx.y]) return;
+    const int n = *D.curN;
+    MatsFromParam mats{curMats};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      project_point_multi(g, mats, D.curPoints[i], i, rows, cols, D.curZ);
+  } else {
+    const int n = *D.refN;
+    MatsFromState mats{D.state};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      project_point_multi(g, mats, D.refPoints[i], i, rows, cols, D.refZ[which]);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_project_single(const float4 *__restrict__ pts, const int *__restrict__ nPtr,
@@ -97,14 +167,23 @@ __global__ void __launch_bounds__(256) k_project_single(const float4 *__restrict
     project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
 }
 
+__global__ void __launch_bounds__(256) k_project_single_multi(const float4 *__restrict__ pts, const int *__restrict__ nPtr,
+                                                              CamGeom g, const CamMats *__restrict__ matsPtr, int rows,
+                                                              int cols, unsigned long long *__restrict__ z) {
+  int n = *nPtr;
+  MatsFromParam mats{matsPtr};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    project_point_multi(g, mats, pts[i], i, rows, cols, z);
+}
+
 __global__ void k_decode_z(const unsigned long long *__restrict__ z, int n, int *__restrict__ index,
-                           float *__restrict__ depth) {
+                           float *__restrict__ depth, float emptyDepth) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long v = z[i];
   int idx = (int)(unsigned int)(v & 0xFFFFFFFFull);
   if (index) index[i] = idx;
-  if (depth) depth[i] = (v == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(v >> 32));
+  if (depth) depth[i] = (v == kEmptyZ) ? emptyDepth : __uint_as_float((unsigned int)(v >> 32));
 }
 
 __global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int *__restrict__ ownsCur) {
@@ -125,8 +204,39 @@ int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const floa
   return NICP_OK;
 }
 
-int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth) {
-  k_decode_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_z, n, d_index, d_depth);
+// host: per-camera KRt for the projector pose T
+void cam_mats_KRt(const CamSet &cams, const float T[16], CamMats &out) {
+  for (int i = 0; i < cams.n; i++) {
+    float Tc[16], KRt[16];
+    iso_mul(T, cams.offset[i], Tc);
+    compute_KRt(cams.K[i], Tc, KRt);
+    out.M[i] = affine_from(KRt);
+  }
+}
+
+static int upload_cam_mats(nicp_context *ctx, const CamMats &m, CamMats **d_out) {
+  CamMats *d = &ctx->d_cams->curMats;
+  NICP_CUDA(cudaMemcpyAsync(d, &m, sizeof(CamMats), cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = d;
+  return NICP_OK;
+}
+
+int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet &cams, const float T[16], int rows,
+                        int cols, unsigned long long *d_z) {
+  NICP_CUDA(cudaMemsetAsync(d_z, 0xFF, (size_t)rows * cols * sizeof(unsigned long long), ctx->stream));
+  CamMats m, *d_m = nullptr;
+  cam_mats_KRt(cams, T, m);
+  int rc = upload_cam_mats(ctx, m, &d_m);
+  if (rc) return rc;
+  int blocks = (cloud->capacity + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  k_project_single_multi<<<blocks, 256, 0, ctx->stream>>>(cloud->points, cloud->d_n, geom_of(cams), d_m, rows, cols, d_z);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth, float emptyDepth) {
+  k_decode_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_z, n, d_index, d_depth, emptyDepth);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }
@@ -741,7 +851,7 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
     return;
   }
   // aligner.cpp:115-117
-  float T[16], v[6], tmp[16], KRt[16];
+  float T[16], v[6], tmp[16];
   iso_inverse(invT, T);
   t2v(T, v);
   v2t(v, T);
@@ -751,8 +861,7 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
   fix_last_row(invT);
   for (int k = 0; k < 16; k++) st->invT[k] = invT[k];
   iso_mul(T, ac.refOffset, tmp);
-  compute_KRt(ac.K, tmp, KRt);
-  for (int k = 0; k < 16; k++) st->KRt[k] = KRt[k];
+  store_cam_KRt(ac.cams, tmp, st);
 }
 
 __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *__restrict__ statHb) {
@@ -836,9 +945,9 @@ static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used) {
 
 // runs Aligner::align for the nPairs descriptors staged in ctx->h_desc (one lock-step chunk).
 // ownsCur: per pair, 1 if the pair's curZ/curIndex buffers must be produced by it.
-int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const float curKRt[16], int outerIters,
-                    int innerIters, float imgThreshold, int /*nUniqueCur*/, const int *h_ownsCur, bool /*wantTrace*/,
-                    int resultOffset) {
+int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const CamSet &cams, const float curOffset[16],
+                    int outerIters, int innerIters, float imgThreshold, int /*nUniqueCur*/, const int *h_ownsCur,
+                    bool /*wantTrace*/, int resultOffset) {
   cudaStream_t st = ctx->stream;
   const int P = ac.rows * ac.cols;
   const int ppb = pixels_per_block(ctx, P);
@@ -857,17 +966,30 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   NICP_CHECK_LAUNCH(ctx);
   const int projBlocks = (P + 1023) / 1024;  // grid-stride: 4 points per thread at full density
   dim3 pg(projBlocks, nPairs);
-  k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, affine_from(curKRt), ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+  // aligner.cpp:60-63: the current cloud is projected once with projector->setTransform(_currentSensorOffset)
+  CamMats curMats, *d_curMats = nullptr;
+  cam_mats_KRt(cams, curOffset, curMats);
+  const CamGeom geom = geom_of(cams);
+  if (cams.multi) {
+    int rcm = upload_cam_mats(ctx, curMats, &d_curMats);
+    if (rcm) return rcm;
+    k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags);
+  } else {
+    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+  }
   NICP_CHECK_LAUNCH(ctx);
   k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags);
   NICP_CHECK_LAUNCH(ctx);
-  Affine dummy = affine_from(curKRt);
+  const Affine dummy = curMats.M[0];
   dim3 cg(nb, nPairs);
   int parity = 0;
   for (int it = 0; it < outerIters; it++) {
     parity = it & 1;
     NICP_TIME_BEGIN(evProj, evProjUsed);
-    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+    if (cams.multi)
+      k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, parity, geom, d_curMats, ac.rows, ac.cols, d_flags);
+    else
+      k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
     NICP_TIME_END(evProj, evProjUsed);
     NICP_CHECK_LAUNCH(ctx);
     for (int k = 0; k < innerIters; k++) {

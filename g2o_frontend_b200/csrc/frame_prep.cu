@@ -70,10 +70,44 @@ int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// pixel -> sensor-frame point.  Pinhole: _unProject(p, x = c, y = r, d) (pinholepointprojector.cpp:68-91).
+// MultiPointProjector: the inverse of the composite layout the Aligner projects into (row = pixel u,
+// col = pixel v + colOff of the camera): camera of the column block, _unProject(p, x = r, y = c - colOff, d).
+// Returns false for an invalid depth (or a pixel outside every camera); iv = max-interval numerators.
+// ---------------------------------------------------------------------------------------------
+template <bool MULTI>
+__device__ __forceinline__ bool pixel_point(const Affine &iKRt, float minD, float maxD, float ivx0, float ivy0,
+                                            const PrepCams *__restrict__ pc, int r, int c, float d, float &x, float &y,
+                                            float &z, float &ivx, float &ivy, int &camOut) {
+  camOut = 0;
+  if (!MULTI) {
+    if (d < minD || d > maxD) return false;
+    xform_point(iKRt, fmul((float)c, d), fmul((float)r, d), d, x, y, z);
+    ivx = ivx0;
+    ivy = ivy0;
+    return true;
+  } else {
+    int cam = -1;
+    for (int i = 0; i < pc->g.n; i++)
+      if (c >= pc->g.colOff[i] && c < pc->g.colOff[i] + pc->g.height[i]) cam = i;
+    if (cam < 0 || r >= pc->g.width[cam]) return false;
+    if (d < pc->g.minD[cam] || d > pc->g.maxD[cam]) return false;
+    const int v = c - pc->g.colOff[cam];
+    camOut = cam;
+    xform_point(pc->iKRt[cam], fmul((float)r, d), fmul((float)v, d), d, x, y, z);
+    ivx = pc->ivx[cam];
+    ivy = pc->ivy[cam];
+    return true;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PointIntegralImage::compute, pass 1 (scatter + prefix along image-x)
 // ---------------------------------------------------------------------------------------------
+template <bool MULTI>
 __global__ void __launch_bounds__(256) k_integral_rows(const float *__restrict__ depth, int rows, int cols, Affine iKRt,
-                                                       float minD, float maxD, float *__restrict__ I) {
+                                                       float minD, float maxD, const PrepCams *__restrict__ pc,
+                                                       float *__restrict__ I) {
   extern __shared__ float sm[];  // [10][stride]
   const int stride = cols + 1;   // +1: the 10 scanning lanes hit 10 different banks
   const int r = blockIdx.x;
@@ -81,12 +115,12 @@ __global__ void __launch_bounds__(256) k_integral_rows(const float *__restrict__
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     float d = drow[c];
     float ch[kIntegralCh];
-    if (d < minD || d > maxD) {
+    float x, y, z, ivx, ivy;
+    int cam;
+    if (!pixel_point<MULTI>(iKRt, minD, maxD, 0.f, 0.f, pc, r, c, d, x, y, z, ivx, ivy, cam)) {
 #pragma unroll
       for (int k = 0; k < kIntegralCh; k++) ch[k] = 0.0f;
     } else {
-      float x, y, z;
-      xform_point(iKRt, fmul((float)c, d), fmul((float)r, d), d, x, y, z);
       ch[0] = 1.0f; ch[1] = x; ch[2] = y; ch[3] = z;
       ch[4] = fmul(x, x); ch[5] = fmul(x, y); ch[6] = fmul(x, z);
       ch[7] = fmul(y, y); ch[8] = fmul(y, z); ch[9] = fmul(z, z);
@@ -284,8 +318,10 @@ __device__ __forceinline__ void rotate_sym(const float *M, const float *Om /*3x3
       NM3(out, r, c) = dot3(NM3(t, r, 0), NM3(t, r, 1), NM3(t, r, 2), NM4(M, c, 0), NM4(M, c, 1), NM4(M, c, 2));
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, const float *__restrict__ I, int rows,
-                                               int cols, StatsConsts sc, float4 *__restrict__ points,
+                                               int cols, StatsConsts sc, const PrepCams *__restrict__ pc,
+                                               float4 *__restrict__ points,
                                                float4 *__restrict__ normals, float4 *__restrict__ omega,
                                                int *__restrict__ index, int *__restrict__ interval,
                                                float *__restrict__ stats16, float *__restrict__ eigvalsOut,
@@ -297,23 +333,36 @@ __global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, 
   const size_t pix = (size_t)r * cols + c;
   if (r == rows - 1 && c == cols - 1) *countOut = (int)I[pix];
   const float d = depth[pix];
-  if (d < sc.minD || d > sc.maxD) {
+  float px, py, pz, ivx, ivy;
+  int cam;
+  if (!pixel_point<MULTI>(sc.iKRt, sc.minD, sc.maxD, sc.ivx, sc.ivy, pc, r, c, d, px, py, pz, ivx, ivy, cam)) {
     index[pix] = -1;
     interval[pix] = -1;
     return;
   }
-  // compacted raster-order index from channel 0 (exact integer counts in float32)
-  float above = r > 0 ? I[(size_t)(r - 1) * cols + cols - 1] : 0.0f;
-  float upto = I[pix] - (r > 0 ? I[pix - cols] : 0.0f);
-  const int idx = (int)above + (int)upto - 1;
+  // compacted index from channel 0 of the integral image (exact integer counts in float32)
+  int idx;
+  if (!MULTI) {
+    // raster order: valid pixels in the rows above + valid pixels of this row up to c
+    float above = r > 0 ? I[(size_t)(r - 1) * cols + cols - 1] : 0.0f;
+    float upto = I[pix] - (r > 0 ? I[pix - cols] : 0.0f);
+    idx = (int)above + (int)upto - 1;
+  } else {
+    // MultiPointProjector::unProject concatenates the children's clouds (multipointprojector.cpp:59-90):
+    // points of the earlier column blocks, then raster order inside this camera's block
+    const int off = pc->g.colOff[cam], last = off + pc->g.height[cam] - 1;
+    const float *Ir = I + (size_t)r * cols;
+    const float *Ip = r > 0 ? Ir - cols : nullptr;
+    float before = off > 0 ? I[(size_t)(rows - 1) * cols + off - 1] : 0.0f;
+    float aboveBlock = Ip ? Ip[last] - (off > 0 ? Ip[off - 1] : 0.0f) : 0.0f;
+    float rowUpTo = (Ir[c] - (Ip ? Ip[c] : 0.0f)) - (off > 0 ? (Ir[off - 1] - (Ip ? Ip[off - 1] : 0.0f)) : 0.0f);
+    idx = (int)before + (int)aboveBlock + (int)rowUpTo - 1;
+  }
   index[pix] = idx;
-
-  float px, py, pz;
-  xform_point(sc.iKRt, fmul((float)c, d), fmul((float)r, d), d, px, py, pz);
 
   // _projectInterval (pinholepointprojector.h:264-274)
   float invd = fdiv(1.0f, d);
-  float ia = fmul(sc.ivx, invd), ib = fmul(sc.ivy, invd);
+  float ia = fmul(ivx, invd), ib = fmul(ivy, invd);
   int k = (ia > ib) ? (int)ia : (int)ib;
   interval[pix] = k;
 
@@ -437,18 +486,40 @@ static bool is_identity16(const float *m) {
 }
 
 int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
-                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index) {
+                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index, const CamSet *cams) {
   const int rows = proj->rows, cols = proj->cols;
+  const bool multi = cams && cams->multi;
+  const PrepCams *d_pc = nullptr;
+  if (multi) {
+    // DepthImageConverterIntegralImage::compute sets the projector to identity, so child i sits at offset_i
+    PrepCams pc;
+    pc.g = geom_of(*cams);
+    for (int i = 0; i < cams->n; i++) {
+      float iKRt[16];
+      compute_iKRt(cams->K[i], cams->offset[i], iKRt);
+      pc.iKRt[i] = affine_from(iKRt);
+      const float *Kc = cams->K[i];
+      pc.ivx[i] = dot3(NM3(Kc, 0, 0), NM3(Kc, 0, 1), NM3(Kc, 0, 2), sp->world_radius, sp->world_radius, 0.0f);
+      pc.ivy[i] = dot3(NM3(Kc, 1, 0), NM3(Kc, 1, 1), NM3(Kc, 1, 2), sp->world_radius, sp->world_radius, 0.0f);
+    }
+    NICP_CUDA(cudaMemcpyAsync(&ctx->d_cams->prep, &pc, sizeof pc, cudaMemcpyHostToDevice, ctx->stream));
+    d_pc = &ctx->d_cams->prep;
+  }
   float I4[16], iKRt[16];
   mat4_identity(I4);
   compute_iKRt(proj->K, I4, iKRt);
   Affine a = affine_from(iKRt);
   size_t smem = (size_t)kIntegralCh * (cols + 1) * sizeof(float);
   if (smem > 48 * 1024) {
-    NICP_CUDA(cudaFuncSetAttribute(k_integral_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NICP_CUDA(cudaFuncSetAttribute(k_integral_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NICP_CUDA(cudaFuncSetAttribute(k_integral_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  k_integral_rows<<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
-                                                    ctx->d_integral);
+  if (multi)
+    k_integral_rows<true><<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
+                                                            d_pc, ctx->d_integral);
+  else
+    k_integral_rows<false><<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
+                                                             d_pc, ctx->d_integral);
   NICP_CHECK_LAUNCH(ctx);
   dim3 gc((cols + 63) / 64, kIntegralCh);
   k_integral_cols<<<gc, 64, 0, ctx->stream>>>(rows, cols, ctx->d_integral);
@@ -477,9 +548,14 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
   dim3 bs(32, 8);
   dim3 gs((cols + 31) / 32, (rows + 7) / 8);
   bool ks = keepStats && cloud->stats16;
-  k_stats<<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, cloud->points, cloud->normals,
-                                      cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
-                                      ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
+  if (multi)
+    k_stats<true><<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, d_pc, cloud->points, cloud->normals,
+                                              cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
+                                              ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
+  else
+    k_stats<false><<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, d_pc, cloud->points, cloud->normals,
+                                               cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
+                                               ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
   NICP_CHECK_LAUNCH(ctx);
   cloud->n_known = false;
   cloud->has_stats = ks;

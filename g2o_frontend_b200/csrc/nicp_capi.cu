@@ -159,6 +159,50 @@ static int ensure_stats(nicp_cloud *cloud) {
   return NICP_OK;
 }
 
+static CamSet camset_pinhole(const nicp_projector *proj) {
+  CamSet c;
+  memset(&c, 0, sizeof c);
+  c.n = 1;
+  c.multi = 0;
+  c.width[0] = proj->cols;
+  c.height[0] = proj->rows;
+  c.minD[0] = proj->min_distance;
+  c.maxD[0] = proj->max_distance;
+  for (int i = 0; i < 9; i++) c.K[0][i] = proj->K[i];
+  mat4_identity(c.offset[0]);
+  return c;
+}
+static int camset_multi(const nicp_multi_projector *mp, CamSet &c, int &rows, int &cols) {
+  memset(&c, 0, sizeof c);
+  if (!mp || mp->num_cameras < 1 || mp->num_cameras > kMaxCams) {
+    set_error("multi projector needs 1..%d cameras", kMaxCams);
+    return NICP_ERR_INVALID;
+  }
+  c.n = mp->num_cameras;
+  c.multi = 1;
+  rows = 0;
+  cols = 0;
+  for (int i = 0; i < c.n; i++) {
+    c.width[i] = mp->camera[i].rows;
+    c.height[i] = mp->camera[i].cols;
+    if (c.width[i] <= 0 || c.height[i] <= 0) return NICP_ERR_INVALID;
+    c.colOff[i] = cols;
+    cols += c.height[i];
+    if (c.width[i] > rows) rows = c.width[i];
+    c.minD[i] = mp->camera[i].min_distance;
+    c.maxD[i] = mp->camera[i].max_distance;
+    for (int k = 0; k < 9; k++) c.K[i][k] = mp->camera[i].K[k];
+    for (int k = 0; k < 16; k++) c.offset[i][k] = mp->sensor_offset[i][k];
+    fix_last_row(c.offset[i]);
+  }
+  return NICP_OK;
+}
+static int upload_cams(nicp_context *ctx, const CamSet &c) {
+  ctx->h_cams = c;
+  NICP_CUDA(cudaMemcpyAsync(&ctx->d_cams->set, &ctx->h_cams, sizeof(CamSet), cudaMemcpyHostToDevice, ctx->stream));
+  return NICP_OK;
+}
+
 static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset) {
   AlignConsts ac;
   memset(&ac, 0, sizeof ac);
@@ -169,6 +213,7 @@ static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_para
   } else {
     mat4_identity(ac.refOffset);
   }
+  ac.cams = nullptr;
   ac.rows = proj->rows;
   ac.cols = proj->cols;
   ac.minD = proj->min_distance;
@@ -447,6 +492,11 @@ int nicp_create(int device, nicp_context **out) {
     ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
     if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
   }
+  {
+    void *p = nullptr;
+    NICP_CUDA(cudaMalloc(&p, sizeof(DeviceCams)));
+    ctx->d_cams = reinterpret_cast<DeviceCams *>(p);
+  }
   NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming));
   NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming));
   ctx->evCorr = new std::vector<cudaEvent_t>();
@@ -467,6 +517,7 @@ void nicp_destroy(nicp_context *ctx) {
   free_align(ctx);
   dev_free(ctx->d_trace);
   if (ctx->d_priors) cudaFree(ctx->d_priors);
+  if (ctx->d_cams) cudaFree(ctx->d_cams);
   dev_free(ctx->d_results);
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -870,7 +921,7 @@ struct HostPrior {
 static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs, const nicp_cloud *const *curs,
                         const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset,
                         const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
-                        bool single, const nicp_prior *priors = nullptr, int numPriors = 0) {
+                        bool single, const nicp_prior *priors = nullptr, int numPriors = 0, const CamSet *multiCams = nullptr) {
   const size_t P = (size_t)proj->rows * proj->cols;
   int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 64);
   if (maxSlots > n) maxSlots = n;
@@ -899,11 +950,13 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   AlignConsts ac = make_consts(proj, ap, refOffset);
-  float eye[16], co[16], curKRt[16];
+  const CamSet cams = multiCams ? *multiCams : camset_pinhole(proj);
+  if ((rc = upload_cams(ctx, cams))) return rc;
+  ac.cams = &ctx->d_cams->set;
+  float eye[16], co[16];
   mat4_identity(eye);
   for (int i = 0; i < 16; i++) co[i] = curOffset ? curOffset[i] : eye[i];
-  fix_last_row(co);
-  compute_KRt(proj->K, co, curKRt);  // aligner.cpp:60: projector->setTransform(_currentSensorOffset)
+  fix_last_row(co);  // aligner.cpp:60: projector->setTransform(_currentSensorOffset)
   const int slots = ctx->slots;
   std::vector<int> owns(slots);
   int chunk = 0, prevBase = 0, prevM = 0;
@@ -936,7 +989,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         ctx->h_desc[i].numPriors = numPriors;
       }
     }
-    if ((rc = run_align_chunk(ctx, m, ac, curKRt, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+    if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
                               owns.data(), single, base)))
       return rc;
     NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
@@ -959,6 +1012,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   ctx->lastAlignCols = proj->cols;
   ctx->lastAlignIters = ap->outer_iterations;
   ctx->lastAlignValid = single;
+  ctx->lastAlignEmptyDepth = cams.multi ? 0.0f : FLT_MAX;
   return NICP_OK;
 }
 
@@ -983,6 +1037,80 @@ int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *referenc
                       frame_inlier_depth_threshold, results, false);
 }
 
+void nicp_multi_image_size(const nicp_multi_projector *mp, int *rows, int *cols) {
+  CamSet c;
+  int r = 0, cc = 0;
+  if (camset_multi(mp, c, r, cc) != NICP_OK) r = cc = 0;
+  if (rows) *rows = r;
+  if (cols) *cols = cc;
+}
+
+int nicp_multi_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_multi_projector *mp, const nicp_stats_params *sp,
+                              const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
+  if (!ctx || !depth || !mp || !sp || !cloud) return NICP_ERR_INVALID;
+  CamSet cams;
+  int rows, cols, rc;
+  if ((rc = camset_multi(mp, cams, rows, cols))) return rc;
+  size_t px = (size_t)rows * cols;
+  if ((size_t)cloud->capacity < px) {
+    set_error("cloud capacity %d smaller than the composite image (%zu pixels)", cloud->capacity, px);
+    return NICP_ERR_INVALID;
+  }
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  if ((rc = upload_cams(ctx, cams))) return rc;
+  if (keep_stats && (rc = ensure_stats(cloud))) return rc;
+  NICP_CUDA(cudaMemcpyAsync(ctx->d_depth, depth, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  nicp_projector proj = mp->camera[0];
+  proj.rows = rows;
+  proj.cols = cols;
+  float eye[16];
+  mat4_identity(eye);
+  if ((rc = launch_frame_prep(ctx, ctx->d_depth, &proj, sp, sensor_offset ? sensor_offset : eye, keep_stats, cloud,
+                              ctx->d_index, &cams)))
+    return rc;
+  if (index) NICP_CUDA(cudaMemcpyAsync(index, ctx->d_index, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+
+int nicp_multi_project(nicp_context *ctx, const nicp_cloud *cloud, const nicp_multi_projector *mp, const float T[16],
+                       int *index, float *depth) {
+  if (!ctx || !cloud || !mp || !T) return NICP_ERR_INVALID;
+  CamSet cams;
+  int rows, cols, rc;
+  if ((rc = camset_multi(mp, cams, rows, cols))) return rc;
+  size_t px = (size_t)rows * cols;
+  if ((rc = ensure_align(ctx, 1, px))) return rc;
+  if ((rc = ensure_prep(ctx, px))) return rc;
+  float Tf[16];
+  for (int i = 0; i < 16; i++) Tf[i] = T[i];
+  fix_last_row(Tf);
+  unsigned long long *z = ctx->d_curZ;
+  if ((rc = launch_project_cams(ctx, cloud, cams, Tf, rows, cols, z))) return rc;
+  if ((rc = launch_decode_z(ctx, z, (int)px, ctx->d_index, ctx->d_depth, 0.0f))) return rc;
+  if (index) NICP_CUDA(cudaMemcpyAsync(index, ctx->d_index, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth) NICP_CUDA(cudaMemcpyAsync(depth, ctx->d_depth, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->lastAlignValid = false;
+  return NICP_OK;
+}
+
+int nicp_multi_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current, const nicp_multi_projector *mp,
+                     const nicp_align_params *ap, const float reference_sensor_offset[16], const float current_sensor_offset[16],
+                     const float initial_guess[16], const nicp_prior *priors, int num_priors, float frame_inlier_depth_threshold,
+                     nicp_align_result *result) {
+  if (!ctx || !reference || !current || !mp || !ap || !result) return NICP_ERR_INVALID;
+  if (num_priors < 0 || (num_priors > 0 && !priors)) return NICP_ERR_INVALID;
+  CamSet cams;
+  int rows, cols, rc;
+  if ((rc = camset_multi(mp, cams, rows, cols))) return rc;
+  nicp_projector proj = mp->camera[0];
+  proj.rows = rows;
+  proj.cols = cols;
+  return align_common(ctx, 1, &reference, &current, &proj, ap, reference_sensor_offset, current_sensor_offset, initial_guess,
+                      frame_inlier_depth_threshold, result, true, priors, num_priors, &cams);
+}
+
 int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *reference_depth, int *current_index,
                          float *current_depth, int *correspondences, float H[36], float b[6]) {
   if (!ctx || !ctx->lastAlignValid) {
@@ -995,13 +1123,14 @@ int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *referen
   const PairDesc &D = ctx->h_desc[0];
   std::vector<int> ci, corrImg;
   if (reference_index || reference_depth) {
-    if ((rc = launch_decode_z(ctx, D.refZ[ctx->lastAlignParity], (int)P, ctx->d_index, ctx->d_depth))) return rc;
+    if ((rc = launch_decode_z(ctx, D.refZ[ctx->lastAlignParity], (int)P, ctx->d_index, ctx->d_depth, ctx->lastAlignEmptyDepth)))
+      return rc;
     if (reference_index) NICP_CUDA(cudaMemcpyAsync(reference_index, ctx->d_index, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (reference_depth) NICP_CUDA(cudaMemcpyAsync(reference_depth, ctx->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   if (current_index || current_depth) {
-    if ((rc = launch_decode_z(ctx, D.curZ, (int)P, ctx->d_index, ctx->d_depth))) return rc;
+    if ((rc = launch_decode_z(ctx, D.curZ, (int)P, ctx->d_index, ctx->d_depth, ctx->lastAlignEmptyDepth))) return rc;
     if (current_index) NICP_CUDA(cudaMemcpyAsync(current_index, ctx->d_index, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (current_depth) NICP_CUDA(cudaMemcpyAsync(current_depth, ctx->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     NICP_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -31,6 +31,7 @@ void set_error(const char *fmt, ...);
     }                                                                                            \
   } while (0)
 
+constexpr int kMaxCams = 8;       // NICP_MAX_CAMERAS
 constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
 constexpr int kIntegralCh = 10;   // n,x,y,z,xx,xy,xz,yy,yz,zz
 constexpr unsigned long long kEmptyZ = 0xFFFFFFFFFFFFFFFFull;
@@ -52,7 +53,7 @@ enum {
 struct PairState {
   float T[16];     // current estimate (reference <- current)
   float invT[16];  // working inverse used by the finder and the lineariser
-  float KRt[16];   // K * (T * referenceSensorOffset)^-1 for the next reference projection
+  float KRt[kMaxCams][16];  // per camera: K_i * (T * referenceSensorOffset * offset_i)^-1, next reference projection
   float H[36];     // last assembled H (column-major 6x6, without damping)
   float b[6];
   float error;     // from the last LOOP linearisation (Aligner::error())
@@ -89,9 +90,45 @@ struct PairDesc {
   float guess[16];
 };
 
+// camera set of the projector: one pinhole (n == 1, offset = I, the PinholePointProjector case) or the
+// children of a MultiPointProjector (multipointprojector.h:14-78).  For n > 1 the composite image is
+// laid out as the Aligner executes it (pointprojector.cpp:17-40 over multipointprojector.cpp:157-205):
+// row = pixel u, col = pixel v + colOff[i], first camera that sees the point wins, empty depth = 0.
+struct CamSet {
+  int n;
+  int multi;                    // 0: plain pinhole image (row = v, col = u)
+  int width[kMaxCams], height[kMaxCams], colOff[kMaxCams];
+  float minD[kMaxCams], maxD[kMaxCams];
+  float K[kMaxCams][9];
+  float offset[kMaxCams][16];
+};
+// per-camera matrices for one projector pose (KRt for project, iKRt for unProject)
+struct CamMats {
+  Affine M[kMaxCams];
+};
+// geometry of a camera set as the kernels need it
+struct CamGeom {
+  int n, multi;
+  int width[kMaxCams], height[kMaxCams], colOff[kMaxCams];
+  float minD[kMaxCams], maxD[kMaxCams];
+};
+// everything frame prep needs for a MultiPointProjector (device memory)
+struct PrepCams {
+  CamGeom g;
+  Affine iKRt[kMaxCams];          // child unProject matrices with the rig at identity
+  float ivx[kMaxCams], ivy[kMaxCams];  // K_i * (worldRadius, worldRadius, 0), rows 0 and 1
+};
+// layout of the ctx->d_cams allocation
+struct DeviceCams {
+  CamSet set;
+  CamMats curMats;
+  PrepCams prep;
+};
+
 struct AlignConsts {
   float K[9];
   float refOffset[16];
+  const CamSet *cams;           // device pointer (ctx->d_cams)
   int rows, cols;
   float minD, maxD;
   float squaredThreshold, normalThreshold, flatCurvature, minRatio, maxRatio;
@@ -155,6 +192,8 @@ struct nicp_context {
   unsigned char *d_descBase, *h_descBase;
   size_t descStride;
   cudaEvent_t evChunk[2];
+  nicp::DeviceCams *d_cams;     // device copy of the camera set (+ derived matrices) of the call in flight
+  nicp::CamSet h_cams;
   void *d_priors;               // device copy of the priors of the last nicp_align
   int priorCap;
   float *d_trace;               // [maxIter][61] for slot 0 (single align)
@@ -176,6 +215,7 @@ struct nicp_context {
 
   // last single-align bookkeeping
   int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;
+  float lastAlignEmptyDepth;
   bool lastAlignValid;
 };
 
@@ -184,7 +224,8 @@ namespace nicp {
 int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int cols, float scale, int step,
                          float maxCov, float *d_out);
 int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
-                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index);
+                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index,
+                      const CamSet *cams = nullptr);
 int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
                      float maxD, nicp_cloud *cloud, int *d_index);
 int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius, int *d_interval);
@@ -192,8 +233,13 @@ int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[1
 // align.cu
 int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
                           float minD, float maxD, unsigned long long *d_z);
-int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth);
-int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const float curKRt[16], int outerIters,
+int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet &cams, const float T[16], int rows,
+                        int cols, unsigned long long *d_z);
+int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth,
+                    float emptyDepth = FLT_MAX);
+void cam_mats_KRt(const CamSet &cams, const float T[16], CamMats &out);
+CamGeom geom_of(const CamSet &c);
+int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const CamSet &cams, const float curOffset[16], int outerIters,
                     int innerIters, float imgThreshold, int nUniqueCur, const int *curSlotOfPair, bool wantTrace,
                     int resultOffset);
 int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);

@@ -16,6 +16,7 @@
 #include <string>
 
 #include "pwn/pwn.h"
+#include "pwn/pyramid.h"
 
 using namespace pwn;
 
@@ -119,6 +120,32 @@ int main(int argc, char **argv) {
 
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");
+    if (get(cfg, "pyramid", 0) != 0) {
+      // BASELINE config 2: 3-level coarse-to-fine alignment of frame 1 against frame 0
+      RawDepthImage r0, r1;
+      if (!readPgm16(argv[3], r0) || !readPgm16(argv[4], r1)) throw std::runtime_error("cannot read the two frames");
+      PyramidAligner pyr(&converter, &aligner);
+      const int steps[3] = {4, 2, 1};
+      for (int i = 0; i < 3; i++) {
+        PyramidLevel L;
+        L.step = steps[i];
+        // pwn_aligner_1_4.conf radii at scale 4, pwn_aligner_1_1.conf at full resolution, in between at scale 2
+        L.minImageRadius = steps[i] == 4 ? 3 : (steps[i] == 2 ? 5 : 10);
+        L.maxImageRadius = steps[i] == 4 ? 6 : (steps[i] == 2 ? 15 : 30);
+        L.minPoints = steps[i] == 4 ? 10 : (steps[i] == 2 ? 25 : 50);
+        L.inlierDistanceThreshold = steps[i] == 1 ? 1.0f : 0.5f;
+        L.outerIterations = (int)get(cfg, "outerIterations", 10);
+        pyr.addLevel(L);
+      }
+      pyr.align(r0, r1, K, sensorOffset, Isometry3f::Identity(), depthScale);
+      for (size_t li = 0; li < pyr.levelTransforms().size(); li++) {
+        fprintf(out, "{\"level\": %zu, \"step\": %d, \"inliers\": %d, \"T\": [", li, steps[li], pyr.levelInliers()[li]);
+        for (int i = 0; i < 16; i++) fprintf(out, "%s%.9g", i ? ", " : "", pyr.levelTransforms()[li].data()[i]);
+        fprintf(out, "]}\n");
+      }
+      fclose(out);
+      return 0;
+    }
     Cloud *previous = 0;
     Isometry3f globalT;
     for (int a = 3; a < argc; a++) {

@@ -125,3 +125,34 @@ def trajectory(n, seed=0, step_t=0.01, step_deg=0.5):
         nxt[:3, 3] = np.clip(nxt[:3, 3], [-0.8, -0.4, -0.3], [0.8, 0.3, 0.5])
         poses.append(nxt)
     return poses
+
+
+def make_rig(n_cameras=4, width=1280, height=960, K=None, zmin=0.5, zmax=4.5):
+    """BASELINE config 5 rig: pinholes yawed 0/90/180/270 deg about the vertical axis, small lever arms
+    (in the spirit of pwn_test/multiprojectortest.cpp:60-67).  width/height are the arguments the
+    reference passes to MultiPointProjector::addPointProjector."""
+    if K is None:
+        K = scaled_K(K_KINECT, width / 640.0)
+    cams = []
+    for i in range(n_cameras):
+        yaw = 360.0 * i / n_cameras
+        off = make_pose((0.0, 0.0, 0.0), (0, 1, 0), yaw) @ make_pose((0.0, 0.0, 0.05))
+        cams.append(dict(K=np.asarray(K, np.float32), width=width, height=height, minD=zmin, maxD=zmax,
+                         offset=off.astype(np.float32)))
+    return cams
+
+
+def render_rig_depth_u16(rig_pose, cams, seed=None):
+    """Composite raw depth image of a MultiPointProjector rig in the layout the Aligner projects into:
+    rows = max width (pixel u), cols = sum of heights (pixel v + column offset): block i is the transpose
+    of camera i's (height x width) image."""
+    rows = max(c["width"] for c in cams)
+    cols = sum(c["height"] for c in cams)
+    out = np.zeros((rows, cols), np.uint16)
+    off = 0
+    for i, c in enumerate(cams):
+        img = render_depth_u16(rig_pose @ c["offset"].astype(np.float64), c["height"], c["width"], c["K"],
+                               seed=None if seed is None else seed + 17 * i, zmin=c["minD"], zmax=c["maxD"])
+        out[:c["width"], off:off + c["height"]] = img.T
+        off += c["height"]
+    return out

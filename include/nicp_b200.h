@@ -46,6 +46,22 @@ typedef struct {
   float max_distance;  /* default 6.0 */
 } nicp_projector;
 
+/* MultiPointProjector (multipointprojector.h:14-78): up to NICP_MAX_CAMERAS child pinholes, each added with
+ * addPointProjector(projector, sensorOffset, width, height).  camera[i].rows / .cols hold that call's width /
+ * height (the child's setImageSize(width, height), multipointprojector.h:61-78).  The composite image is the
+ * one the Aligner really produces for this projector -- the base-class z-buffer PointProjector::project
+ * (pointprojector.cpp:17-40) over the per-point MultiPointProjector::project (multipointprojector.cpp:157-205):
+ * rows = max width (pixel u), cols = sum of heights (pixel v + column offset of the camera), the first camera
+ * that sees a point wins, empty depth pixels are 0 (not FLT_MAX).  unProject is defined as the inverse of
+ * that layout, points ordered by camera then raster order inside the camera's column block (the reference's
+ * own cv::Rect slicing, multipointprojector.cpp:71-72, is inconsistent with it). */
+#define NICP_MAX_CAMERAS 8
+typedef struct {
+  int num_cameras;
+  nicp_projector camera[NICP_MAX_CAMERAS];
+  float sensor_offset[NICP_MAX_CAMERAS][16];  /* ChildProjectorInfo::sensorOffset */
+} nicp_multi_projector;
+
 /* StatsCalculatorIntegralImage (statscalculatorintegralimage.cpp:6-12) +
  * Point/NormalInformationMatrixCalculator (informationmatrixcalculator.h:100-150) */
 typedef struct {
@@ -222,6 +238,23 @@ int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *referenc
                      const nicp_align_params *ap, const float reference_sensor_offset[16],
                      const float current_sensor_offset[16], const float *initial_guesses,
                      float frame_inlier_depth_threshold, nicp_align_result *results);
+
+/* ---- MultiPointProjector (BASELINE config 5) -------------------------------------------------------- */
+/* MultiPointProjector::computeImageSize (multipointprojector.cpp:7-18) */
+void nicp_multi_image_size(const nicp_multi_projector *mp, int *rows, int *cols);
+/* DepthImageConverterIntegralImage::compute with a MultiPointProjector: depth is the composite image */
+int nicp_multi_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_multi_projector *mp,
+                              const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
+                              nicp_cloud *cloud, int *index);
+/* PointProjector::project (base z-buffer) of a MultiPointProjector whose rig pose is T */
+int nicp_multi_project(nicp_context *ctx, const nicp_cloud *cloud, const nicp_multi_projector *mp, const float T[16],
+                       int *index, float *depth);
+/* Aligner::align() with a MultiPointProjector */
+int nicp_multi_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud *current,
+                     const nicp_multi_projector *mp, const nicp_align_params *ap,
+                     const float reference_sensor_offset[16], const float current_sensor_offset[16],
+                     const float initial_guess[16], const nicp_prior *priors, int num_priors,
+                     float frame_inlier_depth_threshold, nicp_align_result *result);
 
 #ifdef __cplusplus
 }

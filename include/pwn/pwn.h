@@ -319,6 +319,86 @@ class PinholePointProjector : public PointProjector {
   Matrix4f _KRt, _iKRt;
 };
 
+// ---- multipointprojector.h ----------------------------------------------------------------------------
+// Composite image layout and unProject order: see nicp_multi_projector in nicp_b200.h.
+class MultiPointProjector : public PointProjector {
+ public:
+  MultiPointProjector() : PointProjector() {}
+  virtual ~MultiPointProjector() {}
+  // multipointprojector.h:23-27: the child is remembered with transform() * sensorOffset_
+  void addPointProjector(PinholePointProjector *pointProjector_, Isometry3f sensorOffset_, int width_, int height_) {
+    ChildProjectorInfo c;
+    c.pointProjector = pointProjector_;
+    c.sensorOffset = transform() * sensorOffset_;
+    c.width = width_;
+    c.height = height_;
+    pointProjector_->setImageSize(width_, height_);
+    _pointProjectors.push_back(c);
+  }
+  void clearProjectors() { _pointProjectors.clear(); }
+  size_t numProjectors() const { return _pointProjectors.size(); }
+  // multipointprojector.cpp:7-18
+  void computeImageSize(int &rows, int &cols) const {
+    nicp_multi_projector mp = abiMultiProjector();
+    nicp_multi_image_size(&mp, &rows, &cols);
+  }
+  // multipointprojector.cpp:207-215
+  virtual void setTransform(const Isometry3f &transform_) {
+    PointProjector::setTransform(transform_);
+    for (size_t i = 0; i < _pointProjectors.size(); i++)
+      _pointProjectors[i].pointProjector->setTransform(transform_ * _pointProjectors[i].sensorOffset);
+  }
+  // what Aligner executes for this projector: pointprojector.cpp:17-40 over multipointprojector.cpp:157-205
+  virtual void project(IntImage &indexImage, DepthImage &depthImage, const Cloud &cloud) const {
+    nicp_multi_projector mp = abiMultiProjector();
+    int rows, cols;
+    nicp_multi_image_size(&mp, &rows, &cols);
+    indexImage.create(rows, cols);
+    depthImage.create(rows, cols);
+    nicpCheck(nicp_multi_project(Context::current().handle(), cloud.device(), &mp, _transform.data(), indexImage.data(),
+                                 depthImage.data()),
+              "MultiPointProjector::project");
+  }
+  virtual void unProject(Cloud &, IntImage &, const DepthImage &) const {
+    throw std::runtime_error("MultiPointProjector::unProject: use DepthImageConverterIntegralImage::compute");
+  }
+  virtual void projectIntervals(IntImage &, const DepthImage &, const float) const {
+    throw std::runtime_error("MultiPointProjector::projectIntervals: use DepthImageConverterIntegralImage::compute");
+  }
+  // multipointprojector.cpp:226-234
+  virtual void scale(float scalingFactor) {
+    for (size_t i = 0; i < _pointProjectors.size(); i++) {
+      _pointProjectors[i].pointProjector->scale(scalingFactor);
+      _pointProjectors[i].width = _pointProjectors[i].pointProjector->imageRows();
+      _pointProjectors[i].height = _pointProjectors[i].pointProjector->imageCols();
+    }
+    int r, c;
+    computeImageSize(r, c);
+    setImageSize(r, c);
+  }
+  nicp_multi_projector abiMultiProjector() const {
+    nicp_multi_projector mp;
+    std::memset(&mp, 0, sizeof mp);
+    mp.num_cameras = (int)_pointProjectors.size();
+    for (int i = 0; i < mp.num_cameras && i < NICP_MAX_CAMERAS; i++) {
+      const ChildProjectorInfo &c = _pointProjectors[i];
+      mp.camera[i] = c.pointProjector->abiProjector();
+      mp.camera[i].rows = c.width;
+      mp.camera[i].cols = c.height;
+      for (int k = 0; k < 16; k++) mp.sensor_offset[i][k] = c.sensorOffset.data()[k];
+    }
+    return mp;
+  }
+
+ protected:
+  struct ChildProjectorInfo {
+    PinholePointProjector *pointProjector;
+    Isometry3f sensorOffset;
+    int width, height;
+  };
+  std::vector<ChildProjectorInfo> _pointProjectors;
+};
+
 // ---- statscalculator.h / statscalculatorintegralimage.h ---------------------------------------------
 class StatsCalculator {
  public:
@@ -443,9 +523,20 @@ class DepthImageConverterIntegralImage : public DepthImageConverter {
 
   // depthimageconverterintegralimage.cpp:15-55
   virtual void compute(Cloud &cloud, const DepthImage &depthImage, const Isometry3f &sensorOffset = Isometry3f::Identity()) {
-    PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_projector);
-    if (!pp) throw std::runtime_error("DepthImageConverterIntegralImage: projector is not a PinholePointProjector");
     nicp_stats_params sp = abiStatsParams();
+    if (MultiPointProjector *mpp = dynamic_cast<MultiPointProjector *>(_projector)) {
+      mpp->setTransform(Isometry3f::Identity());
+      nicp_multi_projector mp = mpp->abiMultiProjector();
+      _indexImage.create(depthImage.rows, depthImage.cols);
+      nicp_cloud *d = cloud.deviceForWrite(depthImage.rows * depthImage.cols);
+      nicpCheck(nicp_multi_depth_to_cloud(Context::current().handle(), depthImage.data(), &mp, &sp, sensorOffset.data(),
+                                          _keepStats ? 1 : 0, d, _indexImage.data()),
+                "DepthImageConverterIntegralImage::compute (MultiPointProjector)");
+      cloud.setHasStats(_keepStats);
+      return;
+    }
+    PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_projector);
+    if (!pp) throw std::runtime_error("DepthImageConverterIntegralImage: unsupported projector type");
     pp->setImageSize(depthImage.rows, depthImage.cols);
     pp->setTransform(Isometry3f::Identity());
     _indexImage.create(depthImage.rows, depthImage.cols);
@@ -660,16 +751,27 @@ class Aligner {
     if (!_projector || !_linearizer || !_correspondenceFinder || !_referenceCloud || !_currentCloud)
       throw std::runtime_error("Aligner: missing projector / linearizer / correspondenceFinder / clouds");
     PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_projector);
-    if (!pp) throw std::runtime_error("Aligner: projector is not a PinholePointProjector");
+    MultiPointProjector *mpp = dynamic_cast<MultiPointProjector *>(_projector);
+    if (!pp && !mpp) throw std::runtime_error("Aligner: unsupported projector type");
     struct timeval tvStart, tvEnd;
     gettimeofday(&tvStart, 0);
     nicp_context *ctx = Context::current().handle();
-    nicp_projector p = pp->abiProjector();
+    nicp_projector p;
     nicp_align_params ap = abiAlignParams();
-    nicpCheck(nicp_align(ctx, _referenceCloud->device(), _currentCloud->device(), &p, &ap, _referenceSensorOffset.data(),
-                         _currentSensorOffset.data(), _initialGuess.data(), _priors.empty() ? 0 : &_priors[0], (int)_priors.size(),
-                         _frameInlierDepthThreshold, &_last),
-              "Aligner::align");
+    if (mpp) {
+      nicp_multi_projector mp = mpp->abiMultiProjector();
+      nicp_multi_image_size(&mp, &p.rows, &p.cols);
+      nicpCheck(nicp_multi_align(ctx, _referenceCloud->device(), _currentCloud->device(), &mp, &ap, _referenceSensorOffset.data(),
+                                 _currentSensorOffset.data(), _initialGuess.data(), _priors.empty() ? 0 : &_priors[0],
+                                 (int)_priors.size(), _frameInlierDepthThreshold, &_last),
+                "Aligner::align (MultiPointProjector)");
+    } else {
+      p = pp->abiProjector();
+      nicpCheck(nicp_align(ctx, _referenceCloud->device(), _currentCloud->device(), &p, &ap, _referenceSensorOffset.data(),
+                           _currentSensorOffset.data(), _initialGuess.data(), _priors.empty() ? 0 : &_priors[0],
+                           (int)_priors.size(), _frameInlierDepthThreshold, &_last),
+                "Aligner::align");
+    }
     for (int i = 0; i < 16; i++) _T.data()[i] = _last.T[i];
     for (int i = 0; i < 36; i++) _omega.m[i] = _last.omega[i];
     _error = _last.error;
@@ -699,7 +801,7 @@ class Aligner {
     Isometry3f invT = _T.inverse();
     _linearizer->setT(invT);
     _linearizer->setResult(H, b, _last.error, _last.inliers);
-    pp->setTransform(_T * _referenceSensorOffset);
+    _projector->setTransform(_T * _referenceSensorOffset);
   }
 
  protected:

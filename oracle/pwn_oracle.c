@@ -582,6 +582,109 @@ int orc_depth_to_cloud(const float *depth, int rows, int cols, const float K[9],
 }
 
 /* ------------------------------------------------------------------------------------------
+ * MultiPointProjector (see pwn_oracle.h for the layout that is restated)
+ * ---------------------------------------------------------------------------------------- */
+void orc_multi_image_size(const orc_multi *m, int *rows, int *cols) { /* computeImageSize, multipointprojector.cpp:7-18 */
+  int r = 0, c = 0;
+  for (int i = 0; i < m->n; i++) {
+    if (m->width[i] > r) r = m->width[i];
+    c += m->height[i];
+  }
+  *rows = r;
+  *cols = c;
+}
+/* child projector matrices for a rig pose T: setTransform(T * sensorOffset_i), multipointprojector.cpp:207-215 */
+static void multi_child_matrices(const orc_multi *m, const float T[16], int i, float KRt[16], float iKRt[16]) {
+  float Tc[16];
+  orc_iso_mul(T, m->offset[i], Tc);
+  /* PointProjector::setTransform rewrites the last row (pointprojector.h:17-20) */
+  fix_last_row(Tc);
+  orc_update_matrices(m->K[i], Tc, KRt, iKRt);
+}
+int orc_multi_unproject(const orc_multi *m, const float T[16], const float *depth, int rows, int cols,
+                        float *points, int *index) {
+  int count = 0, colOff = 0;
+  for (int i = 0; i < rows * cols; i++) index[i] = -1;
+  for (int i = 0; i < m->n; i++) {
+    float KRt[16], iKRt[16];
+    multi_child_matrices(m, T, i, KRt, iKRt);
+    for (int r = 0; r < rows && r < m->width[i]; r++)
+      for (int v = 0; v < m->height[i] && colOff + v < cols; v++) {
+        float d = depth[r * cols + colOff + v];
+        if (d < m->minD[i] || d > m->maxD[i]) continue;
+        float *p = points + 4 * count;
+        xform3(iKRt, r * d, v * d, d, 1.0f, p); /* _unProject(p, x = u = row, y = v) */
+        p[3] = 1.0f;
+        index[r * cols + colOff + v] = count++;
+      }
+    colOff += m->height[i];
+  }
+  return count;
+}
+void orc_multi_intervals(const orc_multi *m, const float *depth, int rows, int cols, float worldRadius, int *interval) {
+  int colOff = 0;
+  for (int i = 0; i < rows * cols; i++) interval[i] = -1;
+  for (int i = 0; i < m->n; i++) {
+    const float *K = m->K[i];
+    float p0 = dot3(M3(K, 0, 0), M3(K, 0, 1), M3(K, 0, 2), worldRadius, worldRadius, 0.0f);
+    float p1 = dot3(M3(K, 1, 0), M3(K, 1, 1), M3(K, 1, 2), worldRadius, worldRadius, 0.0f);
+    for (int r = 0; r < rows && r < m->width[i]; r++)
+      for (int v = 0; v < m->height[i] && colOff + v < cols; v++) {
+        float d = depth[r * cols + colOff + v];
+        if (d < m->minD[i] || d > m->maxD[i]) continue;
+        float s = 1.0f / d;
+        float a = p0 * s, b = p1 * s;
+        interval[r * cols + colOff + v] = (a > b) ? (int)a : (int)b;
+      }
+    colOff += m->height[i];
+  }
+}
+void orc_multi_project(const orc_multi *m, const float T[16], const float *points, int n, int rows, int cols,
+                       int *index, float *depth) {
+  float KRt[ORC_MAX_CAMERAS][16], iKRt[16];
+  for (int i = 0; i < m->n; i++) multi_child_matrices(m, T, i, KRt[i], iKRt);
+  for (int i = 0; i < rows * cols; i++) { depth[i] = 0.0f; index[i] = -1; }
+  for (int pi = 0; pi < n; pi++) {
+    const float *p = points + 4 * pi;
+    int X = -1, Y = -1, colOff = 0;
+    float F = 0.0f;
+    for (int i = 0; i < m->n; i++) {
+      float ip[3];
+      xform3(KRt[i], p[0], p[1], p[2], p[3], ip);
+      float d = ip[2];
+      if (!(d < m->minD[i] || d > m->maxD[i])) {
+        float s = 1.0f / d;
+        float fx = roundf(ip[0] * s), fy = roundf(ip[1] * s);
+        if (!(d < 0.0f) && fx >= 0.0f && fx < (float)m->width[i] && fy >= 0.0f && fy < (float)m->height[i]) {
+          X = (int)fx;
+          Y = (int)fy + colOff;
+          F = d;
+          break;
+        }
+      }
+      colOff += m->height[i];
+    }
+    if (X < 0 || X >= rows || Y < 0 || Y >= cols) continue;
+    float *od = &depth[X * cols + Y];
+    if (!*od || *od > F) { *od = F; index[X * cols + Y] = pi; }
+  }
+}
+int orc_multi_depth_to_cloud(const orc_multi *m, const float *depth, int rows, int cols, const orc_stats_params *p,
+                             const float sensorOffset[16], float *points, float *normals, float *statsM, float *eigvals,
+                             int *statsN, float *curvature, float *omegaP, float *omegaN, int *index, int *interval,
+                             float *integral) {
+  float I4[16];
+  mat4_identity(I4);
+  int n = orc_multi_unproject(m, I4, depth, rows, cols, points, index);
+  orc_multi_intervals(m, depth, rows, cols, p->worldRadius, interval);
+  orc_integral_image(index, points, rows, cols, integral);
+  orc_stats(integral, index, interval, points, rows, cols, n, p, normals, statsM, eigvals, statsN, curvature);
+  orc_information(normals, statsM, eigvals, curvature, n, p, omegaP, omegaN);
+  orc_cloud_transform(sensorOffset, n, points, normals, statsM, omegaP, omegaN);
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------
  * CorrespondenceFinder::compute, correspondencefinder.cpp:20-118
  * ---------------------------------------------------------------------------------------- */
 int orc_correspond(const int *refIndex, const int *curIndex, int rows, int cols,
@@ -1135,14 +1238,23 @@ void orc_align(int nRef, const float *refPoints, const float *refNormals, const 
   int inl = 0, numCorr = 0;
   memset(H, 0, sizeof H);
   memset(b, 0, sizeof b);
-  orc_update_matrices(p->K, p->curSensorOffset, KRt, iKRt);
-  orc_project(curPoints, nCur, p->rows, p->cols, KRt, p->minD, p->maxD, curIndex, curDepth);
+  if (p->multi) {
+    orc_multi_project(p->multi, p->curSensorOffset, curPoints, nCur, p->rows, p->cols, curIndex, curDepth);
+  } else {
+    orc_update_matrices(p->K, p->curSensorOffset, KRt, iKRt);
+    orc_project(curPoints, nCur, p->rows, p->cols, KRt, p->minD, p->maxD, curIndex, curDepth);
+  }
   memcpy(T, p->initialGuess, sizeof T);
   for (int i = 0; i < p->outerIterations; i++) {
     fix_last_row(T);
     orc_iso_mul(T, p->refSensorOffset, tmp);
-    orc_update_matrices(p->K, tmp, KRt, iKRt);
-    orc_project(refPoints, nRef, p->rows, p->cols, KRt, p->minD, p->maxD, refIndex, refDepth);
+    if (p->multi) {
+      fix_last_row(tmp);
+      orc_multi_project(p->multi, tmp, refPoints, nRef, p->rows, p->cols, refIndex, refDepth);
+    } else {
+      orc_update_matrices(p->K, tmp, KRt, iKRt);
+      orc_project(refPoints, nRef, p->rows, p->cols, KRt, p->minD, p->maxD, refIndex, refDepth);
+    }
     orc_iso_inverse(T, invT);
     numCorr = orc_correspond(refIndex, curIndex, p->rows, p->cols, refPoints, refNormals, refCurv,
                              curPoints, curNormals, curCurv, invT, &p->corr, p->numThreads, corr, NULL);

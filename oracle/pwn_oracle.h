@@ -72,6 +72,35 @@ int orc_depth_to_cloud(const float *depth, int rows, int cols, const float K[9],
                        float *curvature, float *omegaP, float *omegaN, int *index, int *interval,
                        float *integral);
 
+/* ---- MultiPointProjector (multipointprojector.{h,cpp}) ------------------------------------------
+ * Composite image layout as the Aligner actually executes it: the
+ * base-class z-buffer PointProjector::project (pointprojector.cpp:17-40) over the per-point
+ * MultiPointProjector::project (multipointprojector.cpp:157-205): composite rows = max child
+ * "width" (the pixel u coordinate), composite cols = sum of child "heights" (v + column offset);
+ * first child whose pinhole projection lands inside [0,width) x [0,height) wins; empty depth = 0.
+ * unProject is DEFINED as the inverse of that layout (the reference's own cv::Rect slicing is
+ * inconsistent with it after the Eigen->cv::Mat port): points ordered by child, raster order inside
+ * the child's column block. */
+#define ORC_MAX_CAMERAS 8
+typedef struct {
+  int n;
+  int width[ORC_MAX_CAMERAS], height[ORC_MAX_CAMERAS];  /* ChildProjectorInfo: setImageSize(width, height) */
+  float minD[ORC_MAX_CAMERAS], maxD[ORC_MAX_CAMERAS];
+  float K[ORC_MAX_CAMERAS][9];
+  float offset[ORC_MAX_CAMERAS][16];                    /* ChildProjectorInfo::sensorOffset */
+} orc_multi;
+
+void orc_multi_image_size(const orc_multi *m, int *rows, int *cols);
+int orc_multi_unproject(const orc_multi *m, const float T[16], const float *depth, int rows, int cols,
+                        float *points, int *index);
+void orc_multi_intervals(const orc_multi *m, const float *depth, int rows, int cols, float worldRadius, int *interval);
+void orc_multi_project(const orc_multi *m, const float T[16], const float *points, int n, int rows, int cols,
+                       int *index, float *depth);
+int orc_multi_depth_to_cloud(const orc_multi *m, const float *depth, int rows, int cols, const orc_stats_params *p,
+                             const float sensorOffset[16], float *points, float *normals, float *statsM, float *eigvals,
+                             int *statsN, float *curvature, float *omegaP, float *omegaN, int *index, int *interval,
+                             float *integral);
+
 /* ---- CorrespondenceFinder ---- */
 typedef struct {
   float inlierDistanceThreshold;
@@ -125,6 +154,7 @@ typedef struct {
   int numThreads;
   int numPriors;
   const orc_prior *priors;
+  const orc_multi *multi;   /* NULL: PinholePointProjector(K); else MultiPointProjector (K, minD, maxD unused) */
 } orc_align_params;
 
 typedef struct {

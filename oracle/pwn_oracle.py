@@ -44,13 +44,66 @@ class Prior(C.Structure):
                 ("info", C.c_float * 36)]
 
 
+MAX_CAMERAS = 8
+
+
+class Multi(C.Structure):
+    _fields_ = [("n", C.c_int), ("width", C.c_int * MAX_CAMERAS), ("height", C.c_int * MAX_CAMERAS),
+                ("minD", C.c_float * MAX_CAMERAS), ("maxD", C.c_float * MAX_CAMERAS),
+                ("K", (C.c_float * 9) * MAX_CAMERAS), ("offset", (C.c_float * 16) * MAX_CAMERAS)]
+
+
+def make_multi(cameras):
+    """cameras: list of dicts {K, width, height, minD, maxD, offset}"""
+    m = Multi()
+    m.n = len(cameras)
+    for i, c in enumerate(cameras):
+        m.width[i], m.height[i] = int(c["width"]), int(c["height"])
+        m.minD[i], m.maxD[i] = c["minD"], c["maxD"]
+        m.K[i][:] = colmajor(c["K"]).tolist()
+        m.offset[i][:] = colmajor(c["offset"]).tolist()
+    return m
+
+
+def multi_image_size(m):
+    r, c = C.c_int(0), C.c_int(0)
+    lib().orc_multi_image_size(C.byref(m), C.byref(r), C.byref(c))
+    return r.value, c.value
+
+
+def multi_project(m, T, points, rows, cols):
+    pts, pp = _f(points)
+    Tc, tp = _f(colmajor(T))
+    idx = np.zeros((rows, cols), np.int32)
+    dep = np.zeros((rows, cols), np.float32)
+    lib().orc_multi_project(C.byref(m), tp, pp, pts.shape[0], rows, cols, _ip(idx), _fp(dep))
+    return idx, dep
+
+
+def multi_depth_to_cloud(m, depth, sp, sensor_offset=None, want_aux=False):
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    so, sop = _f(colmajor(np.eye(4) if sensor_offset is None else sensor_offset))
+    cl = Cloud(rows * cols)
+    idx = np.zeros((rows, cols), np.int32)
+    itv = np.zeros((rows, cols), np.int32)
+    integ = np.zeros((rows, cols, 10), np.float32)
+    n = lib().orc_multi_depth_to_cloud(C.byref(m), dp, rows, cols, C.byref(sp), sop, _fp(cl.points), _fp(cl.normals),
+                                       _fp(cl.statsM), _fp(cl.eigvals), _ip(cl.statsN), _fp(cl.curvature),
+                                       _fp(cl.omegaP), _fp(cl.omegaN), _ip(idx), _ip(itv), _fp(integ))
+    cl = cl.truncated(n)
+    if want_aux:
+        return cl, idx, itv, integ
+    return cl, idx
+
+
 class AlignParams(C.Structure):
     _fields_ = [("outerIterations", C.c_int), ("innerIterations", C.c_int), ("K", C.c_float * 9),
                 ("rows", C.c_int), ("cols", C.c_int), ("minD", C.c_float), ("maxD", C.c_float),
                 ("refSensorOffset", C.c_float * 16), ("curSensorOffset", C.c_float * 16),
                 ("initialGuess", C.c_float * 16), ("corr", CorrParams), ("inlierMaxChi2", C.c_float),
                 ("robustKernel", C.c_int), ("numThreads", C.c_int), ("numPriors", C.c_int),
-                ("priors", C.POINTER(Prior))]
+                ("priors", C.POINTER(Prior)), ("multi", C.POINTER(Multi))]
 
 
 class AlignResult(C.Structure):
@@ -339,7 +392,7 @@ def make_prior(kind, mean, info, reference=None):
 
 
 def make_align_params(K, rows, cols, minD, maxD, cp, outer=10, inner=1, guess=None, ref_offset=None,
-                      cur_offset=None, max_chi2=9e3, robust=True, num_threads=8, priors=()):
+                      cur_offset=None, max_chi2=9e3, robust=True, num_threads=8, priors=(), multi=None):
     p = AlignParams()
     p.outerIterations = outer
     p.innerIterations = inner
@@ -359,6 +412,9 @@ def make_align_params(K, rows, cols, minD, maxD, cp, outer=10, inner=1, guess=No
         arr = (Prior * len(priors))(*priors)
         p._keep = arr
         p.priors = C.cast(arr, C.POINTER(Prior))
+    if multi is not None:
+        p._keep_multi = multi
+        p.multi = C.pointer(multi)
     return p
 
 
@@ -417,11 +473,13 @@ def image_stats(cur_depth, ref_depth, thr=50.0):
 def _declare():
     for fast in (False, True):
         l = lib(fast)
-        for name in ("orc_unproject", "orc_depth_to_cloud", "orc_correspond"):
+        for name in ("orc_unproject", "orc_depth_to_cloud", "orc_correspond", "orc_multi_unproject",
+                     "orc_multi_depth_to_cloud"):
             getattr(l, name).restype = C.c_int
         for name in ("orc_depth_u16_to_f32", "orc_depth_scale", "orc_v2t", "orc_t2v", "orc_update_matrices",
                      "orc_project_intervals", "orc_project", "orc_integral_image", "orc_eigen3", "orc_linearize",
-                     "orc_linearize_f64", "orc_ldlt_solve6", "orc_align", "orc_image_stats"):
+                     "orc_linearize_f64", "orc_ldlt_solve6", "orc_align", "orc_image_stats", "orc_multi_image_size",
+                     "orc_multi_intervals", "orc_multi_project", "orc_set_accumulate_f64"):
             getattr(l, name).restype = None
 
 

@@ -295,6 +295,68 @@ def test_priors(ctx):
         assert np.abs(T - base).max() > 1e-3
 
 
+@pytest.mark.parametrize("width,height,ncam", [(160, 120, 4), (64, 48, 3)])
+def test_multi_point_projector(ctx, width, height, ncam):
+    """MultiPointProjector (BASELINE config 5 layout, scaled down): composite frame prep, base-class z-buffer
+    projection and the full align() against the oracle"""
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    cams = synth.make_rig(ncam, width, height, K=synth.scaled_K(synth.K_KINECT, width / 640.0))
+    if ncam == 3:  # ragged rig: cameras of different sizes and ranges
+        cams[1]["width"], cams[1]["height"] = 48, 40
+        cams[2]["maxD"] = 3.0
+    om, gm = O.make_multi(cams), capi.make_multi_projector(cams)
+    rows, cols = O.multi_image_size(om)
+    assert (rows, cols) == capi.multi_image_size(gm, ctx.verify)
+    poseA = synth.make_pose((0.1, -0.05, 0.2), (0, 1, 0), 10.0)
+    poseB = poseA @ synth.make_pose((0.03, -0.01, 0.04), (0.2, 1.0, 0.1), 2.0)
+    dA = synth.u16_to_m(synth.render_rig_depth_u16(poseA, cams))
+    dB = synth.u16_to_m(synth.render_rig_depth_u16(poseB, cams))
+    assert dA.shape == (rows, cols)
+    osp = O.default_stats_params(minImageRadius=3, maxImageRadius=6, minPoints=10, curvatureThreshold=0.2)
+    gsp = capi.make_stats_params(0.1, 3, 6, 10, 0.2, 0.02)
+    so = synth.make_pose((0.05, 0.0, 0.1), (1.0, 0.2, 0.0), 3.0).astype(np.float32)
+    oA, oiA, oitv, ointeg = O.multi_depth_to_cloud(om, dA, osp, so, want_aux=True)
+    oB, oiB = O.multi_depth_to_cloud(om, dB, osp, so)
+    gA, giA = ctx.multi_depth_to_cloud(dA, gm, gsp, so)
+    gB, giB = ctx.multi_depth_to_cloud(dB, gm, gsp, so)
+    assert gA.size() == oA.n and oA.n > 0.5 * rows * cols
+    assert np.array_equal(giA, oiA) and np.array_equal(giB, oiB)
+    assert np.array_equal(ctx.last_integral_image(rows, cols).view(np.uint32),
+                          O.multi_depth_to_cloud(om, dB, osp, so, want_aux=True)[3].view(np.uint32))
+    dl = gA.download()
+    assert np.array_equal(dl["points"].view(np.uint32), oA.points.view(np.uint32))
+    has = (np.abs(oA.normals[:, :3]).sum(1) > 0) & (np.abs(dl["normals"][:, :3]).sum(1) > 0)
+    assert has.mean() > 0.5
+    dots = (dl["normals"][has, :3].astype(np.float64) * oA.normals[has, :3]).sum(1)
+    assert np.quantile(dots, 0.01) > 1 - 1e-4
+    # projection of the ORACLE's cloud for two rig poses: bit-exact index + depth (empty depth = 0)
+    refc = upload(ctx, oA)
+    for T in (so, (synth.make_pose((0.02, 0.01, -0.03), (0, 1, 0), 4.0) @ so).astype(np.float32)):
+        io, do = O.multi_project(om, T, oA.points, rows, cols)
+        ig, dg = ctx.multi_project(refc, gm, T)
+        assert np.array_equal(ig, io) and np.array_equal(dg.view(np.uint32), do.view(np.uint32))
+        assert (io >= 0).mean() > 0.3
+    # full alignment on the oracle's clouds
+    curc = upload(ctx, oB)
+    cp = O.default_corr_params(inlierDistanceThreshold=0.5, inlierNormalAngularThreshold=0.95)
+    oap = O.make_align_params(cams[0]["K"], rows, cols, 0.5, 4.5, cp, num_threads=1, ref_offset=so, cur_offset=so, multi=om)
+    out = O.align(oA, oB, oap)
+    gap = capi.make_align_params(0.5, 0.95, 0.02, 1.3, 9e3, True, 10, 1)
+    res = ctx.multi_align(refc, curc, gm, gap, so, so)
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], out.T[:3, :3]) <= T_ROT_TOL
+    assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
+    assert abs(res.inliers - out.inliers) <= 2e-3 * out.inliers + 8
+    st = ctx.align_state(rows, cols)
+    assert np.array_equal(st["cur_index"], out.curIndex)
+    assert np.array_equal(st["cur_depth"].view(np.uint32), out.curDepth.view(np.uint32))
+    assert (st["ref_index"] == out.refIndex).mean() > 0.99
+    # the rig moved by poseA^-1 poseB, expressed in the robot frame
+    gt = so.astype(np.float64) @ np.linalg.inv(poseA) @ poseB @ np.linalg.inv(so.astype(np.float64))
+    assert rot_angle(T[:3, :3], gt[:3, :3]) < 1e-2 and np.abs(T[:3, 3] - gt[:3, 3]).max() < 2e-2
+
+
 def test_determinism_and_batch_identity(ctx):
     """two runs are bit-identical; a pair gives the same bits alone or inside a batch"""
     s = get_scene(4, 0, 0.05)
