@@ -17,6 +17,7 @@
 
 #include "pwn/pwn.h"
 #include "pwn/pyramid.h"
+#include "pwn/tracker.h"
 
 using namespace pwn;
 
@@ -120,6 +121,23 @@ int main(int argc, char **argv) {
 
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");
+    if (get(cfg, "tracker", 0) != 0) {
+      // BASELINE config 3: PwnTracker::processFrame over the whole sequence (keyframe logic included)
+      SequentialTracker tracker(&converter, &aligner);
+      tracker.setScale(imageScale);
+      tracker.setNewFrameInliersFraction(get(cfg, "newFrameInliersFraction", 0.4f));
+      for (int a = 3; a < argc; a++) {
+        RawDepthImage raw;
+        if (!readPgm16(argv[a], raw)) throw std::runtime_error(std::string("cannot read ") + argv[a]);
+        tracker.processFrame(raw, sensorOffset, K, Isometry3f::Identity(), depthScale);
+        fprintf(out, "{\"frame\": %d, \"keyframe\": %d, \"keyframes\": %d, \"inliers\": %d, \"globalT\": [", a - 3,
+                tracker.lastWasKeyframe() ? 1 : 0, tracker.numKeyframes(), tracker.lastInliers());
+        for (int i = 0; i < 16; i++) fprintf(out, "%s%.9g", i ? ", " : "", tracker.globalT().data()[i]);
+        fprintf(out, "]}\n");
+      }
+      fclose(out);
+      return 0;
+    }
     if (get(cfg, "pyramid", 0) != 0) {
       // BASELINE config 2: 3-level coarse-to-fine alignment of frame 1 against frame 0
       RawDepthImage r0, r1;
