@@ -357,6 +357,42 @@ def test_multi_point_projector(ctx, width, height, ncam):
     assert rot_angle(T[:3, :3], gt[:3, :3]) < 1e-2 and np.abs(T[:3, 3] - gt[:3, 3]).max() < 2e-2
 
 
+def test_multi_point_projector_config5_full_size():
+    """BASELINE config 5 at full size: 4 pinholes of 1280x960 (composite 1280 x 3840 = 4.9 M pixels), default
+    build only (the oracle needs ~1 minute here).  Frame prep index/points bit-exact, align within tolerance."""
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    ctx = capi.Context(0)
+    cams = synth.make_rig(4, 1280, 960)
+    om, gm = O.make_multi(cams), capi.make_multi_projector(cams)
+    rows, cols = O.multi_image_size(om)
+    assert (rows, cols) == (1280, 3840)
+    poseA = synth.make_pose((0.1, -0.05, 0.2), (0, 1, 0), 10.0)
+    poseB = poseA @ synth.make_pose((0.03, -0.01, 0.04), (0.2, 1.0, 0.1), 2.0)
+    dA = synth.u16_to_m(synth.render_rig_depth_u16(poseA, cams))
+    dB = synth.u16_to_m(synth.render_rig_depth_u16(poseB, cams))
+    osp = O.default_stats_params(curvatureThreshold=0.2)
+    gsp = capi.make_stats_params(0.1, 10, 30, 50, 0.2, 0.02)
+    oA, oiA = O.multi_depth_to_cloud(om, dA, osp)
+    oB, oiB = O.multi_depth_to_cloud(om, dB, osp)
+    gA, giA = ctx.multi_depth_to_cloud(dA, gm, gsp)
+    gB, giB = ctx.multi_depth_to_cloud(dB, gm, gsp)
+    assert gA.size() == oA.n > 4_000_000
+    assert np.array_equal(giA, oiA) and np.array_equal(giB, oiB)
+    assert np.array_equal(gA.download()["points"].view(np.uint32), oA.points.view(np.uint32))
+    cp = O.default_corr_params(inlierDistanceThreshold=1.0, inlierNormalAngularThreshold=0.95)
+    out = O.align(oA, oB, O.make_align_params(cams[0]["K"], rows, cols, 0.5, 4.5, cp, num_threads=8, multi=om))
+    gap = capi.make_align_params(1.0, 0.95, 0.02, 1.3, 9e3, True, 10, 1)
+    res = ctx.multi_align(gA, gB, gm, gap)   # GPU-built clouds end to end
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], out.T[:3, :3]) <= 2e-4
+    assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= 2e-4
+    assert abs(res.inliers - out.inliers) <= 5e-3 * out.inliers
+    gt = np.linalg.inv(poseA) @ poseB
+    assert rot_angle(T[:3, :3], gt[:3, :3]) < 5e-3 and np.abs(T[:3, 3] - gt[:3, 3]).max() < 1e-2
+    ctx.close()
+
+
 def test_determinism_and_batch_identity(ctx):
     """two runs are bit-identical; a pair gives the same bits alone or inside a batch"""
     s = get_scene(4, 0, 0.05)
