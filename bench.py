@@ -292,9 +292,20 @@ def run_ours(args):
     bytes_total = 8.0 * P * n_pairs * args.steps * CONF["outerIterations"] + 56.0 * sumMidx + 48.0 * sumMacc
     achieved = bytes_total / (kt["corr_lin_ms"] * 1e-3) / 1e9 if kt["corr_lin_ms"] > 0 else 0.0
     peak, peak_src = measured_peak()
-    roofline = {"kernel": "k_corr_lin<0> (CorrespondenceFinder::compute + Linearizer::update fused)", "bound": "hbm",
+    # DRAM traffic per launch from the committed ncu capture of this kernel on this workload shape (64 pairs per
+    # launch, 640x480); null if the launch shape differs
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        pairs_per_launch = n_pairs * args.steps * CONF["outerIterations"] / n_launch
+        if abs(pairs_per_launch - tj["pairs_per_launch"]) < 0.5 and (tj["rows"], tj["cols"]) == (ROWS, COLS):
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
+    roofline = {"kernel": "k_corr_lin_tiled<0> (CorrespondenceFinder::compute + Linearizer::update fused)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "avg_launch_ms": kt["corr_lin_ms"] / n_launch, "launches_timed": kt["corr_lin_launches"],
+                "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": kt["corr_lin_ms"] / n_launch,
+                "launches_timed": kt["corr_lin_launches"],
                 "algorithmic_bytes_per_launch": bytes_total / n_launch,
                 "project_avg_launch_ms": kt["project_ms"] / max(kt["project_launches"], 1),
                 "share_of_step": kt["corr_lin_ms"] / dev_ms if dev_ms > 0 else None}

@@ -760,20 +760,33 @@ __device__ void add_priors(const DevPrior *priors, int numPriors, const float *i
 //  mode 1: _computeStatistics' linearisation: store H/b + image statistics, write the result record.
 //  mode 2: stage-level call: store H/b/error/inliers/ncorr only.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict__ desc, int numBlocks, int mode,
-                                                      int lastInner, int firstInner, int iter, AlignConsts ac) {
+constexpr int kReduceThreads = 512;
+constexpr int kReduceWarps = kReduceThreads / 32;
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const PairDesc *__restrict__ desc, int numBlocks, int mode,
+                                                                 int lastInner, int firstInner, int iter, AlignConsts ac) {
   const PairDesc &D = desc[blockIdx.x];
-  __shared__ float red[8][kAccum];
+  __shared__ float red[kReduceWarps][kAccum];
   __shared__ float tot[kAccum];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // warp w adds rows w, w+16, ... in order; 8 loads in flight per step (the rows are L2-resident: the fused
+  // kernel has just written them), the adds stay sequential so the order is fixed
   float s = 0.0f;
-  for (int bi = warp; bi < numBlocks; bi += 8) s += D.partials[(size_t)bi * kAccum + lane];
+  const float *__restrict__ rows = D.partials + lane;
+  int bi = warp;
+  for (; bi + 7 * kReduceWarps < numBlocks; bi += 8 * kReduceWarps) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = rows[(size_t)(bi + u * kReduceWarps) * kAccum];
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += v[u];
+  }
+  for (; bi < numBlocks; bi += kReduceWarps) s += rows[(size_t)bi * kAccum];
   red[warp][lane] = s;
   __syncthreads();
   if (warp == 0) {
     float t = red[0][lane];
 #pragma unroll
-    for (int w = 1; w < 8; w++) t += red[w][lane];
+    for (int w = 1; w < kReduceWarps; w++) t += red[w][lane];
     tot[lane] = t;
   }
   __syncthreads();
@@ -1001,7 +1014,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
         launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 0, 0.0f);
       }
       NICP_CHECK_LAUNCH(ctx);
-      k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
+      k_reduce_solve<<<nPairs, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
       NICP_CHECK_LAUNCH(ctx);
     }
   }
@@ -1013,7 +1026,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
   launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 1, imgThreshold);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<<<nPairs, 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
+  k_reduce_solve<<<nPairs, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
   NICP_CHECK_LAUNCH(ctx);
@@ -1029,7 +1042,7 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   dim3 cg(nb, 1);
   launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, ac, numPixels, ppb, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<<<1, 256, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
+  k_reduce_solve<<<1, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }
