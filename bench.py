@@ -178,6 +178,19 @@ def cpu_reference_run(steps, warmup, sample_pairs, n_threads=None):
     return value, cores, total / len(times) * 1e3
 
 
+def workload_config(n_cur, n_cand, world):
+    """the `config` object both arms report (same workload name; the reference arm times a bounded sample of it)"""
+    n_pairs = n_cur * n_cand
+    P = ROWS * COLS
+    return {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/GPU/step = "
+                        "%d current x %d candidate 640x480 frames, 10 outer iterations, "
+                        "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
+            "pairs_per_gpu_per_step": n_pairs, "rows": ROWS, "cols": COLS,
+            "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per step)" %
+                         ((n_cur + n_cand) * P * 80 / 1e9, 64 * P * 32 / 1e9),
+            "parallelism": "pair-sharded x%d" % world}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -189,8 +202,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batched loop-closure candidate verification, 640x480, 10 iters (bounded CPU sample)",
-                       "pairs_per_step": n},
+            "config": workload_config(args.currents, args.candidates, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -335,13 +347,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/GPU/step = "
-                                       "%d current x %d candidate 640x480 frames, 10 outer iterations, "
-                                       "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
-                           "pairs_per_gpu_per_step": n_pairs, "rows": ROWS, "cols": COLS,
-                           "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per step)" %
-                                        (n_frames * P * 80 / 1e9, 64 * P * 32 / 1e9),
-                           "parallelism": "pair-sharded x%d" % world},
+                "config": workload_config(n_cur, n_cand, world),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps},
