@@ -20,7 +20,7 @@ SYMBOLS = [
     "nicp_launch_count", "nicp_stream", "nicp_set_kernel_timing", "nicp_get_kernel_timing",
     "nicp_update_matrices", "nicp_v2t", "nicp_t2v",
     "nicp_cloud_create", "nicp_cloud_destroy", "nicp_cloud_size", "nicp_cloud_upload", "nicp_cloud_download",
-    "nicp_cloud_download_stats", "nicp_cloud_transform",
+    "nicp_cloud_download_stats", "nicp_cloud_transform", "nicp_cloud_append",
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
     "nicp_raw_depth_to_cloud", "nicp_last_integral_image", "nicp_last_interval_image",
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
@@ -261,6 +261,11 @@ class Cloud:
     def transform(self, T):
         t = colmajor(T)
         _check(self.ctx.L, self.ctx.L.nicp_cloud_transform(self.ctx.handle, self.handle, _fptr(t)))
+
+    def append(self, other, T=None):
+        """Cloud::add(other, T): append a transformed copy of `other`"""
+        t = colmajor(np.eye(4) if T is None else T)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_append(self.ctx.handle, self.handle, other.handle, _fptr(t)))
 
 
 class Context:

@@ -700,6 +700,63 @@ __global__ void k_cloud_transform(int capacity, const int *__restrict__ nPtr, Af
   }
 }
 
+// Cloud::add (cloud.cpp:145-171): dst[nDst + i] = T * src[i]
+__global__ void k_cloud_append(int srcCapacity, const int *__restrict__ srcN, const int *__restrict__ dstN, int dstCapacity,
+                               Affine M, int identity, const float4 *__restrict__ sp, const float4 *__restrict__ sn,
+                               const float4 *__restrict__ so, float4 *__restrict__ dp, float4 *__restrict__ dn,
+                               float4 *__restrict__ dom) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *srcN || i >= srcCapacity) return;
+  const size_t o = (size_t)*dstN + i;
+  if (o >= (size_t)dstCapacity) return;
+  float4 p = sp[i], nn = sn[i];
+  float4 o0 = so[3 * (size_t)i], o1 = so[3 * (size_t)i + 1], o2 = so[3 * (size_t)i + 2];
+  if (!identity) {
+    float M16[16];
+    mat4_identity(M16);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 4; c++) NM4(M16, r, c) = M.r[r][c];
+    float x, y, z;
+    xform_point(M, p.x, p.y, p.z, x, y, z);
+    p = make_float4(x, y, z, 1.0f);
+    xform_normal(M, nn.x, nn.y, nn.z, x, y, z);
+    nn = make_float4(x, y, z, nn.w);
+    float OP[9] = {o0.x, o0.y, o0.z, o0.y, o0.w, o1.x, o0.z, o1.x, o1.y};
+    float ON[9] = {o1.z, o1.w, o2.x, o1.w, o2.y, o2.z, o2.x, o2.z, o2.w};
+    float tp[9], tn[9];
+    rotate_sym(M16, OP, tp);
+    rotate_sym(M16, ON, tn);
+    o0 = make_float4(NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1));
+    o1 = make_float4(NM3(tp, 1, 2), NM3(tp, 2, 2), NM3(tn, 0, 0), NM3(tn, 0, 1));
+    o2 = make_float4(NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2));
+  }
+  dp[o] = p;
+  dn[o] = nn;
+  dom[3 * o] = o0;
+  dom[3 * o + 1] = o1;
+  dom[3 * o + 2] = o2;
+}
+__global__ void k_add_count(int *dstN, const int *srcN, int dstCapacity) {
+  int n = *dstN + *srcN;
+  *dstN = n > dstCapacity ? dstCapacity : n;
+}
+
+int launch_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]) {
+  float m[16];
+  for (int i = 0; i < 16; i++) m[i] = T[i];
+  fix_last_row(m);
+  k_cloud_append<<<(src->capacity + 255) / 256, 256, 0, ctx->stream>>>(src->capacity, src->d_n, dst->d_n, dst->capacity,
+                                                                      affine_from(m), is_identity16(m) ? 1 : 0, src->points,
+                                                                      src->normals, src->omega, dst->points, dst->normals,
+                                                                      dst->omega);
+  NICP_CHECK_LAUNCH(ctx);
+  k_add_count<<<1, 1, 0, ctx->stream>>>(dst->d_n, src->d_n, dst->capacity);
+  NICP_CHECK_LAUNCH(ctx);
+  dst->n_known = false;
+  dst->has_stats = false;
+  return NICP_OK;
+}
+
 int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]) {
   float m[16];
   for (int i = 0; i < 16; i++) m[i] = T[i];

@@ -689,6 +689,21 @@ int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *c, const float T[16]) {
   return launch_cloud_transform(ctx, c, T);
 }
 
+int nicp_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]) {
+  if (!ctx || !dst || !src || !T || dst == src) return NICP_ERR_INVALID;
+  int rc;
+  if ((rc = cloud_sync_n(ctx, dst))) return rc;
+  if ((rc = cloud_sync_n(ctx, src))) return rc;
+  if (dst->n_host + src->n_host > dst->capacity) {
+    set_error("cloud append: %d + %d points exceed the destination capacity %d", dst->n_host, src->n_host, dst->capacity);
+    return NICP_ERR_INVALID;
+  }
+  if ((rc = launch_cloud_append(ctx, dst, src, T))) return rc;
+  dst->n_host += src->n_host;
+  dst->n_known = true;
+  return NICP_OK;
+}
+
 // ---- depth helpers ---------------------------------------------------------------------------
 int nicp_depth_prepare(nicp_context *ctx, const uint16_t *raw, int rows, int cols, float depth_scale, int step,
                        float max_depth_cov, float *out) {

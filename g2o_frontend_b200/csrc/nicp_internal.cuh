@@ -230,6 +230,7 @@ int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols
                      float maxD, nicp_cloud *cloud, int *d_index);
 int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius, int *d_interval);
 int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]);
+int launch_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]);
 // align.cu
 int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
                           float minD, float maxD, unsigned long long *d_z);

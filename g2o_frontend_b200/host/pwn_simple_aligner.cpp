@@ -7,6 +7,7 @@
 // images in millimetres (the format of PlaneEx_gui/test_images/*.pgm), aligns every frame to the previous one and
 // writes one JSON line per frame: the relative transform, the accumulated global transform (as t2v), inliers,
 // error, correspondences and the image statistics of PwnMatcherBase::matchClouds.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -121,6 +122,53 @@ int main(int argc, char **argv) {
 
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");
+    if (get(cfg, "cloudio", 0) != 0) {
+      // Cloud::save / load round trip (ASCII and binary .pwn) and Cloud::add on the first frame
+      RawDepthImage raw;
+      if (!readPgm16(argv[3], raw)) throw std::runtime_error("cannot read frame");
+      DepthImage depth;
+      DepthImage_convertAndScale(depth, raw, imageScale, depthScale);
+      projector.setCameraMatrix(K);
+      projector.setImageSize(raw.rows, raw.cols);
+      projector.scale(1.0f / imageScale);
+      converter.setKeepStats(true);
+      Cloud cloud;
+      converter.compute(cloud, depth, sensorOffset);
+      std::string base(argv[2]);
+      Isometry3f pose = sensorOffset, Ta, Tb;
+      cloud.save((base + ".ascii.pwn").c_str(), pose, 1, false);
+      cloud.save((base + ".bin.pwn").c_str(), pose, 1, true);
+      Cloud a, b;
+      bool okA = a.load(Ta, (base + ".ascii.pwn").c_str());
+      bool okB = b.load(Tb, (base + ".bin.pwn").c_str());
+      double maxAsciiErr = 0, maxBinErr = 0;
+      for (size_t i = 0; i < cloud.size(); i++)
+        for (int k = 0; k < 3; k++) {
+          maxAsciiErr = std::max(maxAsciiErr, (double)std::fabs(a.points()[i][k] - cloud.points()[i][k]));
+          maxBinErr = std::max(maxBinErr, (double)std::fabs(b.points()[i][k] - cloud.points()[i][k]));
+          maxBinErr = std::max(maxBinErr, (double)std::fabs(b.normals()[i][k] - cloud.normals()[i][k]));
+          maxBinErr = std::max(maxBinErr, (double)std::fabs(b.stats()[i](k, 3) - cloud.stats()[i](k, 3)));
+        }
+      size_t n0 = cloud.size();
+      Isometry3f shift;
+      shift.setTranslation(0.5f, 0.0f, 0.0f);
+      Cloud sum;
+      sum.add(cloud);
+      sum.add(cloud, shift);
+      double addErr = 0;
+      for (size_t i = 0; i < n0; i++) {
+        addErr = std::max(addErr, (double)std::fabs(sum.points()[n0 + i][0] - (cloud.points()[i][0] + 0.5f)));
+        addErr = std::max(addErr, (double)std::fabs(sum.points()[i][1] - cloud.points()[i][1]));
+        addErr = std::max(addErr, (double)std::fabs(sum.normals()[n0 + i][2] - cloud.normals()[i][2]));
+      }
+      fprintf(out, "{\"points\": %zu, \"ascii_ok\": %d, \"bin_ok\": %d, \"ascii_points\": %zu, \"bin_points\": %zu, "
+                   "\"max_ascii_err\": %.9g, \"max_bin_err\": %.9g, \"sum_points\": %zu, \"add_err\": %.9g, "
+                   "\"pose_err\": %.9g}\n",
+              n0, okA ? 1 : 0, okB ? 1 : 0, a.size(), b.size(), maxAsciiErr, maxBinErr, sum.size(), addErr,
+              (double)std::fabs(Tb.data()[12] - pose.data()[12]));
+      fclose(out);
+      return 0;
+    }
     if (get(cfg, "tracker", 0) != 0) {
       // BASELINE config 3: PwnTracker::processFrame over the whole sequence (keyframe logic included)
       SequentialTracker tracker(&converter, &aligner);

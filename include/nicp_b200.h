@@ -161,6 +161,9 @@ int nicp_cloud_download_stats(nicp_context *ctx, const nicp_cloud *cloud, float 
                               float *eigenvalues3, int *n_points);
 /* Cloud::transformInPlace (cloud.cpp:173-186) */
 int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]);
+/* Cloud::add (cloud.cpp:145-171): append a copy of src transformed by T (points, normals, curvature, information
+ * matrices; Stats are not carried over).  Fails with NICP_ERR_INVALID if dst's capacity is too small. */
+int nicp_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]);
 
 /* ---- depth image helpers (pwn_static.cpp:5-68) ----------------------------------------------- */
 /* DepthImage_convert_16UC1_to_32FC1 followed by DepthImage_scale(step) on the device.

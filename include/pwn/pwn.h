@@ -20,6 +20,9 @@
 #pragma once
 #include <cfloat>
 #include <cmath>
+#include <fstream>
+#include <iostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <sys/time.h>
@@ -104,6 +107,130 @@ class Cloud {
     _pointInformationMatrix.clear(); _normalInformationMatrix.clear();
     _hostValid = true;
     _deviceValid = false;
+  }
+
+  // Cloud::add (cloud.cpp:145-171): append a copy of `cloud` transformed by T.  Stats are not carried over on
+  // the device (they are only materialised on request); everything the aligner reads is.
+  void add(const Cloud &cloud, const Isometry3f &T = Isometry3f::Identity()) {
+    nicp_context *ctx = Context::current().handle();
+    const int n0 = (int)size(), n1 = (int)cloud.size();
+    nicp_cloud *src = cloud.device();
+    nicp_cloud *old = n0 > 0 ? device() : 0;
+    nicp_cloud *merged = 0;
+    nicpCheck(nicp_cloud_create(ctx, n0 + n1 > 0 ? n0 + n1 : 1, &merged), "nicp_cloud_create");
+    Isometry3f I;
+    if (old) nicpCheck(nicp_cloud_append(ctx, merged, old, I.data()), "Cloud::add");
+    nicpCheck(nicp_cloud_append(ctx, merged, src, T.data()), "Cloud::add");
+    release();
+    _dev = merged;
+    _capacity = n0 + n1 > 0 ? n0 + n1 : 1;
+    _deviceValid = true;
+    _hostValid = false;
+    _hasStats = false;
+  }
+
+  // Cloud::save / Cloud::load (cloud.cpp:25-133): "PWNCLOUD n binary" + pose 6-vector + one record per point.
+  // ASCII records ("POINTWITHSTATS x y z nx ny nz <16 stats>") are written exactly like the reference.  The
+  // reference's binary mode dumps its C++ objects raw (os.write(&point, sizeof(Point)) ...), i.e. including each
+  // object's vptr and padding: on LP64 / Itanium ABI that is 32 B per Point (8 vptr, 8 pad, 4 floats), 32 B per
+  // Normal, 112 B per Stats (8 vptr, 8 pad, 16 floats column-major, int n, 3 eigenvalues, bool, float curvature,
+  // pad).  We write zeros into the vptr/padding bytes and ignore them on load.
+  bool save(std::ostream &os, Isometry3f T = Isometry3f::Identity(), int step = 1, bool binary = true) const {
+    ensureHost();
+    os << "PWNCLOUD " << _points.size() / step << " " << binary << std::endl;
+    Vector6f transform = t2v(T);
+    os << transform[0] << " " << transform[1] << " " << transform[2] << " " << transform[3] << " " << transform[4] << " "
+       << transform[5] << " " << std::endl;
+    for (size_t i = 0; i < _points.size(); i += step) {
+      const Point &point = _points[i];
+      const Normal &normal = _normals[i];
+      const Stats &stats = _stats[i];
+      if (!binary) {
+        os << "POINTWITHSTATS ";
+        for (int k = 0; k < 3; k++) os << point[k] << " ";
+        for (int k = 0; k < 3; k++) os << normal[k] << " ";
+        for (int r = 0; r < 4; r++)
+          for (int c = 0; c < 4; c++) os << stats(r, c) << " ";
+        os << std::endl;
+      } else {
+        unsigned char rec[32 + 32 + 112];
+        std::memset(rec, 0, sizeof rec);
+        std::memcpy(rec + 16, point.m, 16);
+        std::memcpy(rec + 32 + 16, normal.m, 16);
+        std::memcpy(rec + 64 + 16, stats.m, 64);
+        int n = stats._n;
+        float curv = stats.curvature();
+        std::memcpy(rec + 64 + 80, &n, 4);
+        std::memcpy(rec + 64 + 84, stats._eigenValues.m, 12);
+        rec[64 + 96] = 1;  // _curvatureComputed
+        std::memcpy(rec + 64 + 100, &curv, 4);
+        os.write((const char *)rec, sizeof rec);
+      }
+    }
+    return os.good();
+  }
+  bool save(const char *filename, Isometry3f T = Isometry3f::Identity(), int step = 1, bool binary = true) const {
+    std::ofstream os(filename);
+    if (!os) return false;
+    return save(os, T, step, binary);
+  }
+  bool load(Isometry3f &T, std::istream &is) {
+    clear();
+    char buf[1024];
+    is.getline(buf, 1024);
+    std::istringstream ls(buf);
+    std::string tag;
+    size_t numPoints = 0;
+    bool binary = false;
+    ls >> tag;
+    if (tag != "PWNCLOUD") return false;
+    ls >> numPoints >> binary;
+    _points.resize(numPoints);
+    _normals.resize(numPoints);
+    _stats.assign(numPoints, Stats());
+    _pointInformationMatrix.assign(numPoints, InformationMatrix());
+    _normalInformationMatrix.assign(numPoints, InformationMatrix());
+    is.getline(buf, 1024);
+    std::istringstream lst(buf);
+    Vector6f transform;
+    lst >> transform[0] >> transform[1] >> transform[2] >> transform[3] >> transform[4] >> transform[5];
+    T = v2t(transform);
+    size_t k = 0;
+    while (k < _points.size() && is.good()) {
+      Point &point = _points[k];
+      Normal &normal = _normals[k];
+      Stats &stats = _stats[k];
+      if (!binary) {
+        is.getline(buf, 1024);
+        std::istringstream l2(buf);
+        std::string s;
+        l2 >> s;
+        if (s != "POINTWITHSTATS") continue;
+        for (int i = 0; i < 3 && l2; i++) l2 >> point[i];
+        for (int i = 0; i < 3 && l2; i++) l2 >> normal[i];
+        for (int r = 0; r < 4 && l2; r++)
+          for (int c = 0; c < 4 && l2; c++) l2 >> stats(r, c);
+      } else {
+        unsigned char rec[32 + 32 + 112];
+        is.read((char *)rec, sizeof rec);
+        std::memcpy(point.m, rec + 16, 16);
+        std::memcpy(normal.m, rec + 32 + 16, 16);
+        std::memcpy(stats.m, rec + 64 + 16, 64);
+        std::memcpy(&stats._n, rec + 64 + 80, 4);
+        std::memcpy(stats._eigenValues.m, rec + 64 + 84, 12);
+      }
+      point[3] = 1.0f;
+      normal[3] = 0.0f;
+      k++;
+    }
+    _hostValid = true;
+    _deviceValid = false;
+    return is.good() || is.eof();
+  }
+  bool load(Isometry3f &T, const char *filename) {
+    std::ifstream is(filename);
+    if (!is) return false;
+    return load(T, is);
   }
 
   // Cloud::transformInPlace (cloud.cpp:173-186)

@@ -479,7 +479,7 @@ def _declare():
         for name in ("orc_depth_u16_to_f32", "orc_depth_scale", "orc_v2t", "orc_t2v", "orc_update_matrices",
                      "orc_project_intervals", "orc_project", "orc_integral_image", "orc_eigen3", "orc_linearize",
                      "orc_linearize_f64", "orc_ldlt_solve6", "orc_align", "orc_image_stats", "orc_multi_image_size",
-                     "orc_multi_intervals", "orc_multi_project", "orc_set_accumulate_f64"):
+                     "orc_multi_intervals", "orc_multi_project", "orc_set_accumulate_f64", "orc_cloud_transform"):
             getattr(l, name).restype = None
 
 

@@ -393,6 +393,77 @@ def test_multi_point_projector_config5_full_size():
     ctx.close()
 
 
+def test_real_kinect_frame(ctx):
+    """real sensor data (holes, noise): the one Kinect frame the reference ships as data, full resolution"""
+    import os
+    from conftest import ROOT, CONF_1_1
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "real_depth_640x480.npz"))["raw"]
+    c = CONF_1_1
+    K = synth.K_KINECT
+    d = O.depth_u16_to_f32(raw)
+    sp = O.default_stats_params(minImageRadius=c["minImageRadius"], maxImageRadius=c["maxImageRadius"],
+                                minPoints=c["minPoints"], curvatureThreshold=c["curvatureThreshold"])
+    oc, oidx, oitv, ointeg = O.depth_to_cloud(d, K, c["minD"], c["maxD"], sp, want_aux=True)
+    proj = capi.make_projector(K, 480, 640, c["minD"], c["maxD"])
+    gsp = capi.make_stats_params(c["worldRadius"], c["minImageRadius"], c["maxImageRadius"], c["minPoints"],
+                                 c["curvatureThreshold"], c["omegaCurvatureThreshold"])
+    gc, gidx = ctx.raw_depth_to_cloud(raw, proj, gsp, want_index=True)
+    assert gc.size() == oc.n and np.array_equal(gidx, oidx)
+    assert np.array_equal(ctx.last_integral_image(480, 640).view(np.uint32), ointeg.view(np.uint32))
+    dl = gc.download()
+    assert np.array_equal(dl["points"].view(np.uint32), oc.points.view(np.uint32))
+    has_o = np.abs(oc.normals[:, :3]).sum(1) > 0
+    has_g = np.abs(dl["normals"][:, :3]).sum(1) > 0
+    assert (has_o != has_g).mean() < 1e-3
+    both = has_o & has_g
+    dots = (dl["normals"][both, :3].astype(np.float64) * oc.normals[both, :3]).sum(1)
+    assert np.quantile(dots, 0.01) > 1 - 1e-5
+    # self-alignment from a perturbed guess: GPU on its own cloud vs the oracle on its own cloud
+    guess = synth.make_pose((0.02, -0.01, 0.015), (0.3, 1.0, 0.2), 1.5).astype(np.float32)
+    cp = O.default_corr_params(inlierDistanceThreshold=c["inlierDistanceThreshold"],
+                               inlierNormalAngularThreshold=c["inlierNormalAngularThreshold"])
+    out = O.align(oc, oc, O.make_align_params(K, 480, 640, c["minD"], c["maxD"], cp, guess=guess, num_threads=8))
+    ap = capi.make_align_params(c["inlierDistanceThreshold"], c["inlierNormalAngularThreshold"], 0.02, 1.3, 9e3, True, 10, 1)
+    res = ctx.align(gc, gc, proj, ap, guess=guess)
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], out.T[:3, :3]) <= 2e-4 and np.abs(T[:3, 3] - out.T[:3, 3]).max() <= 2e-4
+    assert np.abs(T - np.eye(4)).max() < 5e-3
+    assert abs(res.inliers - out.inliers) <= 5e-3 * out.inliers
+
+
+def test_cloud_append(ctx):
+    """Cloud::add (cloud.cpp:145-171) on the device vs transform + concatenate with the oracle"""
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    import ctypes as C
+    s = get_scene(4, 0, 0.05)
+    a, b = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    T = synth.make_pose((0.3, -0.1, 0.2), (0.2, 1.0, 0.4), 25.0).astype(np.float32)
+    dst = ctx.new_cloud(s.cloudA.n + s.cloudB.n)
+    dst.append(a)
+    dst.append(b, T)
+    assert dst.size() == s.cloudA.n + s.cloudB.n
+    d = dst.download()
+    ob = s.cloudB.truncated(s.cloudB.n)
+    pts, nrm, st, op, on = (ob.points.copy(), ob.normals.copy(), ob.statsM.copy(), ob.omegaP.copy(), ob.omegaN.copy())
+    Tc = O.colmajor(T)
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    O.lib().orc_cloud_transform(fp(Tc), ob.n, fp(pts), fp(nrm), fp(st), fp(op), fp(on))
+    n0 = s.cloudA.n
+    assert np.array_equal(d["points"][:n0].view(np.uint32), s.cloudA.points.view(np.uint32))
+    assert np.array_equal(d["points"][n0:].view(np.uint32), pts.view(np.uint32))
+    assert np.array_equal(d["normals"][n0:, :3].view(np.uint32), nrm[:, :3].view(np.uint32))
+    assert np.array_equal(d["curvature"][n0:], ob.curvature)
+    # information matrices: the device rotates the symmetric completion of the stored upper triangle
+    ref6 = O.sym6(op)
+    err = np.abs(d["omega_p"][n0:] - ref6).max(1) / np.maximum(np.abs(ref6).max(1), 1e-9)
+    assert np.nanquantile(err, 0.999) < 1e-5
+    with pytest.raises(Exception):
+        dst.append(a)  # capacity exceeded -> NICP_ERR_INVALID, not silent truncation
+
+
 def test_determinism_and_batch_identity(ctx):
     """two runs are bit-identical; a pair gives the same bits alone or inside a batch"""
     s = get_scene(4, 0, 0.05)

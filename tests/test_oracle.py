@@ -270,3 +270,21 @@ def test_image_stats_bit_trick():
     assert m.tolist() == [0.0, 50.0, 3.90625]
     assert inl == int((m < 50.0).sum()) == 2 and outl == 1
     assert abs(rd - m.sum() / 3) < 1e-4
+
+
+def test_real_kinect_frame_self_alignment():
+    """self-alignment of the in-tree real depth frame (PlaneEx_gui/test_images/image.pgm,
+    committed as tests/golden/real_depth_640x480.npz) from a perturbed guess returns ~identity."""
+    from g2o_frontend_b200 import synth
+    raw = np.load(os.path.join(GOLD, "real_depth_640x480.npz"))["raw"]
+    d = O.depth_scale(O.depth_u16_to_f32(raw), 2)
+    K = synth.scaled_K(synth.K_KINECT, 0.5)
+    sp = O.default_stats_params(minImageRadius=5, maxImageRadius=15, minPoints=25, curvatureThreshold=0.2)
+    cloud, idx = O.depth_to_cloud(d, K, 0.5, 4.5, sp)
+    assert cloud.n > 0.6 * d.size
+    assert (np.abs(cloud.normals[:, :3]).sum(1) > 0).mean() > 0.7
+    guess = synth.make_pose((0.02, -0.01, 0.015), (0.3, 1.0, 0.2), 1.5).astype(np.float32)
+    cp = O.default_corr_params(inlierDistanceThreshold=0.5, inlierNormalAngularThreshold=0.95)
+    out = O.align(cloud, cloud, O.make_align_params(K, 240, 320, 0.5, 4.5, cp, guess=guess, outer=20))
+    assert np.abs(out.T - np.eye(4)).max() < 2e-3, out.T
+    assert out.inliers > 0.7 * cloud.n
