@@ -658,7 +658,7 @@ struct DevPrior {
   float info[36];
 };
 
-__device__ void prior_error(const DevPrior &pr, const float *mean, const float *invT, float *e) {
+__device__ __noinline__ void prior_error(const DevPrior &pr, const float *mean, const float *invT, float *e) {
   float t[16];
   if (pr.kind == 0) {
     iso_mul(invT, mean, t);
@@ -669,7 +669,7 @@ __device__ void prior_error(const DevPrior &pr, const float *mean, const float *
   }
   t2v(t, e);
 }
-__device__ void mat6_mul(const float *A, const float *B, float *C) {
+__device__ __noinline__ void mat6_mul(const float *A, const float *B, float *C) {
   float t[36];
   for (int c = 0; c < 6; c++)
     for (int r = 0; r < 6; r++) {
@@ -679,13 +679,13 @@ __device__ void mat6_mul(const float *A, const float *B, float *C) {
     }
   for (int i = 0; i < 36; i++) C[i] = t[i];
 }
-__device__ void mat6_transpose(const float *A, float *At) {
+__device__ __noinline__ void mat6_transpose(const float *A, float *At) {
   float t[36];
   for (int r = 0; r < 6; r++)
     for (int c = 0; c < 6; c++) NM6(t, r, c) = NM6(A, c, r);
   for (int i = 0; i < 36; i++) At[i] = t[i];
 }
-__device__ void mat6_inverse(const float *A, float *Ai) {
+__device__ __noinline__ void mat6_inverse(const float *A, float *Ai) {
   double a[6][12];
   for (int r = 0; r < 6; r++)
     for (int c = 0; c < 6; c++) {
@@ -710,7 +710,7 @@ __device__ void mat6_inverse(const float *A, float *Ai) {
   for (int r = 0; r < 6; r++)
     for (int c = 0; c < 6; c++) NM6(Ai, r, c) = (float)a[r][c + 6];
 }
-__device__ void add_priors(const DevPrior *priors, int numPriors, const float *invT, float *H, float *b) {
+__device__ __noinline__ void add_priors(const DevPrior *priors, int numPriors, const float *invT, float *H, float *b) {
   const float epsilon = 1e-3f, iEps = fdiv(0.5f, epsilon);
   for (int j = 0; j < numPriors; j++) {
     const DevPrior &pr = priors[j];
@@ -760,36 +760,53 @@ __device__ void add_priors(const DevPrior *priors, int numPriors, const float *i
 //  mode 1: _computeStatistics' linearisation: store H/b + image statistics, write the result record.
 //  mode 2: stage-level call: store H/b/error/inliers/ncorr only.
 // ---------------------------------------------------------------------------------------------
-constexpr int kReduceThreads = 512;
-constexpr int kReduceWarps = kReduceThreads / 32;
-__global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const PairDesc *__restrict__ desc, int numBlocks, int mode,
-                                                                 int lastInner, int firstInner, int iter, AlignConsts ac) {
-  const PairDesc &D = desc[blockIdx.x];
-  __shared__ float red[kReduceWarps][kAccum];
-  __shared__ float tot[kAccum];
+// First level of the deterministic final pass: kRowGroups CTAs per pair, CTA g adds the partial rows of its
+// contiguous group (warp w takes rows w, w+8, ... of the group in order, 8 loads in flight; the 8 warps are
+// added in order) and writes one row of partials2.  The rows are L2-resident (just written by the fused kernel).
+constexpr int kRowGroups = 16;
+__global__ void __launch_bounds__(256) k_reduce_rows(const PairDesc *__restrict__ desc, int numBlocks) {
+  const PairDesc &D = desc[blockIdx.y];
+  __shared__ float red[8][kAccum];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // warp w adds rows w, w+16, ... in order; 8 loads in flight per step (the rows are L2-resident: the fused
-  // kernel has just written them), the adds stay sequential so the order is fixed
+  const int per = (numBlocks + kRowGroups - 1) / kRowGroups;
+  const int begin = blockIdx.x * per, end = min(begin + per, numBlocks);
   float s = 0.0f;
   const float *__restrict__ rows = D.partials + lane;
-  int bi = warp;
-  for (; bi + 7 * kReduceWarps < numBlocks; bi += 8 * kReduceWarps) {
+  int bi = begin + warp;
+  for (; bi + 7 * 8 < end; bi += 8 * 8) {
     float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = rows[(size_t)(bi + u * kReduceWarps) * kAccum];
+    for (int u = 0; u < 8; u++) v[u] = rows[(size_t)(bi + u * 8) * kAccum];
 #pragma unroll
     for (int u = 0; u < 8; u++) s += v[u];
   }
-  for (; bi < numBlocks; bi += kReduceWarps) s += rows[(size_t)bi * kAccum];
+  for (; bi < end; bi += 8) s += rows[(size_t)bi * kAccum];
   red[warp][lane] = s;
   __syncthreads();
   if (warp == 0) {
     float t = red[0][lane];
 #pragma unroll
-    for (int w = 1; w < kReduceWarps; w++) t += red[w][lane];
+    for (int w = 1; w < 8; w++) t += red[w][lane];
+    D.partials2[blockIdx.x * kAccum + lane] = t;
+  }
+}
+
+// Second level + solve: one warp adds the kRowGroups rows in order, thread 0 does the dense part.
+// PRIORS selects the instantiation that carries the SE(3)-prior code (numeric Jacobians, 6x6 float64 inverse): it is
+// ~4x the size of the plain one, and the solving thread's run time is dominated by instruction fetch.
+template <bool PRIORS>
+__global__ void __launch_bounds__(32) k_reduce_solve(const PairDesc *__restrict__ desc, int mode, int lastInner, int firstInner,
+                                                     int iter, AlignConsts ac) {
+  const PairDesc &D = desc[blockIdx.x];
+  __shared__ float tot[kAccum];
+  {
+    const int lane = threadIdx.x;
+    float t = 0.0f;
+#pragma unroll
+    for (int g = 0; g < kRowGroups; g++) t += D.partials2[g * kAccum + lane];
     tot[lane] = t;
   }
-  __syncthreads();
+  __syncwarp();
   if (threadIdx.x != 0) return;
 
   PairState *st = D.state;
@@ -853,7 +870,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const PairDesc 
   for (int d = 0; d < 6; d++) NM6(H, d, d) = fadd(fadd(NM6(H, d, d), 1.0f), 1000.0f);
   float nb[6], dx[6], dT[16], invT[16];
   for (int k = 0; k < 16; k++) invT[k] = st->invT[k];
-  if (D.numPriors > 0) add_priors(reinterpret_cast<const DevPrior *>(D.priors), D.numPriors, invT, H, b);
+  if (PRIORS) {
+    if (D.numPriors > 0) add_priors(reinterpret_cast<const DevPrior *>(D.priors), D.numPriors, invT, H, b);
+  }
   for (int k = 0; k < 6; k++) nb[k] = -b[k];
   ldlt_solve6(H, nb, dx);
   v2t(dx, dT);
@@ -1014,7 +1033,12 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
         launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 0, 0.0f);
       }
       NICP_CHECK_LAUNCH(ctx);
-      k_reduce_solve<<<nPairs, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
+      k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
+      NICP_CHECK_LAUNCH(ctx);
+      if (ctx->h_desc[0].numPriors > 0)
+        k_reduce_solve<true><<<nPairs, 32, 0, st>>>(ctx->d_desc, 0, k == innerIters - 1, k == 0, it, ac);
+      else
+        k_reduce_solve<false><<<nPairs, 32, 0, st>>>(ctx->d_desc, 0, k == innerIters - 1, k == 0, it, ac);
       NICP_CHECK_LAUNCH(ctx);
     }
   }
@@ -1026,7 +1050,9 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
   launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 1, imgThreshold);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<<<nPairs, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
+  k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
+  NICP_CHECK_LAUNCH(ctx);
+  k_reduce_solve<false><<<nPairs, 32, 0, st>>>(ctx->d_desc, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
   NICP_CHECK_LAUNCH(ctx);
@@ -1042,7 +1068,9 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   dim3 cg(nb, 1);
   launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, ac, numPixels, ppb, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<<<1, kReduceThreads, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
+  k_reduce_rows<<<dim3(kRowGroups, 1), 256, 0, st>>>(ctx->d_desc, nb);
+  NICP_CHECK_LAUNCH(ctx);
+  k_reduce_solve<false><<<1, 32, 0, st>>>(ctx->d_desc, 2, 0, 1, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }

@@ -75,6 +75,7 @@ static void free_align(nicp_context *ctx) {
   dev_free(ctx->d_curIndex);
   dev_free(ctx->d_corrImage);
   dev_free(ctx->d_partials);
+  dev_free(ctx->d_partials2);
   dev_free(ctx->d_state);
   dev_free(ctx->d_descBase);
   if (ctx->h_descBase) cudaFreeHost(ctx->h_descBase);
@@ -96,6 +97,7 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_corrImage, (size_t)slots * pixels))) return rc;
   ctx->partialRows = partial_rows_for(ctx, pixels);
   if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->partialRows * kAccum))) return rc;
+  if ((rc = dev_alloc(&ctx->d_partials2, (size_t)slots * 16 * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   // two sets of: descriptors followed by one int flag per slot
   size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
@@ -246,6 +248,7 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   D.curIndex = ctx->d_curIndex + (size_t)curSlot * P;
   D.corrImage = ctx->d_corrImage + (size_t)slot * P;
   D.partials = ctx->d_partials + (size_t)slot * ctx->partialRows * kAccum;
+  D.partials2 = ctx->d_partials2 + (size_t)slot * 16 * kAccum;
   D.state = ctx->d_state + slot;
   D.trace = d_trace;
   D.result = d_result;
@@ -499,6 +502,10 @@ int nicp_create(int device, nicp_context **out) {
   }
   NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[0], cudaEventDisableTiming));
   NICP_CUDA(cudaEventCreateWithFlags(&ctx->evChunk[1], cudaEventDisableTiming));
+  {
+    const char *g = getenv("NICP_GRAPH");
+    ctx->graphsEnabled = (g && g[0] == '0') ? 0 : 1;
+  }
   ctx->evCorr = new std::vector<cudaEvent_t>();
   ctx->evProj = new std::vector<cudaEvent_t>();
   *out = ctx;
@@ -522,6 +529,7 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
   if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
+  if (ctx->graphValid) cudaGraphExecDestroy(ctx->graphExec);
   for (cudaEvent_t e : *ctx->evCorr) cudaEventDestroy(e);
   for (cudaEvent_t e : *ctx->evProj) cudaEventDestroy(e);
   delete ctx->evCorr;
@@ -933,6 +941,17 @@ struct HostPrior {
   float info[36];
 };
 
+// everything a captured single-pair graph has baked in
+struct GraphKey {
+  AlignConsts ac;
+  float co[16];
+  int outer, inner, numPriors, corrVariant, tileConfig, slots, partialRows;
+  float imgThr;
+  size_t slotPixels;
+  const void *desc, *results, *statHb, *trace, *priors, *refZ;
+};
+static_assert(sizeof(GraphKey) <= 512, "graph key fits the context buffer");
+
 static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs, const nicp_cloud *const *curs,
                         const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset,
                         const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
@@ -1004,13 +1023,58 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         ctx->h_desc[i].numPriors = numPriors;
       }
     }
-    if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
-                              owns.data(), single, base)))
-      return rc;
-    NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-    NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb + (size_t)base * 42, ctx->d_statHb + (size_t)base * 42, sizeof(float) * 42 * m,
-                              cudaMemcpyDeviceToHost, ctx->stream));
+    const bool useGraph = single && ctx->graphsEnabled && !cams.multi && !ctx->timing;
+    bool replayed = false;
+    if (useGraph) {
+      GraphKey key;
+      memset(&key, 0, sizeof key);
+      key.ac = ac;
+      memcpy(key.co, co, sizeof co);
+      key.outer = ap->outer_iterations; key.inner = ap->inner_iterations; key.numPriors = numPriors;
+      key.corrVariant = ctx->corrVariant; key.tileConfig = ctx->tileConfig; key.slots = ctx->slots;
+      key.partialRows = ctx->partialRows; key.imgThr = imgThr; key.slotPixels = ctx->slotPixels;
+      key.desc = ctx->d_desc; key.results = ctx->d_results; key.statHb = ctx->d_statHb; key.trace = ctx->d_trace;
+      key.priors = ctx->d_priors; key.refZ = ctx->d_refZ;
+      if (ctx->graphValid && memcmp(&key, ctx->graphKey, sizeof key) == 0) {
+        NICP_CUDA(cudaGraphLaunch(ctx->graphExec, ctx->stream));
+        ctx->launches += 2 + 5 + 4 * (long long)ap->outer_iterations * (ap->inner_iterations > 0 ? ap->inner_iterations : 0) + 4;
+        replayed = true;
+      } else {
+        if (ctx->graphValid) {
+          cudaGraphExecDestroy(ctx->graphExec);
+          ctx->graphValid = false;
+        }
+        cudaGraph_t graph = nullptr;
+        NICP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+                             owns.data(), single, base);
+        cudaError_t e1 = cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
+                                         cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e2 = cudaMemcpyAsync(ctx->h_statHb + (size_t)base * 42, ctx->d_statHb + (size_t)base * 42,
+                                         sizeof(float) * 42 * m, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e3 = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) return rc;
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || !graph) {
+          set_error("CUDA graph capture of nicp_align failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : (e1 != cudaSuccess ? e1 : e2)));
+          return NICP_ERR_CUDA;
+        }
+        NICP_CUDA(cudaGraphInstantiate(&ctx->graphExec, graph, 0));
+        cudaGraphDestroy(graph);
+        memcpy(ctx->graphKey, &key, sizeof key);
+        ctx->graphValid = true;
+        NICP_CUDA(cudaGraphLaunch(ctx->graphExec, ctx->stream));
+        replayed = true;
+      }
+    }
+    if (!replayed) {
+      if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+                                owns.data(), single, base)))
+        return rc;
+      NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+      NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb + (size_t)base * 42, ctx->d_statHb + (size_t)base * 42, sizeof(float) * 42 * m,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
     NICP_CUDA(cudaEventRecord(ctx->evChunk[chunk & 1], ctx->stream));
     // while this chunk runs on the GPU, finish the previous one on the host (Aligner::_computeStatistics tail)
     if (chunk > 0) {

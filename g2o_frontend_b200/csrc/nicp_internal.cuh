@@ -82,6 +82,7 @@ struct PairDesc {
   int *curIndex;                // decoded current index image
   int *corrImage;               // accepted reference index per pixel or -1
   float *partials;              // [blocksPerPair][kAccum]
+  float *partials2;             // [16][kAccum]: first-level sums of the partial rows
   PairState *state;
   float *trace;                 // may be null
   nicp_align_result *result;
@@ -184,6 +185,7 @@ struct nicp_context {
   int *d_curIndex;              // [slots][P]
   int *d_corrImage;             // [slots][P]
   float *d_partials;            // [slots][blocksPerPair][kAccum]
+  float *d_partials2;           // [slots][16][kAccum]
   nicp::PairState *d_state;     // [slots]
   // descriptor staging is double buffered so that the host can fill chunk c+1 (and post-process chunk
   // c-1) while chunk c runs; d_desc / h_desc point at the set of the chunk being issued
@@ -212,6 +214,13 @@ struct nicp_context {
   size_t evCorrUsed, evProjUsed;
   double msCorr, msProj;
   long long nCorr, nProj;
+
+  // CUDA graph of the last single-pair nicp_align (47 launches + copies replayed as one graph launch when
+  // every baked-in value -- thresholds, K, offsets, iteration counts, image size, buffers -- is unchanged)
+  int graphsEnabled;
+  cudaGraphExec_t graphExec;
+  bool graphValid;
+  unsigned char graphKey[512];
 
   // last single-align bookkeeping
   int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;

@@ -110,16 +110,24 @@ NICP_HD void t2v(const float *T, float *v) {
     q[1] = fmul(fsub(NM4(T, 0, 2), NM4(T, 2, 0)), t);
     q[2] = fmul(fsub(NM4(T, 1, 0), NM4(T, 0, 1)), t);
   } else {
+    // i = index of the largest diagonal entry (ties -> lowest), j = (i+1)%3, k = (j+1)%3; written out per case so
+    // that every array index is a compile-time constant (the matrices stay in registers on the device)
     int i = 0;
     if (NM4(T, 1, 1) > NM4(T, 0, 0)) i = 1;
-    if (NM4(T, 2, 2) > NM4(T, i, i)) i = 2;
-    int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = fsqrt(fadd(fsub(fsub(NM4(T, i, i), NM4(T, j, j)), NM4(T, k, k)), 1.0f));
-    q[i] = fmul(0.5f, t);
-    t = fdiv(0.5f, t);
-    q[3] = fmul(fsub(NM4(T, k, j), NM4(T, j, k)), t);
-    q[j] = fmul(fadd(NM4(T, j, i), NM4(T, i, j)), t);
-    q[k] = fmul(fadd(NM4(T, k, i), NM4(T, i, k)), t);
+    if (NM4(T, 2, 2) > (i == 1 ? NM4(T, 1, 1) : NM4(T, 0, 0))) i = 2;
+#define NICP_T2V_CASE(I, J, K)                                                                      \
+  {                                                                                                 \
+    t = fsqrt(fadd(fsub(fsub(NM4(T, I, I), NM4(T, J, J)), NM4(T, K, K)), 1.0f));                    \
+    q[I] = fmul(0.5f, t);                                                                           \
+    t = fdiv(0.5f, t);                                                                              \
+    q[3] = fmul(fsub(NM4(T, K, J), NM4(T, J, K)), t);                                               \
+    q[J] = fmul(fadd(NM4(T, J, I), NM4(T, I, J)), t);                                               \
+    q[K] = fmul(fadd(NM4(T, K, I), NM4(T, I, K)), t);                                               \
+  }
+    if (i == 0) NICP_T2V_CASE(0, 1, 2)
+    else if (i == 1) NICP_T2V_CASE(1, 2, 0)
+    else NICP_T2V_CASE(2, 0, 1)
+#undef NICP_T2V_CASE
   }
   float nrm = fsqrt(fadd(fadd(fadd(fmul(q[0], q[0]), fmul(q[1], q[1])), fmul(q[2], q[2])), fmul(q[3], q[3])));
   for (int i = 0; i < 4; i++) q[i] = fdiv(q[i], nrm);
@@ -197,59 +205,97 @@ NICP_HD void compute_iKRt(const float *K, const float *T, float *iKRt) {
 // ---- Eigen::LDLT<Matrix6f> compute + solve (Eigen 3.2 unblocked, diagonal pivoting) ----------
 // x = H^-1 b (aligner.cpp:110 calls it with -b)
 NICP_HD void ldlt_solve6(const float *Hin, const float *bin, float *x) {
+  // Every loop has compile-time bounds and every array index is a compile-time constant after unrolling; the
+  // data-dependent pivot is applied as predicated swaps against each candidate row.  (On the device this keeps
+  // the 6x6 in registers: the solving thread is a single thread on the critical path of every iteration.)
   const int N = 6;
   float m[36];
   int tr[6];
+#pragma unroll
   for (int i = 0; i < 36; i++) m[i] = Hin[i];
+#pragma unroll
   for (int k = 0; k < N; k++) {
     int big = k;
     float bv = fabsf(NM6(m, k, k));
+#pragma unroll
     for (int i = k + 1; i < N; i++) {
       float a = fabsf(NM6(m, i, i));
       if (a > bv) { bv = a; big = i; }
     }
     tr[k] = big;
-    if (big != k) {
-      float t;
-      for (int j = 0; j < k; j++) { t = NM6(m, k, j); NM6(m, k, j) = NM6(m, big, j); NM6(m, big, j) = t; }
-      for (int i = big + 1; i < N; i++) { t = NM6(m, i, k); NM6(m, i, k) = NM6(m, i, big); NM6(m, i, big) = t; }
-      t = NM6(m, k, k); NM6(m, k, k) = NM6(m, big, big); NM6(m, big, big) = t;
-      for (int i = k + 1; i < big; i++) { t = NM6(m, i, k); NM6(m, i, k) = NM6(m, big, i); NM6(m, big, i) = t; }
+    // symmetric row/column swap k <-> big in the lower triangle
+#pragma unroll
+    for (int cand = k + 1; cand < N; cand++) {
+      if (cand == big) {
+        float t;
+#pragma unroll
+        for (int j = 0; j < k; j++) { t = NM6(m, k, j); NM6(m, k, j) = NM6(m, cand, j); NM6(m, cand, j) = t; }
+#pragma unroll
+        for (int i = cand + 1; i < N; i++) { t = NM6(m, i, k); NM6(m, i, k) = NM6(m, i, cand); NM6(m, i, cand) = t; }
+        t = NM6(m, k, k); NM6(m, k, k) = NM6(m, cand, cand); NM6(m, cand, cand) = t;
+#pragma unroll
+        for (int i = k + 1; i < cand; i++) { t = NM6(m, i, k); NM6(m, i, k) = NM6(m, cand, i); NM6(m, cand, i) = t; }
+      }
     }
     if (k > 0) {
       float temp[6];
+#pragma unroll
       for (int j = 0; j < k; j++) temp[j] = fmul(NM6(m, j, j), NM6(m, k, j));
       float s = 0.0f;
+#pragma unroll
       for (int j = 0; j < k; j++) s = fadd(s, fmul(NM6(m, k, j), temp[j]));
       NM6(m, k, k) = fsub(NM6(m, k, k), s);
+#pragma unroll
       for (int i = k + 1; i < N; i++) {
         float s2 = 0.0f;
+#pragma unroll
         for (int j = 0; j < k; j++) s2 = fadd(s2, fmul(NM6(m, i, j), temp[j]));
         NM6(m, i, k) = fsub(NM6(m, i, k), s2);
       }
     }
     float akk = NM6(m, k, k);
-    if (fabsf(akk) > 0.0f)
+    if (fabsf(akk) > 0.0f) {
+#pragma unroll
       for (int i = k + 1; i < N; i++) NM6(m, i, k) = fdiv(NM6(m, i, k), akk);
+    }
   }
   float y[6];
+#pragma unroll
   for (int i = 0; i < N; i++) y[i] = bin[i];
-  for (int k = 0; k < N; k++) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+  // y = P b: transpositions applied in order
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+#pragma unroll
+    for (int cand = k + 1; cand < N; cand++)
+      if (cand == tr[k]) { float t = y[k]; y[k] = y[cand]; y[cand] = t; }
+  }
+#pragma unroll
   for (int i = 0; i < N; i++) {
     float s = y[i];
+#pragma unroll
     for (int j = 0; j < i; j++) s = fsub(s, fmul(NM6(m, i, j), y[j]));
     y[i] = s;
   }
+#pragma unroll
   for (int i = 0; i < N; i++) {
     float d = NM6(m, i, i);
     y[i] = (fabsf(d) > FLT_MIN) ? fdiv(y[i], d) : 0.0f;
   }
+#pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     float s = y[i];
+#pragma unroll
     for (int j = i + 1; j < N; j++) s = fsub(s, fmul(NM6(m, j, i), y[j]));
     y[i] = s;
   }
-  for (int k = N - 1; k >= 0; k--) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+  // x = P^T y: transpositions in reverse order
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+#pragma unroll
+    for (int cand = k + 1; cand < N; cand++)
+      if (cand == tr[k]) { float t = y[k]; y[k] = y[cand]; y[cand] = t; }
+  }
+#pragma unroll
   for (int i = 0; i < N; i++) x[i] = y[i];
 }
 
