@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256) k_integral_cols_smem(int rows, int cols, 
   float *plane = I + (size_t)blockIdx.y * rows * cols;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const bool inside = x0 + lx < cols;
+#pragma unroll 8
   for (int y = ly; y < rows; y += 8) strip[y * 32 + lx] = inside ? plane[(size_t)y * cols + x0 + lx] : 0.0f;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -510,8 +511,10 @@ __global__ void __launch_bounds__(256) k_integral_cols_smem(int rows, int cols, 
     for (; y < rows; y++) { v = fadd(strip[y * 32 + lx], v); strip[y * 32 + lx] = v; }
   }
   __syncthreads();
-  if (inside)
+  if (inside) {
+#pragma unroll 8
     for (int y = ly; y < rows; y += 8) plane[(size_t)y * cols + x0 + lx] = strip[y * 32 + lx];
+  }
 }
 
 int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
