@@ -136,8 +136,17 @@ __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ de
     z = D.refZ[which];
     KRt = affine_from(D.state->KRt[0]);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+  // four independent point loads in flight per thread (the loop was load -> compute -> atomic, one at a time)
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const float4 p0 = pts[i], p1 = pts[i + stride], p2 = pts[i + 2 * stride], p3 = pts[i + 3 * stride];
+    project_point(KRt, p0, i, rows, cols, minD, maxD, z);
+    project_point(KRt, p1, i + stride, rows, cols, minD, maxD, z);
+    project_point(KRt, p2, i + 2 * stride, rows, cols, minD, maxD, z);
+    project_point(KRt, p3, i + 3 * stride, rows, cols, minD, maxD, z);
+  }
+  for (; i < n; i += stride) project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
 }
 
 // the same for a MultiPointProjector camera set
