@@ -529,7 +529,8 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
   if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
-  if (ctx->graphValid) cudaGraphExecDestroy(ctx->graphExec);
+  for (int g = 0; g < nicp_context::kGraphCache; g++)
+    if (ctx->graphValid[g]) cudaGraphExecDestroy(ctx->graphExec[g]);
   for (cudaEvent_t e : *ctx->evCorr) cudaEventDestroy(e);
   for (cudaEvent_t e : *ctx->evProj) cudaEventDestroy(e);
   delete ctx->evCorr;
@@ -1035,14 +1036,29 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       key.partialRows = ctx->partialRows; key.imgThr = imgThr; key.slotPixels = ctx->slotPixels;
       key.desc = ctx->d_desc; key.results = ctx->d_results; key.statHb = ctx->d_statHb; key.trace = ctx->d_trace;
       key.priors = ctx->d_priors; key.refZ = ctx->d_refZ;
-      if (ctx->graphValid && memcmp(&key, ctx->graphKey, sizeof key) == 0) {
-        NICP_CUDA(cudaGraphLaunch(ctx->graphExec, ctx->stream));
+      int hit = -1, victim = 0;
+      for (int g = 0; g < nicp_context::kGraphCache; g++) {
+        if (ctx->graphValid[g] && memcmp(&key, ctx->graphKey[g], sizeof key) == 0) hit = g;
+        if (!ctx->graphValid[g]) victim = g;
+      }
+      if (hit < 0) {
+        bool anyFree = false;
+        for (int g = 0; g < nicp_context::kGraphCache; g++) anyFree = anyFree || !ctx->graphValid[g];
+        if (!anyFree) {
+          victim = 0;
+          for (int g = 1; g < nicp_context::kGraphCache; g++)
+            if (ctx->graphUse[g] < ctx->graphUse[victim]) victim = g;  // least recently used
+        }
+      }
+      if (hit >= 0) {
+        NICP_CUDA(cudaGraphLaunch(ctx->graphExec[hit], ctx->stream));
+        ctx->graphUse[hit] = ++ctx->graphClock;
         ctx->launches += 2 + 5 + 4 * (long long)ap->outer_iterations * (ap->inner_iterations > 0 ? ap->inner_iterations : 0) + 4;
         replayed = true;
       } else {
-        if (ctx->graphValid) {
-          cudaGraphExecDestroy(ctx->graphExec);
-          ctx->graphValid = false;
+        if (ctx->graphValid[victim]) {
+          cudaGraphExecDestroy(ctx->graphExec[victim]);
+          ctx->graphValid[victim] = false;
         }
         cudaGraph_t graph = nullptr;
         NICP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1058,11 +1074,12 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
           set_error("CUDA graph capture of nicp_align failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : (e1 != cudaSuccess ? e1 : e2)));
           return NICP_ERR_CUDA;
         }
-        NICP_CUDA(cudaGraphInstantiate(&ctx->graphExec, graph, 0));
+        NICP_CUDA(cudaGraphInstantiate(&ctx->graphExec[victim], graph, 0));
         cudaGraphDestroy(graph);
-        memcpy(ctx->graphKey, &key, sizeof key);
-        ctx->graphValid = true;
-        NICP_CUDA(cudaGraphLaunch(ctx->graphExec, ctx->stream));
+        memcpy(ctx->graphKey[victim], &key, sizeof key);
+        ctx->graphValid[victim] = true;
+        ctx->graphUse[victim] = ++ctx->graphClock;
+        NICP_CUDA(cudaGraphLaunch(ctx->graphExec[victim], ctx->stream));
         replayed = true;
       }
     }

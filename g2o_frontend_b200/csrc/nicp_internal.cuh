@@ -218,9 +218,11 @@ struct nicp_context {
   // CUDA graph of the last single-pair nicp_align (47 launches + copies replayed as one graph launch when
   // every baked-in value -- thresholds, K, offsets, iteration counts, image size, buffers -- is unchanged)
   int graphsEnabled;
-  cudaGraphExec_t graphExec;
-  bool graphValid;
-  unsigned char graphKey[512];
+  static constexpr int kGraphCache = 4;   // e.g. the three levels of a pyramid + one tracker configuration
+  cudaGraphExec_t graphExec[kGraphCache];
+  bool graphValid[kGraphCache];
+  unsigned long long graphUse[kGraphCache], graphClock;
+  unsigned char graphKey[kGraphCache][512];
 
   // last single-align bookkeeping
   int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;
