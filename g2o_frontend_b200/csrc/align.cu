@@ -2,15 +2,16 @@
 //
 // Replaces, for a batch of independent (reference, current) cloud pairs processed in lock step:
 //   PinholePointProjector::project      pinholepointprojector.cpp:33-66   -> k_project
-//   CorrespondenceFinder::compute       correspondencefinder.cpp:20-118  \  k_corr_lin<0> (fused)
-//   Linearizer::update                  linearizer.cpp:17-115            /  k_corr_lin<1> (from the stored correspondences)
+//   CorrespondenceFinder::compute       correspondencefinder.cpp:20-118  \  k_corr_lin_tiled<0> (fused)
+//   Linearizer::update                  linearizer.cpp:17-115            /  k_corr_lin_tiled<1> (from the stored correspondences)
 //   Aligner::align loop body            aligner.cpp:66-118                -> k_reduce_solve
-//   PwnMatcherBase::matchClouds stats   pwn_tracker2/pwn_matcher_base.cpp:167-196 -> folded into k_corr_lin<1>
+//   PwnMatcherBase::matchClouds stats   pwn_tracker2/pwn_matcher_base.cpp:167-196 -> folded into k_corr_lin_tiled<1>
 //
-// z-buffer: one 64-bit word per pixel, (float_bits(depth) << 32) | pointIndex, filled with
-// atomicMin.  depth > 0 so unsigned order == float order: the nearest point wins and, on equal
-// depth, the lowest point index wins -- exactly the outcome of the reference's sequential scatter
-// with its strict `otherDistance > d` test.  Empty = all ones (index decodes to -1).
+// z-buffer: one 64-bit word per pixel, (epoch | float_bits(depth * 2^-110)) << 32 | pointIndex, filled
+// with atomicMin (z_encode in nicp_internal.cuh).  depth > 0 so unsigned order == float order: the
+// nearest point wins and, on equal depth, the lowest point index wins -- exactly the outcome of the
+// reference's sequential scatter with its strict `otherDistance > d` test.  Fresh = all ones
+// (index decodes to -1); the epoch tag lets later iterations reuse a buffer without clearing it.
 //
 // Reduction: every thread accumulates 30 float sums over its pixels (21 unique H entries, 6 b,
 // chi2, inliers, correspondences), a transposing warp butterfly leaves component j in lane j
@@ -61,7 +62,7 @@ __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
 // _project (pinholepointprojector.h:224-233) + the z-test of project (pinholepointprojector.cpp:52-64)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i, int rows, int cols, float minD,
-                                              float maxD, unsigned long long *__restrict__ z) {
+                                              float maxD, unsigned long long *__restrict__ z, int epoch) {
   float ix, iy, d;
   xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
   if (d < minD || d > maxD) return;
@@ -69,8 +70,7 @@ __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i
   float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
   if (!(fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows)) return;
   int x = (int)fx, y = (int)fy;
-  unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
-  atomicMin(&z[(size_t)y * cols + x], key);
+  atomicMin(&z[(size_t)y * cols + x], z_encode(d, i, epoch));
 }
 
 CamGeom geom_of(const CamSet &c) {
@@ -89,7 +89,7 @@ CamGeom geom_of(const CamSet &c) {
 // [0,width) x [0,height) wins; composite pixel = (row u, col v + colOff).
 template <typename MatSrc>
 __device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatSrc &mats, float4 p, int i, int rows,
-                                                    int cols, unsigned long long *__restrict__ z) {
+                                                    int cols, unsigned long long *__restrict__ z, int epoch) {
   for (int c = 0; c < g.n; c++) {
     const Affine KRt = mats(c);
     float ix, iy, d;
@@ -99,10 +99,7 @@ __device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatS
     float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
     if (d < 0.0f || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
     int X = (int)fx, Y = (int)fy + g.colOff[c];
-    if (X < rows && Y < cols) {
-      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
-      atomicMin(&z[(size_t)X * cols + Y], key);
-    }
+    if (X < rows && Y < cols) atomicMin(&z[(size_t)X * cols + Y], z_encode(d, i, epoch));
     return;
   }
 }
@@ -118,7 +115,8 @@ struct MatsFromParam {
 // which: 0/1 = reference cloud into refZ[which] with the pair's KRt; 2 = current cloud into curZ
 // with the (shared) current-sensor KRt, only for the pair that owns that buffer.
 __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ desc, int which, Affine curKRt, int rows,
-                                                 int cols, float minD, float maxD, const int *__restrict__ ownsCur) {
+                                                 int cols, float minD, float maxD, const int *__restrict__ ownsCur,
+                                                 int epoch) {
   const PairDesc &D = desc[blockIdx.y];
   const float4 *pts;
   unsigned long long *z;
@@ -141,30 +139,30 @@ __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ de
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + 3 * stride < n; i += 4 * stride) {
     const float4 p0 = pts[i], p1 = pts[i + stride], p2 = pts[i + 2 * stride], p3 = pts[i + 3 * stride];
-    project_point(KRt, p0, i, rows, cols, minD, maxD, z);
-    project_point(KRt, p1, i + stride, rows, cols, minD, maxD, z);
-    project_point(KRt, p2, i + 2 * stride, rows, cols, minD, maxD, z);
-    project_point(KRt, p3, i + 3 * stride, rows, cols, minD, maxD, z);
+    project_point(KRt, p0, i, rows, cols, minD, maxD, z, epoch);
+    project_point(KRt, p1, i + stride, rows, cols, minD, maxD, z, epoch);
+    project_point(KRt, p2, i + 2 * stride, rows, cols, minD, maxD, z, epoch);
+    project_point(KRt, p3, i + 3 * stride, rows, cols, minD, maxD, z, epoch);
   }
-  for (; i < n; i += stride) project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+  for (; i < n; i += stride) project_point(KRt, pts[i], i, rows, cols, minD, maxD, z, epoch);
 }
 
 // the same for a MultiPointProjector camera set
 __global__ void __launch_bounds__(256) k_project_multi(const PairDesc *__restrict__ desc, int which, CamGeom g,
                                                        const CamMats *__restrict__ curMats, int rows, int cols,
-                                                       const int *__restrict__ ownsCur) {
+                                                       const int *__restrict__ ownsCur, int epoch) {
   const PairDesc &D = desc[blockIdx.y];
   if (which == 2) {
     if (!ownsCur[blockIdx.y]) return;
     const int n = *D.curN;
     MatsFromParam mats{curMats};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      project_point_multi(g, mats, D.curPoints[i], i, rows, cols, D.curZ);
+      project_point_multi(g, mats, D.curPoints[i], i, rows, cols, D.curZ, epoch);
   } else {
     const int n = *D.refN;
     MatsFromState mats{D.state};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      project_point_multi(g, mats, D.refPoints[i], i, rows, cols, D.refZ[which]);
+      project_point_multi(g, mats, D.refPoints[i], i, rows, cols, D.refZ[which], epoch);
   }
 }
 
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(256) k_project_single(const float4 *__restrict
                                                         unsigned long long *__restrict__ z) {
   int n = *nPtr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    project_point(KRt, pts[i], i, rows, cols, minD, maxD, z);
+    project_point(KRt, pts[i], i, rows, cols, minD, maxD, z, kEpochFresh);
 }
 
 __global__ void __launch_bounds__(256) k_project_single_multi(const float4 *__restrict__ pts, const int *__restrict__ nPtr,
@@ -182,24 +180,23 @@ __global__ void __launch_bounds__(256) k_project_single_multi(const float4 *__re
   int n = *nPtr;
   MatsFromParam mats{matsPtr};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    project_point_multi(g, mats, pts[i], i, rows, cols, z);
+    project_point_multi(g, mats, pts[i], i, rows, cols, z, kEpochFresh);
 }
 
 __global__ void k_decode_z(const unsigned long long *__restrict__ z, int n, int *__restrict__ index,
-                           float *__restrict__ depth, float emptyDepth) {
+                           float *__restrict__ depth, float emptyDepth, int epoch) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long v = z[i];
-  int idx = (int)(unsigned int)(v & 0xFFFFFFFFull);
-  if (index) index[i] = idx;
-  if (depth) depth[i] = (v == kEmptyZ) ? emptyDepth : __uint_as_float((unsigned int)(v >> 32));
+  if (index) index[i] = z_index(v, epoch);
+  if (depth) depth[i] = z_depth(v, epoch, emptyDepth);
 }
 
 __global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int *__restrict__ ownsCur) {
   if (!ownsCur[blockIdx.y]) return;
   const PairDesc &D = desc[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
-    D.curIndex[i] = (int)(unsigned int)(D.curZ[i] & 0xFFFFFFFFull);
+    D.curIndex[i] = z_index(D.curZ[i], kEpochFresh);
 }
 
 int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
@@ -244,8 +241,9 @@ int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet
   return NICP_OK;
 }
 
-int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth, float emptyDepth) {
-  k_decode_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_z, n, d_index, d_depth, emptyDepth);
+int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth, float emptyDepth,
+                    int epoch) {
+  k_decode_z<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_z, n, d_index, d_depth, emptyDepth, epoch);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }
@@ -320,112 +318,12 @@ __device__ __forceinline__ void accumulate_term(float (&acc)[kAccum], float rpx,
   acc[A_BR + 2] += ks * ((px * ep1 - py * ep0) + (qx * en1 - qy * en0));
 }
 
-// MODE 0: correspondence gates + linearise at state->invT; writes the correspondence image and
-//         resets the other reference z-buffer for the next iteration's projection.
-// MODE 1: linearise at state->invT over the stored correspondence image (inner iterations > 0,
-//         _computeStatistics) and, if imgStats, accumulate the matchClouds image statistics
-//         (slots 29,30,31 = reprojection sum, nonZeros, inliers).
-template <int MODE>
-__global__ void __launch_bounds__(256) k_corr_lin(const PairDesc *__restrict__ desc, int parity, AlignConsts ac,
-                                                  int numPixels, int pixelsPerBlock, int imgStats, float imgThreshold) {
-  const PairDesc &D = desc[blockIdx.y];
-  const Affine T = affine_from(D.state->invT);
-  const float4 *__restrict__ refPoints = D.refPoints;
-  const float4 *__restrict__ refNormals = D.refNormals;
-  const float4 *__restrict__ curPoints = D.curPoints;
-  const float4 *__restrict__ curNormals = D.curNormals;
-  const float4 *__restrict__ curOmega = D.curOmega;
-  const int *__restrict__ curIndex = D.curIndex;
-  int *__restrict__ corrImage = D.corrImage;
-  const unsigned long long *__restrict__ zref = D.refZ[parity];
-  unsigned long long *__restrict__ znext = D.refZ[parity ^ 1];
-  const unsigned long long *__restrict__ zcur = D.curZ;
-
-  float acc[kAccum];
-#pragma unroll
-  for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
-
-  const int begin = blockIdx.x * pixelsPerBlock;
-  const int end = min(begin + pixelsPerBlock, numPixels);
-  for (int pix = begin + threadIdx.x; pix < end; pix += blockDim.x) {
-    int ri, ci = curIndex[pix];
-    if (MODE == 0) {
-      unsigned long long zr = zref[pix];
-      znext[pix] = kEmptyZ;
-      ri = (int)(unsigned int)(zr & 0xFFFFFFFFull);
-    } else {
-      ri = corrImage[pix];
-      if (imgStats) {
-        // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
-        unsigned long long zc = zcur[pix], zr = zref[pix];
-        float dc = (zc == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zc >> 32));
-        float dr = (zr == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zr >> 32));
-        unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
-        unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
-        if (c16 > 0 && r16 > 0) {
-          float df = fabsf(fsub((float)c16, (float)r16));
-          float dm = __uint_as_float(__float_as_uint(df) & 0x437F0000u);
-          acc[30] += 1.0f;
-          if (dm < imgThreshold) acc[31] += 1.0f;
-          acc[29] += dm;
-        }
-      }
-    }
-    if (ri < 0 || ci < 0) {
-      if (MODE == 0) corrImage[pix] = -1;
-      continue;
-    }
-    if (MODE == 0) acc[A_MIDX] += 1.0f;
-    const float4 cn = curNormals[ci];
-    const float4 rn0 = refNormals[ri];
-    const float4 cp = curPoints[ci];
-    const float4 rp0 = refPoints[ri];
-    float rpx, rpy, rpz, rnx, rny, rnz;
-    xform_point(T, rp0.x, rp0.y, rp0.z, rpx, rpy, rpz);
-    xform_normal(T, rn0.x, rn0.y, rn0.z, rnx, rny, rnz);
-    if (MODE == 0) {
-      bool ok = true;
-      // correspondencefinder.cpp:69: zero normals are skipped
-      if (dot3(cn.x, cn.y, cn.z, cn.x, cn.y, cn.z) == 0.0f || dot3(rn0.x, rn0.y, rn0.z, rn0.x, rn0.y, rn0.z) == 0.0f)
-        ok = false;
-      // :78 normal angle
-      if (ok && dot3(cn.x, cn.y, cn.z, rnx, rny, rnz) < ac.normalThreshold) ok = false;
-      // :84 point distance
-      if (ok) {
-        float dx = fsub(cp.x, rpx), dy = fsub(cp.y, rpy), dz = fsub(cp.z, rpz);
-        if (dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold) ok = false;
-      }
-      // :87-99 curvature ratio, evaluated in double like the reference's (float + 1e-5) / (float + 1e-5)
-      if (ok) {
-        float rc = rn0.w, cc = cn.w;
-        if (rc < ac.flatCurvature) rc = ac.flatCurvature;
-        if (cc < ac.flatCurvature) cc = ac.flatCurvature;
-        float ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
-        if (ratio < ac.minRatio || ratio > ac.maxRatio) ok = false;
-      }
-      corrImage[pix] = ok ? ri : -1;
-      if (!ok) continue;
-      acc[A_NCORR] += 1.0f;
-    }
-    const float4 o0 = curOmega[3 * (size_t)ci], o1 = curOmega[3 * (size_t)ci + 1], o2 = curOmega[3 * (size_t)ci + 2];
-    accumulate_term(acc, rpx, rpy, rpz, rnx, rny, rnz, cp, cn, o0, o1, o2, ac.maxChi2, ac.robust);
-  }
-
-  __shared__ float red[8][kAccum];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float tot = warp_transpose_reduce(acc, lane);
-  red[warp][lane] = tot;
-  __syncthreads();
-  if (warp == 0) {
-    float s = red[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; w++) s += red[w][lane];
-    D.partials[(size_t)blockIdx.x * kAccum + lane] = s;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Tiled variant of the fused kernel (the default): one CTA of NT threads owns a tile of NT*TK pixels.
+// The fused CorrespondenceFinder::compute + Linearizer::update kernel: one CTA of NT threads owns a tile of NT*TK pixels.
+// MODE 0: correspondence gates + linearise at state->invT; the correspondence image is written only when asked for
+//         (last outer iteration, inner iterations > 1, stage-level call).
+// MODE 1: linearise at state->invT over the stored correspondence image (inner iterations > 0, _computeStatistics)
+//         and, if imgStats, accumulate the matchClouds image statistics (slots A_IMGSUM, A_IMGNZ, A_IMGINL).
 //   stage 1  every thread loads the z-buffer word / current index of its TK pixels, then issues the
 //            4*TK gathers (float4 each) back to back -- 5*TK independent loads in flight per thread
 //            instead of 3 dependent round trips per pixel -- transforms the reference point/normal,
@@ -460,8 +358,9 @@ struct TileSmem {
 };
 
 template <int MODE, int NT, int TK, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, AlignConsts ac,
-                                                             int numPixels, int imgStats, float imgThreshold) {
+__global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, int epoch,
+                                                             int writeCorr, AlignConsts ac, int numPixels, int imgStats,
+                                                             float imgThreshold) {
   constexpr int NW = NT / 32;
   constexpr int TILE = NT * TK;
   static_assert(TK * NW <= 32, "prefix scan is done by one warp");
@@ -478,7 +377,6 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   const int *__restrict__ curIndex = D.curIndex;
   int *__restrict__ corrImage = D.corrImage;
   const unsigned long long *__restrict__ zref = D.refZ[parity];
-  unsigned long long *__restrict__ znext = D.refZ[parity ^ 1];
   const unsigned long long *__restrict__ zcur = D.curZ;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -496,8 +394,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
     if (pix < numPixels) {
       ci[k] = curIndex[pix];
       if (MODE == 0) {
-        unsigned long long zr = zref[pix];
-        ri[k] = (int)(unsigned int)(zr & 0xFFFFFFFFull);
+        ri[k] = z_index(zref[pix], epoch);
       } else {
         ri[k] = corrImage[pix];
       }
@@ -514,21 +411,14 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       rp0[k] = refPoints[ri[k]];
     }
   }
-  if (MODE == 0) {
-#pragma unroll
-    for (int k = 0; k < TK; k++) {
-      const int pix = base + k * NT + threadIdx.x;
-      if (pix < numPixels) znext[pix] = kEmptyZ;
-    }
-  } else if (imgStats) {
+  if (MODE == 1 && imgStats) {
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       const int pix = base + k * NT + threadIdx.x;
       if (pix < numPixels) {
         // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
-        unsigned long long zc = zcur[pix], zr = zref[pix];
-        float dc = (zc == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zc >> 32));
-        float dr = (zr == kEmptyZ) ? FLT_MAX : __uint_as_float((unsigned int)(zr >> 32));
+        const float dc = z_depth(zcur[pix], kEpochFresh, FLT_MAX);
+        const float dr = z_depth(zref[pix], epoch, FLT_MAX);
         unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
         unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
         if (c16 > 0 && r16 > 0) {
@@ -575,7 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       rn0[k].x = rnx; rn0[k].y = rny; rn0[k].z = rnz;
     }
     ok[k] = good;
-    if (MODE == 0) {
+    if (MODE == 0 && writeCorr) {
       const int pix = base + k * NT + threadIdx.x;
       if (pix < numPixels) corrImage[pix] = good ? ri[k] : -1;
     }
@@ -921,11 +811,7 @@ struct TileCfg { int nt, tk; };
 static const TileCfg kTileCfgs[] = {{64, 2}, {128, 2}, {256, 4}};
 static int tile_px(const nicp_context *ctx) { return kTileCfgs[ctx->tileConfig].nt * kTileCfgs[ctx->tileConfig].tk; }
 
-static int pixels_per_block(const nicp_context *ctx, int P) {
-  if (ctx->corrVariant == 1) return tile_px(ctx);
-  int ppb = (P + ctx->blocksPerPair - 1) / ctx->blocksPerPair;
-  return ppb < 256 ? 256 : ppb;
-}
+static int pixels_per_block(const nicp_context *ctx, int /*P*/) { return tile_px(ctx); }
 static int num_blocks_for(const nicp_context *ctx, int P) {
   int ppb = pixels_per_block(ctx, P);
   int nb = (P + ppb - 1) / ppb;
@@ -937,37 +823,32 @@ int partial_rows_for(const nicp_context *ctx, size_t pixels) {
 }
 
 template <int MODE, int NT, int TK, int MINB>
-static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, const AlignConsts &ac, int P, int imgStats, float imgThr) {
+static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac, int P,
+                         int imgStats, float imgThr) {
   size_t smem = sizeof(TileSmem<NT, TK>);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  k_corr_lin_tiled<MODE, NT, TK, MINB><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, ac, P, imgStats, imgThr);
+  k_corr_lin_tiled<MODE, NT, TK, MINB><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
+                                                                         imgThr);
 }
-template <int MODE>
-static void launch_tiled_cfg(nicp_context *ctx, dim3 grid, int parity, const AlignConsts &ac, int P, int imgStats, float imgThr) {
-  switch (ctx->tileConfig) {
-    case 1: launch_tiled<MODE, 128, 2, 6>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
-    case 2: launch_tiled<MODE, 256, 4, 2>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
-    default: launch_tiled<MODE, 64, 2, 12>(ctx, grid, parity, ac, P, imgStats, imgThr); break;
-  }
-}
-// MODE 0 / 1 launch of the fused kernel in the context's variant
-static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, const AlignConsts &ac, int P, int ppb,
-                            int imgStats, float imgThr) {
-  cudaStream_t st = ctx->stream;
-  if (ctx->corrVariant == 1) {
-    if (mode == 0)
-      launch_tiled_cfg<0>(ctx, grid, parity, ac, P, imgStats, imgThr);
-    else
-      launch_tiled_cfg<1>(ctx, grid, parity, ac, P, imgStats, imgThr);
+// MODE 0 / 1 launch of the fused kernel in the context's tile configuration
+static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac,
+                            int P, int imgStats, float imgThr) {
+  if (mode == 0) {
+    switch (ctx->tileConfig) {
+      case 1: launch_tiled<0, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 2: launch_tiled<0, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      default: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+    }
   } else {
-    if (mode == 0)
-      k_corr_lin<0><<<grid, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, imgStats, imgThr);
-    else
-      k_corr_lin<1><<<grid, 256, 0, st>>>(ctx->d_desc, parity, ac, P, ppb, imgStats, imgThr);
+    switch (ctx->tileConfig) {
+      case 1: launch_tiled<1, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 2: launch_tiled<1, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      default: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+    }
   }
 }
 
@@ -991,7 +872,6 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
                     bool /*wantTrace*/, int resultOffset) {
   cudaStream_t st = ctx->stream;
   const int P = ac.rows * ac.cols;
-  const int ppb = pixels_per_block(ctx, P);
   const int nb = num_blocks_for(ctx, P);
   // descriptors + ownership flags (flags live right after the descriptors in the staging buffer)
   int *h_flags = reinterpret_cast<int *>(ctx->h_desc + ctx->slots);
@@ -999,10 +879,14 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
   NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * nPairs, cudaMemcpyHostToDevice, st));
-  // reference z-buffer 0 and the current z-buffers start empty (all ones)
+  // both reference z-buffers and the current z-buffers start fresh (all ones = epoch 15, index -1); after that the
+  // epoch tag replaces per-iteration clearing (see z_encode in nicp_internal.cuh)
   // (slot buffers are contiguous: refZ is laid out [2][slots][slotPixels], curZ [slots][slotPixels])
-  NICP_CUDA(cudaMemsetAsync(ctx->d_refZ, 0xFF, sizeof(unsigned long long) * ctx->slotPixels * nPairs, st));
-  NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, sizeof(unsigned long long) * ctx->slotPixels * nPairs, st));
+  const size_t zBytes = sizeof(unsigned long long) * ctx->slotPixels * nPairs;
+  unsigned long long *const refZbuf[2] = {ctx->d_refZ, ctx->d_refZ + (size_t)ctx->slots * ctx->slotPixels};
+  NICP_CUDA(cudaMemsetAsync(refZbuf[0], 0xFF, zBytes, st));
+  NICP_CUDA(cudaMemsetAsync(refZbuf[1], 0xFF, zBytes, st));
+  NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, zBytes, st));
   k_init_pairs<<<(nPairs + 63) / 64, 64, 0, st>>>(ctx->d_desc, nPairs, ac);
   NICP_CHECK_LAUNCH(ctx);
   const int projBlocks = (P + 1023) / 1024;  // grid-stride: 4 points per thread at full density
@@ -1014,32 +898,36 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   if (cams.multi) {
     int rcm = upload_cam_mats(ctx, curMats, &d_curMats);
     if (rcm) return rcm;
-    k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags);
+    k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags, kEpochFresh);
   } else {
-    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, kEpochFresh);
   }
   NICP_CHECK_LAUNCH(ctx);
   k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags);
   NICP_CHECK_LAUNCH(ctx);
   const Affine dummy = curMats.M[0];
   dim3 cg(nb, nPairs);
-  int parity = 0;
+  int parity = 0, epoch = kEpochFresh;
   for (int it = 0; it < outerIters; it++) {
     parity = it & 1;
+    epoch = epoch_of_iteration(it);
+    // the 4-bit epoch wraps every 32 iterations: start that buffer fresh again
+    if (it >= 2 && epoch == kEpochFresh) NICP_CUDA(cudaMemsetAsync(refZbuf[parity], 0xFF, zBytes, st));
+    const int writeCorr = (it == outerIters - 1 || innerIters > 1) ? 1 : 0;
     NICP_TIME_BEGIN(evProj, evProjUsed);
     if (cams.multi)
-      k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, parity, geom, d_curMats, ac.rows, ac.cols, d_flags);
+      k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, parity, geom, d_curMats, ac.rows, ac.cols, d_flags, epoch);
     else
-      k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags);
+      k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, epoch);
     NICP_TIME_END(evProj, evProjUsed);
     NICP_CHECK_LAUNCH(ctx);
     for (int k = 0; k < innerIters; k++) {
       if (k == 0) {
         NICP_TIME_BEGIN(evCorr, evCorrUsed);
-        launch_corr_lin(ctx, 0, cg, parity, ac, P, ppb, 0, 0.0f);
+        launch_corr_lin(ctx, 0, cg, parity, epoch, writeCorr, ac, P, 0, 0.0f);
         NICP_TIME_END(evCorr, evCorrUsed);
       } else {
-        launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 0, 0.0f);
+        launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 0, 0.0f);
       }
       NICP_CHECK_LAUNCH(ctx);
       k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
@@ -1057,7 +945,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
       NICP_CUDA(cudaMemsetAsync(ctx->h_desc[i].corrImage, 0xFF, sizeof(int) * P, st));
   }
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
-  launch_corr_lin(ctx, 1, cg, parity, ac, P, ppb, 1, imgThreshold);
+  launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 1, imgThreshold);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
   NICP_CHECK_LAUNCH(ctx);
@@ -1066,6 +954,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
   NICP_CHECK_LAUNCH(ctx);
   ctx->lastAlignParity = parity;
+  ctx->lastAlignEpoch = epoch;
   return NICP_OK;
 }
 
@@ -1075,7 +964,7 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   const int ppb = pixels_per_block(ctx, numPixels);
   const int nb = (numPixels + ppb - 1) / ppb;
   dim3 cg(nb, 1);
-  launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, ac, numPixels, ppb, 0, 0.0f);
+  launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, kEpochFresh, 1, ac, numPixels, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_rows<<<dim3(kRowGroups, 1), 256, 0, st>>>(ctx->d_desc, nb);
   NICP_CHECK_LAUNCH(ctx);

@@ -894,7 +894,7 @@ int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, co
   AlignConsts ac = make_consts(&proj, ap, nullptr);
   fill_desc(ctx, 0, 0, reference, current, nullptr, nullptr, nullptr);
   std::vector<unsigned long long> z(px);
-  for (size_t i = 0; i < px; i++) z[i] = reference_index[i] < 0 ? kEmptyZ : (unsigned long long)(unsigned int)reference_index[i];
+  for (size_t i = 0; i < px; i++) z[i] = reference_index[i] < 0 ? kEmptyZ : ((unsigned long long)kEpochFresh << 60) | (unsigned int)reference_index[i];
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].refZ[0], z.data(), px * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, current_index, px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -1219,7 +1219,8 @@ int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *referen
   const PairDesc &D = ctx->h_desc[0];
   std::vector<int> ci, corrImg;
   if (reference_index || reference_depth) {
-    if ((rc = launch_decode_z(ctx, D.refZ[ctx->lastAlignParity], (int)P, ctx->d_index, ctx->d_depth, ctx->lastAlignEmptyDepth)))
+    if ((rc = launch_decode_z(ctx, D.refZ[ctx->lastAlignParity], (int)P, ctx->d_index, ctx->d_depth, ctx->lastAlignEmptyDepth,
+                              ctx->lastAlignEpoch)))
       return rc;
     if (reference_index) NICP_CUDA(cudaMemcpyAsync(reference_index, ctx->d_index, P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (reference_depth) NICP_CUDA(cudaMemcpyAsync(reference_depth, ctx->d_depth, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -36,6 +36,31 @@ constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
 constexpr int kIntegralCh = 10;   // n,x,y,z,xx,xy,xz,yy,yz,zz
 constexpr unsigned long long kEmptyZ = 0xFFFFFFFFFFFFFFFFull;
 
+// z-buffer word (one per pixel, filled with 64-bit atomicMin):
+//   [63:60] epoch   [59:32] float bits of depth * 2^-110   [31:0] point index
+// depth * 2^-110 is exact (power of two, no underflow above 1.5e-5 m) and its biased exponent stays below 32 for
+// depth < 32 km, so the top four bits of the float are free.  Smaller word wins: nearest depth, then lowest index --
+// the reference's sequential scatter with its strict `otherDistance > d` test (pinholepointprojector.cpp:52-64).
+// The epoch makes NEWER projections smaller than anything an older iteration left in the same buffer, so the buffer
+// is never cleared between iterations (the fused kernel used to spend 8 B/pixel/iteration on that): iteration `it`
+// projects into buffer it&1 with epoch 15 - ((it>>1) & 15) and a word is valid only if it carries that epoch.
+// A fresh buffer is all ones = epoch 15 with index -1.
+constexpr int kEpochFresh = 15;
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long z_encode(float d, int idx, int epoch) {
+  unsigned int hi = __float_as_uint(__fmul_rn(d, 0x1p-110f)) | ((unsigned int)epoch << 28);
+  return ((unsigned long long)hi << 32) | (unsigned int)idx;
+}
+__device__ __forceinline__ int z_index(unsigned long long v, int epoch) {
+  return ((unsigned int)(v >> 60) == (unsigned int)epoch) ? (int)(unsigned int)(v & 0xFFFFFFFFull) : -1;
+}
+__device__ __forceinline__ float z_depth(unsigned long long v, int epoch, float emptyDepth) {
+  if ((unsigned int)(v >> 60) != (unsigned int)epoch || (unsigned int)(v & 0xFFFFFFFFull) == 0xFFFFFFFFu) return emptyDepth;
+  return __fmul_rn(__uint_as_float((unsigned int)(v >> 32) & 0x0FFFFFFFu), 0x1p110f);
+}
+#endif
+inline int epoch_of_iteration(int it) { return kEpochFresh - ((it >> 1) & 15); }
+
 // accumulator slot layout of the fused correspondence+linearise reduction
 enum {
   A_HTT = 0,   // 6: xx xy xz yy yz zz
@@ -176,8 +201,8 @@ struct nicp_context {
   // align scratch
   int slots;          // allocated slots
   size_t slotPixels;  // pixels per slot
-  int blocksPerPair;            // CTAs per pair of the per-pixel variant (NICP_CORR_VARIANT=0)
-  int corrVariant;              // 1 = tiled fused kernel (default), 0 = per-pixel fused kernel (A/B only)
+  int blocksPerPair;            // lower bound of the partial-row allocation
+  int corrVariant;              // reserved (one fused-kernel variant is compiled)
   int tileConfig;               // index into the tiled kernel's (threads, pixels/thread) table
   int partialRows;              // rows of d_partials per slot
   unsigned long long *d_refZ;   // [slots][2][P]
@@ -225,7 +250,7 @@ struct nicp_context {
   unsigned char graphKey[kGraphCache][512];
 
   // last single-align bookkeeping
-  int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity;
+  int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity, lastAlignEpoch;
   float lastAlignEmptyDepth;
   bool lastAlignValid;
 };
@@ -248,7 +273,7 @@ int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const floa
 int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet &cams, const float T[16], int rows,
                         int cols, unsigned long long *d_z);
 int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth,
-                    float emptyDepth = FLT_MAX);
+                    float emptyDepth = FLT_MAX, int epoch = kEpochFresh);
 void cam_mats_KRt(const CamSet &cams, const float T[16], CamMats &out);
 CamGeom geom_of(const CamSet &c);
 int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const CamSet &cams, const float curOffset[16], int outerIters,
