@@ -357,7 +357,15 @@ struct TileSmem {
   float red[NT / 32][kAccum];
 };
 
-template <int MODE, int NT, int TK, int MINB>
+// shared memory of the in-place variant: only the Omega blocks (fetched with cp.async into the slot of the thread that
+// owns the pixel) and the CTA reduction scratch
+template <int NT, int TK>
+struct TileSmemInplace {
+  float4 om[3][NT * TK];
+  float red[NT / 32][kAccum];
+};
+
+template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, int epoch,
                                                              int writeCorr, AlignConsts ac, int numPixels, int imgStats,
                                                              float imgThreshold) {
@@ -365,7 +373,8 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   constexpr int TILE = NT * TK;
   static_assert(TK * NW <= 32, "prefix scan is done by one warp");
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  TileSmem<NT, TK> &S = *reinterpret_cast<TileSmem<NT, TK> *>(smemRaw);
+  using Smem = typename std::conditional<INPLACE, TileSmemInplace<NT, TK>, TileSmem<NT, TK>>::type;
+  Smem &S = *reinterpret_cast<Smem *>(smemRaw);
 
   const PairDesc &D = desc[blockIdx.y];
   const Affine T = affine_from(D.state->invT);
@@ -471,6 +480,33 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
     }
   }
 
+  float acc[kAccum];
+  if constexpr (INPLACE) {
+    // ---- in-place stage 2: the thread that owns the pixel accumulates its term; Omega through its own smem slot ----
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      if (ok[k]) {
+        const float4 *om = curOmega + 3 * (size_t)ci[k];
+        cp_async16(&S.om[0][k * NT + threadIdx.x], om);
+        cp_async16(&S.om[1][k * NT + threadIdx.x], om + 1);
+        cp_async16(&S.om[2][k * NT + threadIdx.x], om + 2);
+      }
+    }
+    cp_async_wait_all();
+#pragma unroll
+    for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      if (__any_sync(0xffffffffu, ok[k])) {
+        if (ok[k]) {
+          const float4 o0 = S.om[0][k * NT + threadIdx.x], o1 = S.om[1][k * NT + threadIdx.x],
+                       o2 = S.om[2][k * NT + threadIdx.x];
+          accumulate_term(acc, rp0[k].x, rp0[k].y, rp0[k].z, rn0[k].x, rn0[k].y, rn0[k].z, cp[k], cn[k], o0, o1, o2,
+                          ac.maxChi2, ac.robust);
+        }
+      }
+    }
+  } else {
   // ---- compaction (fixed order: pixel slot k, then warp, then lane) ----
   unsigned int bal[TK];
 #pragma unroll
@@ -510,7 +546,6 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   const int nAcc = S.total;
 
   // ---- stage 2 ----
-  float acc[kAccum];
 #pragma unroll
   for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
   for (int e = threadIdx.x; e < nAcc; e += NT) {
@@ -519,6 +554,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
     const float4 cnv = make_float4(S.f[9][e], S.f[10][e], S.f[11][e], 0.0f);
     accumulate_term(acc, S.f[0][e], S.f[1][e], S.f[2][e], S.f[3][e], S.f[4][e], S.f[5][e], cpv, cnv, o0, o1, o2, ac.maxChi2,
                     ac.robust);
+  }
   }
   if (MODE == 0) {
     acc[A_MIDX] = midx;
@@ -534,6 +570,10 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
 
   // ---- stage 3 ----
   float tot = warp_transpose_reduce(acc, lane);
+  if constexpr (NW == 1) {
+    D.partials[(size_t)blockIdx.x * kAccum + lane] = tot;
+    return;
+  }
   S.red[warp][lane] = tot;
   __syncthreads();
   if (warp == 0) {
@@ -808,7 +848,7 @@ __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *_
 struct TileCfg { int nt, tk; };
 // (measured on a B200, 64 pairs x 640x480 per launch: {64,2} 371 us, {128,2} 381 us, {128,2}@88 regs 423 us,
 //  {256,4} 519 us; see profiles/r1_corr_lin_tuning.md)
-static const TileCfg kTileCfgs[] = {{64, 2}, {128, 2}, {256, 4}};
+static const TileCfg kTileCfgs[] = {{64, 2}, {128, 2}, {256, 4}, {64, 4}, {32, 4}, {64, 3}, {32, 2}, {64, 3}, {128, 3}, {32, 3}, {96, 2}, {96, 3}, {32, 2}, {64, 3}, {32, 3}, {32, 4}, {64, 4}, {32, 3}};
 static int tile_px(const nicp_context *ctx) { return kTileCfgs[ctx->tileConfig].nt * kTileCfgs[ctx->tileConfig].tk; }
 
 static int pixels_per_block(const nicp_context *ctx, int /*P*/) { return tile_px(ctx); }
@@ -822,17 +862,17 @@ int partial_rows_for(const nicp_context *ctx, size_t pixels) {
   return a > ctx->blocksPerPair ? a : ctx->blocksPerPair;
 }
 
-template <int MODE, int NT, int TK, int MINB>
+template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac, int P,
                          int imgStats, float imgThr) {
-  size_t smem = sizeof(TileSmem<NT, TK>);
+  size_t smem = INPLACE ? sizeof(TileSmemInplace<NT, TK>) : sizeof(TileSmem<NT, TK>);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  k_corr_lin_tiled<MODE, NT, TK, MINB><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
-                                                                         imgThr);
+  k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P,
+                                                                                  imgStats, imgThr);
 }
 // MODE 0 / 1 launch of the fused kernel in the context's tile configuration
 static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac,
@@ -841,12 +881,42 @@ static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, 
     switch (ctx->tileConfig) {
       case 1: launch_tiled<0, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
       case 2: launch_tiled<0, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 3: launch_tiled<0, 64, 4, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 4: launch_tiled<0, 32, 4, 16>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 5: launch_tiled<0, 64, 3, 10>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 6: launch_tiled<0, 32, 2, 24>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 7: launch_tiled<0, 64, 3, 9>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 8: launch_tiled<0, 128, 3, 5>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 9: launch_tiled<0, 32, 3, 20>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 10: launch_tiled<0, 96, 2, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 11: launch_tiled<0, 96, 3, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 12: launch_tiled<0, 32, 2, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 13: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 14: launch_tiled<0, 32, 3, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 15: launch_tiled<0, 32, 4, 16, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 16: launch_tiled<0, 64, 4, 8, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 17: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
       default: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
     }
   } else {
     switch (ctx->tileConfig) {
       case 1: launch_tiled<1, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
       case 2: launch_tiled<1, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 3: launch_tiled<1, 64, 4, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 4: launch_tiled<1, 32, 4, 16>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 5: launch_tiled<1, 64, 3, 10>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 6: launch_tiled<1, 32, 2, 24>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 7: launch_tiled<1, 64, 3, 9>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 8: launch_tiled<1, 128, 3, 5>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 9: launch_tiled<1, 32, 3, 20>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 10: launch_tiled<1, 96, 2, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 11: launch_tiled<1, 96, 3, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 12: launch_tiled<1, 32, 2, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 13: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 14: launch_tiled<1, 32, 3, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 15: launch_tiled<1, 32, 4, 16, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 16: launch_tiled<1, 64, 4, 8, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 17: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
       default: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
     }
   }

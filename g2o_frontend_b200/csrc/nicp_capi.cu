@@ -492,8 +492,8 @@ int nicp_create(int device, nicp_context **out) {
     const char *v = getenv("NICP_CORR_VARIANT");
     ctx->corrVariant = (v && v[0] == '0') ? 0 : 1;
     // fixed per build (not per batch) so that a pair's H/b never depend on batch size or GPU count
-    ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
-    if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
+    ctx->tileConfig = env_int("NICP_TILE_CONFIG", 18) - 1;
+    if (ctx->tileConfig < 0 || ctx->tileConfig > 17) ctx->tileConfig = 0;
   }
   {
     void *p = nullptr;
