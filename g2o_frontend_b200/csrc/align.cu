@@ -465,9 +465,18 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
           if (rc < ac.flatCurvature) rc = ac.flatCurvature;
           if (cc < ac.flatCurvature) cc = ac.flatCurvature;
           // (rc + 1e-5) / (cc + 1e-5) in double, rounded to float; identical operands give exactly 1
-          float ratio = 1.0f;
-          if (rc != cc) ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
-          if (ratio < ac.minRatio || ratio > ac.maxRatio) good = false;
+          // float32 pre-test: the float64 quotient is only needed within 1e-4 (relative) of a threshold
+          if (rc != cc) {
+            const float q = __fdividef(rc + 1e-5f, cc + 1e-5f);
+            const float lo = ac.minRatio * (1.0f - 1e-4f), hi = ac.maxRatio * (1.0f + 1e-4f);
+            const float loIn = ac.minRatio * (1.0f + 1e-4f), hiIn = ac.maxRatio * (1.0f - 1e-4f);
+            if (q < lo || q > hi) {
+              good = false;
+            } else if (!(q > loIn && q < hiIn)) {
+              const float ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
+              if (ratio < ac.minRatio || ratio > ac.maxRatio) good = false;
+            }
+          }
         }
       }
       rp0[k].x = rpx; rp0[k].y = rpy; rp0[k].z = rpz;
