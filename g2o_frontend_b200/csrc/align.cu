@@ -70,7 +70,7 @@ __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i
   float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
   if (!(fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows)) return;
   int x = (int)fx, y = (int)fy;
-  atomicMin(&z[(size_t)y * cols + x], z_encode(d, i, epoch));
+  z_min(&z[(size_t)y * cols + x], z_encode(d, i, epoch));
 }
 
 CamGeom geom_of(const CamSet &c) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatS
     float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
     if (d < 0.0f || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
     int X = (int)fx, Y = (int)fy + g.colOff[c];
-    if (X < rows && Y < cols) atomicMin(&z[(size_t)X * cols + Y], z_encode(d, i, epoch));
+    if (X < rows && Y < cols) z_min(&z[(size_t)X * cols + Y], z_encode(d, i, epoch));
     return;
   }
 }

@@ -51,6 +51,10 @@ __device__ __forceinline__ unsigned long long z_encode(float d, int idx, int epo
   unsigned int hi = __float_as_uint(__fmul_rn(d, 0x1p-110f)) | ((unsigned int)epoch << 28);
   return ((unsigned long long)hi << 32) | (unsigned int)idx;
 }
+// fire-and-forget 64-bit minimum into global memory (RED, no return path, no generic-address dispatch)
+__device__ __forceinline__ void z_min(unsigned long long *p, unsigned long long key) {
+  asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(key) : "memory");
+}
 __device__ __forceinline__ int z_index(unsigned long long v, int epoch) {
   return ((unsigned int)(v >> 60) == (unsigned int)epoch) ? (int)(unsigned int)(v & 0xFFFFFFFFull) : -1;
 }
