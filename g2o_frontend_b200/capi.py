@@ -26,7 +26,12 @@ SYMBOLS = [
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
     "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch",
     "nicp_multi_image_size", "nicp_multi_depth_to_cloud", "nicp_multi_project", "nicp_multi_align",
+    "nicp_cloud_compute_gaussians", "nicp_cloud_has_gaussians", "nicp_cloud_download_gaussians",
+    "nicp_cloud_upload_gaussians", "nicp_merge", "nicp_voxelize",
 ]
+
+GAUSS_FLOATS = 24
+GAUSS_MOMENTS, GAUSS_INFO = 1, 2
 
 
 class Projector(C.Structure):
@@ -47,6 +52,17 @@ class StatsParams(C.Structure):
                 ("min_points", C.c_int), ("curvature_threshold", C.c_float),
                 ("omega_curvature_threshold", C.c_float), ("flat_omega_p", C.c_float * 3),
                 ("flat_omega_n", C.c_float * 3), ("nonflat_omega_n", C.c_float * 3)]
+
+
+class MergeParams(C.Structure):
+    """Merger defaults (merger.cpp:5-13)"""
+    _fields_ = [("distance_threshold", C.c_float), ("normal_threshold", C.c_float), ("max_point_depth", C.c_float)]
+
+
+def make_merge_params(distance_threshold=0.1, normal_threshold=None, max_point_depth=10.0):
+    if normal_threshold is None:
+        normal_threshold = float(np.cos(np.float32(10 * np.pi / 180.0)))  # cosf(10 * M_PI / 180.0f)
+    return MergeParams(distance_threshold, normal_threshold, max_point_depth)
 
 
 class AlignParams(C.Structure):
@@ -261,6 +277,50 @@ class Cloud:
     def transform(self, T):
         t = colmajor(T)
         _check(self.ctx.L, self.ctx.L.nicp_cloud_transform(self.ctx.handle, self.handle, _fptr(t)))
+
+    # ---- local-map maintenance (Gaussian3f sensor model, Merger, VoxelCalculator) ----
+    def compute_gaussians(self, depth, proj, baseline=0.075, alpha=0.1, sensor_offset=None):
+        """gaussians of PinholePointProjector::unProject for the depth image this cloud was built from"""
+        d = np.ascontiguousarray(depth, np.float32)
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_compute_gaussians(self.ctx.handle, self.handle, _fptr(d), C.byref(proj),
+                                                                    C.c_float(baseline), C.c_float(alpha), _fptr(so)))
+
+    def has_gaussians(self):
+        return bool(self.ctx.L.nicp_cloud_has_gaussians(self.handle))
+
+    def download_gaussians(self):
+        n = self.size()
+        g = np.zeros((n, GAUSS_FLOATS), np.float32)
+        f = np.zeros(n, np.int32)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_download_gaussians(self.ctx.handle, self.handle, _fptr(g), _iptr(f)))
+        return g, f
+
+    def upload_gaussians(self, gauss, flags):
+        g = np.ascontiguousarray(gauss, np.float32)
+        f = np.ascontiguousarray(flags, np.int32)
+        assert g.shape == (self.size(), GAUSS_FLOATS) and f.shape == (self.size(),)
+        _check(self.ctx.L, self.ctx.L.nicp_cloud_upload_gaussians(self.ctx.handle, self.handle, _fptr(g), _iptr(f)))
+
+    def merge(self, proj, T=None, params=None):
+        """Merger::merge(cloud, T) -> (new size, _collapsedIndices of the input points)"""
+        n = self.size()
+        t = colmajor(np.eye(4) if T is None else T)
+        mp = params if params is not None else make_merge_params()
+        collapsed = np.zeros(max(n, 1), np.int32)
+        new_size = C.c_int(0)
+        _check(self.ctx.L, self.ctx.L.nicp_merge(self.ctx.handle, self.handle, C.byref(proj), _fptr(t), C.byref(mp),
+                                                  _iptr(collapsed), C.byref(new_size)))
+        return new_size.value, collapsed[:n]
+
+    def voxelize(self, resolution=0.01):
+        """VoxelCalculator::compute(cloud, resolution) -> (new size, indices of the kept input points in output order)"""
+        n = self.size()
+        rep = np.zeros(max(n, 1), np.int32)
+        new_size = C.c_int(0)
+        _check(self.ctx.L, self.ctx.L.nicp_voxelize(self.ctx.handle, self.handle, C.c_float(resolution), _iptr(rep),
+                                                     C.byref(new_size)))
+        return new_size.value, rep[:new_size.value].copy()
 
     def append(self, other, T=None):
         """Cloud::add(other, T): append a transformed copy of `other`"""

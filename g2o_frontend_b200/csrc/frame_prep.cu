@@ -793,6 +793,8 @@ int launch_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *sr
                                                                       src->normals, src->omega, dst->points, dst->normals,
                                                                       dst->omega);
   NICP_CHECK_LAUNCH(ctx);
+  int rcg = launch_gauss_append(ctx, dst, src, T);
+  if (rcg) return rcg;
   k_add_count<<<1, 1, 0, ctx->stream>>>(dst->d_n, src->d_n, dst->capacity);
   NICP_CHECK_LAUNCH(ctx);
   dst->n_known = false;
@@ -809,6 +811,7 @@ int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[1
       cloud->capacity, cloud->d_n, affine_from(m), cloud->points, cloud->normals, cloud->omega,
       cloud->has_stats ? cloud->stats16 : nullptr);
   NICP_CHECK_LAUNCH(ctx);
+  if (cloud->has_gauss) return launch_gauss_transform(ctx, cloud, nullptr, 0, cloud->d_n, cloud->capacity, T);
   return NICP_OK;
 }
 

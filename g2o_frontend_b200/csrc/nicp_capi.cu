@@ -525,6 +525,7 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_trace);
   if (ctx->d_priors) cudaFree(ctx->d_priors);
   if (ctx->d_cams) cudaFree(ctx->d_cams);
+  if (ctx->d_mapScratch) cudaFree(ctx->d_mapScratch);
   dev_free(ctx->d_results);
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -608,6 +609,8 @@ void nicp_cloud_destroy(nicp_cloud *c) {
   dev_free(c->stats16);
   dev_free(c->eigvals);
   dev_free(c->statsN);
+  dev_free(c->gauss);
+  dev_free(c->gflags);
   dev_free(c->d_n);
   delete c;
 }
@@ -711,6 +714,70 @@ int nicp_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src,
   dst->n_host += src->n_host;
   dst->n_known = true;
   return NICP_OK;
+}
+
+// ---- local-map maintenance (map_ops.cu) ------------------------------------------------------------
+int nicp_cloud_compute_gaussians(nicp_context *ctx, nicp_cloud *c, const float *depth, const nicp_projector *proj,
+                                 float baseline, float alpha, const float sensor_offset[16]) {
+  if (!ctx || !c || !depth || !proj || !sensor_offset || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  return run_compute_gaussians(ctx, c, depth, proj, baseline, alpha, sensor_offset);
+}
+int nicp_cloud_has_gaussians(const nicp_cloud *c) { return c && c->has_gauss ? 1 : 0; }
+int nicp_cloud_download_gaussians(nicp_context *ctx, const nicp_cloud *c, float *gauss24, int *flags) {
+  if (!ctx || !c) return NICP_ERR_INVALID;
+  if (!c->has_gauss) {
+    set_error("the cloud carries no gaussians (nicp_cloud_compute_gaussians / nicp_cloud_upload_gaussians first)");
+    return NICP_ERR_INVALID;
+  }
+  int rc;
+  if ((rc = cloud_sync_n(ctx, c))) return rc;
+  const size_t n = (size_t)c->n_host;
+  if (gauss24 && n) NICP_CUDA(cudaMemcpyAsync(gauss24, c->gauss, sizeof(float) * NICP_GAUSS_FLOATS * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (flags && n) NICP_CUDA(cudaMemcpyAsync(flags, c->gflags, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NICP_OK;
+}
+int nicp_cloud_upload_gaussians(nicp_context *ctx, nicp_cloud *c, const float *gauss24, const int *flags) {
+  if (!ctx || !c || !gauss24 || !flags) return NICP_ERR_INVALID;
+  int rc;
+  if ((rc = cloud_sync_n(ctx, c))) return rc;
+  if ((rc = cloud_ensure_gaussians(ctx, c))) return rc;
+  const size_t n = (size_t)c->n_host;
+  if (n) {
+    NICP_CUDA(cudaMemcpyAsync(c->gauss, gauss24, sizeof(float) * NICP_GAUSS_FLOATS * n, cudaMemcpyHostToDevice, ctx->stream));
+    NICP_CUDA(cudaMemcpyAsync(c->gflags, flags, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  c->has_gauss = true;
+  return NICP_OK;
+}
+int nicp_merge(nicp_context *ctx, nicp_cloud *c, const nicp_projector *proj, const float transform[16],
+               const nicp_merge_params *params, int *collapsed, int *new_size) {
+  if (!ctx || !c || !proj || !transform || !params || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  if (!c->has_gauss) {
+    set_error("nicp_merge: the cloud carries no gaussians (Merger::merge fuses cloud->gaussians())");
+    return NICP_ERR_INVALID;
+  }
+  int rc;
+  if ((rc = cloud_sync_n(ctx, c))) return rc;
+  if (c->n_host == 0) {
+    if (new_size) *new_size = 0;
+    return NICP_OK;
+  }
+  return run_merge(ctx, c, proj, transform, params, c->n_host, collapsed, new_size);
+}
+int nicp_voxelize(nicp_context *ctx, nicp_cloud *c, float resolution, int *representatives, int *new_size) {
+  if (!ctx || !c || !(resolution > 0.0f)) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = cloud_sync_n(ctx, c))) return rc;
+  if (c->n_host == 0) {
+    if (new_size) *new_size = 0;
+    return NICP_OK;
+  }
+  return run_voxelize(ctx, c, resolution, c->n_host, representatives, new_size);
 }
 
 // ---- depth helpers ---------------------------------------------------------------------------

@@ -182,6 +182,9 @@ struct nicp_cloud {
   int n_host;       // host mirror (valid if n_known)
   bool n_known;
   bool has_stats;
+  float *gauss;     // optional: Gaussian3f per point, NICP_GAUSS_FLOATS floats each (map_ops.cu)
+  int *gflags;      // NICP_GAUSS_MOMENTS | NICP_GAUSS_INFO
+  bool has_gauss;
 };
 
 struct nicp_context {
@@ -253,6 +256,10 @@ struct nicp_context {
   unsigned long long graphUse[kGraphCache], graphClock;
   unsigned char graphKey[kGraphCache][512];
 
+  // local-map maintenance scratch (map_ops.cu), grow-only
+  void *d_mapScratch;
+  size_t mapScratchBytes;
+
   // last single-align bookkeeping
   int lastAlignRows, lastAlignCols, lastAlignIters, lastAlignParity, lastAlignEpoch;
   float lastAlignEmptyDepth;
@@ -285,4 +292,14 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
                     int resultOffset);
 int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);
 int partial_rows_for(const nicp_context *ctx, size_t pixels);
+// map_ops.cu
+int cloud_ensure_gaussians(nicp_context *ctx, nicp_cloud *cloud);
+int launch_gauss_transform(nicp_context *ctx, nicp_cloud *cloud, const int *d_first, int first, const int *d_count,
+                           int maxCount, const float T[16]);
+int launch_gauss_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]);
+int run_compute_gaussians(nicp_context *ctx, nicp_cloud *cloud, const float *depth, const nicp_projector *proj,
+                          float baseline, float alpha, const float sensorOffset[16]);
+int run_merge(nicp_context *ctx, nicp_cloud *cloud, const nicp_projector *proj, const float transform[16],
+              const nicp_merge_params *mp, int n, int *collapsedHost, int *newSize);
+int run_voxelize(nicp_context *ctx, nicp_cloud *cloud, float resolution, int n, int *repHost, int *newSize);
 }  // namespace nicp

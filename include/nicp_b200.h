@@ -165,6 +165,43 @@ int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[16]
  * matrices; Stats are not carried over).  Fails with NICP_ERR_INVALID if dst's capacity is too small. */
 int nicp_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]);
 
+/* ---- local-map maintenance -------------------------------------------
+ * Gaussian3f (basemath/gaussian.h): 24 floats per point -- mean (3), covariance (column-major 3x3),
+ * information vector (3), information matrix (3x3) -- plus a flag word saying which form is valid
+ * (the reference keeps both with lazy conversion through Matrix3f::inverse()). */
+#define NICP_GAUSS_FLOATS 24
+#define NICP_GAUSS_MOMENTS 1 /* Gaussian::_momentsUpdated */
+#define NICP_GAUSS_INFO 2    /* Gaussian::_infoUpdated */
+/* The sensor-model gaussians PinholePointProjector::unProject(points, gaussians, index, depth) produces
+ * (pinholepointprojector.cpp:93-133: J = iK [z 0 c; 0 z r; 0 0 1], cov = J diag(3, 3, alpha z^2 / (baseline fx + alpha z)) J^T)
+ * followed by Gaussian3fVector::transformInPlace(sensor_offset) (gaussian3.h:26-36), attached to a cloud that was
+ * built from the SAME depth image, projector and sensor offset by nicp_depth_to_cloud (one gaussian per point, raster
+ * order).  PinholePointProjector defaults: baseline 0.075, alpha 0.1 (pinholepointprojector.cpp:5-13). */
+int nicp_cloud_compute_gaussians(nicp_context *ctx, nicp_cloud *cloud, const float *depth, const nicp_projector *proj,
+                                 float baseline, float alpha, const float sensor_offset[16]);
+/* 1 if the cloud carries gaussians.  nicp_cloud_transform / nicp_cloud_append carry them along (cloud.cpp:145-186). */
+int nicp_cloud_has_gaussians(const nicp_cloud *cloud);
+int nicp_cloud_download_gaussians(nicp_context *ctx, const nicp_cloud *cloud, float *gauss24, int *flags);
+int nicp_cloud_upload_gaussians(nicp_context *ctx, nicp_cloud *cloud, const float *gauss24, const int *flags);
+/* Merger (merger.cpp:5-13 defaults) */
+typedef struct {
+  float distance_threshold; /* 0.1 */
+  float normal_threshold;   /* cosf(10 deg) */
+  float max_point_depth;    /* 10 */
+} nicp_merge_params;
+/* Merger::merge(cloud, transform) (merger.cpp:15-119) with the Merger's image size = proj->rows x proj->cols: projects the
+ * cloud with the projector at `transform`, fuses every point that lands on another point's pixel within the distance /
+ * normal thresholds into that z-buffer winner (information-form addition in the reference's order), moves the winners to
+ * the mean of their gaussian and removes the fused points (order preserving).  The cloud must carry gaussians.
+ * collapsed (host, one int per input point, may be NULL) receives Merger::_collapsedIndices. */
+int nicp_merge(nicp_context *ctx, nicp_cloud *cloud, const nicp_projector *proj, const float transform[16],
+               const nicp_merge_params *params, int *collapsed, int *new_size);
+/* VoxelCalculator::compute(cloud, resolution) (voxelcalculator.cpp:15-73): keeps the first point of every occupied voxel
+ * of side `resolution` (voxel = truncated point * (1/resolution)), output ordered by voxel (x, then y, then z).  The
+ * reference's map comparator (voxelcalculator.h:40-46) is not a strict weak ordering; this is the lexicographic order
+ * it intends.  representatives (host, capacity = current size, may be NULL) receives the kept input indices. */
+int nicp_voxelize(nicp_context *ctx, nicp_cloud *cloud, float resolution, int *representatives, int *new_size);
+
 /* ---- depth image helpers (pwn_static.cpp:5-68) ----------------------------------------------- */
 /* DepthImage_convert_16UC1_to_32FC1 followed by DepthImage_scale(step) on the device.
  * out has (rows/step) x (cols/step) floats.  step <= 1 skips the scaling. */

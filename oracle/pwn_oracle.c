@@ -1324,3 +1324,161 @@ void orc_image_stats(const float *curDepth, const float *refDepth, int n, float 
   *outliers = nz - inl;
   *reprojectionDistance = sum / nz;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Gaussian3f sensor model and Merger (local-map maintenance)
+ * ---------------------------------------------------------------------------------------- */
+static void mat3_mulf(const float *A, const float *B, float *C) { /* C = A*B, canonical dot order */
+  float o[9];
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++)
+      M3(o, r, c) = dot3(M3(A, r, 0), M3(A, r, 1), M3(A, r, 2), M3(B, 0, c), M3(B, 1, c), M3(B, 2, c));
+  memcpy(C, o, sizeof o);
+}
+static void mat3_mul_bt(const float *A, const float *B, float *C) { /* C = A*B^T */
+  float o[9];
+  for (int c = 0; c < 3; c++)
+    for (int r = 0; r < 3; r++)
+      M3(o, r, c) = dot3(M3(A, r, 0), M3(A, r, 1), M3(A, r, 2), M3(B, c, 0), M3(B, c, 1), M3(B, c, 2));
+  memcpy(C, o, sizeof o);
+}
+static void mat3_vec(const float *A, const float *v, float *o) {
+  float t[3];
+  for (int r = 0; r < 3; r++) t[r] = dot3(M3(A, r, 0), M3(A, r, 1), M3(A, r, 2), v[0], v[1], v[2]);
+  o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+/* Gaussian::_updateMoments / _updateInfo, basemath/gaussian.h:76-90 */
+static void gauss_update_moments(float *g, int *f) {
+  if (*f & ORC_GAUSS_MOMENTS) return;
+  mat3_inverse(g + 15, g + 3);
+  mat3_vec(g + 3, g + 12, g);
+  *f |= ORC_GAUSS_MOMENTS;
+}
+static void gauss_update_info(float *g, int *f) {
+  if (*f & ORC_GAUSS_INFO) return;
+  mat3_inverse(g + 3, g + 15);
+  mat3_vec(g + 15, g, g + 12);
+  *f |= ORC_GAUSS_INFO;
+}
+/* pinholepointprojector.cpp:93-133 */
+int orc_unproject_gaussians(const float *depth, int rows, int cols, const float K[9], const float iKRt[16],
+                            float minD, float maxD, float baseline, float alpha, float *points, int *index,
+                            float *gauss, int *gflags) {
+  float iK[9];
+  mat3_inverse(K, iK);
+  const float fB = baseline * M3(K, 0, 0);
+  int count = 0;
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < cols; c++) {
+      float z = depth[r * cols + c];
+      if (z < minD || z > maxD) { index[r * cols + c] = -1; continue; }
+      float *p = points + 4 * count;
+      xform3(iKRt, c * z, r * z, z, 1.0f, p);
+      p[3] = 1.0f;
+      float zVariation = (alpha * z * z) / (fB + z * alpha);
+      float J[9] = {z, 0.0f, 0.0f, 0.0f, z, 0.0f, (float)c, (float)r, 1.0f}; /* column-major [z 0 c; 0 z r; 0 0 1] */
+      mat3_mulf(iK, J, J);
+      float JD[9];
+      const float dg[3] = {3.0f, 3.0f, zVariation};
+      for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) M3(JD, i, j) = M3(J, i, j) * dg[j];
+      float *g = gauss + (size_t)ORC_GAUSS_FLOATS * count;
+      memset(g, 0, sizeof(float) * ORC_GAUSS_FLOATS);
+      g[0] = p[0]; g[1] = p[1]; g[2] = p[2];
+      mat3_mul_bt(JD, J, g + 3);
+      gflags[count] = ORC_GAUSS_MOMENTS;
+      index[r * cols + c] = count++;
+    }
+  return count;
+}
+/* gaussian3.h:26-36 */
+void orc_gaussians_transform(const float T[16], int n, float *gauss, int *gflags) {
+  float m[16];
+  memcpy(m, T, sizeof m);
+  fix_last_row(m);
+  int ident = 1;
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++)
+      if (M4(m, r, c) != (r == c ? 1.0f : 0.0f)) ident = 0;
+  if (ident) return;
+  float R[9], t[3];
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) M3(R, r, c) = M4(m, r, c);
+    t[r] = M4(m, r, 3);
+  }
+  for (int i = 0; i < n; i++) {
+    float *g = gauss + (size_t)ORC_GAUSS_FLOATS * i;
+    gauss_update_moments(g, &gflags[i]);
+    float mean[3], RC[9];
+    mat3_vec(R, g, mean);
+    g[0] = mean[0] + t[0]; g[1] = mean[1] + t[1]; g[2] = mean[2] + t[2];
+    mat3_mulf(R, g + 3, RC);
+    mat3_mul_bt(RC, R, g + 3);
+    gflags[i] = ORC_GAUSS_MOMENTS;
+  }
+}
+/* merger.cpp:15-119 */
+int orc_merge(int n, float *points, float *normals, float *statsM, float *omegaP, float *omegaN, float *gauss,
+              int *gflags, int rows, int cols, const float K[9], const float T[16], float minD, float maxD,
+              float distanceThreshold, float normalThreshold, float maxPointDepth, int *collapsedOut) {
+  float KRt[16], iKRt[16];
+  orc_update_matrices(K, T, KRt, iKRt);
+  int *indexImage = (int *)malloc(sizeof(int) * rows * cols);
+  float *depthImage = (float *)malloc(sizeof(float) * rows * cols);
+  int *collapsed = (int *)malloc(sizeof(int) * (n > 0 ? n : 1));
+  orc_project(points, n, rows, cols, KRt, minD, maxD, indexImage, depthImage);
+  for (int i = 0; i < n; i++) collapsed[i] = -1;
+  for (int i = 0; i < n; i++) {
+    const float *p = points + 4 * i, *cn = normals + 4 * i;
+    int r = -1, c = -1;
+    float ip[3];
+    xform3(KRt, p[0], p[1], p[2], p[3], ip);
+    float depth = ip[2];
+    if (!(depth < minD || depth > maxD)) { /* _project, pinholepointprojector.h:224-233 */
+      float s = 1.0f / depth;
+      c = (int)roundf(ip[0] * s);
+      r = (int)roundf(ip[1] * s);
+    }
+    if (depth < 0 || depth > maxPointDepth || r < 0 || r >= rows || c < 0 || c >= cols) continue;
+    float targetZ = depthImage[r * cols + c];
+    int targetIndex = indexImage[r * cols + c];
+    if (targetIndex < 0) continue;
+    const float *tn = normals + 4 * targetIndex;
+    if (targetIndex == i) {
+      collapsed[i] = i;
+    } else if (fabsf(depth - targetZ) < distanceThreshold &&
+               dot4(cn[0], cn[1], cn[2], cn[3], tn[0], tn[1], tn[2], tn[3]) > normalThreshold) {
+      float *tg = gauss + (size_t)ORC_GAUSS_FLOATS * targetIndex, *cg = gauss + (size_t)ORC_GAUSS_FLOATS * i;
+      gauss_update_info(tg, &gflags[targetIndex]); /* Gaussian::addInformation, gaussian.h:49-55 */
+      gauss_update_info(cg, &gflags[i]);
+      for (int k = 0; k < 9; k++) tg[15 + k] += cg[15 + k];
+      for (int k = 0; k < 3; k++) tg[12 + k] += cg[12 + k];
+      gflags[targetIndex] &= ~ORC_GAUSS_MOMENTS;
+      collapsed[i] = targetIndex;
+    }
+  }
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    int ci = collapsed[i];
+    if (ci == i) {
+      float *g = gauss + (size_t)ORC_GAUSS_FLOATS * i;
+      gauss_update_moments(g, &gflags[i]);
+      points[4 * i] = g[0]; points[4 * i + 1] = g[1]; points[4 * i + 2] = g[2];
+    }
+    if (ci < 0 || ci == i) {
+      if (k != i) {
+        memcpy(points + 4 * k, points + 4 * i, sizeof(float) * 4);
+        memcpy(normals + 4 * k, normals + 4 * i, sizeof(float) * 4);
+        if (statsM) memcpy(statsM + 16 * k, statsM + 16 * i, sizeof(float) * 16);
+        if (omegaP) memcpy(omegaP + 16 * k, omegaP + 16 * i, sizeof(float) * 16);
+        if (omegaN) memcpy(omegaN + 16 * k, omegaN + 16 * i, sizeof(float) * 16);
+        memcpy(gauss + (size_t)ORC_GAUSS_FLOATS * k, gauss + (size_t)ORC_GAUSS_FLOATS * i, sizeof(float) * ORC_GAUSS_FLOATS);
+        gflags[k] = gflags[i];
+      }
+      k++;
+    }
+  }
+  if (collapsedOut) memcpy(collapsedOut, collapsed, sizeof(int) * n);
+  free(indexImage); free(depthImage); free(collapsed);
+  return k;
+}

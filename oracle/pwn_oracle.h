@@ -184,6 +184,27 @@ void orc_set_accumulate_f64(int on);
 void orc_image_stats(const float *curDepth, const float *refDepth, int n, float inlierDepthThreshold,
                      int *nonZeros, int *inliers, int *outliers, float *reprojectionDistance);
 
+/* ---- local-map maintenance -------------------------------------------
+ * Gaussian3f sensor model (pinholepointprojector.cpp:93-133, basemath/gaussian.h, gaussian3.h:26-36),
+ * Merger::merge (merger.cpp:15-119).  A Gaussian is 24 floats + a flag word:
+ *   g[0..2] mean, g[3..11] covariance (column-major 3x3), g[12..14] information vector,
+ *   g[15..23] information matrix; flags bit 0 = _momentsUpdated, bit 1 = _infoUpdated
+ * (the reference keeps both forms with lazy conversion through Matrix3f::inverse()). */
+#define ORC_GAUSS_FLOATS 24
+#define ORC_GAUSS_MOMENTS 1
+#define ORC_GAUSS_INFO 2
+/* unProject(points, gaussians, index, depth): gaussians of the valid pixels in raster order */
+int orc_unproject_gaussians(const float *depth, int rows, int cols, const float K[9], const float iKRt[16],
+                            float minD, float maxD, float baseline, float alpha, float *points, int *index,
+                            float *gauss, int *gflags);
+/* Gaussian3fVector::transformInPlace (skipped, like Cloud::transformInPlace, when T is the identity) */
+void orc_gaussians_transform(const float T[16], int n, float *gauss, int *gflags);
+/* Merger::merge.  All arrays are compacted in place; returns the new point count.  collapsed (n ints, may be
+ * NULL) receives _collapsedIndices; omegaP/omegaN/statsM may be NULL. */
+int orc_merge(int n, float *points, float *normals, float *statsM, float *omegaP, float *omegaN, float *gauss,
+              int *gflags, int rows, int cols, const float K[9], const float T[16], float minD, float maxD,
+              float distanceThreshold, float normalThreshold, float maxPointDepth, int *collapsed);
+
 #ifdef __cplusplus
 }
 #endif

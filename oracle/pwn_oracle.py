@@ -19,8 +19,10 @@ def build(force=False):
     so = os.path.join(_HERE, "build", "liboracle.so")
     so2 = os.path.join(_HERE, "build", "liboracle_fast.so")
     src = os.path.join(_HERE, "pwn_oracle.c")
-    stale = (not os.path.exists(so) or not os.path.exists(so2)
-             or os.path.getmtime(so) < os.path.getmtime(src))
+    so3 = os.path.join(_HERE, "build", "libvoxel_oracle.so")
+    src3 = os.path.join(_HERE, "voxel_oracle.cpp")
+    stale = (not os.path.exists(so) or not os.path.exists(so2) or not os.path.exists(so3)
+             or os.path.getmtime(so) < os.path.getmtime(src) or os.path.getmtime(so3) < os.path.getmtime(src3))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
     return so
@@ -469,17 +471,98 @@ def image_stats(cur_depth, ref_depth, thr=50.0):
     return nz.value, inl.value, outl.value, rd.value
 
 
+# ---- local-map maintenance: Gaussian3f sensor model, Merger, VoxelCalculator ----
+GAUSS_FLOATS = 24
+GAUSS_MOMENTS, GAUSS_INFO = 1, 2
+
+
+def unproject_gaussians(depth, K, minD, maxD, baseline=0.075, alpha=0.1, sensor_offset=None):
+    """PinholePointProjector::unProject with gaussians (projector transform = identity, as in
+    DepthImageConverterIntegralImage::compute) followed by Gaussian3fVector::transformInPlace(sensor_offset).
+    Returns (gauss (n,24), flags (n,), points (n,4) before the sensor offset, index image)."""
+    depth, dp = _f(depth)
+    rows, cols = depth.shape
+    Kc, kp = _f(colmajor(K))
+    _, iKRt = update_matrices(K, np.eye(4, dtype=np.float32))
+    ik, ikp = _f(colmajor(iKRt))
+    pts = np.zeros((rows * cols, 4), np.float32)
+    idx = np.zeros((rows, cols), np.int32)
+    g = np.zeros((rows * cols, GAUSS_FLOATS), np.float32)
+    fl = np.zeros(rows * cols, np.int32)
+    n = lib().orc_unproject_gaussians(dp, rows, cols, kp, ikp, C.c_float(minD), C.c_float(maxD), C.c_float(baseline),
+                                      C.c_float(alpha), _fp(pts), _ip(idx), _fp(g), _ip(fl))
+    g, fl, pts = np.ascontiguousarray(g[:n]), np.ascontiguousarray(fl[:n]), np.ascontiguousarray(pts[:n])
+    if sensor_offset is not None:
+        so, sop = _f(colmajor(sensor_offset))
+        lib().orc_gaussians_transform(sop, n, _fp(g), _ip(fl))
+    return g, fl, pts, idx
+
+
+def gaussians_transform(T, gauss, flags):
+    g = np.ascontiguousarray(gauss, np.float32).copy()
+    fl = np.ascontiguousarray(flags, np.int32).copy()
+    Tc, tp = _f(colmajor(T))
+    lib().orc_gaussians_transform(tp, g.shape[0], _fp(g), _ip(fl))
+    return g, fl
+
+
+def merge(cloud, gauss, flags, rows, cols, K, T, minD, maxD, distance_threshold=0.1,
+          normal_threshold=float(np.cos(np.float32(10 * np.pi / 180.0))), max_point_depth=10.0):
+    """Merger::merge on copies.  Returns (Cloud, gauss, flags, collapsed indices of the input points)."""
+    n = cloud.n
+    out = cloud.truncated(n)
+    for k in ("points", "normals", "statsM", "omegaP", "omegaN"):
+        setattr(out, k, np.ascontiguousarray(getattr(out, k)).copy())
+    g = np.ascontiguousarray(gauss, np.float32).copy()
+    fl = np.ascontiguousarray(flags, np.int32).copy()
+    collapsed = np.zeros(max(n, 1), np.int32)
+    Kc, kp = _f(colmajor(K))
+    Tc, tp = _f(colmajor(T))
+    k = lib().orc_merge(n, _fp(out.points), _fp(out.normals), _fp(out.statsM), _fp(out.omegaP), _fp(out.omegaN),
+                        _fp(g), _ip(fl), rows, cols, kp, tp, C.c_float(minD), C.c_float(maxD),
+                        C.c_float(distance_threshold), C.c_float(normal_threshold), C.c_float(max_point_depth),
+                        _ip(collapsed))
+    keep = (collapsed[:n] < 0) | (collapsed[:n] == np.arange(n))
+    res = out.truncated(k)
+    # the per-point arrays orc_merge does not carry are compacted with the same keep mask
+    res.eigvals = np.ascontiguousarray(cloud.eigvals[keep])
+    res.statsN = np.ascontiguousarray(cloud.statsN[keep])
+    res.curvature = np.ascontiguousarray(cloud.curvature[keep])
+    return res, np.ascontiguousarray(g[:k]), np.ascontiguousarray(fl[:k]), collapsed[:n].copy()
+
+
+def _voxel_lib():
+    if "voxel" not in _LIBS:
+        build()
+        so = os.path.join(_HERE, "build", "libvoxel_oracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+        _LIBS["voxel"] = C.CDLL(so)
+        _LIBS["voxel"].orc_voxelize.restype = C.c_int
+    return _LIBS["voxel"]
+
+
+def voxelize(points, resolution=0.01, strict=True):
+    """VoxelCalculator::compute -> indices of the representative points in output order.
+    strict=False: the reference's comparator exactly as written (not a strict weak order);
+    strict=True: lexicographic order (what the CUDA path implements)."""
+    pts, pp = _f(points)
+    rep = np.zeros(max(pts.shape[0], 1), np.int32)
+    m = _voxel_lib().orc_voxelize(pp, pts.shape[0], C.c_float(resolution), 1 if strict else 0, _ip(rep))
+    return rep[:m].copy()
+
+
 # restype declarations that are not int
 def _declare():
     for fast in (False, True):
         l = lib(fast)
         for name in ("orc_unproject", "orc_depth_to_cloud", "orc_correspond", "orc_multi_unproject",
-                     "orc_multi_depth_to_cloud"):
+                     "orc_multi_depth_to_cloud", "orc_unproject_gaussians", "orc_merge"):
             getattr(l, name).restype = C.c_int
         for name in ("orc_depth_u16_to_f32", "orc_depth_scale", "orc_v2t", "orc_t2v", "orc_update_matrices",
                      "orc_project_intervals", "orc_project", "orc_integral_image", "orc_eigen3", "orc_linearize",
                      "orc_linearize_f64", "orc_ldlt_solve6", "orc_align", "orc_image_stats", "orc_multi_image_size",
-                     "orc_multi_intervals", "orc_multi_project", "orc_set_accumulate_f64", "orc_cloud_transform"):
+                     "orc_multi_intervals", "orc_multi_project", "orc_set_accumulate_f64", "orc_cloud_transform", "orc_gaussians_transform"):
             getattr(l, name).restype = None
 
 

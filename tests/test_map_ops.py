@@ -1,0 +1,320 @@
+"""Local-map maintenance: Gaussian3f sensor model, Cloud::add with gaussians,
+Merger::merge and VoxelCalculator::compute.
+
+CPU part: the oracle (oracle/pwn_oracle.c, oracle/voxel_oracle.cpp) against independent float64 / numpy
+restatements and hand-built cases.  GPU part (-m gpu): the CUDA path through the C-ABI against the oracle on the
+same inputs, bit-exact (every operation that feeds a stored value is exactly rounded float32 in the oracle's order).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import get_scene
+
+BASELINE, ALPHA = 0.075, 0.1  # PinholePointProjector defaults (pinholepointprojector.cpp:5-13)
+
+
+def two_frame_map(s):
+    """oracle: cloud A + Cloud::add(cloud B, T_AB) with gaussians -> (Cloud, gauss, flags)"""
+    from oracle import pwn_oracle as O
+    c = s.conf
+    gA, fA, _, _ = O.unproject_gaussians(s.depthA, s.K, c["minD"], c["maxD"], BASELINE, ALPHA, s.sensor_offset)
+    gB, fB, _, _ = O.unproject_gaussians(s.depthB, s.K, c["minD"], c["maxD"], BASELINE, ALPHA, s.sensor_offset)
+    T = s.gt
+    ob = s.cloudB.truncated(s.cloudB.n)
+    pts, nrm, st, op, on = (ob.points.copy(), ob.normals.copy(), ob.statsM.copy(), ob.omegaP.copy(), ob.omegaN.copy())
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    Tc = O.colmajor(T)
+    O.lib().orc_cloud_transform(fp(Tc), ob.n, fp(pts), fp(nrm), fp(st), fp(op), fp(on))
+    gB, fB = O.gaussians_transform(T, gB, fB)
+    m = O.Cloud(s.cloudA.n + ob.n)
+    m.points = np.ascontiguousarray(np.concatenate([s.cloudA.points, pts]))
+    m.normals = np.ascontiguousarray(np.concatenate([s.cloudA.normals, nrm]))
+    m.statsM = np.ascontiguousarray(np.concatenate([s.cloudA.statsM, st]))
+    m.eigvals = np.ascontiguousarray(np.concatenate([s.cloudA.eigvals, ob.eigvals]))
+    m.statsN = np.ascontiguousarray(np.concatenate([s.cloudA.statsN, ob.statsN]))
+    m.curvature = np.ascontiguousarray(np.concatenate([s.cloudA.curvature, ob.curvature]))
+    m.omegaP = np.ascontiguousarray(np.concatenate([s.cloudA.omegaP, op]))
+    m.omegaN = np.ascontiguousarray(np.concatenate([s.cloudA.omegaN, on]))
+    return m, np.ascontiguousarray(np.concatenate([gA, gB])), np.ascontiguousarray(np.concatenate([fA, fB]))
+
+
+# ================================================================================================
+# CPU: the oracle itself
+# ================================================================================================
+def test_oracle_gaussians_against_float64():
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05, True)
+    c = s.conf
+    g, f, pts, idx = O.unproject_gaussians(s.depthA, s.K, c["minD"], c["maxD"], BASELINE, ALPHA)
+    assert g.shape[0] == s.cloudA.n and np.all(f == O.GAUSS_MOMENTS)
+    K = s.K.astype(np.float64)
+    iK = np.linalg.inv(K)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, g.shape[0], 50):
+        r, cc = np.argwhere(idx == i)[0]
+        z = float(s.depthA[r, cc])
+        J = iK @ np.array([[z, 0, cc], [0, z, r], [0, 0, 1.0]])
+        zv = ALPHA * z * z / (BASELINE * K[0, 0] + z * ALPHA)
+        cov = J @ np.diag([3.0, 3.0, zv]) @ J.T
+        got = g[i, 3:12].reshape(3, 3).T
+        assert np.abs(got - cov).max() <= 1e-5 * np.abs(cov).max()
+        assert np.array_equal(g[i, :3], pts[i, :3])  # mean = the unprojected point
+    # transformInPlace: mean' = R mean + t, cov' = R cov R^T
+    T = s.sensor_offset.astype(np.float64)
+    g2, f2 = O.gaussians_transform(s.sensor_offset, g, f)
+    i = 1234
+    assert np.allclose(g2[i, :3], T[:3, :3] @ g[i, :3].astype(np.float64) + T[:3, 3], atol=1e-5)
+    cov2 = T[:3, :3] @ g[i, 3:12].reshape(3, 3).T.astype(np.float64) @ T[:3, :3].T
+    assert np.abs(g2[i, 3:12].reshape(3, 3).T - cov2).max() <= 1e-5 * np.abs(cov2).max()
+    # identity is skipped bit for bit
+    g3, _ = O.gaussians_transform(np.eye(4, dtype=np.float32), g, f)
+    assert np.array_equal(g3, g)
+
+
+def _tiny_cloud(points, normals, covs):
+    from oracle import pwn_oracle as O
+    n = len(points)
+    cl = O.Cloud(n)
+    cl.points[:, :3] = points
+    cl.points[:, 3] = 1
+    cl.normals[:, :3] = normals
+    g = np.zeros((n, O.GAUSS_FLOATS), np.float32)
+    g[:, :3] = points
+    for i, cv in enumerate(covs):
+        g[i, 3:12] = np.asarray(cv, np.float32).T.reshape(-1)
+    return cl, g, np.full(n, O.GAUSS_MOMENTS, np.int32)
+
+
+def test_oracle_merge_hand_built_cases():
+    """Merger::merge gates and the information-form fusion against float64 algebra"""
+    from oracle import pwn_oracle as O
+    K = np.array([[100, 0, 32], [0, 100, 24], [0, 0, 1]], np.float32)
+    rows, cols = 48, 64
+    ray = np.array([0.05, -0.02, 1.0])
+    pts = [ray * 1.00, ray * 1.02, ray * 1.05, ray * 1.5, ray * 1.03, np.array([0.2, 0.1, 2.0]), ray * 20.0]
+    nz = np.array([0, 0, -1.0])
+    tilted = np.array([0, np.sin(0.5), -np.cos(0.5)])
+    nrm = [nz, nz, nz, nz, tilted, nz, nz]
+    covs = [np.diag([1e-4, 2e-4, 3e-4]) * (1 + k) for k in range(len(pts))]
+    cl, g, f = _tiny_cloud(pts, nrm, covs)
+    res, g2, f2, col = O.merge(cl, g, f, rows, cols, K, np.eye(4, dtype=np.float32), 0.01, 30.0,
+                               distance_threshold=0.1, max_point_depth=10.0)
+    # 0 wins its pixel; 1, 2 fuse into it; 3 is too far (0.5 m); 4 has an incompatible normal; 5 is alone on its
+    # pixel (its own winner); 6 is deeper than maxPointDepth and is skipped
+    assert col.tolist() == [0, 0, 0, -1, -1, 5, -1]
+    assert res.n == 5
+    Om = [np.linalg.inv(np.asarray(cv, np.float64)) for cv in covs]
+    info = Om[0] + Om[1] + Om[2]
+    vec = Om[0] @ pts[0] + Om[1] @ pts[1] + Om[2] @ pts[2]
+    mean = np.linalg.solve(info, vec)
+    assert np.allclose(res.points[0, :3], mean, rtol=1e-5, atol=1e-6)
+    assert np.allclose(g2[0, 3:12].reshape(3, 3).T, np.linalg.inv(info), rtol=1e-4)
+    assert f2[0] == (O.GAUSS_MOMENTS | O.GAUSS_INFO)
+    # survivors keep their order: 0, 3, 4, 5, 6
+    assert np.allclose(res.points[1:, :3], np.asarray(pts, np.float32)[[3, 4, 5, 6]])
+    # a winner nothing was fused into keeps its moments untouched (lazy evaluation: mean() recomputes nothing)
+    assert np.array_equal(g2[3], g[5]) and f2[3] == O.GAUSS_MOMENTS
+
+
+def test_oracle_merge_two_frame_map():
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05, True)
+    m, g, f = two_frame_map(s)
+    res, g2, f2, col = O.merge(m, g, f, s.rows, s.cols, s.K, np.eye(4, dtype=np.float32), s.conf["minD"], s.conf["maxD"])
+    n = m.n
+    ident = np.arange(n)
+    fused = (col >= 0) & (col != ident)
+    assert res.n == n - fused.sum()
+    assert fused.sum() > 0.3 * s.cloudB.n          # the two frames overlap: a large part of B disappears into A
+    assert np.all(col[col >= 0][...] <= n)
+    # every target of a fused point is a winner that stays
+    assert np.all(col[col[fused]] == col[fused])
+    # fusing moves a winner by at most a few centimetres
+    winners = np.unique(col[fused])
+    keep = (col < 0) | (col == ident)
+    newpos = np.cumsum(keep) - 1
+    d = np.linalg.norm(res.points[newpos[winners], :3] - m.points[winners, :3], axis=1)
+    assert d.max() < 0.1 and np.median(d) < 0.01
+
+
+def _numpy_voxelize(points, res):
+    inv = np.float32(1.0) / np.float32(res)
+    key = (points[:, :3].astype(np.float32) * inv).astype(np.int32)  # truncation toward zero, like (int)
+    order = np.lexsort((np.arange(len(key)), key[:, 2], key[:, 1], key[:, 0]))
+    ks = key[order]
+    head = np.ones(len(ks), bool)
+    head[1:] = np.any(ks[1:] != ks[:-1], axis=1)
+    return order[head].astype(np.int32)
+
+
+@pytest.mark.parametrize("res", [0.01, 0.05, 0.2])
+def test_oracle_voxelize(res, capsys):
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05, True)
+    m, _, _ = two_frame_map(s)
+    rep = O.voxelize(m.points, res, strict=True)
+    assert np.array_equal(rep, _numpy_voxelize(m.points, res))
+    # the comparator exactly as the reference writes it is not a strict weak ordering: report how far a libstdc++
+    # std::map built with it is from the lexicographic result
+    raw = O.voxelize(m.points, res, strict=False)
+    common = len(np.intersect1d(rep, raw))
+    with capsys.disabled():
+        print("\n[voxel %.2f] lexicographic: %d voxels; comparator as written: %d entries, %d in common, same order: %s"
+              % (res, len(rep), len(raw), common, np.array_equal(rep, raw)))
+    assert common >= 0.5 * len(rep)
+    # negative coordinates truncate toward zero (two cells collapse around 0), exactly as (int) does
+    pts = np.array([[-0.004, 0, 1, 1], [0.004, 0, 1, 1], [-0.011, 0, 1, 1]], np.float32)
+    assert O.voxelize(pts, 0.01).tolist() == [2, 0]
+
+
+# ================================================================================================
+# GPU: the CUDA path against the oracle
+# ================================================================================================
+@pytest.fixture(scope="module", params=["verify", "default"])
+def ctx(request):
+    from g2o_frontend_b200 import capi
+    c = capi.Context(0, verify=(request.param == "verify"))
+    yield c
+    c.close()
+
+
+def _upload(ctx, oc, g=None, f=None):
+    cl = ctx.new_cloud(max(oc.n, 1))
+    cl.upload(oc.points, oc.normals, oc.curvature, oc.omegaP6(), oc.omegaN6())
+    if g is not None:
+        cl.upload_gaussians(g, f)
+    return cl
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step,seed,dropout,offset", [(4, None, 0.0, False), (4, 0, 0.05, True), (1, 1, 0.05, True)])
+def test_gpu_gaussians_bit_exact(ctx, step, seed, dropout, offset):
+    from oracle import pwn_oracle as O
+    s = get_scene(step, seed, dropout, offset)
+    c = s.conf
+    cl, _ = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params(), s.sensor_offset)
+    assert not cl.has_gaussians()
+    cl.compute_gaussians(s.depthA, s.projector(), BASELINE, ALPHA, s.sensor_offset)
+    assert cl.has_gaussians()
+    g, f = cl.download_gaussians()
+    go, fo, _, _ = O.unproject_gaussians(s.depthA, s.K, c["minD"], c["maxD"], BASELINE, ALPHA, s.sensor_offset)
+    assert np.array_equal(f, fo)
+    assert np.array_equal(_bits(g[:, :12]), _bits(go[:, :12]))
+    # a depth image that does not belong to the cloud is refused
+    with pytest.raises(Exception):
+        cl.compute_gaussians(s.depthB, s.projector(), BASELINE, ALPHA, s.sensor_offset)
+
+
+@pytest.mark.gpu
+def test_gpu_cloud_add_carries_gaussians(ctx):
+    s = get_scene(4, 0, 0.05, True)
+    m, g, f = two_frame_map(s)
+    a, _ = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params(), s.sensor_offset)
+    a.compute_gaussians(s.depthA, s.projector(), BASELINE, ALPHA, s.sensor_offset)
+    b, _ = ctx.depth_to_cloud(s.depthB, s.projector(), s.stats_params(), s.sensor_offset)
+    b.compute_gaussians(s.depthB, s.projector(), BASELINE, ALPHA, s.sensor_offset)
+    dst = ctx.new_cloud(m.n)
+    dst.append(a)
+    dst.append(b, s.gt)
+    assert dst.size() == m.n and dst.has_gaussians()
+    gd, fd = dst.download_gaussians()
+    assert np.array_equal(fd, f)
+    assert np.array_equal(_bits(gd[:, :12]), _bits(g[:, :12]))
+    # Cloud::transformInPlace moves the gaussians too
+    from oracle import pwn_oracle as O
+    T = s.sensor_offset
+    dst.transform(T)
+    g2, f2 = O.gaussians_transform(T, g, f)
+    gd2, _ = dst.download_gaussians()
+    assert np.array_equal(_bits(gd2[:, :12]), _bits(g2[:, :12]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step,seed,dropout,offset", [(4, 0, 0.05, True), (1, None, 0.0, False)])
+def test_gpu_merge_bit_exact(ctx, step, seed, dropout, offset):
+    """Merger::merge on a two-frame local map: teacher-forced inputs (the oracle's map), every output compared bitwise"""
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import capi
+    s = get_scene(step, seed, dropout, offset)
+    m, g, f = two_frame_map(s)
+    c = s.conf
+    for T, mp in ((np.eye(4, dtype=np.float32), capi.make_merge_params()),
+                  (s.gt, capi.make_merge_params(0.05, 0.99, 3.0))):
+        res, go, fo, col = O.merge(m, g, f, s.rows, s.cols, s.K, T, c["minD"], c["maxD"], mp.distance_threshold,
+                                   mp.normal_threshold, mp.max_point_depth)
+        cl = _upload(ctx, m, g, f)
+        k, col_d = cl.merge(s.projector(), T, mp)
+        assert np.array_equal(col_d, col)
+        assert k == res.n == cl.size()
+        d = cl.download()
+        assert np.array_equal(_bits(d["points"]), _bits(res.points))
+        assert np.array_equal(_bits(d["normals"][:, :3]), _bits(res.normals[:, :3]))
+        assert np.array_equal(_bits(d["curvature"]), _bits(res.curvature))
+        assert np.array_equal(_bits(d["omega_p"]), _bits(res.omegaP6()))
+        assert np.array_equal(_bits(d["omega_n"]), _bits(res.omegaN6()))
+        gd, fd = cl.download_gaussians()
+        assert np.array_equal(fd, fo)
+        mom = (fo & O.GAUSS_MOMENTS) != 0
+        inf = (fo & O.GAUSS_INFO) != 0
+        assert np.array_equal(_bits(gd[mom, :12]), _bits(go[mom, :12]))
+        assert np.array_equal(_bits(gd[inf, 12:]), _bits(go[inf, 12:]))
+        cl.close()
+
+
+@pytest.mark.gpu
+def test_gpu_merge_edge_cases(ctx):
+    from oracle import pwn_oracle as O
+    s = get_scene(4)
+    c = s.conf
+    # a single frame: every point is the winner of its own pixel, nothing is removed, points become gaussian means
+    g, f, _, _ = O.unproject_gaussians(s.depthA, s.K, c["minD"], c["maxD"], BASELINE, ALPHA)
+    cl = _upload(ctx, s.cloudA, g, f)
+    k, col = cl.merge(s.projector())
+    assert k == s.cloudA.n and np.array_equal(col, np.arange(k))
+    assert np.array_equal(_bits(cl.download()["points"][:, :3]), _bits(g[:, :3]))
+    # merging without gaussians is an error, not a silent no-op
+    bare = _upload(ctx, s.cloudA)
+    with pytest.raises(Exception):
+        bare.merge(s.projector())
+    # empty cloud
+    empty = ctx.new_cloud(16)
+    assert empty.voxelize(0.01)[0] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", [0.01, 0.05, 0.5, 100.0])
+def test_gpu_voxelize(ctx, res):
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05, True)
+    m, g, f = two_frame_map(s)
+    rep_o = O.voxelize(m.points, res, strict=True)
+    cl = _upload(ctx, m, g, f)
+    k, rep = cl.voxelize(res)
+    assert k == len(rep_o) == cl.size()
+    assert np.array_equal(rep, rep_o)
+    d = cl.download()
+    assert np.array_equal(_bits(d["points"]), _bits(m.points[rep_o]))
+    assert np.array_equal(_bits(d["normals"][:, :3]), _bits(m.normals[rep_o, :3]))
+    assert np.array_equal(_bits(d["omega_p"]), _bits(m.omegaP6()[rep_o]))
+    gd, fd = cl.download_gaussians()
+    assert np.array_equal(_bits(gd[:, :12]), _bits(g[rep_o, :12])) and np.array_equal(fd, f[rep_o])
+    # idempotent: one point per voxel stays one point per voxel, order unchanged
+    k2, rep2 = cl.voxelize(res)
+    assert k2 == k and np.array_equal(rep2, np.arange(k))
+
+
+@pytest.mark.gpu
+def test_gpu_voxelize_full_resolution_map(ctx):
+    """640x480 two-frame map (about 600k points), 1 cm voxels, against numpy's lexsort"""
+    s = get_scene(1, None, 0.0, False)
+    m, g, f = two_frame_map(s)
+    cl = _upload(ctx, m)
+    k, rep = cl.voxelize(0.01)
+    assert np.array_equal(rep, _numpy_voxelize(m.points, 0.01))
+    assert k == len(rep)
