@@ -169,6 +169,70 @@ int main(int argc, char **argv) {
       fclose(out);
       return 0;
     }
+    if (get(cfg, "localmap", 0) != 0) {
+      // the scene-based odometry of pwn_core/pwn_aligner.cpp:140-215: every frame is aligned against the local map
+      // re-rendered at the predicted pose, added to the map (Cloud::add) and fused into it (Merger::merge); the map is
+      // voxelised at the end (VoxelCalculator)
+      converter.setKeepGaussians(true);
+      Merger merger;
+      merger.setDepthImageConverter(&converter);
+      merger.setDistanceThreshold(get(cfg, "mergerDistanceThreshold", 0.1f));
+      merger.setNormalThreshold(get(cfg, "mergerNormalThreshold", cosf(10 * M_PI / 180.0f)));
+      merger.setMaxPointDepth(get(cfg, "mergerMaxPointDepth", 10.0f));
+      Cloud referenceScene, subscene;
+      Isometry3f globalT, sceneT;
+      bool firstDepth = true;
+      for (int a = 3; a < argc; a++) {
+        RawDepthImage raw;
+        if (!readPgm16(argv[a], raw)) throw std::runtime_error(std::string("cannot read ") + argv[a]);
+        DepthImage scaledDepth;
+        DepthImage_convertAndScale(scaledDepth, raw, imageScale, depthScale);
+        if (firstDepth) {
+          projector.setCameraMatrix(K);
+          projector.setImageSize(raw.rows, raw.cols);
+          projector.scale(1.0f / imageScale);
+          correspondenceFinder.setImageSize(scaledDepth.rows, scaledDepth.cols);
+          merger.setImageSize(scaledDepth.rows, scaledDepth.cols);
+        }
+        Cloud cloud;
+        converter.compute(cloud, scaledDepth, sensorOffset);
+        int inliers = 0;
+        if (!firstDepth) {
+          IntImage scaledIndexImage;
+          projector.setTransform(sceneT * sensorOffset);
+          projector.project(scaledIndexImage, scaledDepth, referenceScene);
+          converter.setKeepGaussians(false);
+          converter.compute(subscene, scaledDepth, sensorOffset);
+          converter.setKeepGaussians(true);
+          projector.setTransform(Isometry3f::Identity());
+          aligner.setReferenceCloud(&subscene);
+          aligner.setCurrentCloud(&cloud);
+          aligner.setInitialGuess(Isometry3f::Identity());
+          aligner.setSensorOffset(sensorOffset);
+          aligner.align();
+          inliers = aligner.inliers();
+          globalT = globalT * aligner.T();
+          sceneT = sceneT * aligner.T();
+        }
+        const size_t before = referenceScene.size() + cloud.size();
+        referenceScene.add(cloud, sceneT);
+        merger.merge(&referenceScene, sceneT * sensorOffset);
+        projector.setTransform(Isometry3f::Identity());
+        fprintf(out, "{\"frame\": %d, \"inliers\": %d, \"added\": %zu, \"map_points\": %zu, \"globalT\": [", a - 3, inliers,
+                before, referenceScene.size());
+        for (int i = 0; i < 16; i++) fprintf(out, "%s%.9g", i ? ", " : "", globalT.data()[i]);
+        fprintf(out, "]}\n");
+        firstDepth = false;
+      }
+      VoxelCalculator voxelCalculator;
+      voxelCalculator.setResolution(get(cfg, "voxelResolution", 0.01f));
+      const size_t n0 = referenceScene.size();
+      voxelCalculator.compute(referenceScene);
+      fprintf(out, "{\"map_points\": %zu, \"voxel_points\": %zu, \"has_gaussians\": %d}\n", n0, referenceScene.size(),
+              referenceScene.hasGaussians() ? 1 : 0);
+      fclose(out);
+      return 0;
+    }
     if (get(cfg, "tracker", 0) != 0) {
       // BASELINE config 3: PwnTracker::processFrame over the whole sequence (keyframe logic included)
       SequentialTracker tracker(&converter, &aligner);

@@ -81,6 +81,19 @@ inline Vector6f t2v(const Isometry3f &T) {
 }
 
 // ---- cloud.h -------------------------------------------------------------------------------------
+// basemath/gaussian.h Gaussian<float, 3>: both forms with the reference's lazy conversion (host view)
+struct Gaussian3f {
+  Vector3f _mean, _informationVector;
+  Matrix3f _covarianceMatrix, _informationMatrix;
+  bool _momentsUpdated, _infoUpdated;
+  Gaussian3f() : _momentsUpdated(false), _infoUpdated(false) {}
+  const Vector3f &mean() const { return _mean; }
+  const Matrix3f &covarianceMatrix() const { return _covarianceMatrix; }
+  const Vector3f &informationVector() const { return _informationVector; }
+  const Matrix3f &informationMatrix() const { return _informationMatrix; }
+};
+typedef std::vector<Gaussian3f> Gaussian3fVector;
+
 class Cloud {
  public:
   Cloud() : _dev(0), _capacity(0), _deviceValid(false), _hostValid(true), _hasStats(false) {}
@@ -239,6 +252,29 @@ class Cloud {
     nicpCheck(nicp_cloud_transform(Context::current().handle(), d, T.data()), "Cloud::transformInPlace");
     _hostValid = false;
   }
+
+  // Gaussian3f per point (basemath/gaussian.h), read-only host view: mean, covariance, information vector / matrix
+  // and which of the two forms is valid.  Present when the converter ran with setKeepGaussians(true).
+  bool hasGaussians() const { return _deviceValid && _dev && nicp_cloud_has_gaussians(_dev); }
+  Gaussian3fVector gaussians() const {
+    Gaussian3fVector out;
+    if (!hasGaussians()) return out;
+    const int n = nicp_cloud_size(_dev);
+    std::vector<float> g((size_t)NICP_GAUSS_FLOATS * n);
+    std::vector<int> f(n);
+    nicpCheck(nicp_cloud_download_gaussians(Context::current().handle(), _dev, g.data(), f.data()), "Cloud::gaussians");
+    out.resize(n);
+    for (int i = 0; i < n; i++) {
+      const float *q = &g[(size_t)NICP_GAUSS_FLOATS * i];
+      for (int k = 0; k < 3; k++) { out[i]._mean(k) = q[k]; out[i]._informationVector(k) = q[12 + k]; }
+      for (int k = 0; k < 9; k++) { out[i]._covarianceMatrix.m[k] = q[3 + k]; out[i]._informationMatrix.m[k] = q[15 + k]; }
+      out[i]._momentsUpdated = (f[i] & NICP_GAUSS_MOMENTS) != 0;
+      out[i]._infoUpdated = (f[i] & NICP_GAUSS_INFO) != 0;
+    }
+    return out;
+  }
+  // after a device-side operation changed the cloud (Merger, VoxelCalculator)
+  void deviceChanged() { _hostValid = false; _deviceValid = true; }
 
   // device side (used by the converter / aligner)
   nicp_cloud *deviceForWrite(int capacity) {
@@ -599,7 +635,7 @@ class DepthImageConverter {
                       NormalInformationMatrixCalculator *normalInformationMatrixCalculator_ = 0)
       : _projector(projector_), _statsCalculator(statsCalculator_),
         _pointInformationMatrixCalculator(pointInformationMatrixCalculator_),
-        _normalInformationMatrixCalculator(normalInformationMatrixCalculator_), _keepStats(false) {}
+        _normalInformationMatrixCalculator(normalInformationMatrixCalculator_), _keepStats(false), _keepGaussians(false) {}
   virtual ~DepthImageConverter() {}
   virtual void compute(Cloud &cloud, const DepthImage &depthImage, const Isometry3f &sensorOffset = Isometry3f::Identity()) = 0;
   PointProjector *projector() { return _projector; }
@@ -613,6 +649,9 @@ class DepthImageConverter {
   IntImage &indexImage() { return _indexImage; }
   // pwn::Stats (eigenvectors, mean, eigenvalues, n) are only materialised on request
   void setKeepStats(bool v) { _keepStats = v; }
+  // the sensor-model gaussians of unProject(points, gaussians, ...) (pinholepointprojector.cpp:93-133) are only needed
+  // by the Merger; the reference always computes them, here they are opt-in
+  void setKeepGaussians(bool v) { _keepGaussians = v; }
 
  protected:
   PointProjector *_projector;
@@ -620,7 +659,7 @@ class DepthImageConverter {
   PointInformationMatrixCalculator *_pointInformationMatrixCalculator;
   NormalInformationMatrixCalculator *_normalInformationMatrixCalculator;
   IntImage _indexImage;
-  bool _keepStats;
+  bool _keepStats, _keepGaussians;
 };
 
 class DepthImageConverterIntegralImage : public DepthImageConverter {
@@ -673,10 +712,84 @@ class DepthImageConverterIntegralImage : public DepthImageConverter {
                                   d, _indexImage.data()),
               "DepthImageConverterIntegralImage::compute");
     cloud.setHasStats(_keepStats);
+    if (_keepGaussians)
+      nicpCheck(nicp_cloud_compute_gaussians(Context::current().handle(), d, depthImage.data(), &p, pp->baseline(), pp->alpha(),
+                                             sensorOffset.data()),
+                "DepthImageConverterIntegralImage::compute (gaussians)");
     StatsCalculatorIntegralImage *sc = dynamic_cast<StatsCalculatorIntegralImage *>(_statsCalculator);
     sc->intervalImage().create(depthImage.rows, depthImage.cols);
     nicpCheck(nicp_last_interval_image(Context::current().handle(), sc->intervalImage().data()), "interval image");
   }
+};
+
+// ---- merger.h ----------------------------------------------------------------------------------------
+class Merger {
+ public:
+  Merger() : _distanceThreshold(0.1f), _normalThreshold(cosf(10 * M_PI / 180.0f)), _maxPointDepth(10.0f),  // merger.cpp:5-13
+             _depthImageConverter(0), _rows(0), _cols(0) {}
+  virtual ~Merger() {}
+  float distanceThreshold() const { return _distanceThreshold; }
+  void setDistanceThreshold(float v) { _distanceThreshold = v; }
+  float normalThreshold() const { return _normalThreshold; }
+  void setNormalThreshold(float v) { _normalThreshold = v; }
+  float maxPointDepth() const { return _maxPointDepth; }
+  void setMaxPointDepth(float v) { _maxPointDepth = v; }
+  DepthImageConverter *depthImageConverter() const { return _depthImageConverter; }
+  void setDepthImageConverter(DepthImageConverter *c) { _depthImageConverter = c; }
+  void setImageSize(int r, int c) { _rows = r; _cols = c; }
+  int imageRows() const { return _rows; }
+  int imageCols() const { return _cols; }
+  const std::vector<int> &collapsedIndices() const { return _collapsedIndices; }
+
+  // merger.cpp:15-119
+  void merge(Cloud *cloud, Isometry3f transform = Isometry3f::Identity()) {
+    if (_rows <= 0 || _cols <= 0) throw std::runtime_error("Merger: _indexImage has zero size");
+    if (!_depthImageConverter || !_depthImageConverter->projector()) throw std::runtime_error("Merger: missing _depthImageConverter / projector");
+    PinholePointProjector *pp = dynamic_cast<PinholePointProjector *>(_depthImageConverter->projector());
+    if (!pp) throw std::runtime_error("Merger: the projector must be a PinholePointProjector");
+    pp->setTransform(transform);
+    nicp_projector p = pp->abiProjector();
+    p.rows = _rows;
+    p.cols = _cols;
+    nicp_merge_params mp = {_distanceThreshold, _normalThreshold, _maxPointDepth};
+    nicp_cloud *d = cloud->device();
+    _collapsedIndices.assign(cloud->size(), -1);
+    int k = 0;
+    nicpCheck(nicp_merge(Context::current().handle(), d, &p, transform.data(), &mp,
+                         _collapsedIndices.empty() ? 0 : _collapsedIndices.data(), &k),
+              "Merger::merge");
+    cloud->deviceChanged();
+  }
+
+ protected:
+  float _distanceThreshold, _normalThreshold, _maxPointDepth;
+  DepthImageConverter *_depthImageConverter;
+  int _rows, _cols;
+  std::vector<int> _collapsedIndices;
+};
+
+// ---- voxelcalculator.h ---------------------------------------------------------------------------------
+class VoxelCalculator {
+ public:
+  VoxelCalculator() : _resolution(0.01f) {}
+  virtual ~VoxelCalculator() {}
+  float resolution() const { return _resolution; }
+  void setResolution(float r) { _resolution = r; }
+  void compute(Cloud &cloud, float res) {
+    float old = _resolution;
+    _resolution = res;
+    compute(cloud);
+    _resolution = old;
+  }
+  // voxelcalculator.cpp:15-73 (first point of every occupied voxel, lexicographic voxel order; see nicp_voxelize)
+  void compute(Cloud &cloud) {
+    int k = 0;
+    nicpCheck(nicp_voxelize(Context::current().handle(), cloud.device(), _resolution, 0, &k), "VoxelCalculator::compute");
+    cloud.deviceChanged();
+  }
+
+ protected:
+  float _resolution;
 };
 
 // ---- correspondencefinder.h ----------------------------------------------------------------------------
