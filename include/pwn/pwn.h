@@ -129,14 +129,19 @@ class Cloud {
     const int n0 = (int)size(), n1 = (int)cloud.size();
     nicp_cloud *src = cloud.device();
     nicp_cloud *old = n0 > 0 ? device() : 0;
-    nicp_cloud *merged = 0;
-    nicpCheck(nicp_cloud_create(ctx, n0 + n1 > 0 ? n0 + n1 : 1, &merged), "nicp_cloud_create");
-    Isometry3f I;
-    if (old) nicpCheck(nicp_cloud_append(ctx, merged, old, I.data()), "Cloud::add");
-    nicpCheck(nicp_cloud_append(ctx, merged, src, T.data()), "Cloud::add");
-    release();
-    _dev = merged;
-    _capacity = n0 + n1 > 0 ? n0 + n1 : 1;
+    if (old && _capacity >= n0 + n1) {  // room left: append in place
+      nicpCheck(nicp_cloud_append(ctx, old, src, T.data()), "Cloud::add");
+    } else {  // grow geometrically so that a local map is not reallocated for every frame
+      const int cap = n0 + n1 > 0 ? (old ? 2 * (n0 + n1) : n0 + n1) : 1;
+      nicp_cloud *merged = 0;
+      nicpCheck(nicp_cloud_create(ctx, cap, &merged), "nicp_cloud_create");
+      Isometry3f I;
+      if (old) nicpCheck(nicp_cloud_append(ctx, merged, old, I.data()), "Cloud::add");
+      nicpCheck(nicp_cloud_append(ctx, merged, src, T.data()), "Cloud::add");
+      release();
+      _dev = merged;
+      _capacity = cap;
+    }
     _deviceValid = true;
     _hostValid = false;
     _hasStats = false;
