@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--candidates", type=int, default=64)
     ap.add_argument("--cpu-sample-pairs", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
     return ap.parse_args()
 
 
@@ -196,7 +197,7 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cpu_sample_pairs
-    value, cores, ms = cpu_reference_run(args.steps, args.warmup, n)
+    value, cores, ms = cpu_reference_run(args.steps, args.warmup, n, args.cpu_threads or None)
     sample = ("per step: 1 cloud build from a raw 640x480 frame + %d alignments (10 iterations) of the "
               "loop-closure workload, CPU oracle performance build (-O3 -march=x86-64-v3 -fopenmp)" % n)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -316,6 +317,7 @@ def run_ours(args):
         pass
     roofline = {"kernel": "k_corr_lin_tiled<0> (CorrespondenceFinder::compute + Linearizer::update fused)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": kt["corr_lin_ms"] / n_launch,
                 "launches_timed": kt["corr_lin_launches"],
                 "algorithmic_bytes_per_launch": bytes_total / n_launch,
@@ -358,6 +360,18 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "1 cloud build + %d alignments (10 iterations) of the same workload, CPU "
                                               "oracle performance build, 1 warm-up + 1 timed pass" % args.cpu_sample_pairs}
+            # single-thread figure: a fresh process, because OpenMP reads OMP_NUM_THREADS once
+            try:
+                import subprocess
+                env = dict(os.environ, OMP_NUM_THREADS="1")
+                for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+                    env.pop(k, None)
+                o = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-threads", "1",
+                                    "--steps", "1", "--warmup", "0", "--cpu-sample-pairs", "2"], env=env,
+                                   capture_output=True, text=True, timeout=300)
+                line["cpu_baseline"]["value_1_thread"] = json.loads(o.stdout.strip().splitlines()[-1])["value"]
+            except Exception:
+                line["cpu_baseline"]["value_1_thread"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
