@@ -865,11 +865,13 @@ __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *_
 // ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
-// tiled-kernel configurations (NICP_TILE_CONFIG): threads per CTA, pixels per thread, min CTAs per SM
+// fused-kernel configurations (NICP_TILE_CONFIG = 1..3): threads per CTA, pixels per thread.  Measured on a B200, 64
+// pairs x 640x480 per launch (profiles/r1e_summary.md):
+//   1  {32, 3} in-place Linearizer stage, 20 one-warp CTAs/SM (default)          293 us
+//   2  {64, 3} in-place Linearizer stage, 10 CTAs/SM                              299 us
+//   3  {64, 2} shared-memory compaction of the accepted terms (round-1 structure) 355 us
 struct TileCfg { int nt, tk; };
-// (measured on a B200, 64 pairs x 640x480 per launch: {64,2} 371 us, {128,2} 381 us, {128,2}@88 regs 423 us,
-//  {256,4} 519 us; see profiles/r1_corr_lin_tuning.md)
-static const TileCfg kTileCfgs[] = {{64, 2}, {128, 2}, {256, 4}, {64, 4}, {32, 4}, {64, 3}, {32, 2}, {64, 3}, {128, 3}, {32, 3}, {96, 2}, {96, 3}, {32, 2}, {64, 3}, {32, 3}, {32, 4}, {64, 4}, {32, 3}};
+static const TileCfg kTileCfgs[] = {{32, 3}, {64, 3}, {64, 2}};
 static int tile_px(const nicp_context *ctx) { return kTileCfgs[ctx->tileConfig].nt * kTileCfgs[ctx->tileConfig].tk; }
 
 static int pixels_per_block(const nicp_context *ctx, int /*P*/) { return tile_px(ctx); }
@@ -900,45 +902,15 @@ static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, 
                             int P, int imgStats, float imgThr) {
   if (mode == 0) {
     switch (ctx->tileConfig) {
-      case 1: launch_tiled<0, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 2: launch_tiled<0, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 3: launch_tiled<0, 64, 4, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 4: launch_tiled<0, 32, 4, 16>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 5: launch_tiled<0, 64, 3, 10>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 6: launch_tiled<0, 32, 2, 24>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 7: launch_tiled<0, 64, 3, 9>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 8: launch_tiled<0, 128, 3, 5>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 9: launch_tiled<0, 32, 3, 20>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 10: launch_tiled<0, 96, 2, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 11: launch_tiled<0, 96, 3, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 12: launch_tiled<0, 32, 2, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 13: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 14: launch_tiled<0, 32, 3, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 15: launch_tiled<0, 32, 4, 16, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 16: launch_tiled<0, 64, 4, 8, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 17: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      default: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 1: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 2: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      default: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
     }
   } else {
     switch (ctx->tileConfig) {
-      case 1: launch_tiled<1, 128, 2, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 2: launch_tiled<1, 256, 4, 2>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 3: launch_tiled<1, 64, 4, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 4: launch_tiled<1, 32, 4, 16>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 5: launch_tiled<1, 64, 3, 10>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 6: launch_tiled<1, 32, 2, 24>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 7: launch_tiled<1, 64, 3, 9>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 8: launch_tiled<1, 128, 3, 5>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 9: launch_tiled<1, 32, 3, 20>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 10: launch_tiled<1, 96, 2, 8>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 11: launch_tiled<1, 96, 3, 6>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 12: launch_tiled<1, 32, 2, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 13: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 14: launch_tiled<1, 32, 3, 21, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 15: launch_tiled<1, 32, 4, 16, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 16: launch_tiled<1, 64, 4, 8, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 17: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      default: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 1: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 2: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      default: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
     }
   }
 }

@@ -486,15 +486,11 @@ int nicp_create(int device, nicp_context **out) {
   cudaDeviceProp prop;
   NICP_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
-  // fixed so that H/b of a pair do not depend on batch size or GPU count (2 CTAs per SM on a B200)
-  ctx->blocksPerPair = env_int("NICP_BLOCKS_PER_PAIR", 296);
-  {
-    const char *v = getenv("NICP_CORR_VARIANT");
-    ctx->corrVariant = (v && v[0] == '0') ? 0 : 1;
-    // fixed per build (not per batch) so that a pair's H/b never depend on batch size or GPU count
-    ctx->tileConfig = env_int("NICP_TILE_CONFIG", 18) - 1;
-    if (ctx->tileConfig < 0 || ctx->tileConfig > 17) ctx->tileConfig = 0;
-  }
+  ctx->blocksPerPair = 296;  // lower bound of the partial-row allocation
+  ctx->corrVariant = 1;
+  // fixed per context (not per batch) so that a pair's H/b never depend on batch size or GPU count
+  ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
+  if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
   {
     void *p = nullptr;
     NICP_CUDA(cudaMalloc(&p, sizeof(DeviceCams)));

@@ -68,7 +68,7 @@ def main():
     voxel()
     resv = [voxel() for _ in range(5)]
     t_vox = np.mean([r[0] for r in resv]) * 1e3
-    print("GPU  640x480 two-frame map (%d points): gaussians %.2f ms | Cloud::add x2 %.2f ms | Merger::merge %.2f ms "
+    print("GPU  640x480 two-frame map (%d points): gaussians %.2f ms | allocate + Cloud::add x2 %.2f ms | transformInPlace of the map %.2f ms | Merger::merge %.2f ms "
           "(-> %d points) | VoxelCalculator 1 cm %.2f ms (-> %d points)" % (n, t_g, t_add, t_tr, t_merge, res[0][1], t_vox, resv[0][1]))
 
     # CPU oracle on the same map
