@@ -318,3 +318,77 @@ def test_gpu_voxelize_full_resolution_map(ctx):
     k, rep = cl.voxelize(0.01)
     assert np.array_equal(rep, _numpy_voxelize(m.points, 0.01))
     assert k == len(rep)
+
+
+def _random_cloud(n, seed, spread=2.0):
+    """n random points in front of a 64x48 camera, many per pixel, with random normals and covariances"""
+    from oracle import pwn_oracle as O
+    rng = np.random.default_rng(seed)
+    cl = O.Cloud(n)
+    z = rng.uniform(0.6, 3.0, n)
+    cl.points[:, 0] = rng.uniform(-0.35, 0.35, n) * z * spread / 2
+    cl.points[:, 1] = rng.uniform(-0.25, 0.25, n) * z * spread / 2
+    cl.points[:, 2] = z
+    cl.points[:, 3] = 1
+    nr = rng.normal(size=(n, 3)) * 0.15 + np.array([0, 0, -1.0])
+    cl.normals[:, :3] = nr / np.linalg.norm(nr, axis=1, keepdims=True)
+    cl.curvature[:] = rng.uniform(0, 0.1, n)
+    A = rng.normal(size=(n, 3, 3)) * 0.01
+    cov = A @ A.transpose(0, 2, 1) + np.eye(3) * 1e-4
+    g = np.zeros((n, O.GAUSS_FLOATS), np.float32)
+    g[:, :3] = cl.points[:, :3]
+    g[:, 3:12] = cov.transpose(0, 2, 1).reshape(n, 9)
+    for k in range(3):
+        cl.omegaP[:, 5 * k] = rng.uniform(1, 1000, n)
+        cl.omegaN[:, 5 * k] = rng.uniform(1, 100, n)
+    return cl, g, np.full(n, O.GAUSS_MOMENTS, np.int32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 33, 2047, 2049, 20000])
+def test_gpu_merge_random_clouds(ctx, n):
+    """many points per pixel: long contributor lists, the order of the float32 information sums matters"""
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import capi
+    K = np.array([[80, 0, 32], [0, 80, 24], [0, 0, 1]], np.float32)
+    rows, cols = 48, 64
+    cl, g, f = _random_cloud(n, n)
+    proj = capi.make_projector(K, rows, cols, 0.5, 4.0)
+    mp = capi.make_merge_params(0.5, 0.9, 2.5)
+    T = np.eye(4, dtype=np.float32)
+    res, go, fo, col = O.merge(cl, g, f, rows, cols, K, T, 0.5, 4.0, mp.distance_threshold, mp.normal_threshold,
+                               mp.max_point_depth)
+    d = _upload(ctx, cl, g, f)
+    k, col_d = d.merge(proj, T, mp)
+    assert np.array_equal(col_d, col) and k == res.n
+    if n >= 2047:
+        fused = (col >= 0) & (col != np.arange(n))
+        assert np.bincount(col[fused]).max() >= 3  # several contributors per winner
+    out = d.download()
+    assert np.array_equal(_bits(out["points"]), _bits(res.points))
+    gd, fd = d.download_gaussians()
+    assert np.array_equal(fd, fo)
+    mom, inf = (fo & O.GAUSS_MOMENTS) != 0, (fo & O.GAUSS_INFO) != 0
+    assert np.array_equal(_bits(gd[mom, :12]), _bits(go[mom, :12]))
+    assert np.array_equal(_bits(gd[inf, 12:]), _bits(go[inf, 12:]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2047, 2048, 2049, 70001])
+def test_gpu_voxelize_random_clouds(ctx, n):
+    """negative coordinates, duplicates, ragged tile sizes of the radix sort, multi-pass keys"""
+    from oracle import pwn_oracle as O
+    rng = np.random.default_rng(n)
+    pts = np.ones((n, 4), np.float32)
+    pts[:, :3] = rng.uniform(-3, 3, (n, 3))
+    pts[::3, :3] = np.round(pts[::3, :3], 1)           # exact duplicates / shared voxels
+    pts[1::7, :3] = pts[::7, :3][: len(pts[1::7])]
+    cl = O.Cloud(n)
+    cl.points = pts
+    for res in (0.003, 0.05, 1.0):
+        d = _upload(ctx, cl)
+        k, rep = d.voxelize(res)
+        ref = _numpy_voxelize(pts, res)
+        assert k == len(ref) and np.array_equal(rep, ref), (n, res)
+        assert np.array_equal(rep, O.voxelize(pts, res, strict=True))
+        d.close()
