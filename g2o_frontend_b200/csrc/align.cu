@@ -66,6 +66,8 @@ __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i
   float ix, iy, d;
   xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
   if (d < minD || d > maxD) return;
+  // the packed z-buffer word orders positive depths below 32 km (z_encode); anything else cannot be a valid range image
+  if (!(d > 0.0f && d < 32768.0f)) return;
   float s = fdiv(1.0f, d);
   float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
   if (!(fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows)) return;
@@ -97,7 +99,7 @@ __device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatS
     if (d < g.minD[c] || d > g.maxD[c]) continue;
     float s = fdiv(1.0f, d);
     float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
-    if (d < 0.0f || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
+    if (!(d > 0.0f && d < 32768.0f) || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
     int X = (int)fx, Y = (int)fy + g.colOff[c];
     if (X < rows && Y < cols) z_min(&z[(size_t)X * cols + Y], z_encode(d, i, epoch));
     return;
@@ -1016,8 +1018,6 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   NICP_CHECK_LAUNCH(ctx);
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
   NICP_CHECK_LAUNCH(ctx);
-  ctx->lastAlignParity = parity;
-  ctx->lastAlignEpoch = epoch;
   return NICP_OK;
 }
 

@@ -1170,6 +1170,10 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   ctx->lastAlignRows = proj->rows;
   ctx->lastAlignCols = proj->cols;
   ctx->lastAlignIters = ap->outer_iterations;
+  // which reference z-buffer / epoch the last iteration used (set here, not in run_align_chunk: a CUDA-graph replay
+  // does not pass through it)
+  ctx->lastAlignParity = ap->outer_iterations > 0 ? ((ap->outer_iterations - 1) & 1) : 0;
+  ctx->lastAlignEpoch = ap->outer_iterations > 0 ? epoch_of_iteration(ap->outer_iterations - 1) : kEpochFresh;
   ctx->lastAlignValid = single;
   ctx->lastAlignEmptyDepth = cams.multi ? 0.0f : FLT_MAX;
   return NICP_OK;

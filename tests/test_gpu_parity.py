@@ -270,6 +270,34 @@ def test_inner_iterations(ctx):
     assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
 
 
+def test_many_outer_iterations_epoch_wrap(ctx):
+    """70 outer iterations: the 4-bit epoch of the z-buffer words wraps twice (every 32 iterations the buffer is
+    started fresh); the final z-buffer, correspondences and pose still follow the oracle"""
+    from g2o_frontend_b200 import capi
+    from oracle import pwn_oracle as O
+    s = get_scene(4, 0, 0.05)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    for outer in (33, 70):
+        out = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=outer, num_threads=1))
+        res = ctx.align(ref, cur, s.projector(), s.align_params(outer=outer))
+        T = capi.result_T(res)
+        assert rot_angle(T[:3, :3], out.T[:3, :3]) <= T_ROT_TOL
+        assert np.abs(T[:3, 3] - out.T[:3, 3]).max() <= T_TRA_TOL
+        st = ctx.align_state(s.rows, s.cols)
+        assert (st["ref_index"] == out.refIndex).mean() >= 0.99
+        # nothing stale survives: the same call restarted at the last pose for ONE iteration gives the same images
+        r1 = ctx.align(ref, cur, s.projector(), s.align_params(outer=1), guess=out.trace_T[outer - 1])
+        o1 = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=1, guess=out.trace_T[outer - 1], num_threads=1))
+        st1 = ctx.align_state(s.rows, s.cols)
+        assert np.array_equal(st1["ref_index"], o1.refIndex)
+        assert np.array_equal(st1["ref_depth"].view(np.uint32), o1.refDepth.view(np.uint32))
+    # a batch (no CUDA graph) takes the same path
+    rb = ctx.align_batch([ref, ref], [cur, cur], s.projector(), s.align_params(outer=40))
+    o40 = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=40, num_threads=1))
+    Tb = rb["T"][0].reshape(4, 4).T
+    assert rot_angle(Tb[:3, :3], o40.T[:3, :3]) <= T_ROT_TOL and np.array_equal(rb["T"][0], rb["T"][1])
+
+
 def test_priors(ctx):
     """Aligner::addRelativePrior / addAbsolutePrior (se3_prior.cpp) on the device path vs the oracle"""
     from g2o_frontend_b200 import capi, synth
