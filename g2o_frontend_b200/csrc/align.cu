@@ -374,7 +374,7 @@ struct TileSmemInplace {
 template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, int epoch,
                                                              int writeCorr, AlignConsts ac, int numPixels, int imgStats,
-                                                             float imgThreshold) {
+                                                             float imgThreshold, int pairFast) {
   constexpr int NW = NT / 32;
   constexpr int TILE = NT * TK;
   static_assert(TK * NW <= 32, "prefix scan is done by one warp");
@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   using Smem = typename std::conditional<INPLACE, TileSmemInplace<NT, TK>, TileSmem<NT, TK>>::type;
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
 
-  const PairDesc &D = desc[blockIdx.y];
+  // pair-fastest block order: the CTAs that are resident together work on the SAME tile of different pairs, so the
+  // current-cloud data shared by the pairs of a chunk (index image, points, normals, Omega) is served by L1/L2
+  const int pairId = pairFast ? blockIdx.x : blockIdx.y;
+  const int tileId = pairFast ? blockIdx.y : blockIdx.x;
+  const PairDesc &D = desc[pairId];
   const Affine T = affine_from(D.state->invT);
   const float4 *__restrict__ refPoints = D.refPoints;
   const float4 *__restrict__ refNormals = D.refNormals;
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   const unsigned long long *__restrict__ zcur = D.curZ;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int base = blockIdx.x * TILE;
+  const int base = tileId * TILE;
   float midx = 0.0f, imgSum = 0.0f, imgNz = 0.0f, imgInl = 0.0f;
 
   // ---- stage 1: loads ----
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
   // ---- stage 3 ----
   float tot = warp_transpose_reduce(acc, lane);
   if constexpr (NW == 1) {
-    D.partials[(size_t)blockIdx.x * kAccum + lane] = tot;
+    D.partials[(size_t)tileId * kAccum + lane] = tot;
     return;
   }
   S.red[warp][lane] = tot;
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
     float s = S.red[0][lane];
 #pragma unroll
     for (int w = 1; w < NW; w++) s += S.red[w][lane];
-    D.partials[(size_t)blockIdx.x * kAccum + lane] = s;
+    D.partials[(size_t)tileId * kAccum + lane] = s;
   }
 }
 
@@ -896,8 +900,11 @@ static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, in
     cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<grid, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P,
-                                                                                  imgStats, imgThr);
+  static const int pairFast = getenv("NICP_PAIR_FAST") ? atoi(getenv("NICP_PAIR_FAST")) : 1;
+  const bool swap = pairFast && grid.x <= 65535;
+  const dim3 g = swap ? dim3(grid.y, grid.x) : grid;
+  k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<g, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
+                                                                               imgThr, swap ? 1 : 0);
 }
 // MODE 0 / 1 launch of the fused kernel in the context's tile configuration
 static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac,
