@@ -1,4 +1,4 @@
-"""Timing harness (not part of the product): local-map maintenance at 640x480 -- gaussians, Cloud::add, Merger::merge,
+"""Timing harness (test infrastructure, not part of the product; lives under tests/ because it runs the oracle): local-map maintenance at 640x480 -- gaussians, Cloud::add, Merger::merge,
 VoxelCalculator -- on a two-frame map, GPU (C-ABI, host-synchronised calls) vs the CPU oracle."""
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from conftest import get_scene  # noqa: E402
 from g2o_frontend_b200 import capi  # noqa: E402
 from oracle import pwn_oracle as O  # noqa: E402
@@ -76,7 +76,7 @@ def main():
     t0 = time.perf_counter()
     O.unproject_gaussians(s.depthA, s.K, c["minD"], c["maxD"])
     t_cg = (time.perf_counter() - t0) * 1e3
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from test_map_ops import two_frame_map
     m, g, f = two_frame_map(s)
     t0 = time.perf_counter()
