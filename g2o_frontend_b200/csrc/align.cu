@@ -419,6 +419,21 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       }
     }
   }
+  // MODE 1 + image statistics: the two z-buffer words are fetched with the indices (same round trip) and decoded
+  // while the gathers are in flight
+  unsigned long long zc[TK], zr[TK];
+  if (MODE == 1 && imgStats) {
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      const int pix = base + k * NT + threadIdx.x;
+      zc[k] = kEmptyZ;
+      zr[k] = kEmptyZ;
+      if (pix < numPixels) {
+        zc[k] = zcur[pix];
+        zr[k] = zref[pix];
+      }
+    }
+  }
   float4 cn[TK], rn0[TK], cp[TK], rp0[TK];
 #pragma unroll
   for (int k = 0; k < TK; k++) {
@@ -444,8 +459,8 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       const int pix = base + k * NT + threadIdx.x;
       if (pix < numPixels) {
         // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
-        const float dc = z_depth(zcur[pix], kEpochFresh, FLT_MAX);
-        const float dr = z_depth(zref[pix], epoch, FLT_MAX);
+        const float dc = z_depth(zc[k], kEpochFresh, FLT_MAX);
+        const float dr = z_depth(zr[k], epoch, FLT_MAX);
         unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
         unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
         if (c16 > 0 && r16 > 0) {
