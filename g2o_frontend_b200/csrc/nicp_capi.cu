@@ -266,10 +266,13 @@ static void jacobi_sym(int n, double *A, double *V, double *w) {
   for (int i = 0; i < n * n; i++) V[i] = 0;
   for (int i = 0; i < n; i++) V[i * n + i] = 1;
   for (int sweep = 0; sweep < 60; sweep++) {
-    double off = 0;
-    for (int p = 0; p < n; p++)
+    double off = 0, diag = 0;
+    for (int p = 0; p < n; p++) {
+      diag += A[p * n + p] * A[p * n + p];
       for (int q = p + 1; q < n; q++) off += A[q * n + p] * A[q * n + p];
-    if (off < 1e-300) break;
+    }
+    /* converged to double precision (the old absolute 1e-300 test never fired and all 60 sweeps ran) */
+    if (off <= 1e-32 * (diag + off)) break;
     for (int p = 0; p < n; p++)
       for (int q = p + 1; q < n; q++) {
         double apq = A[q * n + p];
