@@ -56,6 +56,7 @@ __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
   st->img_sum = 0.f;
   st->sumMidx = 0.f;
   st->sumMacc = 0.f;
+  st->ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -741,55 +742,14 @@ __device__ __noinline__ void add_priors(const DevPrior *priors, int numPriors, c
 //  mode 1: _computeStatistics' linearisation: store H/b + image statistics, write the result record.
 //  mode 2: stage-level call: store H/b/error/inliers/ncorr only.
 // ---------------------------------------------------------------------------------------------
-// First level of the deterministic final pass: kRowGroups CTAs per pair, CTA g adds the partial rows of its
-// contiguous group (warp w takes rows w, w+8, ... of the group in order, 8 loads in flight; the 8 warps are
-// added in order) and writes one row of partials2.  The rows are L2-resident (just written by the fused kernel).
-constexpr int kRowGroups = 16;
-__global__ void __launch_bounds__(256) k_reduce_rows(const PairDesc *__restrict__ desc, int numBlocks) {
-  const PairDesc &D = desc[blockIdx.y];
-  __shared__ float red[8][kAccum];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (numBlocks + kRowGroups - 1) / kRowGroups;
-  const int begin = blockIdx.x * per, end = min(begin + per, numBlocks);
-  float s = 0.0f;
-  const float *__restrict__ rows = D.partials + lane;
-  int bi = begin + warp;
-  for (; bi + 7 * 8 < end; bi += 8 * 8) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = rows[(size_t)(bi + u * 8) * kAccum];
-#pragma unroll
-    for (int u = 0; u < 8; u++) s += v[u];
-  }
-  for (; bi < end; bi += 8) s += rows[(size_t)bi * kAccum];
-  red[warp][lane] = s;
-  __syncthreads();
-  if (warp == 0) {
-    float t = red[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; w++) t += red[w][lane];
-    D.partials2[blockIdx.x * kAccum + lane] = t;
-  }
-}
+constexpr int kRowGroups = 16;  // first-level CTAs per pair (see k_reduce_solve)
 
-// Second level + solve: one warp adds the kRowGroups rows in order, thread 0 does the dense part.
+// the dense part, executed by one thread: tot = the 32 sums of the pair
 // PRIORS selects the instantiation that carries the SE(3)-prior code (numeric Jacobians, 6x6 float64 inverse): it is
 // ~4x the size of the plain one, and the solving thread's run time is dominated by instruction fetch.
 template <bool PRIORS>
-__global__ void __launch_bounds__(32) k_reduce_solve(const PairDesc *__restrict__ desc, int mode, int lastInner, int firstInner,
-                                                     int iter, AlignConsts ac) {
-  const PairDesc &D = desc[blockIdx.x];
-  __shared__ float tot[kAccum];
-  {
-    const int lane = threadIdx.x;
-    float t = 0.0f;
-#pragma unroll
-    for (int g = 0; g < kRowGroups; g++) t += D.partials2[g * kAccum + lane];
-    tot[lane] = t;
-  }
-  __syncwarp();
-  if (threadIdx.x != 0) return;
-
+__device__ __forceinline__ void solve_step(const PairDesc &D, const float *tot, int mode, int lastInner, int firstInner, int iter,
+                                           const AlignConsts &ac) {
   PairState *st = D.state;
   float H[36], b[6];
   // Htt / Hrr upper triangles mirrored, Htr full
@@ -875,6 +835,54 @@ __global__ void __launch_bounds__(32) k_reduce_solve(const PairDesc *__restrict_
   for (int k = 0; k < 16; k++) st->invT[k] = invT[k];
   iso_mul(T, ac.refOffset, tmp);
   store_cam_KRt(ac.cams, tmp, st);
+}
+
+// Deterministic final pass + solve in ONE launch: kRowGroups CTAs per pair; CTA g adds the partial rows of its contiguous
+// group (warp w takes rows w, w+8, ... in order, 8 loads in flight; the 8 warps are added in order) and writes one row of
+// partials2.  The CTA that finishes last (ticket in PairState) adds the kRowGroups rows in order and runs the dense
+// step, so H, b and the pose do not depend on which CTA that is.
+template <bool PRIORS>
+__global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict__ desc, int numBlocks, int mode, int lastInner,
+                                                      int firstInner, int iter, AlignConsts ac) {
+  const PairDesc &D = desc[blockIdx.y];
+  __shared__ float red[8][kAccum];
+  __shared__ float tot[kAccum];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = (numBlocks + kRowGroups - 1) / kRowGroups;
+  const int begin = blockIdx.x * per, end = min(begin + per, numBlocks);
+  float s = 0.0f;
+  const float *__restrict__ rows = D.partials + lane;
+  int bi = begin + warp;
+  for (; bi + 7 * 8 < end; bi += 8 * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = rows[(size_t)(bi + u * 8) * kAccum];
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += v[u];
+  }
+  for (; bi < end; bi += 8) s += rows[(size_t)bi * kAccum];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp != 0) return;
+  float t = red[0][lane];
+#pragma unroll
+  for (int w = 1; w < 8; w++) t += red[w][lane];
+  D.partials2[blockIdx.x * kAccum + lane] = t;
+  __threadfence();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atomicAdd(&D.state->ticket, 1) == kRowGroups - 1) ? 1 : 0;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  float sum = 0.0f;
+#pragma unroll
+  for (int g = 0; g < kRowGroups; g++) sum += __ldcg(&D.partials2[g * kAccum + lane]);
+  tot[lane] = sum;
+  __syncwarp();
+  if (lane != 0) return;
+  D.state->ticket = 0;
+  solve_step<PRIORS>(D, tot, mode, lastInner, firstInner, iter, ac);
 }
 
 __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *__restrict__ statHb) {
@@ -1017,12 +1025,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
         launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 0, 0.0f);
       }
       NICP_CHECK_LAUNCH(ctx);
-      k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
-      NICP_CHECK_LAUNCH(ctx);
       if (ctx->h_desc[0].numPriors > 0)
-        k_reduce_solve<true><<<nPairs, 32, 0, st>>>(ctx->d_desc, 0, k == innerIters - 1, k == 0, it, ac);
+        k_reduce_solve<true><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
       else
-        k_reduce_solve<false><<<nPairs, 32, 0, st>>>(ctx->d_desc, 0, k == innerIters - 1, k == 0, it, ac);
+        k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
       NICP_CHECK_LAUNCH(ctx);
     }
   }
@@ -1034,9 +1040,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
   launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 1, imgThreshold);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_rows<<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb);
-  NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<false><<<nPairs, 32, 0, st>>>(ctx->d_desc, 1, 0, 0, 0, ac);
+  k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
   NICP_CHECK_LAUNCH(ctx);
@@ -1051,9 +1055,7 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   dim3 cg(nb, 1);
   launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, kEpochFresh, 1, ac, numPixels, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
-  k_reduce_rows<<<dim3(kRowGroups, 1), 256, 0, st>>>(ctx->d_desc, nb);
-  NICP_CHECK_LAUNCH(ctx);
-  k_reduce_solve<false><<<1, 32, 0, st>>>(ctx->d_desc, 2, 0, 1, 0, ac);
+  k_reduce_solve<false><<<dim3(kRowGroups, 1), 256, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }

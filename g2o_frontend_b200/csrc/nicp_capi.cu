@@ -99,6 +99,7 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->partialRows * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_partials2, (size_t)slots * 16 * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
+  NICP_CUDA(cudaMemset(ctx->d_state, 0, sizeof(PairState) * (size_t)slots));  // the reduction tickets start at 0
   // two sets of: descriptors followed by one int flag per slot
   size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
   descBytes = (descBytes + 255) & ~(size_t)255;
@@ -1119,7 +1120,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       if (hit >= 0) {
         NICP_CUDA(cudaGraphLaunch(ctx->graphExec[hit], ctx->stream));
         ctx->graphUse[hit] = ++ctx->graphClock;
-        ctx->launches += 2 + 5 + 4 * (long long)ap->outer_iterations * (ap->inner_iterations > 0 ? ap->inner_iterations : 0) + 4;
+        ctx->launches += ctx->graphLaunches[hit];  // the kernels the captured chunk launches
         replayed = true;
       } else {
         if (ctx->graphValid[victim]) {
@@ -1127,6 +1128,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
           ctx->graphValid[victim] = false;
         }
         cudaGraph_t graph = nullptr;
+        const long long launchesBefore = ctx->launches;
         NICP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
                              owns.data(), single, base);
@@ -1144,6 +1146,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         cudaGraphDestroy(graph);
         memcpy(ctx->graphKey[victim], &key, sizeof key);
         ctx->graphValid[victim] = true;
+        ctx->graphLaunches[victim] = ctx->launches - launchesBefore;
         ctx->graphUse[victim] = ++ctx->graphClock;
         NICP_CUDA(cudaGraphLaunch(ctx->graphExec[victim], ctx->stream));
         replayed = true;

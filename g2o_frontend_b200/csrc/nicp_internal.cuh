@@ -94,7 +94,7 @@ struct PairState {
   float img_sum;
   float sumMidx;   // sum over outer iterations of pixels with both indices valid (roofline accounting)
   float sumMacc;   // sum over outer iterations of accepted correspondences
-  int pad;
+  int ticket;      // k_reduce_solve: how many of the kRowGroups first-level CTAs are done (0 between launches)
 };
 
 // per-pair descriptor for the batched kernels (device memory, filled by the host per chunk)
@@ -247,13 +247,14 @@ struct nicp_context {
   double msCorr, msProj;
   long long nCorr, nProj;
 
-  // CUDA graph of the last single-pair nicp_align (47 launches + copies replayed as one graph launch when
+  // CUDA graph of the last single-pair nicp_align (36 kernels + memsets + copies replayed as one graph launch when
   // every baked-in value -- thresholds, K, offsets, iteration counts, image size, buffers -- is unchanged)
   int graphsEnabled;
   static constexpr int kGraphCache = 4;   // e.g. the three levels of a pyramid + one tracker configuration
   cudaGraphExec_t graphExec[kGraphCache];
   bool graphValid[kGraphCache];
   unsigned long long graphUse[kGraphCache], graphClock;
+  long long graphLaunches[kGraphCache];   // kernels in the captured chunk (for nicp_launch_count on replays)
   unsigned char graphKey[kGraphCache][512];
 
   // local-map maintenance scratch (map_ops.cu), grow-only
