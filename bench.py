@@ -76,8 +76,9 @@ def make_workload(n_cur, n_cand, rank):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, indices):
+        """indices: the GPUs to watch (one nvidia-smi process for all of them, started by rank 0 only); None = off"""
+        self.index = None if indices is None else ",".join(str(i) for i in indices)
         self.proc = None
         self.lines = []
 
@@ -85,8 +86,10 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        if self.index is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -277,7 +280,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         align_step()
     ctx.set_kernel_timing(True)
-    sampler = ClockSampler(local_rank)
+    # rank 0 watches every GPU of the job (one sampler process, not one per rank)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else None)
     barrier()
     launches0 = ctx.launch_count()
     sampler.start()
