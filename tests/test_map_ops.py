@@ -392,3 +392,54 @@ def test_gpu_voxelize_random_clouds(ctx, n):
         assert k == len(ref) and np.array_equal(rep, ref), (n, res)
         assert np.array_equal(rep, O.voxelize(pts, res, strict=True))
         d.close()
+
+
+def _numpy_merge_collapsed(points, normals, K, T, rows, cols, minD, maxD, dist_thr, normal_thr, max_depth):
+    """independent float64 restatement of the first loop of Merger::merge (merger.cpp:44-79): z-buffer, then the
+    classification of every point.  Float64 rounding can differ from the float32 oracle only for points within
+    ~1e-6 of a pixel border or a threshold; the caller excludes those."""
+    Kd, Td = K.astype(np.float64), T.astype(np.float64)
+    Ti = np.linalg.inv(Td)
+    KRt = np.eye(4)
+    KRt[:3, :3] = Kd @ Ti[:3, :3]
+    KRt[:3, 3] = Kd @ Ti[:3, 3]
+    ip = points.astype(np.float64) @ KRt.T
+    d = ip[:, 2]
+    ok = (d >= minD) & (d <= maxD)
+    u = np.where(ok, ip[:, 0] / np.where(ok, d, 1.0), -1.0)
+    v = np.where(ok, ip[:, 1] / np.where(ok, d, 1.0), -1.0)
+    x, y = np.rint(np.abs(u)) * np.sign(u), np.rint(np.abs(v)) * np.sign(v)   # round half away from zero
+    inside = ok & (x >= 0) & (x < cols) & (y >= 0) & (y < rows)
+    margin = np.minimum(np.abs(u - np.floor(u) - 0.5), np.abs(v - np.floor(v) - 0.5))
+    zbuf_i = -np.ones((rows, cols), np.int64)
+    zbuf_d = np.full((rows, cols), np.inf)
+    for i in np.nonzero(inside)[0]:
+        r, c = int(y[i]), int(x[i])
+        if d[i] < zbuf_d[r, c]:
+            zbuf_d[r, c], zbuf_i[r, c] = d[i], i
+    col = -np.ones(len(points), np.int64)
+    for i in np.nonzero(inside & (d <= max_depth))[0]:
+        r, c = int(y[i]), int(x[i])
+        t = zbuf_i[r, c]
+        if t == i:
+            col[i] = i
+        elif abs(d[i] - zbuf_d[r, c]) < dist_thr and float(normals[i, :3].astype(np.float64) @ normals[t, :3].astype(np.float64)) > normal_thr:
+            col[i] = t
+    return col, margin
+
+
+def test_oracle_merge_against_independent_numpy():
+    from oracle import pwn_oracle as O
+    K = np.array([[80, 0, 32], [0, 80, 24], [0, 0, 1]], np.float32)
+    rows, cols = 48, 64
+    for seed in (1, 2, 3):
+        cl, g, f = _random_cloud(3000, seed)
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = [0.01 * seed, -0.02, 0.03]
+        _, _, _, col = O.merge(cl, g, f, rows, cols, K, T, 0.5, 4.0, 0.5, 0.9, 2.5)
+        ref, margin = _numpy_merge_collapsed(cl.points, cl.normals, K, T, rows, cols, 0.5, 4.0, 0.5, 0.9, 2.5)
+        # a point whose pixel is ambiguous in float64-vs-float32 also makes its whole pixel ambiguous: compare the rest
+        clear = margin > 1e-4
+        agree = (col == ref)
+        assert agree[clear].mean() > 0.995, agree[clear].mean()
+        assert (col >= 0).sum() > 1000 and ((col >= 0) & (col != np.arange(3000))).sum() > 300
