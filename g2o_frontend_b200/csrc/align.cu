@@ -984,7 +984,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, zBytes, st));
   k_init_pairs<<<(nPairs + 63) / 64, 64, 0, st>>>(ctx->d_desc, nPairs, ac);
   NICP_CHECK_LAUNCH(ctx);
-  const int projBlocks = (P + 1023) / 1024;  // grid-stride: 4 points per thread at full density
+  // grid-stride, 8 points per thread at full density (two rounds of four loads in flight).  The kernel is DRAM bound
+  // (16-byte points + read-modify-write of the z-buffer sectors): 64/128/256 threads x 4/8/16 points all land on 82-86 us
+  constexpr int projThreads = 256, projPerThread = 8;
+  const int projBlocks = (P + projThreads * projPerThread - 1) / (projThreads * projPerThread);
   dim3 pg(projBlocks, nPairs);
   // aligner.cpp:60-63: the current cloud is projected once with projector->setTransform(_currentSensorOffset)
   CamMats curMats, *d_curMats = nullptr;
@@ -995,7 +998,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     if (rcm) return rcm;
     k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags, kEpochFresh);
   } else {
-    k_project<<<pg, 256, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, kEpochFresh);
+    k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, kEpochFresh);
   }
   NICP_CHECK_LAUNCH(ctx);
   k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags);
@@ -1013,7 +1016,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     if (cams.multi)
       k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, parity, geom, d_curMats, ac.rows, ac.cols, d_flags, epoch);
     else
-      k_project<<<pg, 256, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, epoch);
+      k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, epoch);
     NICP_TIME_END(evProj, evProjUsed);
     NICP_CHECK_LAUNCH(ctx);
     for (int k = 0; k < innerIters; k++) {
