@@ -137,6 +137,50 @@ __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ de
     z = D.refZ[which];
     KRt = affine_from(D.state->KRt[0]);
   }
+  if (which != 2 && D.refPoints3) {
+    // 12-byte point stream (the kernel is DRAM bound and the w = 1 lane of the float4 points is a quarter of its read
+    // traffic).  A warp takes 128 consecutive points = 96 float4, loaded fully coalesced (3 per lane), parked in shared
+    // memory and read back as x,y,z of points lane, lane+32, lane+64, lane+96 (word stride 3: conflict free).
+    __shared__ float4 stage[8][2][96];
+    const float4 *__restrict__ q = reinterpret_cast<const float4 *>(D.refPoints3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (n + 127) >> 7;
+    const int wstride = gridDim.x * (blockDim.x >> 5);
+    for (int c = blockIdx.x * (blockDim.x >> 5) + warp; c < chunks; c += 2 * wstride) {
+      const int c2 = c + wstride;
+      const bool two = c2 < chunks;
+      float4 a[3], b[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) a[m] = q[(size_t)c * 96 + lane + 32 * m];
+      if (two) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) b[m] = q[(size_t)c2 * 96 + lane + 32 * m];
+      }
+#pragma unroll
+      for (int m = 0; m < 3; m++) stage[warp][0][lane + 32 * m] = a[m];
+      if (two) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) stage[warp][1][lane + 32 * m] = b[m];
+      }
+      __syncwarp();
+      const float *f0 = reinterpret_cast<const float *>(stage[warp][0]);
+      const float *f1 = reinterpret_cast<const float *>(stage[warp][1]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int l = lane + 32 * j, i = c * 128 + l;
+        if (i < n) project_point(KRt, make_float4(f0[3 * l], f0[3 * l + 1], f0[3 * l + 2], 1.0f), i, rows, cols, minD, maxD, z, epoch);
+      }
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int l = lane + 32 * j, i = c2 * 128 + l;
+          if (i < n) project_point(KRt, make_float4(f1[3 * l], f1[3 * l + 1], f1[3 * l + 2], 1.0f), i, rows, cols, minD, maxD, z, epoch);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
   // four independent point loads in flight per thread (the loop was load -> compute -> atomic, one at a time)
   const int stride = gridDim.x * blockDim.x;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,6 +244,37 @@ __global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int
   const PairDesc &D = desc[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
     D.curIndex[i] = z_index(D.curZ[i], kEpochFresh);
+}
+
+// x,y,z of every point packed at 12 bytes (the buffer holds capacity rounded up to 128 points, so a warp of
+// k_project can always load a whole chunk)
+__global__ void k_pack3(const float4 *__restrict__ pts, const int *__restrict__ nPtr, int capacity, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*nPtr, capacity);
+  if (i >= n) return;
+  const float4 p = pts[i];
+  out[3 * (size_t)i] = p.x;
+  out[3 * (size_t)i + 1] = p.y;
+  out[3 * (size_t)i + 2] = p.z;
+}
+int ensure_points3(nicp_context *ctx, nicp_cloud *cloud) {
+#ifndef NICP_VERIFY_BUILD
+  if (cloud->points3 && cloud->points3_valid) return NICP_OK;
+#endif  // the verification build never trusts the cache: it repacks for every alignment
+  if (!cloud->points3) {
+    NICP_CUDA(cudaSetDevice(ctx->device));
+    const size_t floats = 3 * (((size_t)cloud->capacity + 127) & ~(size_t)127);
+    cudaError_t e = cudaMalloc(&cloud->points3, floats * sizeof(float));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of the packed point stream (%zu bytes) failed: %s", floats * sizeof(float), cudaGetErrorString(e));
+      return NICP_ERR_ALLOC;
+    }
+    NICP_CUDA(cudaMemsetAsync(cloud->points3, 0, floats * sizeof(float), ctx->stream));
+  }
+  k_pack3<<<(cloud->capacity + 255) / 256, 256, 0, ctx->stream>>>(cloud->points, cloud->d_n, cloud->capacity, cloud->points3);
+  NICP_CHECK_LAUNCH(ctx);
+  cloud->points3_valid = true;
+  return NICP_OK;
 }
 
 int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,

@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(256) k_integral_cols_smem(int rows, int cols, 
 
 int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
                       const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index, const CamSet *cams) {
+  cloud->points3_valid = false;
   const int rows = proj->rows, cols = proj->cols;
   const bool multi = cams && cams->multi;
   const PrepCams *d_pc = nullptr;
@@ -674,6 +675,7 @@ __global__ void __launch_bounds__(256) k_unproject_rows(const float *__restrict_
 
 int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
                      float maxD, nicp_cloud *cloud, int *d_index) {
+  cloud->points3_valid = false;
   int *rowCount = ctx->d_interval;  // scratch (rows ints)
   k_row_counts<<<rows, 256, 0, ctx->stream>>>(d_depth, rows, cols, minD, maxD, rowCount);
   NICP_CHECK_LAUNCH(ctx);
@@ -785,6 +787,7 @@ __global__ void k_add_count(int *dstN, const int *srcN, int dstCapacity) {
 }
 
 int launch_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]) {
+  dst->points3_valid = false;
   float m[16];
   for (int i = 0; i < 16; i++) m[i] = T[i];
   fix_last_row(m);
@@ -807,6 +810,7 @@ int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[1
   for (int i = 0; i < 16; i++) m[i] = T[i];
   fix_last_row(m);
   if (is_identity16(m)) return NICP_OK;
+  cloud->points3_valid = false;
   k_cloud_transform<<<(cloud->capacity + 255) / 256, 256, 0, ctx->stream>>>(
       cloud->capacity, cloud->d_n, affine_from(m), cloud->points, cloud->normals, cloud->omega,
       cloud->has_stats ? cloud->stats16 : nullptr);

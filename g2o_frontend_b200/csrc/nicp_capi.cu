@@ -237,6 +237,7 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   PairDesc &D = ctx->h_desc[slot];
   const size_t P = ctx->slotPixels;
   D.refPoints = ref->points;
+  D.refPoints3 = nullptr;
   D.refNormals = ref->normals;
   D.refN = ref->d_n;
   D.curPoints = cur->points;
@@ -611,6 +612,7 @@ void nicp_cloud_destroy(nicp_cloud *c) {
   dev_free(c->statsN);
   dev_free(c->gauss);
   dev_free(c->gflags);
+  dev_free(c->points3);
   dev_free(c->d_n);
   delete c;
 }
@@ -637,6 +639,7 @@ int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *poin
     if (omega_n6)
       for (int k = 0; k < 6; k++) om[12 * (size_t)i + 6 + k] = omega_n6[6 * (size_t)i + k];
   }
+  c->points3_valid = false;
   NICP_CUDA(cudaMemcpyAsync(c->points, points4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(c->normals, nrm.data(), sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(c->omega, om.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1086,6 +1089,12 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       }
       fill_desc(ctx, i, cs, r, c, guesses ? guesses + 16 * (size_t)(base + i) : nullptr, ctx->d_results + base + i,
                 single ? ctx->d_trace : nullptr);
+      // big chunks are DRAM bound: the pinhole projection kernel streams the reference points from the packed copy
+      // (a lone pair is latency bound and keeps the direct float4 loads)
+      if (!cams.multi && m >= 8) {
+        if ((rc = ensure_points3(ctx, const_cast<nicp_cloud *>(r)))) return rc;
+        ctx->h_desc[i].refPoints3 = r->points3;
+      }
       if (numPriors > 0) {
         ctx->h_desc[i].priors = ctx->d_priors;
         ctx->h_desc[i].numPriors = numPriors;

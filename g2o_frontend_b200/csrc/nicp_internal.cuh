@@ -100,6 +100,7 @@ struct PairState {
 // per-pair descriptor for the batched kernels (device memory, filled by the host per chunk)
 struct PairDesc {
   const float4 *refPoints;
+  const float *refPoints3;   // the same points packed at 12 bytes (projection stream), or null
   const float4 *refNormals;  // w = curvature
   const int *refN;
   const float4 *curPoints;
@@ -182,6 +183,8 @@ struct nicp_cloud {
   int n_host;       // host mirror (valid if n_known)
   bool n_known;
   bool has_stats;
+  float *points3;   // cache: x,y,z packed at 12 bytes per point, the stream k_project reads (ensure_points3)
+  bool points3_valid;  // every writer of `points` clears it
   float *gauss;     // optional: Gaussian3f per point, NICP_GAUSS_FLOATS floats each (map_ops.cu)
   int *gflags;      // NICP_GAUSS_MOMENTS | NICP_GAUSS_INFO
   bool has_gauss;
@@ -284,6 +287,7 @@ int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const floa
                           float minD, float maxD, unsigned long long *d_z);
 int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet &cams, const float T[16], int rows,
                         int cols, unsigned long long *d_z);
+int ensure_points3(nicp_context *ctx, nicp_cloud *cloud);
 int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth,
                     float emptyDepth = FLT_MAX, int epoch = kEpochFresh);
 void cam_mats_KRt(const CamSet &cams, const float T[16], CamMats &out);
