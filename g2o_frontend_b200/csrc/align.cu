@@ -239,11 +239,11 @@ __global__ void k_decode_z(const unsigned long long *__restrict__ z, int n, int 
   if (depth) depth[i] = z_depth(v, epoch, emptyDepth);
 }
 
-__global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int *__restrict__ ownsCur) {
+__global__ void k_decode_cur(const PairDesc *__restrict__ desc, int P, const int *__restrict__ ownsCur, int epoch) {
   if (!ownsCur[blockIdx.y]) return;
   const PairDesc &D = desc[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
-    D.curIndex[i] = z_index(D.curZ[i], kEpochFresh);
+    D.curIndex[i] = z_index(D.curZ[i], epoch);
 }
 
 // x,y,z of every point packed at 12 bytes (the buffer holds capacity rounded up to 128 points, so a warp of
@@ -450,7 +450,7 @@ struct TileSmemInplace {
 template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__restrict__ desc, int parity, int epoch,
                                                              int writeCorr, AlignConsts ac, int numPixels, int imgStats,
-                                                             float imgThreshold, int pairFast) {
+                                                             float imgThreshold, int pairFast, int curEpoch) {
   constexpr int NW = NT / 32;
   constexpr int TILE = NT * TK;
   static_assert(TK * NW <= 32, "prefix scan is done by one warp");
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       const int pix = base + k * NT + threadIdx.x;
       if (pix < numPixels) {
         // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
-        const float dc = z_depth(zc[k], kEpochFresh, FLT_MAX);
+        const float dc = z_depth(zc[k], curEpoch, FLT_MAX);
         const float dr = z_depth(zr[k], epoch, FLT_MAX);
         unsigned short c16 = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
         unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
@@ -991,7 +991,7 @@ int partial_rows_for(const nicp_context *ctx, size_t pixels) {
 
 template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac, int P,
-                         int imgStats, float imgThr) {
+                         int imgStats, float imgThr, int curEpoch) {
   size_t smem = INPLACE ? sizeof(TileSmemInplace<NT, TK>) : sizeof(TileSmem<NT, TK>);
   static bool configured = false;
   if (!configured) {
@@ -1002,22 +1002,22 @@ static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, in
   const bool swap = pairFast && grid.x <= 65535;
   const dim3 g = swap ? dim3(grid.y, grid.x) : grid;
   k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<g, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
-                                                                               imgThr, swap ? 1 : 0);
+                                                                               imgThr, swap ? 1 : 0, curEpoch);
 }
 // MODE 0 / 1 launch of the fused kernel in the context's tile configuration
 static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac,
-                            int P, int imgStats, float imgThr) {
+                            int P, int imgStats, float imgThr, int curEpoch = kEpochFresh) {
   if (mode == 0) {
     switch (ctx->tileConfig) {
-      case 1: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 2: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      default: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 1: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      case 2: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      default: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
     }
   } else {
     switch (ctx->tileConfig) {
-      case 1: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      case 2: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
-      default: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr); break;
+      case 1: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      case 2: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      default: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
     }
   }
 }
@@ -1039,7 +1039,7 @@ static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used) {
 // ownsCur: per pair, 1 if the pair's curZ/curIndex buffers must be produced by it.
 int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const CamSet &cams, const float curOffset[16],
                     int outerIters, int innerIters, float imgThreshold, int /*nUniqueCur*/, const int *h_ownsCur,
-                    bool /*wantTrace*/, int resultOffset) {
+                    bool fresh, int resultOffset) {
   cudaStream_t st = ctx->stream;
   const int P = ac.rows * ac.cols;
   const int nb = num_blocks_for(ctx, P);
@@ -1049,14 +1049,39 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
   NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * nPairs, cudaMemcpyHostToDevice, st));
-  // both reference z-buffers and the current z-buffers start fresh (all ones = epoch 15, index -1); after that the
-  // epoch tag replaces per-iteration clearing (see z_encode in nicp_internal.cuh)
+  // z-buffer words carry an epoch tag instead of being cleared per iteration (z_encode in nicp_internal.cuh).
   // (slot buffers are contiguous: refZ is laid out [2][slots][slotPixels], curZ [slots][slotPixels])
-  const size_t zBytes = sizeof(unsigned long long) * ctx->slotPixels * nPairs;
+  //  fresh (single-pair nicp_align, the CUDA-graph path): this call clears its own slots and counts its iterations
+  //    from 0; the buffers as a whole are left inconsistent (zIter / zCurGen = -1).
+  //  batch: all slots share one running iteration count zIter across chunks and calls, so the reference z-buffers are
+  //    cleared only when the 4-bit epoch wraps (every 32 iterations) and the current z-buffers every 16 chunks, always
+  //    over all slots.
   unsigned long long *const refZbuf[2] = {ctx->d_refZ, ctx->d_refZ + (size_t)ctx->slots * ctx->slotPixels};
-  NICP_CUDA(cudaMemsetAsync(refZbuf[0], 0xFF, zBytes, st));
-  NICP_CUDA(cudaMemsetAsync(refZbuf[1], 0xFF, zBytes, st));
-  NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, zBytes, st));
+  const size_t zBytes = sizeof(unsigned long long) * ctx->slotPixels * nPairs;
+  const size_t zBytesAll = sizeof(unsigned long long) * ctx->slotPixels * ctx->slots;
+  long long iterBase = 0;
+  int curEpoch = kEpochFresh;
+  if (fresh) {
+    NICP_CUDA(cudaMemsetAsync(refZbuf[0], 0xFF, zBytes, st));
+    NICP_CUDA(cudaMemsetAsync(refZbuf[1], 0xFF, zBytes, st));
+    NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, zBytes, st));
+    ctx->zIter = -1;
+    ctx->zCurGen = -1;
+  } else {
+    if (ctx->zIter < 0) {
+      NICP_CUDA(cudaMemsetAsync(refZbuf[0], 0xFF, zBytesAll, st));
+      NICP_CUDA(cudaMemsetAsync(refZbuf[1], 0xFF, zBytesAll, st));
+      ctx->zIter = 0;
+    }
+    if (ctx->zCurGen < 0 || (ctx->zCurGen & 15) == 0) {
+      NICP_CUDA(cudaMemsetAsync(ctx->d_curZ, 0xFF, zBytesAll, st));
+      if (ctx->zCurGen < 0) ctx->zCurGen = 0;
+    }
+    iterBase = ctx->zIter;
+    curEpoch = kEpochFresh - (ctx->zCurGen & 15);
+    ctx->zIter += outerIters > 0 ? outerIters : 0;
+    ctx->zCurGen++;
+  }
   k_init_pairs<<<(nPairs + 63) / 64, 64, 0, st>>>(ctx->d_desc, nPairs, ac);
   NICP_CHECK_LAUNCH(ctx);
   // grid-stride, 8 points per thread at full density (two rounds of four loads in flight).  The kernel is DRAM bound
@@ -1071,21 +1096,23 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   if (cams.multi) {
     int rcm = upload_cam_mats(ctx, curMats, &d_curMats);
     if (rcm) return rcm;
-    k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags, kEpochFresh);
+    k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags, curEpoch);
   } else {
-    k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, kEpochFresh);
+    k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, curEpoch);
   }
   NICP_CHECK_LAUNCH(ctx);
-  k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags);
+  k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags, curEpoch);
   NICP_CHECK_LAUNCH(ctx);
   const Affine dummy = curMats.M[0];
   dim3 cg(nb, nPairs);
-  int parity = 0, epoch = kEpochFresh;
+  int parity = (int)(iterBase & 1), epoch = epoch_of_iteration((int)(iterBase & 1023));
   for (int it = 0; it < outerIters; it++) {
-    parity = it & 1;
-    epoch = epoch_of_iteration(it);
+    const long long G = iterBase + it;
+    parity = (int)(G & 1);
+    epoch = epoch_of_iteration((int)(G & 1023));
     // the 4-bit epoch wraps every 32 iterations: start that buffer fresh again
-    if (it >= 2 && epoch == kEpochFresh) NICP_CUDA(cudaMemsetAsync(refZbuf[parity], 0xFF, zBytes, st));
+    if (G >= 2 && epoch == kEpochFresh)
+      NICP_CUDA(cudaMemsetAsync(refZbuf[parity], 0xFF, fresh ? zBytes : zBytesAll, st));
     const int writeCorr = (it == outerIters - 1 || innerIters > 1) ? 1 : 0;
     NICP_TIME_BEGIN(evProj, evProjUsed);
     if (cams.multi)
@@ -1100,7 +1127,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
         launch_corr_lin(ctx, 0, cg, parity, epoch, writeCorr, ac, P, 0, 0.0f);
         NICP_TIME_END(evCorr, evCorrUsed);
       } else {
-        launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 0, 0.0f);
+        launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 0, 0.0f, curEpoch);
       }
       NICP_CHECK_LAUNCH(ctx);
       if (ctx->h_desc[0].numPriors > 0)
@@ -1116,7 +1143,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
       NICP_CUDA(cudaMemsetAsync(ctx->h_desc[i].corrImage, 0xFF, sizeof(int) * P, st));
   }
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
-  launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 1, imgThreshold);
+  launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 1, imgThreshold, curEpoch);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);

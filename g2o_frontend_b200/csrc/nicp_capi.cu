@@ -113,6 +113,8 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   ctx->h_desc = reinterpret_cast<PairDesc *>(ctx->h_descBase);
   ctx->slots = slots;
   ctx->slotPixels = pixels;
+  ctx->zIter = -1;  // new z-buffers: the batch path clears them before use
+  ctx->zCurGen = -1;
   return NICP_OK;
 }
 static int ensure_results(nicp_context *ctx, int n) {
@@ -506,6 +508,8 @@ int nicp_create(int device, nicp_context **out) {
   {
     const char *g = getenv("NICP_GRAPH");
     ctx->graphsEnabled = (g && g[0] == '0') ? 0 : 1;
+    ctx->zIter = -1;
+    ctx->zCurGen = -1;
   }
   ctx->evCorr = new std::vector<cudaEvent_t>();
   ctx->evProj = new std::vector<cudaEvent_t>();
@@ -969,6 +973,7 @@ int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, co
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].refZ[0], z.data(), px * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, current_index, px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = stage_set_T(ctx, T))) return rc;
+  ctx->zIter = ctx->zCurGen = -1;  // slot 0 was staged by hand
   if ((rc = run_correspond_linearize(ctx, ac, false, (int)px))) return rc;
   if (corr_image)
     NICP_CUDA(cudaMemcpyAsync(corr_image, ctx->h_desc[0].corrImage, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -998,6 +1003,7 @@ int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cl
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].corrImage, ri.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, ci.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = stage_set_T(ctx, T))) return rc;
+  ctx->zIter = ctx->zCurGen = -1;
   if ((rc = run_correspond_linearize(ctx, ac, true, (int)px))) return rc;
   ctx->lastAlignValid = false;
   return fetch_stage_result(ctx, H, b, error, inliers, nullptr);
@@ -1034,6 +1040,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
   if ((rc = ensure_align(ctx, maxSlots, P))) return rc;
   if ((rc = ensure_results(ctx, n))) return rc;
   if (single && (rc = ensure_trace(ctx, ap->outer_iterations > 0 ? ap->outer_iterations : 1))) return rc;
+  if (single) ctx->zIter = ctx->zCurGen = -1;  // slot 0 is about to be used with its own epochs (also by a graph replay)
   if (numPriors > 0) {
     // SE3AbsolutePrior keeps the inverse of its reference transform (se3_prior.h setReferenceTransform)
     std::vector<HostPrior> hp(numPriors);

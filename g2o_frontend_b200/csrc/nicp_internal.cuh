@@ -260,6 +260,11 @@ struct nicp_context {
   long long graphLaunches[kGraphCache];   // kernels in the captured chunk (for nicp_launch_count on replays)
   unsigned char graphKey[kGraphCache][512];
 
+  // epoch bookkeeping of the batch path (run_align_chunk): reference-projection iterations since the reference
+  // z-buffers were last cleared as a whole, chunks since the current z-buffers were; -1 = must be cleared first
+  long long zIter;
+  int zCurGen;
+
   // local-map maintenance scratch (map_ops.cu), grow-only
   void *d_mapScratch;
   size_t mapScratchBytes;

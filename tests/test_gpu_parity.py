@@ -658,3 +658,35 @@ def test_no_gpu_fallback_symbols(ctx):
     for name in capi.SYMBOLS:
         assert hasattr(ctx.L, name)
     assert ctx.launch_count() >= 0
+
+
+def test_many_chunks_epoch_continuity(monkeypatch):
+    """the batch path keeps one running epoch count over chunks and calls (the z-buffers are cleared only when the 4-bit
+    epoch wraps): 44 chunks of 2 slots -> the reference buffers wrap 13 times, the current buffers twice; single
+    alignments and a differently sized batch in between; every record must equal the record of the pair aligned alone"""
+    from g2o_frontend_b200 import capi, synth
+    monkeypatch.setenv("NICP_BATCH_SLOTS", "2")
+    ctx = capi.Context(0)
+    try:
+        s = get_scene(4, 0, 0.05)
+        ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+        rng = np.random.default_rng(5)
+        n = 88
+        guesses = np.stack([synth.perturbed_pose(rng, np.eye(4), 0.03, 1.5) for _ in range(n)]).astype(np.float32)
+        refs = [ref if i % 3 else cur for i in range(n)]
+        curs = [cur if i % 3 else ref for i in range(n)]
+        alone = [bytes(ctx.align(refs[i], curs[i], s.projector(), s.align_params(), guess=guesses[i])) for i in range(n)]
+        b1 = ctx.align_batch(refs, curs, s.projector(), s.align_params(), guesses)
+        for i in range(n):
+            assert b1[i].tobytes() == alone[i], i
+        # a single alignment in between dirties slot 0; odd iteration counts flip the buffer parity between chunks
+        ctx.align(ref, cur, s.projector(), s.align_params(outer=3))
+        b2 = ctx.align_batch(refs[:37], curs[:37], s.projector(), s.align_params(outer=7), guesses[:37])
+        b3 = ctx.align_batch(refs, curs, s.projector(), s.align_params(), guesses)
+        for i in range(n):
+            assert b3[i].tobytes() == alone[i], i
+        for i in (0, 5, 36):
+            r = ctx.align(refs[i], curs[i], s.projector(), s.align_params(outer=7), guess=guesses[i])
+            assert b2[i].tobytes() == bytes(r), i
+    finally:
+        ctx.close()
