@@ -690,3 +690,36 @@ def test_many_chunks_epoch_continuity(monkeypatch):
             assert b2[i].tobytes() == bytes(r), i
     finally:
         ctx.close()
+
+
+def test_packed_point_stream_is_invalidated(ctx):
+    """chunks of 8+ pairs project the reference cloud from a packed 12-byte copy that is cached per cloud: every
+    writer of the points (frame prep into the same handle, upload, transformInPlace, Cloud::add) must invalidate it"""
+    from g2o_frontend_b200 import synth
+    s = get_scene(4, 0, 0.05)
+    proj, sp, ap = s.projector(), s.stats_params(), s.align_params()
+    cur = upload(ctx, s.cloudB)
+    rng = np.random.default_rng(3)
+    guesses = np.stack([synth.perturbed_pose(rng, np.eye(4), 0.02, 1.0) for _ in range(9)]).astype(np.float32)
+
+    def batch(ref):
+        return ctx.align_batch([ref] * 9, [cur] * 9, proj, ap, guesses).tobytes()
+
+    def alone(ref):
+        return b"".join(bytes(ctx.align(ref, cur, proj, ap, guess=g)) for g in guesses)  # float4 path, no cache
+
+    ref = ctx.new_cloud(s.rows * s.cols)
+    ctx.depth_to_cloud(s.depthA, proj, sp, cloud=ref)
+    assert batch(ref) == alone(ref)
+    ctx.depth_to_cloud(s.depthB, proj, sp, cloud=ref)          # same handle, new frame
+    assert batch(ref) == alone(ref)
+    T = synth.make_pose((0.02, -0.01, 0.03), (0.1, 1.0, 0.2), 2.0).astype(np.float32)
+    ref.transform(T)                                           # Cloud::transformInPlace
+    assert batch(ref) == alone(ref)
+    ref.upload(s.cloudA.points, s.cloudA.normals, s.cloudA.curvature, s.cloudA.omegaP6(), s.cloudA.omegaN6())
+    assert batch(ref) == alone(ref)
+    big = ctx.new_cloud(2 * s.rows * s.cols)
+    big.append(ref)
+    assert batch(big) == alone(big)
+    big.append(cur, T)                                         # Cloud::add grows the cloud behind the cache
+    assert batch(big) == alone(big)
