@@ -64,7 +64,7 @@ static int ensure_raw(nicp_context *ctx, size_t pixels) {
   dev_free(ctx->d_raw);
   ctx->rawPixels = 0;
   int rc;
-  if ((rc = dev_alloc(&ctx->d_raw, pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_raw, 2 * pixels))) return rc;
   ctx->rawPixels = pixels;
   return NICP_OK;
 }
@@ -490,6 +490,11 @@ int nicp_create(int device, nicp_context **out) {
   memset(ctx, 0, sizeof *ctx);
   ctx->device = device;
   NICP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  NICP_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawCopied[i], cudaEventDisableTiming));
+    NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawUsed[i], cudaEventDisableTiming));
+  }
   cudaDeviceProp prop;
   NICP_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
@@ -543,6 +548,11 @@ void nicp_destroy(nicp_context *ctx) {
   delete ctx->evProj;
   cudaEventDestroy(ctx->evChunk[0]);
   cudaEventDestroy(ctx->evChunk[1]);
+  for (int i = 0; i < 2; i++) {
+    cudaEventDestroy(ctx->evRawCopied[i]);
+    cudaEventDestroy(ctx->evRawUsed[i]);
+  }
+  cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -887,9 +897,17 @@ int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows
   int rc;
   if ((rc = ensure_raw(ctx, rpx))) return rc;
   if ((rc = ensure_prep(ctx, px))) return rc;
-  NICP_CUDA(cudaMemcpyAsync(ctx->d_raw, raw, rpx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = launch_depth_convert(ctx, ctx->d_raw, raw_rows, raw_cols, depth_scale, step, max_depth_cov, ctx->d_depth)))
+  // the upload runs on its own stream into one of two staging images, so the copy of this frame overlaps the
+  // kernels of the previous one (from pinned host memory; a pageable source is staged by the driver as before)
+  const int b = (ctx->rawToggle ^= 1);
+  uint16_t *d_raw = ctx->d_raw + (size_t)b * ctx->rawPixels;
+  NICP_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evRawUsed[b], 0));
+  NICP_CUDA(cudaMemcpyAsync(d_raw, raw, rpx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copyStream));
+  NICP_CUDA(cudaEventRecord(ctx->evRawCopied[b], ctx->copyStream));
+  NICP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evRawCopied[b], 0));
+  if ((rc = launch_depth_convert(ctx, d_raw, raw_rows, raw_cols, depth_scale, step, max_depth_cov, ctx->d_depth)))
     return rc;
+  NICP_CUDA(cudaEventRecord(ctx->evRawUsed[b], ctx->stream));
   return depth_to_cloud_device(ctx, proj, sp, sensor_offset, keep_stats, cloud, index);
 }
 

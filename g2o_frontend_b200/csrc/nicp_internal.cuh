@@ -199,8 +199,11 @@ struct nicp_context {
   // frame-prep scratch
   size_t prepPixels;
   float *d_depth;
-  uint16_t *d_raw;
-  size_t rawPixels;
+  uint16_t *d_raw;    // two staging images back to back: frame i+1 is uploaded while frame i is being converted
+  size_t rawPixels;   // pixels per staging image
+  cudaStream_t copyStream;
+  cudaEvent_t evRawCopied[2], evRawUsed[2];
+  int rawToggle;
   float *d_integral;  // planar [10][rows][cols]
   int *d_interval;
   int *d_index;
