@@ -1,0 +1,78 @@
+"""BOSS configuration files: the record format of g2o_frontend/pwn_boss, parsed into
+the C-ABI parameter structs.  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from g2o_frontend_b200 import boss_config as B
+
+FIXTURE = os.path.join(ROOT, "tests", "golden", "boss_pipeline.conf")
+REF_CONF = "/root/reference/g2o_frontend/pwn_tracker2/conf"
+
+
+def test_parse_fixture_and_resolve_pointers():
+    objs = B.load(FIXTURE)
+    assert [o.cls for o in objs][:2] == ["PinholePointProjector", "StatsCalculatorIntegralImage"]
+    p = B.pipeline(objs)
+    a = p["align"]
+    assert a["outer_iterations"] == 10 and a["inner_iterations"] == 1 and a["robust_kernel"] == 1
+    assert a["inlier_max_chi2"] == 9000 and abs(a["inlier_normal_angular_threshold"] - 0.95) < 1e-7
+    K = a["projector"]["K"]
+    assert K.shape == (3, 3) and K[0, 2] == np.float32(79.875) and K[1, 1] == np.float32(131.25)  # row-major values
+    assert (a["projector"]["rows"], a["projector"]["cols"]) == (120, 160)
+    s = p["stats"]
+    assert (s["min_image_radius"], s["max_image_radius"], s["min_points"]) == (3, 6, 10)
+    assert s["flat_omega_p"] == [1000.0, 1.0, 1.0] and s["flat_omega_n"] == [100.0, 100.0, 100.0]
+    assert p["merger"]["max_point_depth"] == 10 and p["voxel_resolution"] == 0.02
+    # poses are t2v vectors: translation + vector part of a unit quaternion
+    T = a["reference_sensor_offset"]
+    assert np.allclose(T[:3, 3], [0.05, -0.02, 0.1]) and np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-6)
+    Tp = a["projector"]["transform"]
+    assert abs(np.degrees(np.arctan2(Tp[1, 0], Tp[0, 0])) - 10.0) < 1e-3   # qz = sin(5 deg) -> 10 deg about z
+
+
+def test_v2t_matches_the_oracle():
+    from oracle import pwn_oracle as O
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        v = np.concatenate([rng.uniform(-1, 1, 3), rng.uniform(-0.4, 0.4, 3)]).astype(np.float32)
+        assert np.allclose(B.v2t(v), O.v2t(v), atol=2e-6)
+
+
+def test_round_trip():
+    objs = B.load(FIXTURE)
+    again = B.loads(B.dumps(objs))
+    assert [(o.cls, o.fields) for o in objs] == [(o.cls, o.fields) for o in again]
+    with pytest.raises(ValueError):
+        B.loads('Aligner { "#id": 1 }')          # class name must be quoted
+    with pytest.raises(ValueError):
+        B.loads('"Aligner" [1, 2]')              # record body must be an object
+
+
+def test_to_capi_structs():
+    capi = pytest.importorskip("g2o_frontend_b200.capi")
+    proj, sp, ap, mp = B.to_capi(B.pipeline(B.load(FIXTURE)))
+    assert (proj.rows, proj.cols) == (120, 160) and abs(proj.max_distance - 4.5) < 1e-6
+    assert abs(proj.K[6] - 79.875) < 1e-6      # column-major in the ABI: K(0,2) is element 6
+    assert sp.min_image_radius == 3 and sp.max_image_radius == 6 and list(sp.flat_omega_p) == [1000.0, 1.0, 1.0]
+    assert ap.outer_iterations == 10 and ap.robust_kernel == 1 and abs(ap.inlier_max_chi2 - 9000) < 1e-3
+    assert abs(mp.normal_threshold - 0.984808) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="reference tree not present (GPU box)")
+def test_reference_tracker_configurations_parse():
+    files = sorted(glob.glob(os.path.join(REF_CONF, "*.conf")))
+    assert files
+    seen_aligner = 0
+    for f in files:
+        objs = B.load(f)
+        assert objs, f
+        p = B.pipeline(objs)
+        if p["align"] is not None:
+            seen_aligner += 1
+            assert p["align"]["outer_iterations"] >= 1
+            assert p["stats"] is None or p["stats"]["min_points"] > 0
+    assert seen_aligner >= 3
