@@ -17,6 +17,7 @@
 #include <string>
 
 #include "pwn/pwn.h"
+#include "pwn/boss_config.h"
 #include "pwn/pyramid.h"
 #include "pwn/tracker.h"
 
@@ -64,7 +65,60 @@ static bool readPgm16(const char *path, RawDepthImage &img) {
   return true;
 }
 
+// --dump-config <file.conf>: parse a BOSS configuration of the reference's trackers (pwn_tracker2/conf/*.conf) into the
+// pwn:: objects and print what they ended up with as one JSON object (no GPU is touched)
+static int dumpBossConfig(const char *path) {
+  PinholePointProjector alignerProjector, converterProjector;
+  StatsCalculatorIntegralImage statsCalculator;
+  PointInformationMatrixCalculator pointInfo;
+  NormalInformationMatrixCalculator normalInfo;
+  CorrespondenceFinder finder;
+  Linearizer linearizer;
+  Aligner aligner;
+  Merger merger;
+  VoxelCalculator voxel;
+  BossPipeline p;
+  p.alignerProjector = &alignerProjector; p.converterProjector = &converterProjector; p.statsCalculator = &statsCalculator;
+  p.pointInformationMatrixCalculator = &pointInfo; p.normalInformationMatrixCalculator = &normalInfo;
+  p.correspondenceFinder = &finder; p.linearizer = &linearizer; p.aligner = &aligner; p.merger = &merger;
+  p.voxelCalculator = &voxel;
+  std::vector<BossRecord> recs = bossLoad(path);
+  configureFromBoss(recs, p);
+  printf("{\"records\": %zu, \"outer_iterations\": %d, \"inner_iterations\": %d, \"inlier_max_chi2\": %.9g, \"robust_kernel\": %d, ",
+         recs.size(), aligner.outerIterations(), aligner.innerIterations(), linearizer.inlierMaxChi2(), linearizer.robustKernel() ? 1 : 0);
+  printf("\"inlier_distance_threshold\": %.9g, \"inlier_normal_angular_threshold\": %.9g, \"flat_curvature_threshold\": %.9g, "
+         "\"inlier_curvature_ratio_threshold\": %.9g, ",
+         finder.inlierDistanceThreshold(), finder.inlierNormalAngularThreshold(), finder.flatCurvatureThreshold(),
+         finder.inlierCurvatureRatioThreshold());
+  printf("\"K\": [");
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) printf("%s%.9g", r + c ? ", " : "", alignerProjector.cameraMatrix()(r, c));
+  printf("], \"rows\": %d, \"cols\": %d, \"min_distance\": %.9g, \"max_distance\": %.9g, ", alignerProjector.imageRows(),
+         alignerProjector.imageCols(), alignerProjector.minDistance(), alignerProjector.maxDistance());
+  printf("\"reference_sensor_offset\": [");
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) printf("%s%.9g", r + c ? ", " : "", aligner.referenceSensorOffset().matrix()(r, c));
+  printf("], \"world_radius\": %.9g, \"min_image_radius\": %d, \"max_image_radius\": %d, \"min_points\": %d, "
+         "\"curvature_threshold\": %.9g, ",
+         statsCalculator.worldRadius(), statsCalculator.minImageRadius(), statsCalculator.maxImageRadius(),
+         statsCalculator.minPoints(), statsCalculator.curvatureThreshold());
+  printf("\"flat_omega_p\": [%.9g, %.9g, %.9g], \"flat_omega_n\": [%.9g, %.9g, %.9g], ", pointInfo.flatInformationMatrix()(0, 0),
+         pointInfo.flatInformationMatrix()(1, 1), pointInfo.flatInformationMatrix()(2, 2), normalInfo.flatInformationMatrix()(0, 0),
+         normalInfo.flatInformationMatrix()(1, 1), normalInfo.flatInformationMatrix()(2, 2));
+  printf("\"merger\": [%.9g, %.9g, %.9g], \"voxel_resolution\": %.9g}\n", merger.distanceThreshold(), merger.normalThreshold(),
+         merger.maxPointDepth(), voxel.resolution());
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc == 3 && std::string(argv[1]) == "--dump-config") {
+    try {
+      return dumpBossConfig(argv[2]);
+    } catch (const std::exception &e) {
+      fprintf(stderr, "pwn_simple_aligner: %s\n", e.what());
+      return 1;
+    }
+  }
   if (argc < 5) {
     fprintf(stderr, "usage: %s config.conf out.jsonl depth0.pgm depth1.pgm ...\n", argv[0]);
     return 2;
@@ -120,6 +174,15 @@ int main(int argc, char **argv) {
     aligner.setMinInliers((int)get(cfg, "minInliers", 100));
     aligner.setSensorOffset(sensorOffset);
 
+    if (bossLooksLikeBoss(argv[1])) {
+      // a BOSS file of the reference's trackers instead of a `key value` file: the records configure the same objects
+      BossPipeline bp;
+      bp.alignerProjector = &projector; bp.statsCalculator = &statsCalculator;
+      bp.pointInformationMatrixCalculator = &pointInformationMatrixCalculator;
+      bp.normalInformationMatrixCalculator = &normalInformationMatrixCalculator;
+      bp.correspondenceFinder = &correspondenceFinder; bp.linearizer = &linearizer; bp.aligner = &aligner;
+      configureFromBoss(bossLoad(argv[1]), bp);
+    }
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");
     if (get(cfg, "cloudio", 0) != 0) {

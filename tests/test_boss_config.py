@@ -76,3 +76,51 @@ def test_reference_tracker_configurations_parse():
             assert p["align"]["outer_iterations"] >= 1
             assert p["stats"] is None or p["stats"]["min_points"] > 0
     assert seen_aligner >= 3
+
+
+BIN = os.path.join(ROOT, "g2o_frontend_b200", "lib", "pwn_simple_aligner")
+
+
+def _cpp_dump(path):
+    import json
+    import subprocess
+    return json.loads(subprocess.check_output([BIN, "--dump-config", path]).decode())
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="host driver not built")
+def test_cpp_reader_agrees_with_python_reader():
+    """include/pwn/boss_config.h (what a C++ caller uses) and boss_config.py resolve a file to the same parameters"""
+    files = [FIXTURE]
+    if os.path.isdir(REF_CONF):
+        files += sorted(glob.glob(os.path.join(REF_CONF, "*.conf")))
+    checked = 0
+    for f in files:
+        p = B.pipeline(B.load(f))
+        if p["align"] is None or "projector" not in p["align"]:
+            continue
+        d = _cpp_dump(f)
+        a = p["align"]
+        assert d["records"] == len(B.load(f))
+        assert d["outer_iterations"] == a["outer_iterations"] and d["inner_iterations"] == a["inner_iterations"], f
+        assert d["robust_kernel"] == a["robust_kernel"]
+        for k in ("inlier_max_chi2", "inlier_distance_threshold", "inlier_normal_angular_threshold",
+                  "flat_curvature_threshold", "inlier_curvature_ratio_threshold"):
+            assert abs(d[k] - a[k]) <= 1e-6 * max(1.0, abs(a[k])), (f, k)
+        q = a["projector"]
+        assert np.allclose(np.array(d["K"]).reshape(3, 3), q["K"]) and (d["rows"], d["cols"]) == (q["rows"], q["cols"])
+        assert abs(d["max_distance"] - q["max_distance"]) < 1e-6
+        assert np.allclose(np.array(d["reference_sensor_offset"]).reshape(4, 4), a["reference_sensor_offset"], atol=2e-6)
+        if p["stats"] is not None and "IntegralImage" in "".join(o.cls for o in B.load(f)):
+            s = p["stats"]
+            assert (d["min_image_radius"], d["max_image_radius"], d["min_points"]) == \
+                   (s["min_image_radius"], s["max_image_radius"], s["min_points"]), f
+            assert np.allclose(d["flat_omega_p"], s["flat_omega_p"]) and np.allclose(d["flat_omega_n"], s["flat_omega_n"])
+        if p["merger"] is not None:
+            assert np.allclose(d["merger"], [p["merger"][k] for k in ("distance_threshold", "normal_threshold", "max_point_depth")])
+        checked += 1
+    assert checked >= 1
+    # a malformed file is an error, not a silent default
+    import subprocess
+    bad = os.path.join(ROOT, "tests", "golden", "boss_pipeline.conf")
+    r = subprocess.run([BIN, "--dump-config", bad + ".does_not_exist"], capture_output=True)
+    assert r.returncode != 0
