@@ -157,10 +157,11 @@ def merger_params(o):
 
 def pipeline(objects):
     """the first Aligner and the first DepthImageConverterIntegralImage of a file, resolved:
-    -> {"align": ..., "converter_projector": ..., "stats": ..., "merger": ... or None, "voxel_resolution": ... or None}"""
+    -> {"align", "converter_projector", "stats", "merger", "voxel_resolution", "matcher", "tracker"} (None when absent)"""
     table = by_id(objects)
     first = lambda cls: next((o for o in objects if o.cls == cls), None)
-    out = {"align": None, "converter_projector": None, "stats": None, "merger": None, "voxel_resolution": None}
+    out = {"align": None, "converter_projector": None, "stats": None, "merger": None, "voxel_resolution": None,
+           "matcher": None, "tracker": None}
     al = first("Aligner")
     if al is not None:
         out["align"] = align_params(al, table)
@@ -179,6 +180,16 @@ def pipeline(objects):
     vx = first("VoxelCalculator")
     if vx is not None:
         out["voxel_resolution"] = float(vx["resolution"])
+    mt = first("PwnMatcherBase")  # pwn_tracker2/pwn_matcher_base.cpp:20-36
+    if mt is not None:
+        out["matcher"] = {"scale": int(mt["scale"]), "frame_inlier_depth_threshold": float(mt["frameInlierDepthThreshold"])}
+    tr = first("PwnTracker")      # pwn_tracker2/pwn_tracker.cpp serialize
+    if tr is not None:
+        out["tracker"] = {"new_frame_cloud_inliers_fraction": float(tr.get("newFrameCloudInliersFraction", 0.4)),
+                          "min_cloud_inliers": int(tr.get("minCloudInliers", 0)),
+                          "frame_min_non_zero_threshold": int(tr.get("frameMinNonZeroThreshold", 0)),
+                          "frame_max_outliers_threshold": int(tr.get("frameMaxOutliersThreshold", 0)),
+                          "frame_min_inliers_threshold": int(tr.get("frameMinInliersThreshold", 0))}
     return out
 
 

@@ -105,8 +105,11 @@ static int dumpBossConfig(const char *path) {
   printf("\"flat_omega_p\": [%.9g, %.9g, %.9g], \"flat_omega_n\": [%.9g, %.9g, %.9g], ", pointInfo.flatInformationMatrix()(0, 0),
          pointInfo.flatInformationMatrix()(1, 1), pointInfo.flatInformationMatrix()(2, 2), normalInfo.flatInformationMatrix()(0, 0),
          normalInfo.flatInformationMatrix()(1, 1), normalInfo.flatInformationMatrix()(2, 2));
-  printf("\"merger\": [%.9g, %.9g, %.9g], \"voxel_resolution\": %.9g}\n", merger.distanceThreshold(), merger.normalThreshold(),
+  printf("\"merger\": [%.9g, %.9g, %.9g], \"voxel_resolution\": %.9g, ", merger.distanceThreshold(), merger.normalThreshold(),
          merger.maxPointDepth(), voxel.resolution());
+  printf("\"matcher_scale\": %d, \"frame_inlier_depth_threshold\": %.9g, \"new_frame_cloud_inliers_fraction\": %.9g, "
+         "\"has_matcher\": %d, \"has_tracker\": %d}\n",
+         p.matcherScale, p.frameInlierDepthThreshold, p.newFrameCloudInliersFraction, p.hasMatcher ? 1 : 0, p.hasTracker ? 1 : 0);
   return 0;
 }
 
@@ -126,7 +129,7 @@ int main(int argc, char **argv) {
   try {
     std::map<std::string, float> cfg = readConfig(argv[1]);
     // setInputParameters, pwn_simple_aligner.cpp:214-269
-    const int imageScale = (int)get(cfg, "imageScale", 1);
+    int imageScale = (int)get(cfg, "imageScale", 1);
     const float depthScale = get(cfg, "depthScale", 0.001f);
     Matrix3f K;
     K.setIdentity();
@@ -182,6 +185,13 @@ int main(int argc, char **argv) {
       bp.normalInformationMatrixCalculator = &normalInformationMatrixCalculator;
       bp.correspondenceFinder = &correspondenceFinder; bp.linearizer = &linearizer; bp.aligner = &aligner;
       configureFromBoss(bossLoad(argv[1]), bp);
+      if (!bp.hasAligner) throw std::runtime_error("the BOSS file holds no Aligner record");
+      // what the key/value file would have supplied comes from the records: camera matrix and image size of the aligner's
+      // projector, the sensor offset of the aligner, the image scale of the matcher (PwnMatcherBase::scale)
+      K = projector.cameraMatrix();
+      sensorOffset = aligner.referenceSensorOffset();
+      if (bp.hasMatcher) imageScale = bp.matcherScale;
+      if (bp.hasTracker) cfg["newFrameInliersFraction"] = bp.newFrameCloudInliersFraction;
     }
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");

@@ -274,13 +274,35 @@ struct BossPipeline {
   Aligner *aligner;
   Merger *merger;
   VoxelCalculator *voxelCalculator;
+  // outputs: PwnMatcherBase (pwn_tracker2/pwn_matcher_base.cpp:20-36) and PwnTracker records, if present
+  bool hasAligner, hasMatcher, hasTracker;
+  int matcherScale;
+  float frameInlierDepthThreshold, newFrameCloudInliersFraction;
+  int minCloudInliers, frameMinNonZeroThreshold, frameMaxOutliersThreshold, frameMinInliersThreshold;
   BossPipeline()
       : alignerProjector(0), converterProjector(0), statsCalculator(0), pointInformationMatrixCalculator(0),
-        normalInformationMatrixCalculator(0), correspondenceFinder(0), linearizer(0), aligner(0), merger(0), voxelCalculator(0) {}
+        normalInformationMatrixCalculator(0), correspondenceFinder(0), linearizer(0), aligner(0), merger(0), voxelCalculator(0),
+        hasAligner(false), hasMatcher(false), hasTracker(false), matcherScale(1), frameInlierDepthThreshold(50.0f),
+        newFrameCloudInliersFraction(0.4f), minCloudInliers(0), frameMinNonZeroThreshold(0), frameMaxOutliersThreshold(0),
+        frameMinInliersThreshold(0) {}
 };
 inline void configureFromBoss(const std::vector<BossRecord> &recs, BossPipeline &p) {
   using namespace boss_detail;
+  if (const BossRecord *mt = firstOf(recs, "PwnMatcherBase")) {
+    p.hasMatcher = true;
+    p.matcherScale = (int)mt->fields.num("scale");
+    p.frameInlierDepthThreshold = (float)mt->fields.num("frameInlierDepthThreshold");
+  }
+  if (const BossRecord *tr = firstOf(recs, "PwnTracker")) {
+    p.hasTracker = true;
+    p.newFrameCloudInliersFraction = (float)tr->fields.num("newFrameCloudInliersFraction", 0.4);
+    p.minCloudInliers = (int)tr->fields.num("minCloudInliers", 0);
+    p.frameMinNonZeroThreshold = (int)tr->fields.num("frameMinNonZeroThreshold", 0);
+    p.frameMaxOutliersThreshold = (int)tr->fields.num("frameMaxOutliersThreshold", 0);
+    p.frameMinInliersThreshold = (int)tr->fields.num("frameMinInliersThreshold", 0);
+  }
   if (const BossRecord *al = firstOf(recs, "Aligner")) {
+    p.hasAligner = true;
     if (p.aligner) {
       p.aligner->setOuterIterations((int)al->fields.num("outerIterations"));
       p.aligner->setInnerIterations((int)al->fields.num("innerIterations"));

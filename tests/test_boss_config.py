@@ -117,6 +117,12 @@ def test_cpp_reader_agrees_with_python_reader():
             assert np.allclose(d["flat_omega_p"], s["flat_omega_p"]) and np.allclose(d["flat_omega_n"], s["flat_omega_n"])
         if p["merger"] is not None:
             assert np.allclose(d["merger"], [p["merger"][k] for k in ("distance_threshold", "normal_threshold", "max_point_depth")])
+        assert d["has_matcher"] == int(p["matcher"] is not None) and d["has_tracker"] == int(p["tracker"] is not None)
+        if p["matcher"] is not None:
+            assert d["matcher_scale"] == p["matcher"]["scale"]
+            assert abs(d["frame_inlier_depth_threshold"] - p["matcher"]["frame_inlier_depth_threshold"]) < 1e-6
+        if p["tracker"] is not None:
+            assert abs(d["new_frame_cloud_inliers_fraction"] - p["tracker"]["new_frame_cloud_inliers_fraction"]) < 1e-6
         checked += 1
     assert checked >= 1
     # a malformed file is an error, not a silent default
