@@ -64,16 +64,16 @@ __global__ void k_init_pairs(PairDesc *desc, int n, AlignConsts ac) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void project_point(const Affine &KRt, float4 p, int i, int rows, int cols, float minD,
                                               float maxD, unsigned long long *__restrict__ z, int epoch) {
+  // straight-line code with one predicated reduction at the end (the kernel is issue bound; early returns cost
+  // divergence bookkeeping).  A zero / negative / NaN depth fails the range tests below like in the reference.
   float ix, iy, d;
   xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
-  if (d < minD || d > maxD) return;
   // the packed z-buffer word orders positive depths below 32 km (z_encode); anything else cannot be a valid range image
-  if (!(d > 0.0f && d < 32768.0f)) return;
-  float s = fdiv(1.0f, d);
-  float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
-  if (!(fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows)) return;
-  int x = (int)fx, y = (int)fy;
-  z_min(&z[(size_t)y * cols + x], z_encode(d, i, epoch));
+  bool ok = !(d < minD || d > maxD) && d > 0.0f && d < 32768.0f;
+  const float s = frcp(d);
+  const float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
+  ok = ok && fx >= 0.0f && fx < (float)cols && fy >= 0.0f && fy < (float)rows;
+  if (ok) z_min(&z[(size_t)(int)fy * cols + (int)fx], z_encode(d, i, epoch));
 }
 
 CamGeom geom_of(const CamSet &c) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ void project_point_multi(const CamGeom &g, const MatS
     float ix, iy, d;
     xform_point(KRt, p.x, p.y, p.z, ix, iy, d);
     if (d < g.minD[c] || d > g.maxD[c]) continue;
-    float s = fdiv(1.0f, d);
+    float s = frcp(d);
     float fx = roundf(fmul(ix, s)), fy = roundf(fmul(iy, s));
     if (!(d > 0.0f && d < 32768.0f) || !(fx >= 0.0f && fx < (float)g.width[c] && fy >= 0.0f && fy < (float)g.height[c])) continue;
     int X = (int)fx, Y = (int)fy + g.colOff[c];

@@ -448,7 +448,7 @@ __global__ void k_merge_classify(const float4 *__restrict__ points, const float4
   xform_point(KRt, p.x, p.y, p.z, ix, iy, depth);
   int r = -1, c = -1;
   if (!(depth < minD || depth > maxD)) {  // _project, pinholepointprojector.h:224-233
-    const float s = fdiv(1.0f, depth);
+    const float s = frcp(depth);
     c = (int)roundf(fmul(ix, s));
     r = (int)roundf(fmul(iy, s));
   }

@@ -27,6 +27,7 @@ NICP_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
 NICP_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
 NICP_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 NICP_HD float fsqrt(float a) { return __fsqrt_rn(a); }
+NICP_HD float frcp(float a) { return __frcp_rn(a); }  // correctly rounded 1/a == 1.0f / a, fewer instructions than fdiv
 #else
 // host: compiled with -ffp-contract=off
 NICP_HD float fmul(float a, float b) { return a * b; }
@@ -34,6 +35,7 @@ NICP_HD float fadd(float a, float b) { return a + b; }
 NICP_HD float fsub(float a, float b) { return a - b; }
 NICP_HD float fdiv(float a, float b) { return a / b; }
 NICP_HD float fsqrt(float a) { return sqrtf(a); }
+NICP_HD float frcp(float a) { return 1.0f / a; }
 #endif
 
 #define NM4(m, r, c) ((m)[(c) * 4 + (r)])
