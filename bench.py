@@ -191,7 +191,7 @@ def workload_config(n_cur, n_cand, world):
                         "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
             "pairs_per_gpu_per_step": n_pairs, "rows": ROWS, "cols": COLS,
             "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per step)" %
-                         ((n_cur + n_cand) * P * 80 / 1e9, 64 * P * 32 / 1e9),
+                         ((n_cur + n_cand) * P * 80 / 1e9, 256 * P * 32 / 1e9),
             "parallelism": "pair-sharded x%d" % world}
 
 

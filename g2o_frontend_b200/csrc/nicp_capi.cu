@@ -1052,7 +1052,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
                         const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
                         bool single, const nicp_prior *priors = nullptr, int numPriors = 0, const CamSet *multiCams = nullptr) {
   const size_t P = (size_t)proj->rows * proj->cols;
-  int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 64);
+  int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 256);
   if (maxSlots > n) maxSlots = n;
   int rc;
   if ((rc = ensure_align(ctx, maxSlots, P))) return rc;

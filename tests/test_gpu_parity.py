@@ -516,8 +516,8 @@ def test_determinism_and_batch_identity(ctx):
     assert (batch["status"] == 0).all()
 
 
-def test_loop_closure_batch_640x480(ctx):
-    """BASELINE config 4 in small: 3 current x 50 candidate 640x480 frames = 150 pairs = 2.3 lock-step chunks with
+def test_loop_closure_batch_640x480(ctx, monkeypatch):
+    """BASELINE config 4 in small: 3 current x 50 candidate 640x480 frames = 150 pairs = 2.3 lock-step chunks of 64 with
     shared current clouds and perturbed guesses.  Every record equals the record of the same pair aligned alone
     (bit for bit), every pair recovers the true relative pose, one pair is checked against the oracle."""
     import sys, os
@@ -525,6 +525,7 @@ def test_loop_closure_batch_640x480(ctx):
     import bench
     from g2o_frontend_b200 import capi, synth
     from oracle import pwn_oracle as O
+    monkeypatch.setenv("NICP_BATCH_SLOTS", "64")  # the default chunk holds 256 pairs: keep the chunk boundaries in the test
     n_cur, n_cand = 3, 50
     raws_cur, raws_cand, pairs, guesses = bench.make_workload(n_cur, n_cand, 7)
     C = bench.CONF
