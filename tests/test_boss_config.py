@@ -130,3 +130,26 @@ def test_cpp_reader_agrees_with_python_reader():
     bad = os.path.join(ROOT, "tests", "golden", "boss_pipeline.conf")
     r = subprocess.run([BIN, "--dump-config", bad + ".does_not_exist"], capture_output=True)
     assert r.returncode != 0
+
+
+def test_acceptance_masks_follow_the_trackers():
+    """PwnCloser / PwnTracker acceptance (pwn_closer.cpp:164-171, pwn_tracker.cpp:187-191) over a batch of records"""
+    from g2o_frontend_b200 import matcher
+    capi = pytest.importorskip("g2o_frontend_b200.capi")
+    r = np.zeros(6, capi.RESULT_DTYPE)
+    r["image_non_zeros"] = [5000, 2999, 5000, 5000, 5000, 5000]
+    r["image_outliers"] = [100, 100, 2001, 100, 100, 100]
+    r["image_inliers"] = [4900, 2899, 2999, 999, 4900, 4900]
+    r["inliers"] = [20000, 20000, 20000, 20000, 999, 20000]
+    r["status"] = [0, 0, 0, 0, 0, 2]
+    thr = dict(frame_min_non_zero_threshold=3000, frame_max_outliers_threshold=2000, frame_min_inliers_threshold=1000)
+    assert matcher.closer_accept(r, **thr).tolist() == [True, False, False, False, True, False]
+    assert matcher.tracker_accept(r, 1000, **thr).tolist() == [True, False, False, False, False, False]
+    # boundary values are accepted exactly like the reference's strict comparisons
+    e = np.zeros(1, capi.RESULT_DTYPE)
+    e["image_non_zeros"], e["image_outliers"], e["image_inliers"], e["inliers"] = 3000, 2000, 1000, 1000
+    assert matcher.tracker_accept(e, 1000, **thr).all()
+    assert np.array_equal(np.diag(matcher.relation_information("closer")), [100, 100, 100, 1000, 1000, 1000])
+    p = B.pipeline(B.loads('"PwnTracker" {"#id": 1, "minCloudInliers": 1000, "newFrameCloudInliersFraction": 0.5, '
+                           '"frameMinNonZeroThreshold": 3000, "frameMaxOutliersThreshold": 2000, "frameMinInliersThreshold": 1000}'))
+    assert matcher.accept_from_boss(r, p, "tracker").tolist() == [True, False, False, False, False, False]
