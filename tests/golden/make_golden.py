@@ -43,6 +43,28 @@ def main():
         T=out.T, H=out.H, b=out.b, error=out.error, inliers=out.inliers, numCorr=out.numCorrespondences,
         corr=out.corr, refIndex=out.refIndex, refDepth=out.refDepth, curIndex=out.curIndex,
         trace_T=np.stack(out.trace_T), trace_H=np.stack(out.trace_H), trace_b=np.stack(out.trace_b), omega=out.omega)
+    # local-map maintenance: gaussians of frame A, the two-frame map A + add(B, T), Merger::merge, VoxelCalculator
+    gA, fA, _, _ = O.unproject_gaussians(dA, K, 0.5, 4.5, 0.075, 0.1)
+    gB, fB, _, _ = O.unproject_gaussians(dB, K, 0.5, 4.5, 0.075, 0.1)
+    import ctypes as C
+    fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+    T = out.T.astype(np.float32)
+    ptsB, nrmB, stB, opB, onB = (cB.points.copy(), cB.normals.copy(), cB.statsM.copy(), cB.omegaP.copy(), cB.omegaN.copy())
+    O.lib().orc_cloud_transform(fp(O.colmajor(T)), cB.n, fp(ptsB), fp(nrmB), fp(stB), fp(opB), fp(onB))
+    gB, fB = O.gaussians_transform(T, gB, fB)
+    m = O.Cloud(cA.n + cB.n)
+    cat = lambda a, b: np.ascontiguousarray(np.concatenate([a, b]))
+    m.points, m.normals, m.statsM = cat(cA.points, ptsB), cat(cA.normals, nrmB), cat(cA.statsM, stB)
+    m.omegaP, m.omegaN = cat(cA.omegaP, opB), cat(cA.omegaN, onB)
+    m.eigvals, m.statsN, m.curvature = cat(cA.eigvals, cB.eigvals), cat(cA.statsN, cB.statsN), cat(cA.curvature, cB.curvature)
+    mg, mf = cat(gA, gB), cat(fA, fB)
+    res, g2, f2, col = O.merge(m, mg, mf, rows, cols, K, np.eye(4, dtype=np.float32), 0.5, 4.5)
+    vox = O.voxelize(m.points, 0.05, strict=True)
+    vox_raw = O.voxelize(m.points, 0.05, strict=False)
+    np.savez_compressed(os.path.join(HERE, "map_ops_small.npz"), depthA=dA, depthB=dB, K=K, T=T,
+                        gaussA=gA, map_points=m.points, map_normals=m.normals, map_gauss=mg, map_flags=mf,
+                        merged_points=res.points, merged_gauss=g2, merged_flags=f2, collapsed=col,
+                        voxel_rep=vox, voxel_rep_as_written=vox_raw)
     # eigen-solver known answers
     rng = np.random.default_rng(7)
     mats, evs, vecs = [], [], []

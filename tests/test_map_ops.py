@@ -443,3 +443,28 @@ def test_oracle_merge_against_independent_numpy():
         agree = (col == ref)
         assert agree[clear].mean() > 0.995, agree[clear].mean()
         assert (col >= 0).sum() > 1000 and ((col >= 0) & (col != np.arange(3000))).sum() > 300
+
+
+def test_golden_map_ops_reproduced():
+    """tests/golden/map_ops_small.npz (tests/golden/make_golden.py): the oracle reproduces its committed local-map
+    vectors bit for bit (no transcendental functions on this path), and the vectors are self-consistent"""
+    import os
+    from conftest import ROOT
+    from oracle import pwn_oracle as O
+    g = np.load(os.path.join(ROOT, "tests", "golden", "map_ops_small.npz"))
+    K, dA = g["K"], g["depthA"]
+    rows, cols = dA.shape
+    gA, fA, _, _ = O.unproject_gaussians(dA, K, 0.5, 4.5, 0.075, 0.1)
+    assert np.array_equal(_bits(gA), _bits(g["gaussA"]))
+    n = g["map_points"].shape[0]
+    m = O.Cloud(n)
+    m.points, m.normals = np.ascontiguousarray(g["map_points"]), np.ascontiguousarray(g["map_normals"])
+    res, g2, f2, col = O.merge(m, g["map_gauss"], g["map_flags"], rows, cols, K, np.eye(4, dtype=np.float32), 0.5, 4.5)
+    assert np.array_equal(col, g["collapsed"]) and np.array_equal(f2, g["merged_flags"])
+    assert np.array_equal(_bits(res.points), _bits(g["merged_points"]))
+    assert np.array_equal(_bits(g2), _bits(g["merged_gauss"]))
+    assert np.array_equal(O.voxelize(g["map_points"], 0.05, strict=True), g["voxel_rep"])
+    assert np.array_equal(O.voxelize(g["map_points"], 0.05, strict=False), g["voxel_rep_as_written"])
+    assert np.array_equal(g["voxel_rep"], _numpy_voxelize(g["map_points"], 0.05))
+    fused = (col >= 0) & (col != np.arange(n))
+    assert fused.sum() > 100 and res.n == n - fused.sum()
