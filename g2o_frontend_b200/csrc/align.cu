@@ -15,9 +15,10 @@
 //
 // Reduction: every thread accumulates 30 float sums over its pixels (21 unique H entries, 6 b,
 // chi2, inliers, correspondences), a transposing warp butterfly leaves component j in lane j
-// (31 shuffles instead of 160), the 8 warps of a CTA are added in fixed order, and one partial
-// row per CTA goes to global memory.  k_reduce_solve adds the rows in fixed order, so H, b and
-// the pose are bit-reproducible run to run (no float atomics anywhere).
+// (31 shuffles instead of 160) and one partial row per tile goes to global memory (the default
+// configuration is one warp per CTA; wider CTAs add their warps in fixed order first).
+// k_reduce_solve adds the rows in fixed order, so H, b and the pose are bit-reproducible run to
+// run (no float atomics anywhere).
 #include "nicp_internal.cuh"
 
 namespace nicp {
@@ -402,19 +403,21 @@ __device__ __forceinline__ void accumulate_term(float (&acc)[kAccum], float rpx,
 //         (last outer iteration, inner iterations > 1, stage-level call).
 // MODE 1: linearise at state->invT over the stored correspondence image (inner iterations > 0, _computeStatistics)
 //         and, if imgStats, accumulate the matchClouds image statistics (slots A_IMGSUM, A_IMGNZ, A_IMGINL).
-//   stage 1  every thread loads the z-buffer word / current index of its TK pixels, then issues the
-//            4*TK gathers (float4 each) back to back -- 5*TK independent loads in flight per thread
-//            instead of 3 dependent round trips per pixel -- transforms the reference point/normal,
-//            applies the gates and writes the correspondence image.
-//   compact  accepted correspondences get a slot in shared memory through a ballot/prefix compaction
-//            whose order is fixed (pixel slot, warp, lane).  The transformed reference point/normal and
-//            the current point/normal are parked there (12 floats), and the 48 bytes of Omega_P/Omega_N
-//            of the current point are fetched straight into shared memory with cp.async (LDGSTS): the
-//            whole tile's Omega traffic is in flight at once and costs no registers.
-//   stage 2  all threads walk the compacted list (full warps even when only a third of the pixels is
-//            accepted): shared-memory reads + the Linearizer term, 30 sums in registers.
-//   stage 3  transposing warp butterfly + fixed-order CTA reduction -> one partial row.
-// The accumulators only become live in stage 2, so stage 1 can spend the registers on loads.
+// Default configuration (INPLACE, one warp per CTA, TK = 3 pixels per lane):
+//   stage 1  every lane loads the z-buffer word / current index of its TK pixels, then issues the
+//            4*TK gathers (float4 each) back to back together with the cp.async (LDGSTS) of the 48
+//            bytes of Omega_P/Omega_N of the current point into its own shared-memory slot -- two
+//            dependent round trips per tile -- transforms the reference point/normal, applies the
+//            gates in the reference's order and writes the correspondence image when asked to.
+//   stage 2  the lane that owns an accepted pixel accumulates its Linearizer term in place (30 sums
+//            in registers; pixel slots without any accepted lane are skipped warp-wide).  No
+//            compaction, no stash of the terms, no CTA barrier.
+//   stage 3  transposing warp butterfly -> one partial row per tile.
+// The compacting variant (INPLACE = false, NICP_TILE_CONFIG=3; the first structure of the round, kept
+// for comparison) gives accepted correspondences a slot in shared memory through a ballot/prefix
+// compaction whose order is fixed (pixel slot, warp, lane), parks the transformed reference point /
+// normal and the current point / normal there (12 floats), fetches Omega into the compacted slot
+// with cp.async, and lets all threads walk the compacted list.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);

@@ -1102,6 +1102,10 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         set_error("null cloud in pair %d", base + i);
         return NICP_ERR_INVALID;
       }
+      if (r->device != ctx->device || c->device != ctx->device) {
+        set_error("pair %d: cloud lives on GPU %d / %d, the context on GPU %d", base + i, r->device, c->device, ctx->device);
+        return NICP_ERR_INVALID;
+      }
       auto it = curSlot.find(c);
       int cs;
       if (it == curSlot.end()) {

@@ -219,12 +219,18 @@ int nicp_project_intervals(nicp_context *ctx, const float *depth, const nicp_pro
 /* DepthImageConverterIntegralImage::compute (depthimageconverterintegralimage.cpp:15-55):
  * unProject + projectIntervals + PointIntegralImage + StatsCalculatorIntegralImage +
  * Point/NormalInformationMatrixCalculator + Cloud::transformInPlace(sensor_offset).
- * index (rows*cols) may be NULL.  keep_stats != 0 also materialises pwn::Stats. */
+ * index (rows*cols) may be NULL.  keep_stats != 0 also materialises pwn::Stats.
+ * ASYNCHRONOUS when index is NULL: the call returns once the work is queued on the context's stream (the cloud is
+ * consumed in stream order by every later call on this context).  A pageable `depth` has been staged by the time
+ * the call returns; a PINNED `depth` is read by the copy engine later, so it must stay unchanged until the next
+ * synchronous call on this context (or nicp_synchronize) returns.  With index != NULL the call is synchronous. */
 int nicp_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_projector *proj,
                         const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
                         nicp_cloud *cloud, int *index);
 /* same, from a raw 16-bit image: convert (depth_scale) + DepthImage_scale(step) + the above;
- * proj describes the camera AFTER scaling (PwnMatcherBase::makeCloud, pwn_matcher_base.cpp:46-75). */
+ * proj describes the camera AFTER scaling (PwnMatcherBase::makeCloud, pwn_matcher_base.cpp:46-75).
+ * Same asynchrony as nicp_depth_to_cloud; the raw image is uploaded on a second stream into one of two staging
+ * images, so with pinned `raw` buffers the upload of frame i+1 overlaps the kernels of frame i. */
 int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows, int raw_cols,
                             float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
                             const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,

@@ -109,6 +109,9 @@ class Cloud {
   InformationMatrixVector &pointInformationMatrix() { ensureHost(); _deviceValid = false; return _pointInformationMatrix; }
   const InformationMatrixVector &normalInformationMatrix() const { ensureHost(); return _normalInformationMatrix; }
   InformationMatrixVector &normalInformationMatrix() { ensureHost(); _deviceValid = false; return _normalInformationMatrix; }
+  // cloud.h:99-105: host-only side channel of the traversability analysis (never read by the NICP path)
+  const std::vector<int> &traversabilityVector() const { return _traversabilityVector; }
+  std::vector<int> &traversabilityVector() { return _traversabilityVector; }
 
   size_t size() const {
     if (_deviceValid) return (size_t)nicp_cloud_size(_dev);
@@ -118,6 +121,7 @@ class Cloud {
   void clear() {
     _points.clear(); _normals.clear(); _stats.clear();
     _pointInformationMatrix.clear(); _normalInformationMatrix.clear();
+    _traversabilityVector.clear();
     _hostValid = true;
     _deviceValid = false;
   }
@@ -374,6 +378,7 @@ class Cloud {
   NormalVector _normals;
   StatsVector _stats;
   InformationMatrixVector _pointInformationMatrix, _normalInformationMatrix;
+  std::vector<int> _traversabilityVector;
 };
 
 // ---- pointprojector.h / pinholepointprojector.h ---------------------------------------------------
@@ -393,6 +398,8 @@ class PointProjector {
   virtual void project(IntImage &indexImage, DepthImage &depthImage, const Cloud &cloud) const = 0;
   virtual void unProject(Cloud &cloud, IntImage &indexImage, const DepthImage &depthImage) const = 0;
   virtual void projectIntervals(IntImage &intervalImage, const DepthImage &depthImage, const float worldRadius) const = 0;
+  // pointprojector.h:228-233: the base class answers 0
+  virtual int projectInterval(const int, const int, const float, const float) const { return 0; }
   virtual void scale(float scalingFactor) = 0;
 
  protected:
@@ -418,6 +425,19 @@ class PinholePointProjector : public PointProjector {
   void setAlpha(float alpha_) { _alpha = alpha_; }
   const Matrix4f &KRt() const { return _KRt; }
   const Matrix4f &iKRt() const { return _iKRt; }
+  // pinholepointprojector.h:61: K^-1 (closed form for the upper-triangular camera matrix [fx s cx; 0 fy cy; 0 0 1])
+  Matrix3f inverseCameraMatrix() const {
+    Matrix3f iK;
+    const float fx = _cameraMatrix(0, 0), fy = _cameraMatrix(1, 1), sk = _cameraMatrix(0, 1), cx = _cameraMatrix(0, 2),
+                cy = _cameraMatrix(1, 2), w = _cameraMatrix(2, 2);
+    iK(0, 0) = 1.0f / fx;
+    iK(0, 1) = -sk / (fx * fy);
+    iK(0, 2) = (sk * cy - cx * fy) / (fx * fy * w);
+    iK(1, 1) = 1.0f / fy;
+    iK(1, 2) = -cy / (fy * w);
+    iK(2, 2) = 1.0f / w;
+    return iK;
+  }
 
   // pinholepointprojector.cpp:33-66
   virtual void project(IntImage &indexImage, DepthImage &depthImage, const Cloud &cloud) const {
@@ -470,6 +490,15 @@ class PinholePointProjector : public PointProjector {
     p[3] = 1.0f;
     return true;
   }
+  // _projectInterval (pinholepointprojector.h:264-274): p = K (r, r, 0) / d, the larger component truncated
+  virtual int projectInterval(const int, const int, const float d, const float worldRadius) const {
+    if (d < _minDistance || d > _maxDistance) return -1;
+    const float p0 = (_cameraMatrix(0, 0) * worldRadius + _cameraMatrix(0, 1) * worldRadius) + _cameraMatrix(0, 2) * 0.0f;
+    const float p1 = (_cameraMatrix(1, 0) * worldRadius + _cameraMatrix(1, 1) * worldRadius) + _cameraMatrix(1, 2) * 0.0f;
+    const float s = 1.0f / d;
+    const float a = p0 * s, b = p1 * s;
+    return a > b ? (int)a : (int)b;
+  }
   nicp_projector abiProjector() const {
     nicp_projector p;
     for (int i = 0; i < 9; i++) p.K[i] = _cameraMatrix.m[i];
@@ -502,6 +531,12 @@ class MultiPointProjector : public PointProjector {
     c.height = height_;
     pointProjector_->setImageSize(width_, height_);
     _pointProjectors.push_back(c);
+  }
+  // multipointprojector.h:20-27 (like the reference it leaves the remembered width / height of the slot alone)
+  void setPointProjector(PinholePointProjector *pointProjector_, Isometry3f sensorOffset_, int width_, int height_, int position) {
+    _pointProjectors.at(position).pointProjector = pointProjector_;
+    _pointProjectors.at(position).sensorOffset = sensorOffset_;
+    pointProjector_->setImageSize(width_, height_);
   }
   void clearProjectors() { _pointProjectors.clear(); }
   size_t numProjectors() const { return _pointProjectors.size(); }
@@ -744,6 +779,9 @@ class Merger {
   void setImageSize(int r, int c) { _rows = r; _cols = c; }
   int imageRows() const { return _rows; }
   int imageCols() const { return _cols; }
+  // merger.h:95: (rows, cols) of the Merger's index image
+  struct Size2i { int r, c; int x() const { return r; } int y() const { return c; } int operator[](int i) const { return i ? c : r; } };
+  Size2i imageSize() const { Size2i s = {_rows, _cols}; return s; }
   const std::vector<int> &collapsedIndices() const { return _collapsedIndices; }
 
   // merger.cpp:15-119
