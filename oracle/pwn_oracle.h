@@ -10,6 +10,10 @@
  * sources; the Eigen arithmetic it relies on (un-vendored, version only lower-bounded at
  * 3.1.2 by /root/reference/CMakeLists.txt:158) is restated from the published Eigen 3.2.x
  * algorithms with one fixed float32 evaluation order.
+ * PARTLY PINNED since: the reference's own CUDA implementation (g2o_frontend/pwn_cuda, CUDA runtime
+ * only) does build here -- oracle/_ref/libpwn_cuda_ref.so, compiled unmodified from /root/reference by
+ * oracle/Makefile -- and tests/test_reference_pwn_cuda.py checks this file's SE(3) helpers, correspondence
+ * gates and per-correspondence Linearizer terms against it on the CPU.  The Eigen-dependent stages stay unpinned.
  *
  * Conventions: all matrices are column-major float (Eigen default): M(r,c) = m[c*R + r].
  * Images are row-major rows x cols (cv::Mat_).  Points/normals are 4 floats (x,y,z,w).
