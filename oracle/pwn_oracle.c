@@ -1,6 +1,7 @@
 /*
  * pwn_oracle.c -- CPU restatement of the pwn_core NICP hot path (see pwn_oracle.h header:
- * TEST INFRASTRUCTURE ONLY, PARITY UNPINNED).
+ * TEST INFRASTRUCTURE ONLY; pinned against the reference's own sources except for
+ * Eigen's numerical kernels, see pwn_oracle.h).
  *
  * Build (verification flavour, canonical float32 evaluation order, no FMA contraction):
  *     gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC pwn_oracle.c -lm
@@ -1484,4 +1485,20 @@ int orc_merge(int n, float *points, float *normals, float *statsM, float *omegaP
   if (collapsedOut) memcpy(collapsedOut, collapsed, sizeof(int) * n);
   free(indexImage); free(depthImage); free(collapsed);
   return k;
+}
+
+/* ---- exported for oracle/shim (the Eigen stand-in the reference's own sources are compiled against): the numerical
+ * kernels of Eigen that stay "unpinned" are these very restatements ---- */
+void orc_sym_pinv6(const float H[36], float Hi[36]) { sym_pinv6(H, Hi); }
+void orc_mat6_inverse(const float A[36], float Ai[36]) { mat6_inverse(A, Ai); }
+void orc_sym_singular_values3(const float A[9], float sv[3]) {
+  double M[9], V[9], w[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) M[c * 3 + r] = 0.5 * ((double)A[c * 3 + r] + (double)A[r * 3 + c]);
+  jacobi_sym(3, M, V, w);
+  for (int i = 0; i < 3; i++) w[i] = fabs(w[i]);
+  for (int i = 0; i < 3; i++)
+    for (int j = i + 1; j < 3; j++)
+      if (w[j] > w[i]) { double t = w[i]; w[i] = w[j]; w[j] = t; }
+  for (int i = 0; i < 3; i++) sv[i] = (float)w[i];
 }

@@ -10,10 +10,14 @@
  * sources; the Eigen arithmetic it relies on (un-vendored, version only lower-bounded at
  * 3.1.2 by /root/reference/CMakeLists.txt:158) is restated from the published Eigen 3.2.x
  * algorithms with one fixed float32 evaluation order.
- * PARTLY PINNED since: the reference's own CUDA implementation (g2o_frontend/pwn_cuda, CUDA runtime
- * only) does build here -- oracle/_ref/libpwn_cuda_ref.so, compiled unmodified from /root/reference by
- * oracle/Makefile -- and tests/test_reference_pwn_cuda.py checks this file's SE(3) helpers, correspondence
- * gates and per-correspondence Linearizer terms against it on the CPU.  The Eigen-dependent stages stay unpinned.
+ * PINNED since, for everything except Eigen's numerical kernels:
+ *  - oracle/_ref/libpwn_core_ref.so = the reference's own pwn_core sources compiled (oracle/build_ref_pwn_core.sh)
+ *    against the Eigen / OpenCV stand-ins of oracle/shim/; tests/test_reference_pwn_core.py finds this file
+ *    bit-identical to it stage by stage and for whole alignments (all thread counts, priors, sensor offsets);
+ *  - oracle/_ref/libpwn_cuda_ref.so = the reference's own CUDA implementation (pwn_cuda, CUDA runtime only), unmodified;
+ *    tests/test_reference_pwn_cuda.py checks the SE(3) helpers, the gates and the per-correspondence Linearizer terms.
+ * Still UNPINNED: what Eigen computes inside (computeDirect, LDLT, JacobiSVD, Quaternion(R), product summation order) --
+ * the stand-in delegates those to the restatements below, so both sides share them.
  *
  * Conventions: all matrices are column-major float (Eigen default): M(r,c) = m[c*R + r].
  * Images are row-major rows x cols (cv::Mat_).  Points/normals are 4 floats (x,y,z,w).

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- see oracle/pwn_oracle.h.  May be imported from tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, nowhere else.
-PARITY UNPINNED: the reference cannot be built here and ships no golden vectors.
+Pinned against the reference's own sources except for Eigen's numerical kernels (oracle/_ref).
 """
 import ctypes as C
 import os
