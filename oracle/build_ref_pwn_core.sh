@@ -29,7 +29,7 @@ S="$SCRATCH/g2o_frontend/pwn_core"
 SRCS="$S/pwn_static.cpp $S/pointprojector.cpp $S/pinholepointprojector.cpp $S/gaussian3.cpp $S/pointintegralimage.cpp
  $S/statscalculator.cpp $S/statscalculatorintegralimage.cpp $S/informationmatrixcalculator.cpp $S/cloud.cpp
  $S/depthimageconverter.cpp $S/depthimageconverterintegralimage.cpp $S/correspondencefinder.cpp $S/linearizer.cpp
- $S/se3_prior.cpp $S/aligner.cpp $S/merger.cpp $S/voxelcalculator.cpp"
+ $S/se3_prior.cpp $S/aligner.cpp $S/merger.cpp $S/voxelcalculator.cpp $S/multipointprojector.cpp"
 $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC \
   -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$OUT" $SRCS "$HERE/ref_pwn_core.cpp" \
   -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm

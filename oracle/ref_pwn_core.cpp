@@ -8,8 +8,15 @@
 #include <omp.h>
 
 #include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
 #include <vector>
 
+// the wrapper reads the raw state of Gaussian3f (which of its two forms is valid) and Merger::_collapsedIndices; the
+// reference only exposes them through accessors that convert lazily / not at all
+#define protected public
 #include "g2o_frontend/pwn_core/aligner.h"
 #include "g2o_frontend/pwn_core/cloud.h"
 #include "g2o_frontend/pwn_core/correspondencefinder.h"
@@ -17,6 +24,7 @@
 #include "g2o_frontend/pwn_core/informationmatrixcalculator.h"
 #include "g2o_frontend/pwn_core/linearizer.h"
 #include "g2o_frontend/pwn_core/merger.h"
+#include "g2o_frontend/pwn_core/multipointprojector.h"
 #include "g2o_frontend/pwn_core/pinholepointprojector.h"
 #include "g2o_frontend/pwn_core/pwn_static.h"
 #include "g2o_frontend/pwn_core/statscalculatorintegralimage.h"
@@ -261,6 +269,81 @@ int refcore_align(void *href, void *hcur, const float K[9], int rows, int cols, 
       corr[2 * i + 1] = finder.correspondences()[i].currentIndex;
     }
   return n;
+}
+
+// ---- MultiPointProjector (BASELINE config 5) ------------------------------------------------------------------
+// What Aligner::align executes for a MultiPointProjector: the call through PointProjector* binds to the const virtual
+// PointProjector::project (pointprojector.cpp:17-40: the base-class z-buffer, x is the row, empty depth 0, the images
+// pre-sized by the caller), which calls the per-point MultiPointProjector::project (multipointprojector.cpp:157-205);
+// MultiPointProjector's own image-level project is non-const and only hides it.  cams: per camera K (9), sensor offset
+// (16), width, height, minD, maxD = 29 floats.
+void refcore_multi_project(void *h, const float *cams, int numCams, const float T[16], int rows, int cols, int *index,
+                           float *depth) {
+  MultiPointProjector multi;
+  for (int i = 0; i < numCams; i++) {
+    const float *q = cams + 29 * i;
+    PinholePointProjector *p = new PinholePointProjector();
+    p->setCameraMatrix(mat3(q));
+    p->setMinDistance(q[27]);
+    p->setMaxDistance(q[28]);
+    multi.addPointProjector(p, iso(q + 9), (int)q[25], (int)q[26]);
+    p->setImageSize((int)q[25], (int)q[26]);  // what ChildProjectorInfo's constructor does (multipointprojector.h:61-78)
+  }
+  multi.setTransform(iso(T));
+  const PointProjector *base = &multi;
+  IntImage ii(rows, cols);
+  DepthImage di;
+  base->project(ii, di, ((Cloud *)h)->points());
+  for (int r = 0; r < rows; r++) {
+    std::memcpy(index + (size_t)r * cols, &ii(r, 0), sizeof(int) * cols);
+    std::memcpy(depth + (size_t)r * cols, &di(r, 0), sizeof(float) * cols);
+  }
+  multi.clearProjectors();
+}
+
+// ---- local-map maintenance -----------------------------------------------------------------------------------
+// Gaussian3f per point as the oracle lays it out: mean 3, covariance 9 (column-major), information vector 3,
+// information matrix 9; flags bit 0 = _momentsUpdated, bit 1 = _infoUpdated (basemath/gaussian.h)
+int refcore_cloud_gaussians(void *h, float *gauss24, int *flags) {
+  Cloud &c = *(Cloud *)h;
+  for (size_t i = 0; i < c.gaussians().size(); i++) {
+    const Gaussian3f &g = c.gaussians()[i];
+    float *o = gauss24 + 24 * i;
+    std::memcpy(o, g._mean.data(), 12);
+    std::memcpy(o + 3, g._covarianceMatrix.data(), 36);
+    std::memcpy(o + 12, g._informationVector.data(), 12);
+    std::memcpy(o + 15, g._informationMatrix.data(), 36);
+    flags[i] = (g._momentsUpdated ? 1 : 0) | (g._infoUpdated ? 2 : 0);
+  }
+  return (int)c.gaussians().size();
+}
+// Merger::merge (merger.cpp:15-119) with a Merger of image size rows x cols whose converter holds a pinhole projector
+int refcore_merge(void *h, const float K[9], const float T[16], int rows, int cols, float minD, float maxD,
+                  float distanceThreshold, float normalThreshold, float maxPointDepth, int *collapsed) {
+  Cloud &c = *(Cloud *)h;
+  PinholePointProjector projector;
+  setup_projector(projector, K, rows, cols, minD, maxD);
+  DepthImageConverterIntegralImage converter(&projector, 0, 0, 0);
+  Merger merger;
+  merger.setDepthImageConverter(&converter);
+  merger.setImageSize(rows, cols);
+  merger.setDistanceThreshold(distanceThreshold);
+  merger.setNormalThreshold(normalThreshold);
+  merger.setMaxPointDepth(maxPointDepth);
+  std::streambuf *old = std::cerr.rdbuf(0);  // the reference reports to stderr
+  merger.merge(&c, iso(T));
+  std::cerr.rdbuf(old);
+  if (collapsed) std::memcpy(collapsed, merger._collapsedIndices.data(), sizeof(int) * merger._collapsedIndices.size());
+  return (int)c.points().size();
+}
+// VoxelCalculator::compute (voxelcalculator.cpp:15-73)
+int refcore_voxelize(void *h, float resolution) {
+  Cloud &c = *(Cloud *)h;
+  VoxelCalculator v;
+  std::streambuf *old = std::cout.rdbuf(0);
+  v.compute(c, resolution);
+  std::cout.rdbuf(old);
+  return (int)c.points().size();
 }
 
 }  // extern "C"

@@ -38,8 +38,9 @@ class Mat {
  public:
   int rows, cols;
   uchar *data;
-  Mat() : rows(0), cols(0), data(0), _type(CV_8UC1) {}
-  Mat(int r, int c, int type) : rows(0), cols(0), data(0), _type(type) { create(r, c, type); }
+  size_t step;  // bytes per row of the underlying buffer (a region of interest keeps its parent's)
+  Mat() : rows(0), cols(0), data(0), step(0), _type(CV_8UC1) {}
+  Mat(int r, int c, int type) : rows(0), cols(0), data(0), step(0), _type(type) { create(r, c, type); }
   int type() const { return _type; }
   bool empty() const { return rows * cols == 0; }
   size_t total() const { return (size_t)rows * cols; }
@@ -49,12 +50,21 @@ class Mat {
     rows = r;
     cols = c;
     _type = type;
+    step = (size_t)c * cvElemSize(type);
     data = _buf->empty() ? 0 : &(*_buf)[0];
+  }
+  // region of interest: a header onto the same pixels (Rect is x = first column, y = first row, width, height)
+  Mat roi(const Rect &q) const {
+    Mat m(*this);
+    m.rows = q.height;
+    m.cols = q.width;
+    m.data = data + (size_t)q.y * step + (size_t)q.x * cvElemSize(_type);
+    return m;
   }
   Mat clone() const {
     Mat m;
     m.create(rows, cols, _type);
-    if (data) std::memcpy(m.data, data, (size_t)rows * cols * cvElemSize(_type));
+    for (int r = 0; r < rows && data; r++) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * cvElemSize(_type));
     return m;
   }
   Mat &setTo(const Scalar &s) {
@@ -71,7 +81,12 @@ class Mat {
     return *this;
   }
  protected:
-  template <class T> void fill(size_t n, double v) { T *p = (T *)data; for (size_t i = 0; i < n; i++) p[i] = (T)v; }
+  template <class T> void fill(size_t, double v) {
+    for (int r = 0; r < rows; r++) {
+      T *p = (T *)(data + (size_t)r * step);
+      for (int c = 0; c < cols; c++) p[c] = (T)v;
+    }
+  }
   int _type;
   std::shared_ptr<std::vector<uchar> > _buf;
 };
@@ -83,8 +98,11 @@ class Mat_ : public Mat {
   Mat_(int r, int c) : Mat(r, c, DataType<T>::type) {}
   Mat_(const Mat &m) : Mat(m) {}
   void create(int r, int c) { Mat::create(r, c, DataType<T>::type); }
-  T &operator()(int r, int c) { return ((T *)data)[(size_t)r * cols + c]; }
-  const T &operator()(int r, int c) const { return ((const T *)data)[(size_t)r * cols + c]; }
+  T &operator()(int r, int c) { return ((T *)(data + (size_t)r * step))[c]; }
+  const T &operator()(int r, int c) const { return ((const T *)(data + (size_t)r * step))[c]; }
+  Mat_ operator()(const Rect &q) const { return Mat_(roi(q)); }
+  Mat_ &setTo(const Scalar &s) { Mat::setTo(s); return *this; }
+  Mat_ &setTo(double v) { Mat::setTo(Scalar(v)); return *this; }
   Mat_ clone() const { return Mat_(Mat::clone()); }
 };
 }  // namespace cv

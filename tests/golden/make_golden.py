@@ -1,9 +1,12 @@
 """Generates tests/golden/*.npz.
 
-The reference ships no golden vectors and cannot be built here, so these
-fixtures are produced by the CPU oracle (oracle/pwn_oracle.c, verification build) on seeded
-synthetic inputs.  They pin the oracle against accidental change and give the GPU tests
-box-independent expected values; they do NOT pin it against the reference ("parity unpinned").
+The reference ships no golden vectors, so these fixtures are produced by the CPU oracle
+(oracle/pwn_oracle.c, verification build) on seeded synthetic inputs.  They give the GPU tests box-independent
+expected values and pin the oracle against accidental change.  They are CERTIFIED BY THE REFERENCE'S OWN SOURCES:
+tests/test_reference_pwn_core.py::test_committed_golden_fixtures_are_what_the_reference_computes recomputes
+small_pair.npz and map_ops_small.npz with oracle/_ref/libpwn_core_ref.so (g2o_frontend/pwn_core/*.cpp compiled against
+the Eigen / OpenCV stand-ins of oracle/shim) and finds them bit-identical; what Eigen computes internally
+(eigen3.npz: computeDirect) stays unpinned.
 
     python tests/golden/make_golden.py
 """

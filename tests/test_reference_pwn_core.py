@@ -106,6 +106,16 @@ def test_depth_conversion_and_scaling(R):
         out = np.zeros((raw.shape[0] // step, raw.shape[1] // step), np.float32)
         R.refcore_depth_scale(fp(d), raw.shape[0], raw.shape[1], step, C.c_float(0.01), fp(out))
         assert np.array_equal(out, O.depth_scale(d, step)), step
+    # DepthImage_convert_32FC1_to_16UC1 (pwn_static.cpp:38-52), the first step of matchClouds' image statistics: a z-buffer
+    # with empty pixels at FLT_MAX -> millimetres, truncated, 0 where empty
+    z = S.depthA.copy()
+    z[z == 0] = np.finfo(np.float32).max
+    z += np.float32(0.00049)
+    a = np.zeros(z.shape, np.uint16)
+    b = np.zeros(z.shape, np.uint16)
+    R.refcore_depth_f32_to_u16(fp(z), z.shape[0], z.shape[1], C.c_float(1000.0), a.ctypes.data_as(C.POINTER(C.c_ushort)))
+    O.lib().orc_depth_f32_to_u16(fp(z), z.size, C.c_float(1000.0), b.ctypes.data_as(C.POINTER(C.c_ushort)))
+    assert np.array_equal(a, b) and (a > 0).sum() > 1000 and (a == 0).sum() > 0
 
 
 @pytest.mark.parametrize("case", ["clean", "noise_dropout", "sensor_offset", "full_resolution"])
@@ -265,3 +275,183 @@ def test_align_with_priors_is_bit_identical(R):
         orc = O.align(S.cloudA, S.cloudB, ap)
         assert np.array_equal(ref["T"], orc.T), (name, np.abs(ref["T"] - orc.T).max())
         assert ref["inliers"] == orc.inliers and ref["error"] == orc.error, name
+
+
+# ---- local-map maintenance -------------------------------------------------------
+def ref_gaussians(R, cloud):
+    g = np.zeros((cloud.n, 24), np.float32)
+    f = np.zeros(cloud.n, np.int32)
+    n = R.refcore_cloud_gaussians(cloud.h, fp(g), ip(f))
+    return g[:n], f[:n]
+
+
+def ref_two_frame_map(R, S):
+    A = RefCloud(R, S.depthA, S.K, S.conf, S.sensor_offset)
+    B = RefCloud(R, S.depthB, S.K, S.conf, S.sensor_offset)
+    R.refcore_cloud_add(A.h, B.h, fp(cm(S.gt)))  # Cloud::add (cloud.cpp:145-171)
+    n = A.n = R.refcore_cloud_size(A.h)
+    for k, w in (("points", 4), ("normals", 4), ("statsM", 16), ("eigvals", 3), ("omegaP", 16), ("omegaN", 16)):
+        setattr(A, k, np.zeros((n, w), np.float32))
+    A.statsN, A.curvature = np.zeros(n, np.int32), np.zeros(n, np.float32)
+    A.fetch()
+    return A
+
+
+def test_gaussians_add_and_merge_are_bit_identical(R):
+    """unProject with the Gaussian3f sensor model (pinholepointprojector.cpp:93-133) + Gaussian3fVector::transformInPlace,
+    Cloud::add of a transformed cloud, and Merger::merge (merger.cpp:15-119) on the two-frame map"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_map_ops import two_frame_map, BASELINE, ALPHA
+    from oracle import pwn_oracle as O
+    S = get_scene(4, 0, 0.05, True)
+    c = S.conf
+    one = RefCloud(R, S.depthA, S.K, c, S.sensor_offset)
+    g, f = ref_gaussians(R, one)
+    og, of, _, _ = O.unproject_gaussians(S.depthA, S.K, c["minD"], c["maxD"], BASELINE, ALPHA, S.sensor_offset)
+    assert np.array_equal(f, of)
+    assert np.array_equal(g[:, :12], og[:, :12])  # moments form after the sensor offset; the info form is not valid yet
+    m, mg, mf = two_frame_map(S)
+    ref = ref_two_frame_map(R, S)
+    for k in ("points", "normals", "statsM", "omegaP", "omegaN"):
+        assert np.array_equal(getattr(ref, k), getattr(m, k)), k
+    rg, rf = ref_gaussians(R, ref)
+    assert np.array_equal(rf, mf) and np.array_equal(rg[:, :12], mg[:, :12])
+    for T, thr in ((np.eye(4, dtype=np.float32), (0.1, float(np.cos(np.float32(10 * np.pi / 180.0))), 10.0)),
+                   (S.gt, (0.05, 0.99, 3.0))):
+        ref = ref_two_frame_map(R, S)
+        n0 = ref.n
+        col = np.zeros(n0, np.int32)
+        k = R.refcore_merge(ref.h, fp(cm(S.K)), fp(cm(T)), S.rows, S.cols, C.c_float(c["minD"]), C.c_float(c["maxD"]),
+                            C.c_float(thr[0]), C.c_float(thr[1]), C.c_float(thr[2]), ip(col))
+        res, g2, f2, ocol = O.merge(m, mg, mf, S.rows, S.cols, S.K, T, c["minD"], c["maxD"], *thr)
+        assert np.array_equal(col, ocol)
+        assert k == res.n < n0
+        ref.n = k
+        for name, w in (("points", 4), ("normals", 4), ("statsM", 16), ("omegaP", 16), ("omegaN", 16)):
+            setattr(ref, name, np.zeros((k, w), np.float32))
+        ref.eigvals, ref.statsN, ref.curvature = np.zeros((k, 3), np.float32), np.zeros(k, np.int32), np.zeros(k, np.float32)
+        ref.fetch()
+        for name in ("points", "normals", "statsM", "omegaP", "omegaN"):
+            assert np.array_equal(getattr(ref, name), getattr(res, name)), name
+        # the reference forgets gaussians().resize(k) (merger.cpp:108-113): compare the first k
+        rg = np.zeros((n0, 24), np.float32)
+        rf = np.zeros(n0, np.int32)
+        R.refcore_cloud_gaussians(ref.h, fp(rg), ip(rf))
+        assert np.array_equal(rf[:k], f2)
+        mom, inf = (f2 & 1) != 0, (f2 & 2) != 0
+        assert np.array_equal(rg[:k][mom, :12], g2[mom, :12]) and np.array_equal(rg[:k][inf, 12:], g2[inf, 12:])
+
+
+@pytest.mark.parametrize("res", [0.01, 0.05, 0.2])
+def test_voxelcalculator_as_written(R, res):
+    """VoxelCalculator::compute with the reference's own comparator (not a strict weak ordering, voxelcalculator.h:40-46)
+    in libstdc++'s std::map: oracle/voxel_oracle.cpp in its as-written mode reproduces the reference's output exactly;
+    the lexicographic order the CUDA path implements keeps a subset of it (known deviations)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_map_ops import two_frame_map
+    from oracle import pwn_oracle as O
+    S = get_scene(4, 0, 0.05, True)
+    m, _, _ = two_frame_map(S)
+    ref = ref_two_frame_map(R, S)
+    k = R.refcore_voxelize(ref.h, C.c_float(res))
+    pts = np.zeros((k, 4), np.float32)
+    R.refcore_cloud_get(ref.h, fp(pts), None, None, None, None, None, None, None)
+    raw = O.voxelize(m.points, res, strict=False)
+    assert k == len(raw) and np.array_equal(pts, m.points[raw])
+    lex = O.voxelize(m.points, res, strict=True)
+    assert set(lex.tolist()) <= set(raw.tolist())
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_multipointprojector_projection_is_bit_identical(R, ragged):
+    """BASELINE config 5: the projection Aligner::align really runs for a MultiPointProjector -- the const base-class
+    z-buffer PointProjector::project (pointprojector.cpp:17-40) over the per-point MultiPointProjector::project
+    (multipointprojector.cpp:157-205): first camera that sees the point wins, composite pixel (u, v + column offset),
+    empty depth 0."""
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    cams = synth.make_rig(3 if ragged else 4, 64, 48, K=synth.scaled_K(synth.K_KINECT, 64 / 640.0))
+    if ragged:
+        cams[1]["width"], cams[1]["height"] = 48, 40
+        cams[2]["maxD"] = 3.0
+    om = O.make_multi(cams)
+    rows, cols = O.multi_image_size(om)
+    S = get_scene(4)
+    ref = RefCloud(R, S.depthA, S.K, S.conf)
+    packed = np.zeros((len(cams), 29), np.float32)
+    for i, c in enumerate(cams):
+        packed[i, :9] = cm(c["K"])
+        packed[i, 9:25] = cm(c["offset"])
+        packed[i, 25:29] = c["width"], c["height"], c["minD"], c["maxD"]
+    seen = 0
+    for pose in (np.eye(4, dtype=np.float32), synth.make_pose((0.1, -0.05, 0.2), (0, 1, 0), 10.0),
+                 synth.make_pose((-0.3, 0.1, 1.0), (0.2, 1.0, 0.1), 75.0)):
+        ii = np.zeros((rows, cols), np.int32)
+        dd = np.zeros((rows, cols), np.float32)
+        R.refcore_multi_project(ref.h, fp(packed), len(cams), fp(cm(pose)), rows, cols, ip(ii), fp(dd))
+        oi, od = O.multi_project(om, pose.astype(np.float32), S.cloudA.points, rows, cols)
+        assert np.array_equal(ii, oi) and np.array_equal(dd, od)
+        seen += int((ii >= 0).sum())
+    assert seen > 1000
+
+
+def test_committed_golden_fixtures_are_what_the_reference_computes(R):
+    """tests/golden/small_pair.npz and map_ops_small.npz (written by the oracle, tests/golden/make_golden.py; the GPU tests
+    and tests/test_oracle.py read them) certified by the reference's own sources: frame prep of both frames, the
+    free-running 10-iteration alignment, Merger::merge and VoxelCalculator on the two-frame map."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "small_pair.npz"))
+    conf = dict(worldRadius=0.1, minImageRadius=3, maxImageRadius=6, minPoints=10, curvatureThreshold=0.2,
+                omegaCurvatureThreshold=0.02, minD=0.5, maxD=4.5, inlierDistanceThreshold=0.5, inlierNormalAngularThreshold=0.95,
+                flatCurvatureThreshold=0.02, inlierCurvatureRatioThreshold=1.3, inlierMaxChi2=9e3)
+    K = g["K"]
+    A, B = RefCloud(R, g["depthA"], K, conf), RefCloud(R, g["depthB"], K, conf)
+    sym = [0, 4, 8, 5, 9, 10]  # xx xy xz yy yz zz of a column-major 4x4
+    for c, s in ((A, "A"), (B, "B")):
+        assert np.array_equal(c.points, g["points" + s]) and np.array_equal(c.normals, g["normals" + s])
+        assert np.array_equal(c.curvature, g["curvature" + s])
+        assert np.array_equal(c.omegaP[:, sym], g["omegaP" + s]) and np.array_equal(c.omegaN[:, sym], g["omegaN" + s])
+    assert np.array_equal(A.eigvals, g["eigvalsA"]) and np.array_equal(A.statsN, g["statsNA"])
+    assert np.array_equal(A.index, g["indexA"]) and np.array_equal(A.interval, g["intervalA"])
+    assert np.array_equal(A.integral.reshape(-1), g["integralA"].reshape(-1))
+
+    class S:
+        pass
+    S.conf, S.K = conf, K
+    S.rows, S.cols = g["depthA"].shape
+    out = run_ref_align(R, A, B, S)
+    assert np.array_equal(out["T"], g["T"]) and out["error"] == float(g["error"]) and out["inliers"] == int(g["inliers"])
+    assert out["n"] == int(g["numCorr"]) and np.array_equal(out["corr"][:out["n"]], g["corr"])
+    assert np.array_equal(out["refIndex"], g["refIndex"]) and np.array_equal(out["refDepth"], g["refDepth"])
+    assert np.array_equal(out["curIndex"], g["curIndex"])
+    assert np.abs(out["omega"] - g["omega"]).max() <= 1e-5 * np.abs(g["omega"]).max()
+    # the trace of the fixture: T at the start of every outer iteration = the result of an alignment cut short there
+    for k in (1, 4, 9):
+        assert np.array_equal(run_ref_align(R, A, B, S, outer=k)["T"], g["trace_T"][k])
+
+    m = np.load(os.path.join(ROOT, "tests", "golden", "map_ops_small.npz"))
+    R.refcore_cloud_add(A.h, B.h, fp(cm(m["T"])))
+    n = R.refcore_cloud_size(A.h)
+    pts = np.zeros((n, 4), np.float32)
+    nrm = np.zeros((n, 4), np.float32)
+    R.refcore_cloud_get(A.h, fp(pts), fp(nrm), None, None, None, None, None, None)
+    assert np.array_equal(pts, m["map_points"]) and np.array_equal(nrm, m["map_normals"])
+    gg = np.zeros((n, 24), np.float32)
+    ff = np.zeros(n, np.int32)
+    R.refcore_cloud_gaussians(A.h, fp(gg), ip(ff))
+    assert np.array_equal(ff, m["map_flags"]) and np.array_equal(gg[:, :12], m["map_gauss"][:, :12])
+    # VoxelCalculator on a copy of the map (the reference's comparator as written), then Merger::merge on the map
+    V = RefCloud(R, g["depthA"], K, conf)
+    R.refcore_cloud_add(V.h, B.h, fp(cm(m["T"])))
+    k = R.refcore_voxelize(V.h, C.c_float(0.05))
+    vp = np.zeros((k, 4), np.float32)
+    R.refcore_cloud_get(V.h, fp(vp), None, None, None, None, None, None, None)
+    assert np.array_equal(vp, m["map_points"][m["voxel_rep_as_written"]])
+    col = np.zeros(n, np.int32)
+    k = R.refcore_merge(A.h, fp(cm(K)), fp(cm(np.eye(4))), S.rows, S.cols, C.c_float(0.5), C.c_float(4.5), C.c_float(0.1),
+                        C.c_float(float(np.cos(np.float32(10 * np.pi / 180.0)))), C.c_float(10.0), ip(col))
+    assert np.array_equal(col, m["collapsed"]) and k == len(m["merged_points"])
+    mp = np.zeros((k, 4), np.float32)
+    R.refcore_cloud_get(A.h, fp(mp), None, None, None, None, None, None, None)
+    assert np.array_equal(mp, m["merged_points"])
