@@ -455,3 +455,81 @@ def test_committed_golden_fixtures_are_what_the_reference_computes(R):
     mp = np.zeros((k, 4), np.float32)
     R.refcore_cloud_get(A.h, fp(mp), None, None, None, None, None, None, None)
     assert np.array_equal(mp, m["merged_points"])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_randomised_differential(R, seed):
+    """200 random small cases per seed -- ragged image sizes down to 1x1, random / planar / holed / wavy / range-boundary
+    depth images, random camera, radii, minPoints, thresholds, sensor offsets, 1-8 threads, 1-4 outer and 1-2 inner
+    iterations: frame prep and the whole alignment of the oracle and of the reference's own sources stay bit-identical.
+    (Skipped where the reference itself is undefined: an empty cloud makes it take &points[0] of an empty vector.)"""
+    from oracle import pwn_oracle as O
+    rng = np.random.default_rng(seed)
+    done = 0
+    for it in range(200):
+        rows = int(rng.choice([1, 2, 3, 5, 8, 13, 24, 37, 48]))
+        cols = int(rng.choice([1, 2, 4, 7, 16, 31, 53, 64]))
+        f = float(rng.uniform(20, 120))
+        K = np.array([[f, 0, (cols - 1) / 2 + rng.uniform(-2, 2)], [0, f * rng.uniform(0.9, 1.1), (rows - 1) / 2 + rng.uniform(-2, 2)],
+                      [0, 0, 1]], np.float32)
+        kind = int(rng.integers(5))
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        if kind == 0:
+            d = rng.uniform(0.3, 5.0, (rows, cols))
+        elif kind == 1:
+            d = 1.5 + 0.01 * xx + 0.02 * yy + rng.normal(0, 0.002, (rows, cols))
+        elif kind == 2:
+            d = np.full((rows, cols), 2.0)
+            d[rng.random((rows, cols)) < 0.3] = 0
+        elif kind == 3:
+            d = 1.0 + 0.5 * np.sin(xx / 3.0) + 0.3 * np.cos(yy / 2.0)
+        else:  # values on and next to the [minDistance, maxDistance] boundaries
+            d = np.where(rng.random((rows, cols)) < 0.5, 0.5, 4.5) + rng.choice([0, 1e-7, -1e-7], (rows, cols))
+        if rng.random() < 0.5:
+            d = np.round(d * 1000) / 1000
+        d = np.ascontiguousarray(d, np.float32)
+        conf = dict(worldRadius=float(rng.choice([0.05, 0.1, 0.3])), minImageRadius=int(rng.integers(1, 5)),
+                    maxImageRadius=int(rng.integers(5, 12)), minPoints=int(rng.choice([1, 3, 10, 50])),
+                    curvatureThreshold=float(rng.choice([0.02, 0.2, 1.0])), omegaCurvatureThreshold=float(rng.choice([0.002, 0.02, 0.5])),
+                    minD=0.5, maxD=4.5, inlierDistanceThreshold=float(rng.choice([0.1, 0.5, 1.0])),
+                    inlierNormalAngularThreshold=float(rng.choice([0.5, 0.95, 0.999])),
+                    flatCurvatureThreshold=float(rng.choice([0.002, 0.02, 0.2])),
+                    inlierCurvatureRatioThreshold=float(rng.choice([1.05, 1.3, 3.0])), inlierMaxChi2=float(rng.choice([10.0, 9e3])))
+        off = None
+        if rng.random() < 0.4:
+            off = O.v2t(np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.2, 0.2, 3)]).astype(np.float32))
+        sp = O.default_stats_params(minImageRadius=conf["minImageRadius"], maxImageRadius=conf["maxImageRadius"],
+                                    minPoints=conf["minPoints"], curvatureThreshold=conf["curvatureThreshold"],
+                                    worldRadius=conf["worldRadius"], omegaCurvatureThreshold=conf["omegaCurvatureThreshold"])
+        oc, oidx, oitv, ointeg = O.depth_to_cloud(d, K, conf["minD"], conf["maxD"], sp, off, want_aux=True)
+        d2 = np.roll(d, 1, axis=1).copy()
+        oc2, _ = O.depth_to_cloud(d2, K, conf["minD"], conf["maxD"], sp, off)
+        if oc.n == 0 or oc2.n == 0:
+            continue
+        rc, rc2 = RefCloud(R, d, K, conf, off), RefCloud(R, d2, K, conf, off)
+        tag = (seed, it, rows, cols, kind)
+        assert np.array_equal(rc.index, oidx) and np.array_equal(rc.interval, oitv), tag
+        assert np.array_equal(rc.integral.reshape(-1), np.asarray(ointeg, np.float32).reshape(-1)), tag
+        same_cloud(rc, oc)
+
+        class S:
+            pass
+        S.conf, S.K, S.rows, S.cols = conf, K, rows, cols
+        nt = int(rng.choice([1, 2, 3, 8]))
+        guess = O.v2t(np.concatenate([rng.uniform(-0.02, 0.02, 3), rng.uniform(-0.01, 0.01, 3)]).astype(np.float32))
+        outer, inner = int(rng.integers(1, 5)), int(rng.integers(1, 3))
+        ref = run_ref_align(R, rc, rc2, S, outer=outer, inner=inner, guess=guess, ref_off=off, cur_off=off, threads=nt)
+        cp = O.default_corr_params(inlierDistanceThreshold=conf["inlierDistanceThreshold"],
+                                   inlierNormalAngularThreshold=conf["inlierNormalAngularThreshold"],
+                                   flatCurvatureThreshold=conf["flatCurvatureThreshold"],
+                                   inlierCurvatureRatioThreshold=conf["inlierCurvatureRatioThreshold"])
+        ap = O.make_align_params(K, rows, cols, conf["minD"], conf["maxD"], cp, outer=outer, inner=inner, guess=guess,
+                                 ref_offset=off, cur_offset=off, max_chi2=conf["inlierMaxChi2"], num_threads=nt)
+        orc = O.align(oc, oc2, ap)
+        assert np.array_equal(ref["T"], orc.T, equal_nan=True), tag
+        assert ref["inliers"] == orc.inliers and ref["n"] == orc.numCorrespondences, tag
+        assert ref["error"] == orc.error or (np.isnan(ref["error"]) and np.isnan(orc.error)), tag
+        assert np.array_equal(ref["refIndex"], orc.refIndex) and np.array_equal(ref["curIndex"], orc.curIndex), tag
+        assert np.array_equal(ref["refDepth"], orc.refDepth) and np.array_equal(ref["curDepth"], orc.curDepth), tag
+        done += 1
+    assert done > 150
