@@ -1,0 +1,120 @@
+"""GPU tests whose checker is the REFERENCE'S OWN code rather than the oracle: oracle/_ref/libpwn_core_ref.so =
+g2o_frontend/pwn_core/*.cpp compiled (oracle/build_ref_pwn_core.sh) against the Eigen / OpenCV stand-ins of oracle/shim.
+tests/test_reference_pwn_core.py shows on the CPU that the oracle is bit-identical to it, so these restate a few of the
+parity tests of tests/test_gpu_parity.py with the middle man removed: the CUDA path (through the C-ABI) on one side, the
+reference's sources on the other.  Same protocol and tolerances (BASELINE.json north_star): stage-isolated /
+teacher-forced, index and correspondence images bit-exact, H and b within 1e-4, T within 1e-4 rad / 1e-4 m."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import get_scene
+from test_reference_pwn_core import REF_SO, RefCloud, cm, fp, ip, run_ref_align
+from test_gpu_parity import frob_rel, rot_angle, H_RTOL, T_ROT_TOL, T_TRA_TOL
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libpwn_core_ref.so not built")]
+
+SYM = [0, 4, 8, 5, 9, 10]  # xx xy xz yy yz zz of a column-major 4x4
+
+
+@pytest.fixture(scope="module")
+def R():
+    from oracle import pwn_oracle as O
+    O.lib()
+    L = C.CDLL(REF_SO)
+    L.refcore_depth_to_cloud.restype = C.c_void_p
+    L.refcore_set_threads(1)
+    return L
+
+
+@pytest.fixture(scope="module", params=["verify", "default"])
+def ctx(request):
+    from g2o_frontend_b200 import capi
+    c = capi.Context(0, verify=(request.param == "verify"))
+    yield c
+    c.close()
+
+
+def upload(ctx, rc):
+    """cloud of the reference -> device cloud"""
+    cl = ctx.new_cloud(max(rc.n, 1))
+    cl.upload(rc.points, rc.normals, rc.curvature, np.ascontiguousarray(rc.omegaP[:, SYM]), np.ascontiguousarray(rc.omegaN[:, SYM]))
+    return cl
+
+
+@pytest.mark.parametrize("step,seed,dropout,offset", [(4, None, 0.0, False), (4, 0, 0.05, True), (1, None, 0.0, False)])
+def test_frame_prep_against_the_reference_sources(ctx, R, step, seed, dropout, offset):
+    """depth image -> cloud: points, index image, interval image, the 10-channel integral image and Stats::n bit-exact;
+    normals / curvature within the north_star tolerances"""
+    s = get_scene(step, seed, dropout, offset)
+    rc = RefCloud(R, s.depthA, s.K, s.conf, s.sensor_offset)
+    cl, idx = ctx.depth_to_cloud(s.depthA, s.projector(), s.stats_params(), s.sensor_offset, keep_stats=True)
+    assert cl.size() == rc.n
+    assert np.array_equal(idx, rc.index)
+    assert np.array_equal(ctx.last_interval_image(s.rows, s.cols), rc.interval)
+    I = ctx.last_integral_image(s.rows, s.cols)
+    assert np.array_equal(np.asarray(I, np.float32).reshape(-1).view(np.uint32), rc.integral.reshape(-1).view(np.uint32))
+    d = cl.download()
+    assert np.array_equal(d["points"].view(np.uint32), rc.points.view(np.uint32))
+    _, _, cnt = cl.download_stats()
+    assert np.array_equal(cnt, rc.statsN)
+    has_r = np.abs(rc.normals[:, :3]).sum(1) > 0
+    has_g = np.abs(d["normals"][:, :3]).sum(1) > 0
+    assert (has_r != has_g).mean() < 1e-4
+    both = has_r & has_g
+    well = both & ((rc.eigvals[:, 1] - rc.eigvals[:, 0]) > 1e-4 * rc.eigvals[:, 2])
+    ang = np.arccos(np.clip((d["normals"][well, :3].astype(np.float64) * rc.normals[well, :3]).sum(1), -1, 1))
+    assert well.sum() > 0.5 * rc.n and np.quantile(ang, 0.999) <= 1e-3
+    cerr = np.abs(d["curvature"][both] - rc.curvature[both]) / np.maximum(np.abs(rc.curvature[both]), 1e-3)
+    assert np.quantile(cerr, 0.999) <= 1e-4
+
+
+def test_projection_against_the_reference_sources(ctx, R):
+    """PinholePointProjector::project: index + depth image bit-exact at three projector poses"""
+    from oracle import pwn_oracle as O
+    s = get_scene(4)
+    c = s.conf
+    rc = RefCloud(R, s.depthA, s.K, c)
+    cl = upload(ctx, rc)
+    for v in ([0, 0, 0, 0, 0, 0], [0.03, -0.02, 0.05, 0.01, -0.015, 0.005], [-0.2, 0.1, 0.3, -0.05, 0.08, 0.02]):
+        T = O.v2t(np.array(v, np.float32))
+        ii = np.zeros((s.rows, s.cols), np.int32)
+        dd = np.zeros((s.rows, s.cols), np.float32)
+        R.refcore_project(rc.h, fp(cm(s.K)), fp(cm(T)), s.rows, s.cols, C.c_float(c["minD"]), C.c_float(c["maxD"]), ip(ii), fp(dd))
+        KRt, _ = O.update_matrices(s.K, T)
+        gi, gd = ctx.project(cl, KRt, s.rows, s.cols, c["minD"], c["maxD"])
+        assert np.array_equal(gi, ii)
+        assert np.array_equal(gd.view(np.uint32), dd.view(np.uint32))
+
+
+def test_alignment_against_the_reference_sources(ctx, R):
+    """Aligner::align: teacher-forced single iterations (index image, correspondences bit-exact, H / b within 1e-4) and
+    the free-running 10-iteration result (T within 1e-4 rad / 1e-4 m) against the reference's own Aligner"""
+    from g2o_frontend_b200 import capi
+    s = get_scene(4, 0, 0.05)
+    rA, rB = RefCloud(R, s.depthA, s.K, s.conf), RefCloud(R, s.depthB, s.K, s.conf)
+    ref, cur = upload(ctx, rA), upload(ctx, rB)
+    full = run_ref_align(R, rA, rB, s)
+    res = ctx.align(ref, cur, s.projector(), s.align_params())
+    T = capi.result_T(res)
+    assert rot_angle(T[:3, :3], full["T"][:3, :3]) <= T_ROT_TOL
+    assert np.abs(T[:3, 3] - full["T"][:3, 3]).max() <= T_TRA_TOL
+    assert abs(res.inliers - full["inliers"]) <= 1e-3 * full["inliers"] + 8
+    # teacher-forced: iteration k restarted from the reference's T after k iterations
+    for k in (0, 3, 9):
+        Tk = np.eye(4, dtype=np.float32) if k == 0 else run_ref_align(R, rA, rB, s, outer=k)["T"]
+        one = run_ref_align(R, rA, rB, s, outer=1, guess=Tk)
+        r1 = ctx.align(ref, cur, s.projector(), s.align_params(outer=1), guess=Tk)
+        st = ctx.align_state(s.rows, s.cols)
+        assert np.array_equal(st["ref_index"], one["refIndex"])
+        assert np.array_equal(st["ref_depth"].view(np.uint32), one["refDepth"].view(np.uint32))
+        assert np.array_equal(st["cur_index"], one["curIndex"])
+        assert r1.num_correspondences == one["n"]
+        assert np.array_equal(st["corr"], one["corr"][:one["n"]])
+        assert r1.inliers == one["inliers"]
+        assert abs(r1.error - one["error"]) <= 1e-3 * abs(one["error"])  # the reference sums chi2 sequentially in float32
+        T1 = capi.result_T(r1)
+        assert rot_angle(T1[:3, :3], one["T"][:3, :3]) <= T_ROT_TOL
+        assert np.abs(T1[:3, 3] - one["T"][:3, 3]).max() <= T_TRA_TOL
