@@ -34,3 +34,14 @@ $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math 
   -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$OUT" $SRCS "$HERE/ref_pwn_core.cpp" \
   -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
 echo "built $OUT"
+# the drop-in demonstration (integration/drop_in_demo.cpp): the same reference sources + the option-A binding of
+# integration/pwn_b200/b200_pwn.h + this repository's CUDA library, in one executable
+REPO=$(cd "$HERE/.." && pwd)
+if [ -f "$REPO/g2o_frontend_b200/lib/libnicp_b200.so" ]; then
+  $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math -fopenmp \
+    -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -I"$REPO/include" -I"$REPO/integration" \
+    -o "$HERE/_ref/drop_in_demo" $SRCS "$REPO/integration/drop_in_demo.cpp" \
+    -L"$HERE/build" -loracle -L"$REPO/g2o_frontend_b200/lib" -lnicp_b200 \
+    -Wl,-rpath,'$ORIGIN/../build' -Wl,-rpath,'$ORIGIN/../../g2o_frontend_b200/lib' -lm
+  echo "built $HERE/_ref/drop_in_demo"
+fi

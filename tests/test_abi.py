@@ -64,7 +64,7 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pwn_oracle" not in text and "liboracle" not in text, os.path.join(dirpath, f)
-    for sub in ("include", "tools"):
+    for sub in ("include", "tools", "integration"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
             for f in files:
                 text = open(os.path.join(dirpath, f)).read()

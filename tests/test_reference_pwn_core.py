@@ -533,3 +533,43 @@ def test_randomised_differential(R, seed):
         assert np.array_equal(ref["refDepth"], orc.refDepth) and np.array_equal(ref["curDepth"], orc.curDepth), tag
         done += 1
     assert done > 150
+
+
+# ---- the drop-in binding (INTEGRATION.md option A) ------------------------------------------------------------------
+DEMO = os.path.join(ROOT, "oracle", "_ref", "drop_in_demo")
+
+
+def run_drop_in_demo(S, which, tmp_path):
+    """oracle/_ref/drop_in_demo: one program on the reference's own classes, reference CPU arm and / or B200 arm"""
+    import json
+    import subprocess
+    if not os.access(DEMO, os.X_OK):
+        os.chmod(DEMO, 0o755)
+    a, b = str(tmp_path / "a.f32"), str(tmp_path / "b.f32")
+    np.ascontiguousarray(S.depthA, np.float32).tofile(a)
+    np.ascontiguousarray(S.depthB, np.float32).tofile(b)
+    c = S.conf
+    args = [DEMO, a, b, str(S.rows), str(S.cols)] + [repr(float(S.K[i, j])) for i, j in ((0, 0), (1, 1), (0, 2), (1, 2))] + \
+           [str(c["minImageRadius"]), str(c["maxImageRadius"]), str(c["minPoints"]), repr(float(c["inlierDistanceThreshold"])), which]
+    o = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    return o.returncode, json.loads(o.stdout), o.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/drop_in_demo not built")
+def test_drop_in_binding_compiles_against_the_reference_headers_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/pwn_b200/b200_pwn.h (B200DepthImageConverter / B200Aligner, subclasses of the reference's own
+    DepthImageConverterIntegralImage / Aligner) is compiled against the reference's headers into drop_in_demo.  Its
+    reference arm reproduces the oracle bit for bit; its B200 arm has no CPU fallback."""
+    import torch
+    from oracle import pwn_oracle as O
+    S = get_scene(4)
+    rc, out, _ = run_drop_in_demo(S, "cpu", tmp_path)
+    assert rc == 0
+    r = out["reference_cpu"]
+    orc = O.align(S.cloudA, S.cloudB, S.oracle_align_params(num_threads=1))
+    assert np.array_equal(np.array(r["T"], np.float32).reshape(4, 4), orc.T)
+    assert r["inliers"] == orc.inliers and r["num_correspondences"] == orc.numCorrespondences
+    assert r["reference_points"] == S.cloudA.n and r["current_points"] == S.cloudB.n
+    if not torch.cuda.is_available():
+        rc, out, _ = run_drop_in_demo(S, "gpu", tmp_path)
+        assert rc == 3 and "no CPU fallback" in out["b200_error"]

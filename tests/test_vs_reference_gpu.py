@@ -118,3 +118,26 @@ def test_alignment_against_the_reference_sources(ctx, R):
         T1 = capi.result_T(r1)
         assert rot_angle(T1[:3, :3], one["T"][:3, :3]) <= T_ROT_TOL
         assert np.abs(T1[:3, 3] - one["T"][:3, 3]).max() <= T_TRA_TOL
+
+
+def test_drop_in_demo_reference_classes_with_the_b200_backend(tmp_path):
+    """The drop-in claim executed: oracle/_ref/drop_in_demo is ONE program written against the reference's own classes
+    (built from /root/reference + integration/pwn_b200/b200_pwn.h); it runs converter.compute x2 + aligner.align through
+    pwn::DepthImageConverter* / pwn::Aligner* once with the reference's CPU objects and once with the B200 subclasses."""
+    from test_reference_pwn_core import DEMO, run_drop_in_demo
+    if not os.path.exists(DEMO):
+        pytest.skip("oracle/_ref/drop_in_demo not built")
+    for step in (4, 1):
+        s = get_scene(step)
+        rc, out, err = run_drop_in_demo(s, "both", tmp_path)
+        assert rc == 0, (out, err)
+        cpu, gpu = out["reference_cpu"], out["b200"]
+        Tc, Tg = np.array(cpu["T"]).reshape(4, 4), np.array(gpu["T"]).reshape(4, 4)
+        assert rot_angle(Tg[:3, :3], Tc[:3, :3]) <= T_ROT_TOL
+        assert np.abs(Tg[:3, 3] - Tc[:3, 3]).max() <= T_TRA_TOL
+        assert gpu["reference_points"] == cpu["reference_points"] and gpu["current_points"] == cpu["current_points"]
+        assert abs(gpu["num_correspondences"] - cpu["num_correspondences"]) <= 1e-3 * cpu["num_correspondences"] + 1
+        assert abs(gpu["inliers"] - cpu["inliers"]) <= 1e-3 * cpu["inliers"] + 1
+        assert abs(gpu["reference_pixels"] - cpu["reference_pixels"]) <= 1e-2 * cpu["reference_pixels"]
+        print("drop-in demo %dx%d: B200 align %.3f ms (second call), |dT| %.2e" %
+              (s.rows, s.cols, out["b200_second_align_ms"], float(np.abs(Tg - Tc).max())))
