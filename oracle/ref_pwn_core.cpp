@@ -88,6 +88,26 @@ void refcore_depth_scale(const float *depth, int rows, int cols, int step, float
 // PinholePointProjector::_updateMatrices through setTransform + one unProject / project of probe points is indirect;
 // the matrices themselves are protected, so the stage tests below exercise them through project / unProject.
 
+// PinholePointProjector::_updateMatrices (pinholepointprojector.cpp:17-31): the two matrices are protected members
+void refcore_update_matrices(const float K[9], const float T[16], float KRt[16], float iKRt[16]) {
+  PinholePointProjector p;
+  p.setCameraMatrix(mat3(K));
+  p.setTransform(iso(T));
+  std::memcpy(KRt, p._KRt.data(), sizeof(float) * 16);
+  std::memcpy(iKRt, p._iKRt.data(), sizeof(float) * 16);
+}
+// v2t / t2v (bm_se3.h:36-52)
+void refcore_v2t(const float v[6], float T[16]) {
+  Vector6f x;
+  std::memcpy(x.data(), v, sizeof(float) * 6);
+  Eigen::Isometry3f X = v2t(x);
+  std::memcpy(T, X.matrix().data(), sizeof(float) * 16);
+}
+void refcore_t2v(const float T[16], float v[6]) {
+  Vector6f x = t2v(iso(T));
+  std::memcpy(v, x.data(), sizeof(float) * 6);
+}
+
 // ---- clouds -------------------------------------------------------------------------------------------------
 // DepthImageConverterIntegralImage::compute (depthimageconverterintegralimage.cpp:15-55) with the reference's own
 // projector / stats calculator / information matrix calculators.  Returns a Cloud*.

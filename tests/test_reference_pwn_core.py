@@ -573,3 +573,29 @@ def test_drop_in_binding_compiles_against_the_reference_headers_and_fails_loudly
     if not torch.cuda.is_available():
         rc, out, _ = run_drop_in_demo(S, "gpu", tmp_path)
         assert rc == 3 and "no CPU fallback" in out["b200_error"]
+
+
+def test_library_host_helpers_match_the_reference(R):
+    """The part of the PRODUCT that runs without a GPU -- libnicp_b200.so's host-side nicp_update_matrices / nicp_v2t /
+    nicp_t2v, the same functions the device code is compiled from (nicp_math.cuh) -- against the reference's
+    PinholePointProjector::_updateMatrices and bm_se3.h: bit-identical."""
+    from g2o_frontend_b200 import capi
+    rng = np.random.default_rng(5)
+    for verify in (False, True):
+        L = capi.load(verify)
+        for _ in range(500):
+            v = np.concatenate([rng.uniform(-2, 2, 3), rng.uniform(-0.55, 0.55, 3)]).astype(np.float32)
+            Tr, Tl = np.zeros(16, np.float32), np.zeros(16, np.float32)
+            R.refcore_v2t(fp(v), fp(Tr))
+            L.nicp_v2t(fp(v), fp(Tl))
+            assert np.array_equal(Tr, Tl)
+            vr, vl = np.zeros(6, np.float32), np.zeros(6, np.float32)
+            R.refcore_t2v(fp(Tr), fp(vr))
+            L.nicp_t2v(fp(Tr), fp(vl))
+            assert np.array_equal(vr, vl, equal_nan=True)
+            f = float(rng.uniform(100, 1100))
+            K = np.array([[f, 0, rng.uniform(100, 700)], [0, f * rng.uniform(0.95, 1.05), rng.uniform(100, 500)], [0, 0, 1]], np.float32)
+            a, b, c, d = (np.zeros(16, np.float32) for _ in range(4))
+            R.refcore_update_matrices(fp(cm(K)), fp(Tr), fp(a), fp(b))
+            L.nicp_update_matrices(fp(cm(K)), fp(Tr), fp(c), fp(d))
+            assert np.array_equal(a, c) and np.array_equal(b, d)
