@@ -599,3 +599,37 @@ def test_library_host_helpers_match_the_reference(R):
             R.refcore_update_matrices(fp(cm(K)), fp(Tr), fp(a), fp(b))
             L.nicp_update_matrices(fp(cm(K)), fp(Tr), fp(c), fp(d))
             assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_real_kinect_frame_is_bit_identical(R):
+    """real sensor data (holes, noise, 0.4-8 m range): the one Kinect frame the reference ships as data (tests/golden/
+    real_depth_640x480.npz), full resolution, parameters of pwn_aligner_1_1.conf -- frame prep and the self-alignment
+    from a perturbed guess, oracle vs the reference's own sources"""
+    from conftest import CONF_1_1
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "real_depth_640x480.npz"))["raw"]
+    c = CONF_1_1
+    K = synth.K_KINECT
+    d = O.depth_u16_to_f32(raw)
+    sp = O.default_stats_params(minImageRadius=c["minImageRadius"], maxImageRadius=c["maxImageRadius"], minPoints=c["minPoints"],
+                                curvatureThreshold=c["curvatureThreshold"])
+    oc, oidx, oitv, ointeg = O.depth_to_cloud(d, K, c["minD"], c["maxD"], sp, want_aux=True)
+    rc = RefCloud(R, d, K, c)
+    assert np.array_equal(rc.index, oidx) and np.array_equal(rc.interval, oitv)
+    assert np.array_equal(rc.integral.reshape(-1), np.asarray(ointeg, np.float32).reshape(-1))
+    same_cloud(rc, oc)
+    assert oc.n > 0.5 * raw.size
+    guess = synth.make_pose((0.02, -0.01, 0.015), (0.3, 1.0, 0.2), 1.5).astype(np.float32)
+
+    class S:
+        pass
+    S.conf, S.K, S.rows, S.cols = c, K, 480, 640
+    for threads in (1, 8):
+        ref = run_ref_align(R, rc, rc, S, guess=guess, threads=threads)
+        cp = O.default_corr_params(inlierDistanceThreshold=c["inlierDistanceThreshold"],
+                                   inlierNormalAngularThreshold=c["inlierNormalAngularThreshold"])
+        orc = O.align(oc, oc, O.make_align_params(K, 480, 640, c["minD"], c["maxD"], cp, guess=guess, num_threads=threads))
+        assert np.array_equal(ref["T"], orc.T) and ref["inliers"] == orc.inliers and ref["error"] == orc.error
+        assert np.array_equal(ref["refIndex"], orc.refIndex) and np.array_equal(ref["corr"][:ref["n"]], orc.corr)
+        assert np.abs(ref["T"] - np.eye(4)).max() < 5e-3  # a frame aligned with itself: identity
