@@ -34,6 +34,14 @@ $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math 
   -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$OUT" $SRCS "$HERE/ref_pwn_core.cpp" \
   -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
 echo "built $OUT"
+# the reference's own CLI drivers (pwn_core/pwn_simple_aligner.cpp = BASELINE config 0/1, frame-to-frame odometry;
+# pwn_core/pwn_aligner.cpp = scene-based odometry with the local map, Merger and VoxelCalculator), unmodified
+for drv in pwn_simple_aligner pwn_aligner; do
+  $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math -fopenmp \
+    -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$HERE/_ref/${drv}_ref" $SRCS "$S/$drv.cpp" \
+    -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
+  echo "built $HERE/_ref/${drv}_ref"
+done
 # the drop-in demonstration (integration/drop_in_demo.cpp): the same reference sources + the option-A binding of
 # integration/pwn_b200/b200_pwn.h + this repository's CUDA library, in one executable
 REPO=$(cd "$HERE/.." && pwd)

@@ -44,6 +44,22 @@ class Quaternion {
   S y() const { return q[1]; }
   S z() const { return q[2]; }
   S w() const { return q[3]; }
+  S &x() { return q[0]; }
+  S &y() { return q[1]; }
+  S &z() { return q[2]; }
+  S &w() { return q[3]; }
+  // Eigen's QuaternionBase::toRotationMatrix
+  Matrix<S, 3, 3> toRotationMatrix() const {
+    Matrix<S, 3, 3> R;
+    const S tx = S(2) * q[0], ty = S(2) * q[1], tz = S(2) * q[2];
+    const S twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+    const S txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+    const S tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    R(0, 0) = S(1) - (tyy + tzz); R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+    R(1, 0) = txy + twz; R(1, 1) = S(1) - (txx + tzz); R(1, 2) = tyz - twx;
+    R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = S(1) - (txx + tyy);
+    return R;
+  }
 };
 typedef Quaternion<float> Quaternionf;
 typedef Quaternion<double> Quaterniond;

@@ -97,6 +97,7 @@ class Mat_ : public Mat {
   Mat_() : Mat() { _type = DataType<T>::type; }
   Mat_(int r, int c) : Mat(r, c, DataType<T>::type) {}
   Mat_(const Mat &m) : Mat(m) {}
+  Mat_ &operator=(const Mat &m) { Mat::operator=(m); return *this; }
   void create(int r, int c) { Mat::create(r, c, DataType<T>::type); }
   T &operator()(int r, int c) { return ((T *)(data + (size_t)r * step))[c]; }
   const T &operator()(int r, int c) const { return ((const T *)(data + (size_t)r * step))[c]; }

@@ -633,3 +633,74 @@ def test_real_kinect_frame_is_bit_identical(R):
         assert np.array_equal(ref["T"], orc.T) and ref["inliers"] == orc.inliers and ref["error"] == orc.error
         assert np.array_equal(ref["refIndex"], orc.refIndex) and np.array_equal(ref["corr"][:ref["n"]], orc.corr)
         assert np.abs(ref["T"] - np.eye(4)).max() < 5e-3  # a frame aligned with itself: identity
+
+
+# ---- the reference's own CLI driver (BASELINE config 0 / 1) -----------------------------------------------------------
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pwn_simple_aligner_ref")
+
+
+def run_reference_cli(tmp_path, raws, conf, image_scale, threads=1):
+    """pwn_core/pwn_simple_aligner.cpp, compiled unmodified: config file, list of depth images, odometry file out.
+    Returns the global poses (4x4) it wrote, one per frame."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_cpp import write_conf, write_pgm16
+    if not os.access(REF_CLI, os.X_OK):
+        os.chmod(REF_CLI, 0o755)
+    lst = str(tmp_path / "frames.txt")
+    with open(lst, "w") as f:
+        for i, r in enumerate(raws):
+            p = str(tmp_path / ("ref_depth%d.pgm" % i))
+            write_pgm16(p, r)
+            f.write("%d.5 %s\n" % (100 + i, p))
+    cfg = str(tmp_path / "ref_aligner.conf")
+    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0])
+    odo = str(tmp_path / "ref_odometry.txt")
+    subprocess.run([REF_CLI, cfg, lst, odo], check=True, capture_output=True, timeout=900,
+                   env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+    poses = []
+    for line in open(odo):
+        v = [float(x) for x in line.split()[1:]]
+        x, y, z, qx, qy, qz, qw = v
+        Rm = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                       [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                       [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = Rm, (x, y, z)
+        poses.append(T)
+    return poses
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/pwn_simple_aligner_ref not built")
+def test_reference_cli_driver_against_the_oracle_chain(tmp_path):
+    """BASELINE configs[0], "the reference's own CPU-runnable case": pwn_simple_aligner on three synthetic frames
+    (16-bit PGM in, imageScale 4, parameters of pwn_aligner_1_4.conf).  The odometry it writes equals the oracle's chain
+    depth_u16_to_f32 -> depth_scale -> depth_to_cloud -> align(previous, current), composed (the text file carries 6
+    significant digits)."""
+    from conftest import CONF_1_4
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    conf = CONF_1_4
+    poses = [synth.POSE_A, synth.POSE_B, synth.POSE_B @ synth.make_pose((-0.02, 0.01, 0.03), (1.0, 0.3, 0.2), 1.5)]
+    raws = [synth.render_depth_u16(p, seed=3 + i) for i, p in enumerate(poses)]
+    got = run_reference_cli(tmp_path, raws, conf, 4)
+    assert len(got) == 3
+    K = synth.scaled_K(synth.K_KINECT, 0.25)
+    sp = O.default_stats_params(minImageRadius=conf["minImageRadius"], maxImageRadius=conf["maxImageRadius"],
+                                minPoints=conf["minPoints"], curvatureThreshold=conf["curvatureThreshold"],
+                                worldRadius=conf["worldRadius"], omegaCurvatureThreshold=conf["omegaCurvatureThreshold"])
+    cp = O.default_corr_params(inlierDistanceThreshold=conf["inlierDistanceThreshold"],
+                               inlierNormalAngularThreshold=conf["inlierNormalAngularThreshold"],
+                               flatCurvatureThreshold=conf["flatCurvatureThreshold"],
+                               inlierCurvatureRatioThreshold=conf["inlierCurvatureRatioThreshold"])
+    clouds = [O.depth_to_cloud(O.depth_scale(O.depth_u16_to_f32(r), 4), K, conf["minD"], conf["maxD"], sp)[0] for r in raws]
+    G = np.eye(4, dtype=np.float32)
+    assert np.abs(got[0] - np.eye(4)).max() < 1e-6
+    for i in (1, 2):
+        ap = O.make_align_params(K, 120, 160, conf["minD"], conf["maxD"], cp, max_chi2=conf["inlierMaxChi2"], num_threads=1)
+        o = O.align(clouds[i - 1], clouds[i], ap)
+        G = (G.astype(np.float64) @ o.T.astype(np.float64)).astype(np.float32)
+        assert np.abs(got[i] - G).max() < 2e-5, (i, got[i], G)
+    # and it is an odometry: the composed motion is the ground truth of the synthetic sequence
+    assert np.abs(got[2] - poses[2]).max() < 1e-2

@@ -141,3 +141,36 @@ def test_drop_in_demo_reference_classes_with_the_b200_backend(tmp_path):
         assert abs(gpu["reference_pixels"] - cpu["reference_pixels"]) <= 1e-2 * cpu["reference_pixels"]
         print("drop-in demo %dx%d: B200 align %.3f ms (second call), |dT| %.2e" %
               (s.rows, s.cols, out["b200_second_align_ms"], float(np.abs(Tg - Tc).max())))
+
+
+def test_cli_driver_against_the_reference_cli_driver(tmp_path):
+    """BASELINE configs[0]: the reference's own pwn_simple_aligner (oracle/_ref/pwn_simple_aligner_ref, compiled unmodified
+    from /root/reference) and this repository's driver (pwn:: classes -> C-ABI -> CUDA) on the same 16-bit PGM frames and
+    the same configuration: the trajectories agree."""
+    import json
+    import subprocess
+    from conftest import CONF_1_1, CONF_1_4
+    from g2o_frontend_b200 import synth
+    from test_host_cpp import BIN, write_conf, write_pgm16
+    from test_reference_pwn_core import REF_CLI, run_reference_cli
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/pwn_simple_aligner_ref not built")
+    poses = [synth.POSE_A, synth.POSE_B, synth.POSE_B @ synth.make_pose((-0.02, 0.01, 0.03), (1.0, 0.3, 0.2), 1.5)]
+    raws = [synth.render_depth_u16(p, seed=3 + i) for i, p in enumerate(poses)]
+    for image_scale, conf in ((4, CONF_1_4), (1, CONF_1_1)):
+        ref = run_reference_cli(tmp_path, raws, conf, image_scale)
+        files = []
+        for i, r in enumerate(raws):
+            p = str(tmp_path / ("depth%d.pgm" % i))
+            write_pgm16(p, r)
+            files.append(p)
+        cfg = str(tmp_path / "aligner.conf")
+        write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0])
+        out = str(tmp_path / "out.jsonl")
+        subprocess.check_call([BIN, cfg, out] + files)
+        lines = [json.loads(l) for l in open(out)]
+        G = np.eye(4)
+        for i in (1, 2):
+            G = G @ np.array(lines[i]["T"], np.float64).reshape(4, 4).T
+            assert rot_angle(G[:3, :3], ref[i][:3, :3]) <= 3e-4, (image_scale, i)
+            assert np.abs(G[:3, 3] - ref[i][:3, 3]).max() <= 3e-4, (image_scale, i)
