@@ -255,6 +255,11 @@ int main(int argc, char **argv) {
       Cloud referenceScene, subscene;
       Isometry3f globalT, sceneT;
       bool firstDepth = true;
+      // pwn_aligner.cpp:72-73,194-205: after the first alignment and then every chunkStep frames the local map is closed
+      // (the reference saves it as scene-%03d.pwn) and a new one is started from the current frame.  chunkStep 0 (where
+      // the reference would divide by zero) = one map for the whole sequence.
+      const int chunkStep = (int)get(cfg, "chunkStep", 10);
+      int counter = 0;
       for (int a = 3; a < argc; a++) {
         RawDepthImage raw;
         if (!readPgm16(argv[a], raw)) throw std::runtime_error(std::string("cannot read ") + argv[a]);
@@ -287,12 +292,18 @@ int main(int argc, char **argv) {
           globalT = globalT * aligner.T();
           sceneT = sceneT * aligner.T();
         }
+        int newMap = 0;
+        if (!firstDepth && chunkStep > 0 && counter++ % chunkStep == 0) {
+          sceneT = Isometry3f::Identity();
+          referenceScene.clear();
+          newMap = 1;
+        }
         const size_t before = referenceScene.size() + cloud.size();
         referenceScene.add(cloud, sceneT);
         merger.merge(&referenceScene, sceneT * sensorOffset);
         projector.setTransform(Isometry3f::Identity());
-        fprintf(out, "{\"frame\": %d, \"inliers\": %d, \"added\": %zu, \"map_points\": %zu, \"globalT\": [", a - 3, inliers,
-                before, referenceScene.size());
+        fprintf(out, "{\"frame\": %d, \"inliers\": %d, \"added\": %zu, \"map_points\": %zu, \"new_map\": %d, \"globalT\": [", a - 3,
+                inliers, before, referenceScene.size(), newMap);
         for (int i = 0; i < 16; i++) fprintf(out, "%s%.9g", i ? ", " : "", globalT.data()[i]);
         fprintf(out, "]}\n");
         firstDepth = false;

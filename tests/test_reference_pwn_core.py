@@ -704,3 +704,122 @@ def test_reference_cli_driver_against_the_oracle_chain(tmp_path):
         assert np.abs(got[i] - G).max() < 2e-5, (i, got[i], G)
     # and it is an odometry: the composed motion is the ground truth of the synthetic sequence
     assert np.abs(got[2] - poses[2]).max() < 1e-2
+
+
+REF_MAP_CLI = os.path.join(ROOT, "oracle", "_ref", "pwn_aligner_ref")
+
+
+def oracle_scene_odometry(raws, conf, scale, chunk_step=10):
+    """pwn_core/pwn_aligner.cpp:129-222 restated over the oracle: every frame is aligned against the local map re-rendered
+    at the predicted pose, added (Cloud::add) and fused (Merger::merge); after the first alignment and then every
+    chunk_step frames the map is closed and a new one starts from the current frame (chunk_step 0: never).
+    Returns the global pose and the map size after every frame."""
+    from g2o_frontend_b200 import synth
+    from oracle import pwn_oracle as O
+    f32 = np.float32
+    K = (synth.K_KINECT * (f32(1.0) / f32(scale))).astype(f32)
+    K[2, 2] = 1.0
+    rows, cols = 480 // scale, 640 // scale
+    sp = O.default_stats_params(minImageRadius=conf["minImageRadius"], maxImageRadius=conf["maxImageRadius"],
+                                minPoints=conf["minPoints"], curvatureThreshold=conf["curvatureThreshold"],
+                                worldRadius=conf["worldRadius"], omegaCurvatureThreshold=conf["omegaCurvatureThreshold"])
+    cp = O.default_corr_params(inlierDistanceThreshold=conf["inlierDistanceThreshold"],
+                               inlierNormalAngularThreshold=conf["inlierNormalAngularThreshold"],
+                               flatCurvatureThreshold=conf["flatCurvatureThreshold"],
+                               inlierCurvatureRatioThreshold=conf["inlierCurvatureRatioThreshold"])
+    def mul(A, B):  # Isometry3f * Isometry3f in float32 as Eigen does it (R = Ra Rb, t = Ra tb + ta), last row rewritten
+        out = np.zeros(16, f32)
+        O.lib().orc_iso_mul(fp(O.colmajor(A)), fp(O.colmajor(B)), fp(out))
+        M = out.reshape(4, 4).T.copy()
+        M[3] = (0, 0, 0, 1)
+        return M
+    globalT, sceneT = np.eye(4, dtype=f32), np.eye(4, dtype=f32)
+    scene = sg = sf = None
+    counter = 0
+    poses, sizes = [], []
+    for i, r in enumerate(raws):
+        d = O.depth_scale(O.depth_u16_to_f32(r), scale)
+        cloud = O.depth_to_cloud(d, K, conf["minD"], conf["maxD"], sp)[0]
+        g, f, _, _ = O.unproject_gaussians(d, K, conf["minD"], conf["maxD"], 0.075, 0.1)
+        if i > 0:
+            _, rendered = O.project(scene.points, rows, cols, K, sceneT, conf["minD"], conf["maxD"])
+            sub = O.depth_to_cloud(rendered, K, conf["minD"], conf["maxD"], sp)[0]
+            o = O.align(sub, cloud, O.make_align_params(K, rows, cols, conf["minD"], conf["maxD"], cp,
+                                                       max_chi2=conf["inlierMaxChi2"], num_threads=1))
+            globalT, sceneT = mul(globalT, o.T), mul(sceneT, o.T)
+            if chunk_step > 0:
+                if counter % chunk_step == 0:
+                    sceneT = np.eye(4, dtype=f32)
+                    scene = sg = sf = None
+                counter += 1
+        pts, nrm, st, op, on = (cloud.points.copy(), cloud.normals.copy(), cloud.statsM.copy(), cloud.omegaP.copy(), cloud.omegaN.copy())
+        O.lib().orc_cloud_transform(fp(O.colmajor(sceneT)), cloud.n, fp(pts), fp(nrm), fp(st), fp(op), fp(on))
+        g, f = O.gaussians_transform(sceneT, g, f)
+        parts = [] if scene is None else [scene]
+        m = O.Cloud((0 if scene is None else scene.n) + cloud.n)
+        cat = lambda name, new: np.ascontiguousarray(np.concatenate([getattr(p, name) for p in parts] + [new]))
+        m.points, m.normals, m.statsM = cat("points", pts), cat("normals", nrm), cat("statsM", st)
+        m.omegaP, m.omegaN = cat("omegaP", op), cat("omegaN", on)
+        m.eigvals, m.statsN, m.curvature = cat("eigvals", cloud.eigvals), cat("statsN", cloud.statsN), cat("curvature", cloud.curvature)
+        mg = g if scene is None else np.concatenate([sg, g])
+        mf = f if scene is None else np.concatenate([sf, f])
+        scene, sg, sf, _ = O.merge(m, mg, mf, rows, cols, K, sceneT, conf["minD"], conf["maxD"])
+        poses.append(globalT.copy())
+        sizes.append(scene.n)
+    return poses, sizes
+
+
+def run_reference_map_cli(tmp_path, raws, conf, image_scale, chunk_step=None):
+    """pwn_core/pwn_aligner.cpp compiled unmodified: global poses it wrote, one per frame"""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_cpp import write_conf, write_pgm16
+    if not os.access(REF_MAP_CLI, os.X_OK):
+        os.chmod(REF_MAP_CLI, 0o755)
+    lst = str(tmp_path / "map_frames.txt")
+    with open(lst, "w") as f:
+        for i, r in enumerate(raws):
+            p = str(tmp_path / ("map_depth%d.pgm" % i))
+            write_pgm16(p, r)
+            f.write("%d.5 %s\n" % (100 + i, p))
+    cfg = str(tmp_path / "map_aligner.conf")
+    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=None if chunk_step is None else {"chunkStep": chunk_step})
+    odo = str(tmp_path / "map_odometry.txt")
+    subprocess.run([REF_MAP_CLI, cfg, lst, odo], check=True, capture_output=True, timeout=900, cwd=str(tmp_path),
+                   env=dict(os.environ, OMP_NUM_THREADS="1"))
+    poses = []
+    for line in open(odo):
+        x, y, z, qx, qy, qz, qw = [float(v) for v in line.split()[1:]]
+        Rm = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                       [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                       [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = Rm, (x, y, z)
+        poses.append(T)
+    return poses
+
+
+def map_sequence(n=6):
+    from g2o_frontend_b200 import synth
+    poses = [synth.POSE_A]
+    step = synth.make_pose((0.015, -0.01, 0.02), (0.2, 1.0, 0.1), 1.0)
+    for _ in range(n - 1):
+        poses.append(poses[-1] @ step)
+    return poses, [synth.render_depth_u16(p, seed=40 + i) for i, p in enumerate(poses)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MAP_CLI), reason="oracle/_ref/pwn_aligner_ref not built")
+@pytest.mark.parametrize("chunk_step", [None, 2])
+def test_reference_scene_odometry_driver_against_the_oracle_chain(tmp_path, chunk_step):
+    """pwn_core/pwn_aligner.cpp (align against the re-rendered local map, Cloud::add, Merger::merge, a new map after the
+    first alignment and every chunkStep frames) on six synthetic frames: its odometry equals the oracle's restatement"""
+    from conftest import CONF_1_4
+    gt, raws = map_sequence(6)
+    got = run_reference_map_cli(tmp_path, raws, CONF_1_4, 4, chunk_step)
+    want, sizes = oracle_scene_odometry(raws, CONF_1_4, 4, 10 if chunk_step is None else chunk_step)
+    assert len(got) == len(want) == 6
+    for i in range(6):
+        assert np.abs(got[i] - want[i]).max() < 3e-5, (i, got[i], want[i])
+    rel = np.linalg.inv(gt[0]) @ gt[-1]
+    assert np.abs(got[-1][:3, 3] - rel[:3, 3]).max() < 2e-2

@@ -174,3 +174,33 @@ def test_cli_driver_against_the_reference_cli_driver(tmp_path):
             G = G @ np.array(lines[i]["T"], np.float64).reshape(4, 4).T
             assert rot_angle(G[:3, :3], ref[i][:3, :3]) <= 3e-4, (image_scale, i)
             assert np.abs(G[:3, 3] - ref[i][:3, 3]).max() <= 3e-4, (image_scale, i)
+
+
+def test_scene_odometry_driver_against_the_reference_driver(tmp_path):
+    """pwn_core/pwn_aligner.cpp (scene-based odometry: align against the re-rendered local map, Cloud::add, Merger::merge,
+    a new map after the first alignment and every chunkStep frames), the reference's own driver compiled unmodified
+    (oracle/_ref/pwn_aligner_ref) against this repository's driver in its `localmap 1` mode, same PGM frames, same
+    configuration, the reference's default chunkStep."""
+    import json
+    import subprocess
+    from conftest import CONF_1_4
+    from test_host_cpp import BIN, write_conf, write_pgm16
+    from test_reference_pwn_core import REF_MAP_CLI, map_sequence, run_reference_map_cli
+    if not os.path.exists(REF_MAP_CLI):
+        pytest.skip("oracle/_ref/pwn_aligner_ref not built")
+    gt, raws = map_sequence(6)
+    ref = run_reference_map_cli(tmp_path, raws, CONF_1_4, 4, None)
+    files = []
+    for i, r in enumerate(raws):
+        p = str(tmp_path / ("m%d.pgm" % i))
+        write_pgm16(p, r)
+        files.append(p)
+    cfg = str(tmp_path / "map.conf")
+    write_conf(cfg, CONF_1_4, 4, [0, 0, 0, 0, 0, 0], extra={"localmap": 1})
+    out = str(tmp_path / "map.jsonl")
+    subprocess.check_call([BIN, cfg, out] + files)
+    lines = [json.loads(l) for l in open(out)]
+    assert [l["new_map"] for l in lines[:6]] == [0, 1, 0, 0, 0, 0]
+    for i in range(6):
+        G = np.array(lines[i]["globalT"], np.float64).reshape(4, 4).T
+        assert np.abs(G - ref[i]).max() <= 1e-3, (i, G, ref[i])
