@@ -182,6 +182,55 @@ def cpu_reference_run(steps, warmup, sample_pairs, n_threads=None):
     return value, cores, total / len(times) * 1e3
 
 
+def cpu_reference_sources_run(sample_pairs, n_threads=None):
+    """The reference's OWN sources (g2o_frontend/pwn_core/*.cpp compiled from /root/reference against the Eigen / OpenCV
+    stand-ins of oracle/shim with the reference's flags: oracle/_ref/libpwn_core_ref_fast.so) on the same bounded sample:
+    1 cloud build + `sample_pairs` alignments.  Reported next to the oracle port, which is the faster of the two and stays
+    the baseline (the stand-in evaluates Eigen expressions eagerly, without Eigen's SIMD).  None if the library is absent."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libpwn_core_ref_fast.so")
+    if not os.path.exists(so):
+        return None
+    from oracle import pwn_oracle as O
+    from g2o_frontend_b200 import synth
+    O.lib()  # liboracle.so first: the stand-in's numerical kernels resolve against it
+    R = C.CDLL(so)
+    R.refcore_depth_to_cloud.restype = C.c_void_p
+    cores = n_threads or os.cpu_count() or 1
+    while ROWS % cores:
+        cores -= 1
+    R.refcore_set_threads(cores)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    cm = lambda M: np.ascontiguousarray(np.asarray(M, np.float32).T.reshape(-1))
+    raws_cur, raws_cand, pairs, guesses = make_workload(1, sample_pairs, 0)
+    sp = np.array([CONF["worldRadius"], CONF["minImageRadius"], CONF["maxImageRadius"], CONF["minPoints"],
+                   CONF["curvatureThreshold"], CONF["omegaCurvatureThreshold"]], np.float32)
+    eye = cm(np.eye(4))
+    K9 = cm(synth.K_KINECT)
+
+    def build(raw):
+        d = np.ascontiguousarray(O.depth_u16_to_f32(raw, fast=True), np.float32)
+        return C.c_void_p(R.refcore_depth_to_cloud(fp(d), ROWS, COLS, fp(K9), C.c_float(CONF["minD"]), C.c_float(CONF["maxD"]),
+                                                   fp(sp), fp(eye), None, None, None))
+
+    cands = [build(r) for r in raws_cand]
+    fpar = np.array([CONF["inlierDistanceThreshold"], CONF["inlierNormalAngularThreshold"], CONF["flatCurvatureThreshold"],
+                     CONF["inlierCurvatureRatioThreshold"]], np.float32)
+    T = np.zeros(16, np.float32)
+    t0 = time.perf_counter()
+    cur = build(raws_cur[0])
+    for j, (ri, ci) in enumerate(pairs):
+        R.refcore_align(cands[ri], cur, fp(K9), ROWS, COLS, C.c_float(CONF["minD"]), C.c_float(CONF["maxD"]), fp(fpar),
+                        C.c_float(CONF["inlierMaxChi2"]), 1, CONF["outerIterations"], CONF["innerIterations"], fp(cm(guesses[j])),
+                        fp(eye), fp(eye), None, 0, fp(T), None, None, None, None, None, None, None, None, None)
+    dt = time.perf_counter() - t0
+    for h in cands + [cur]:
+        R.refcore_cloud_free(h)
+    return {"value": sample_pairs / dt, "unit": UNIT, "cores": cores,
+            "note": "g2o_frontend/pwn_core sources compiled against the Eigen/OpenCV stand-ins of oracle/shim "
+                    "(-O3 -march=x86-64-v3 -fopenmp), 1 cloud build + %d alignments" % sample_pairs}
+
+
 def workload_config(n_cur, n_cand, world):
     """the `config` object both arms report (same workload name; the reference arm times a bounded sample of it)"""
     n_pairs = n_cur * n_cand
@@ -203,11 +252,16 @@ def run_reference(args):
     value, cores, ms = cpu_reference_run(args.steps, args.warmup, n, args.cpu_threads or None)
     sample = ("per step: 1 cloud build from a raw 640x480 frame + %d alignments (10 iterations) of the "
               "loop-closure workload, CPU oracle performance build (-O3 -march=x86-64-v3 -fopenmp)" % n)
+    try:
+        ref_src = cpu_reference_sources_run(min(n, 4), args.cpu_threads or None)
+    except Exception as e:  # the baseline is the port; this figure is informative
+        ref_src = {"value": None, "note": "failed: %s" % e}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.currents, args.candidates, int(os.environ.get("WORLD_SIZE", "1"))),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "reference_sources": ref_src},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

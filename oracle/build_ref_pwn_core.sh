@@ -34,6 +34,12 @@ $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math 
   -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$OUT" $SRCS "$HERE/ref_pwn_core.cpp" \
   -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
 echo "built $OUT"
+# performance flavour of the same library: the reference's own flags (-O3 -march + OpenMP, /root/reference/CMakeLists.txt:
+# 135,145,171; x86-64-v3 instead of native so that it also runs on the GPU box's host), timed by bench.py next to the oracle port
+$CXX -std=gnu++11 -fpermissive -w -O3 -march=x86-64-v3 -DNDEBUG -fopenmp -shared -fPIC \
+  -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$HERE/_ref/libpwn_core_ref_fast.so" $SRCS "$HERE/ref_pwn_core.cpp" \
+  -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
+echo "built $HERE/_ref/libpwn_core_ref_fast.so"
 # the reference's own CLI drivers (pwn_core/pwn_simple_aligner.cpp = BASELINE config 0/1, frame-to-frame odometry;
 # pwn_core/pwn_aligner.cpp = scene-based odometry with the local map, Merger and VoxelCalculator), unmodified
 for drv in pwn_simple_aligner pwn_aligner; do
