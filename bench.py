@@ -382,6 +382,20 @@ def run_ours(args):
                 "project_avg_launch_ms": kt["project_ms"] / max(kt["project_launches"], 1),
                 "share_of_step": kt["corr_lin_ms"] / dev_ms if dev_ms > 0 else None}
 
+    # the reference-cloud projection kernel by the same accounting (12 N + 8 P bytes per pair and iteration);
+    # informative, never allowed to break the line
+    try:
+        sizes = [c.size() for c in clouds]
+        n_ref_total = float(sum(sizes[n_cur + ri] for ri, ci in pairs))
+        proj_bytes = (12.0 * n_ref_total + 8.0 * P * n_pairs) * args.steps * CONF["outerIterations"]
+        if kt["project_ms"] > 0:
+            roofline["project"] = {"kernel": "k_project (PinholePointProjector::project, packed 64-bit red.min z-buffer)",
+                                   "achieved": proj_bytes / (kt["project_ms"] * 1e-3) / 1e9, "unit": "GB/s",
+                                   "frac": proj_bytes / (kt["project_ms"] * 1e-3) / 1e9 / peak,
+                                   "launches_timed": kt["project_launches"]}
+    except Exception:
+        pass
+
     # ---- e2e: host buffers in, records out, every step -------------------------------------------
     def e2e_step():
         build_clouds()
