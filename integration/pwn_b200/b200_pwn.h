@@ -218,6 +218,24 @@ class B200DepthImageConverter : public DepthImageConverterIntegralImage {
   bool _hostMirror;
 };
 
+// The finder's correspondence count and the lineariser's H / b / error / inliers are protected members without setters;
+// align() has to leave them as the reference's align() does.  A derived class may form a pointer to a protected member of
+// its base and apply it to any object of the base type.
+struct B200FinderAccess : public CorrespondenceFinder {
+  static void setNumCorrespondences(CorrespondenceFinder &f, int n) { f.*(&B200FinderAccess::_numCorrespondences) = n; }
+};
+struct B200LinearizerAccess : public Linearizer {
+  static void set(Linearizer &l, const float *H, const float *b, float error, int inliers) {
+    Matrix6f &Hm = l.*(&B200LinearizerAccess::_H);
+    Vector6f &bm = l.*(&B200LinearizerAccess::_b);
+    for (int c = 0; c < 6; c++)
+      for (int r = 0; r < 6; r++) Hm(r, c) = H[6 * c + r];
+    for (int r = 0; r < 6; r++) bm(r) = b[r];
+    l.*(&B200LinearizerAccess::_error) = error;
+    l.*(&B200LinearizerAccess::_inliers) = inliers;
+  }
+};
+
 // Aligner::align (aligner.cpp:49-150) on the GPU
 class B200Aligner : public Aligner {
  public:
@@ -292,6 +310,11 @@ class B200Aligner : public Aligner {
       }
     cf->correspondences().assign(P, Correspondence());
     for (int k = 0; k < _last.num_correspondences; k++) cf->correspondences()[k] = Correspondence(corr[2 * (size_t)k], corr[2 * (size_t)k + 1]);
+    B200FinderAccess::setNumCorrespondences(*cf, _last.num_correspondences);
+    // the lineariser: T = T^-1 and the H / b of _computeStatistics' linearisation at the final T (aligner.cpp:165-170);
+    // error / inliers are those of the last loop iteration (the record has no separate pair for the final linearisation)
+    _linearizer->setT(_T.inverse());
+    B200LinearizerAccess::set(*_linearizer, H, b, _last.error, _last.inliers);
     _projector->setTransform(_T * _referenceSensorOffset);
     gettimeofday(&tvEnd, 0);
     _totalTime = (tvEnd.tv_sec - tvStart.tv_sec) * 1000.0 + (tvEnd.tv_usec - tvStart.tv_usec) * 0.001;
