@@ -166,6 +166,25 @@ void refcore_cloud_get(void *h, float *points4, float *normals4, float *stats16,
     if (omegaN16) std::memcpy(omegaN16 + 16 * i, c.normalInformationMatrix()[i].data(), 64);
   }
 }
+// Cloud::save / Cloud::load (cloud.cpp:25-133); sizes of the objects the binary mode dumps raw
+int refcore_cloud_save(void *h, const char *path, const float T[16], int step, int binary) {
+  return ((Cloud *)h)->save(path, iso(T), step, binary != 0) ? 1 : 0;
+}
+void *refcore_cloud_load(const char *path, float T[16]) {
+  Cloud *c = new Cloud();
+  Eigen::Isometry3f X;
+  if (!c->load(X, path)) {
+    delete c;
+    return 0;
+  }
+  std::memcpy(T, X.matrix().data(), sizeof(float) * 16);
+  return c;
+}
+void refcore_object_sizes(int sizes[3]) {
+  sizes[0] = (int)sizeof(Point);
+  sizes[1] = (int)sizeof(Normal);
+  sizes[2] = (int)sizeof(Stats);
+}
 // Cloud::transformInPlace (cloud.cpp:173-186), Cloud::add (cloud.cpp:145-171)
 void refcore_cloud_transform(void *h, const float T[16]) { ((Cloud *)h)->transformInPlace(iso(T)); }
 void refcore_cloud_add(void *dst, void *src, const float T[16]) { ((Cloud *)dst)->add(*(Cloud *)src, iso(T)); }

@@ -823,3 +823,54 @@ def test_reference_scene_odometry_driver_against_the_oracle_chain(tmp_path, chun
         assert np.abs(got[i] - want[i]).max() < 3e-5, (i, got[i], want[i])
     rel = np.linalg.inv(gt[0]) @ gt[-1]
     assert np.abs(got[-1][:3, 3] - rel[:3, 3]).max() < 2e-2
+
+
+@pytest.mark.parametrize("binary", [0, 1])
+def test_pwn_cloud_files_are_exchanged_with_the_reference(R, tmp_path, binary):
+    """.pwn cloud files (SURVEY.md 8f rank 4): written by the reference's Cloud::save (cloud.cpp:82-133), read and written
+    back by pwn::Cloud::load / save of include/pwn/pwn.h (a CPU-only program), read by the reference's Cloud::load
+    (cloud.cpp:25-80).  Binary mode dumps the reference's C++ objects raw -- 32 B per Point, 32 B per Normal, 112 B per
+    Stats on LP64 (vptr, padding, payload) -- which is what the header documents, reads and writes."""
+    import subprocess
+    sizes = (C.c_int * 3)()
+    R.refcore_object_sizes(sizes)
+    assert list(sizes) == [32, 32, 112]
+    S = get_scene(4, seed=1, dropout=0.05)
+    rc = RefCloud(R, S.depthA, S.K, S.conf)
+    from g2o_frontend_b200 import synth
+    T = synth.make_pose((0.3, -0.2, 0.5), (0.2, 1.0, 0.1), 12.0).astype(np.float32)
+    a, b = str(tmp_path / "reference.pwn"), str(tmp_path / "ours.pwn")
+    assert R.refcore_cloud_save(rc.h, a.encode(), fp(cm(T)), 1, binary) == 1
+    exe = str(tmp_path / "pwn_file_roundtrip")
+    lib = os.path.join(ROOT, "g2o_frontend_b200", "lib")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "pwn_file_roundtrip.cpp"), "-L", lib, "-lnicp_b200",
+                           "-Wl,-rpath," + lib])
+    out = subprocess.run([exe, a, b, str(binary)], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0 and int(out.stdout.split()[0]) == rc.n, out.stdout + out.stderr
+    T2 = np.zeros(16, np.float32)
+    R.refcore_cloud_load.restype = C.c_void_p
+    h = R.refcore_cloud_load(b.encode(), fp(T2))
+    assert h
+    h = C.c_void_p(h)
+    try:
+        n = R.refcore_cloud_size(h)
+        assert n == rc.n
+        pts, nrm, st = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 16), np.float32)
+        ev, cnt = np.zeros((n, 3), np.float32), np.zeros(n, np.int32)
+        R.refcore_cloud_get(h, fp(pts), fp(nrm), fp(st), fp(ev), ip(cnt), None, None, None)
+        if binary:
+            assert np.array_equal(pts, rc.points) and np.array_equal(nrm, rc.normals) and np.array_equal(st, rc.statsM)
+            assert np.array_equal(ev, rc.eigvals) and np.array_equal(cnt, rc.statsN)
+            assert np.abs(T2.reshape(4, 4).T - T).max() < 1e-5  # the pose line is text in both modes
+        else:  # text with 6 significant digits
+            assert np.allclose(pts, rc.points, rtol=2e-5, atol=1e-6) and np.allclose(nrm, rc.normals, rtol=2e-5, atol=1e-6)
+            assert np.allclose(st, rc.statsM, rtol=2e-5, atol=1e-6)
+    finally:
+        # The reference's binary load reads each Point / Normal / Stats object raw, VPTR INCLUDED (cloud.cpp:72-75).  A file
+        # is therefore only safe to destroy again in the process image that wrote it; our writer stores zeros there (and
+        # our reader ignores those bytes), so the cloud the reference loaded from it is deliberately leaked here: its
+        # element destructors are virtual calls through that pointer.
+        if not binary:
+            R.refcore_cloud_free(h)
