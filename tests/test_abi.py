@@ -69,3 +69,56 @@ def test_product_does_not_import_oracle():
             for f in files:
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pwn_oracle" not in text and "liboracle" not in text and "voxel_oracle" not in text, os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("verify", [False, True])
+def test_null_handles_are_rejected_not_dereferenced(verify):
+    """the reference only asserts on misuse (undefined behaviour in release builds); the C-ABI answers with a status code.
+    Every entry point is called with null handles -- no GPU needed, nothing may crash."""
+    import ctypes as C
+    L = capi.load(verify)
+    N = None
+    f0 = C.c_float(0)
+    L.nicp_cloud_size.restype = C.c_int
+    L.nicp_launch_count.restype = C.c_longlong
+    L.nicp_stream.restype = C.c_void_p
+    assert L.nicp_synchronize(N) == 1                      # NICP_ERR_INVALID
+    assert L.nicp_cloud_create(N, 10, N) == 1
+    assert L.nicp_cloud_size(N) == -1
+    assert L.nicp_launch_count(N) == 0
+    assert L.nicp_stream(N) is None
+    assert L.nicp_set_kernel_timing(N, 1) == 1
+    assert L.nicp_get_kernel_timing(N, N, N, N, N) == 1
+    assert L.nicp_cloud_upload(N, N, 0, N, N, N, N, N) == 1
+    assert L.nicp_cloud_download(N, N, N, N, N, N, N) == 1
+    assert L.nicp_cloud_download_stats(N, N, N, N, N) == 1
+    assert L.nicp_cloud_transform(N, N, N) == 1
+    assert L.nicp_cloud_append(N, N, N, N) == 1
+    assert L.nicp_cloud_compute_gaussians(N, N, N, N, f0, f0, N) == 1
+    assert L.nicp_cloud_has_gaussians(N) == 0
+    assert L.nicp_cloud_download_gaussians(N, N, N, N) == 1
+    assert L.nicp_cloud_upload_gaussians(N, N, N, N) == 1
+    assert L.nicp_merge(N, N, N, N, N, N, N) == 1
+    assert L.nicp_voxelize(N, N, C.c_float(0.01), N, N) == 1
+    assert L.nicp_depth_prepare(N, N, 4, 4, C.c_float(0.001), 1, C.c_float(0.01), N) == 1
+    assert L.nicp_unproject(N, N, 4, 4, N, f0, f0, N, N) == 1
+    assert L.nicp_project_intervals(N, N, N, f0, N) == 1
+    assert L.nicp_depth_to_cloud(N, N, N, N, N, 0, N, N) == 1
+    assert L.nicp_raw_depth_to_cloud(N, N, 4, 4, C.c_float(0.001), 1, C.c_float(0.01), N, N, N, 0, N, N) == 1
+    assert L.nicp_last_integral_image(N, N) == 1
+    assert L.nicp_last_interval_image(N, N) == 1
+    assert L.nicp_project(N, N, N, 4, 4, f0, f0, N, N) == 1
+    assert L.nicp_correspond_linearize(N, N, N, N, N, 4, 4, N, N, N, N, N, N, N, N) == 1
+    assert L.nicp_linearize(N, N, N, N, 0, N, N, N, N, N, N) == 1
+    assert L.nicp_align(N, N, N, N, N, N, N, N, N, 0, f0, N) == 1
+    assert L.nicp_align_get_state(N, N, N, N, N, N, N, N) == 1
+    assert L.nicp_align_get_trace(N, N, 0) == 1
+    assert L.nicp_align_batch(N, 0, N, N, N, N, N, N, N, f0, N) == 1
+    assert L.nicp_multi_depth_to_cloud(N, N, N, N, N, 0, N, N) == 1
+    assert L.nicp_multi_project(N, N, N, N, N, N) == 1
+    assert L.nicp_multi_align(N, N, N, N, N, N, N, N, N, 0, f0, N) == 1
+    L.nicp_destroy(N)
+    L.nicp_cloud_destroy(N)
+    rows, cols = C.c_int(7), C.c_int(7)
+    L.nicp_multi_image_size(N, C.byref(rows), C.byref(cols))
+    assert (rows.value, cols.value) == (0, 0)
