@@ -146,8 +146,9 @@ int main(int argc, char **argv) {
       aligner.setCorrespondenceFinder(&correspondenceFinder);
       aligner.setOuterIterations(10);
       aligner.setInnerIterations(1);
-      if (!first) std::printf(", ");
       Result r = run(&converter, &aligner, &projector, dA, dB);
+      if (!first) std::printf(", ");
+      first = false;
       print("b200", r);
       // second alignment of the same pair: clouds resident, kernels warm
       Result r2 = run(&converter, &aligner, &projector, dA, dB);

@@ -130,7 +130,10 @@ class B200DepthImageConverter : public DepthImageConverterIntegralImage {
   B200DepthImageConverter(B200Context *context, PointProjector *projector_ = 0, StatsCalculator *statsCalculator_ = 0,
                           PointInformationMatrixCalculator *pointInformationMatrixCalculator_ = 0,
                           NormalInformationMatrixCalculator *normalInformationMatrixCalculator_ = 0)
-      : DepthImageConverterIntegralImage(projector_, statsCalculator_, pointInformationMatrixCalculator_,
+      // DepthImageConverter is a VIRTUAL base of DepthImageConverterIntegralImage (depthimageconverterintegralimage.h:15):
+      // the most derived class initialises it
+      : DepthImageConverter(projector_, statsCalculator_, pointInformationMatrixCalculator_, normalInformationMatrixCalculator_),
+        DepthImageConverterIntegralImage(projector_, statsCalculator_, pointInformationMatrixCalculator_,
                                          normalInformationMatrixCalculator_),
         _context(context), _hostMirror(true) {}
   // false: leave the host vectors of the cloud empty (a pure GPU pipeline; align() only needs the device mirror)

@@ -874,3 +874,37 @@ def test_pwn_cloud_files_are_exchanged_with_the_reference(R, tmp_path, binary):
         # element destructors are virtual calls through that pointer.
         if not binary:
             R.refcore_cloud_free(h)
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/drop_in_demo not built")
+def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
+    """The binding's own logic (integration/pwn_b200/b200_pwn.h: buffer layouts, device-mirror bookkeeping, the state it
+    publishes into the reference's finder / lineariser objects) end to end without a GPU: for this one subprocess a test
+    double (tests/cpp/mock_nicp_backend.c, the dozen nicp_* calls the binding makes, answered by the oracle) is put in front
+    of the real library.  The B200 arm of drop_in_demo must then reproduce its reference arm exactly.  The real library is
+    what tests/test_vs_reference_gpu.py runs the same program with on a B200."""
+    import json
+    import subprocess
+    from oracle import pwn_oracle as O
+    O.lib()
+    mock = tmp_path / "mock"
+    mock.mkdir()
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    build = os.path.join(ROOT, "oracle", "build")
+    subprocess.check_call([cc, "-std=gnu11", "-O1", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(ROOT, "oracle"), "-o", str(mock / "libnicp_b200.so"),
+                           os.path.join(ROOT, "tests", "cpp", "mock_nicp_backend.c"), "-L", build, "-loracle", "-Wl,-rpath," + build])
+    S = get_scene(4)
+    a, b = str(tmp_path / "a.f32"), str(tmp_path / "b.f32")
+    np.ascontiguousarray(S.depthA, np.float32).tofile(a)
+    np.ascontiguousarray(S.depthB, np.float32).tofile(b)
+    c = S.conf
+    args = [DEMO, a, b, str(S.rows), str(S.cols)] + [repr(float(S.K[i, j])) for i, j in ((0, 0), (1, 1), (0, 2), (1, 2))] + \
+           [str(c["minImageRadius"]), str(c["maxImageRadius"]), str(c["minPoints"]), repr(float(c["inlierDistanceThreshold"])), "both"]
+    o = subprocess.run(args, capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_LIBRARY_PATH=str(mock)))
+    assert o.returncode == 0, o.stdout + o.stderr
+    out = json.loads(o.stdout)
+    cpu, dev = out["reference_cpu"], out["b200"]
+    assert dev["T"] == cpu["T"]
+    for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error"):
+        assert dev[k] == cpu[k], k
