@@ -876,6 +876,23 @@ def test_pwn_cloud_files_are_exchanged_with_the_reference(R, tmp_path, binary):
             R.refcore_cloud_free(h)
 
 
+def build_mock_backend(tmp_path):
+    """tests/cpp/mock_nicp_backend.c (a test double of the C-ABI answered by the oracle) -> <tmp>/mock/libnicp_b200.so"""
+    import subprocess
+    from oracle import pwn_oracle as O
+    O.lib()
+    O.voxelize(np.zeros((1, 4), np.float32), 0.01)  # makes sure libvoxel_oracle.so is built
+    mock = tmp_path / "mock"
+    mock.mkdir()
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    build = os.path.join(ROOT, "oracle", "build")
+    subprocess.check_call([cc, "-std=gnu11", "-O1", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(ROOT, "oracle"), "-o", str(mock / "libnicp_b200.so"),
+                           os.path.join(ROOT, "tests", "cpp", "mock_nicp_backend.c"), "-L", build, "-loracle", "-lvoxel_oracle",
+                           "-Wl,-rpath," + build])
+    return mock
+
+
 @pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/drop_in_demo not built")
 def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
     """The binding's own logic (integration/pwn_b200/b200_pwn.h: buffer layouts, device-mirror bookkeeping, the state it
@@ -885,15 +902,7 @@ def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
     what tests/test_vs_reference_gpu.py runs the same program with on a B200."""
     import json
     import subprocess
-    from oracle import pwn_oracle as O
-    O.lib()
-    mock = tmp_path / "mock"
-    mock.mkdir()
-    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    build = os.path.join(ROOT, "oracle", "build")
-    subprocess.check_call([cc, "-std=gnu11", "-O1", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I",
-                           os.path.join(ROOT, "oracle"), "-o", str(mock / "libnicp_b200.so"),
-                           os.path.join(ROOT, "tests", "cpp", "mock_nicp_backend.c"), "-L", build, "-loracle", "-Wl,-rpath," + build])
+    mock = build_mock_backend(tmp_path)
     S = get_scene(4)
     a, b = str(tmp_path / "a.f32"), str(tmp_path / "b.f32")
     np.ascontiguousarray(S.depthA, np.float32).tofile(a)
@@ -908,3 +917,18 @@ def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
     assert dev["T"] == cpu["T"]
     for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error"):
         assert dev[k] == cpu[k], k
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(REF_MAP_CLI)), reason="reference CLI drivers not built")
+def test_host_drivers_against_the_reference_drivers_with_a_mock_backend(tmp_path, monkeypatch):
+    """The HOST logic of this repository's CLI driver (pwn:: classes of include/pwn/pwn.h, frame-to-frame odometry and the
+    scene-based odometry with its local map, Merger, chunkStep) against the reference's own drivers, without a GPU: the
+    two comparisons of tests/test_vs_reference_gpu.py are run with the test double of the C-ABI in front of the real
+    library, so every numerical answer is the oracle's and any disagreement is a defect of the host-side flow."""
+    import test_vs_reference_gpu as TG
+    mock = build_mock_backend(tmp_path)
+    monkeypatch.setenv("LD_LIBRARY_PATH", str(mock))
+    (tmp_path / "cli").mkdir()
+    (tmp_path / "map").mkdir()
+    TG.test_cli_driver_against_the_reference_cli_driver(tmp_path / "cli")
+    TG.test_scene_odometry_driver_against_the_reference_driver(tmp_path / "map")
