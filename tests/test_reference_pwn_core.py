@@ -932,3 +932,24 @@ def test_host_drivers_against_the_reference_drivers_with_a_mock_backend(tmp_path
     (tmp_path / "map").mkdir()
     TG.test_cli_driver_against_the_reference_cli_driver(tmp_path / "cli")
     TG.test_scene_odometry_driver_against_the_reference_driver(tmp_path / "map")
+
+
+def test_host_classes_with_a_mock_backend(tmp_path, monkeypatch):
+    """include/pwn/*.h and the CLI driver's other modes without a GPU: the GPU tests of tests/test_host_cpp.py -- CLI odometry
+    at 160x120 and 640x480, the 3-level pyramid (pwn/pyramid.h, BASELINE config 2), the keyframe tracker (pwn/tracker.h,
+    config 3), .pwn file I/O + Cloud::add, configuration through BOSS records -- run with the test double of the C-ABI in
+    front of the real library.  Every numerical answer is then the oracle's, so these check the host-side flow (what is
+    called, in which order, with which matrices) and nothing else."""
+    import test_host_cpp as TH
+    if not os.path.exists(TH.BIN):
+        pytest.skip("host driver not built")
+    mock = build_mock_backend(tmp_path)
+    monkeypatch.setenv("LD_LIBRARY_PATH", str(mock))
+    for i, (fn, args) in enumerate([(TH.test_cli_driver_matches_oracle, (4,)), (TH.test_cli_driver_matches_oracle, (1,)),
+                                    (TH.test_pyramid_matches_oracle_composition, ()),
+                                    (TH.test_sequential_tracker_matches_oracle_loop, ()),
+                                    (TH.test_cloud_file_io_and_add, ()),
+                                    (TH.test_cli_driver_accepts_boss_configuration, ())]):
+        d = tmp_path / ("case%d" % i)
+        d.mkdir()
+        fn(d, *args)
