@@ -11,6 +11,7 @@
 // reference code, so it lives with the other compiled reference artefacts); run by tests/test_vs_reference_gpu.py.
 #include <omp.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,6 +29,8 @@ struct Result {
   float error;
   double ms;
   long refIndexSum;
+  size_t gaussians;
+  double gaussianSum;  // sum over the reference cloud's gaussians of |mean| and |covariance| entries
 };
 
 static bool readDepth(const char *path, int rows, int cols, DepthImage &d) {
@@ -63,6 +66,14 @@ static Result run(DepthImageConverter *converter, Aligner *aligner, PinholePoint
   r.error = aligner->error();
   r.numCorr = aligner->correspondenceFinder()->numCorrespondences();
   r.ms = aligner->totalTime();
+  r.gaussians = reference.gaussians().size();
+  r.gaussianSum = 0.0;
+  for (size_t i = 0; i < reference.gaussians().size(); i++) {
+    const Eigen::Vector3f m = reference.gaussians()[i].mean();
+    const Eigen::Matrix3f C = reference.gaussians()[i].covarianceMatrix();
+    for (int k = 0; k < 3; k++) r.gaussianSum += std::fabs((double)m(k));
+    for (int k = 0; k < 9; k++) r.gaussianSum += std::fabs((double)C.data()[k]);
+  }
   r.refIndexSum = 0;
   const IntImage &ri = aligner->correspondenceFinder()->referenceIndexImage();
   for (int y = 0; y < ri.rows; y++)
@@ -75,8 +86,8 @@ static void print(const char *name, const Result &r) {
   for (int i = 0; i < 4; i++)
     for (int j = 0; j < 4; j++) std::printf("%s%.9g", (i || j) ? ", " : "", r.T.matrix()(i, j));
   std::printf("], \"reference_points\": %d, \"current_points\": %d, \"inliers\": %d, \"num_correspondences\": %d, \"error\": %.9g, "
-              "\"reference_pixels\": %ld, \"align_ms\": %.3f}",
-              r.nRef, r.nCur, r.inliers, r.numCorr, r.error, r.refIndexSum, r.ms);
+              "\"reference_pixels\": %ld, \"gaussians\": %zu, \"gaussian_sum\": %.17g, \"align_ms\": %.3f}",
+              r.nRef, r.nCur, r.inliers, r.numCorr, r.error, r.refIndexSum, r.gaussians, r.gaussianSum, r.ms);
 }
 
 int main(int argc, char **argv) {

@@ -182,7 +182,26 @@ class B200DepthImageConverter : public DepthImageConverterIntegralImage {
     B200Context::check(nicp_last_interval_image(ctx, &index[0]), "nicp_last_interval_image");
     for (int r = 0; r < rows; r++)
       for (int c = 0; c < cols; c++) sc->intervalImage()(r, c) = index[(size_t)r * cols + c];
-    if (_hostMirror) download(ctx, dev, cloud);
+    if (_hostMirror) {
+      download(ctx, dev, cloud);
+      // the reference's converter also fills cloud.gaussians() (unProject with the sensor model, pinholepointprojector.cpp:
+      // 93-133, then transformInPlace(sensorOffset)); Merger::merge indexes them, so a CPU Merger must find them here
+      B200Context::check(nicp_cloud_compute_gaussians(ctx, dev, src, &p, pp->baseline(), pp->alpha(), sensorOffset.matrix().data()),
+                         "nicp_cloud_compute_gaussians");
+      const int n = nicp_cloud_size(dev);
+      std::vector<float> g((size_t)NICP_GAUSS_FLOATS * (n > 0 ? n : 1));
+      std::vector<int> gf(n > 0 ? n : 1);
+      if (n) B200Context::check(nicp_cloud_download_gaussians(ctx, dev, &g[0], &gf[0]), "nicp_cloud_download_gaussians");
+      cloud.gaussians().resize(n);
+      for (int i = 0; i < n; i++) {
+        const float *q = &g[(size_t)NICP_GAUSS_FLOATS * i];
+        Eigen::Vector3f mean(q[0], q[1], q[2]);
+        Eigen::Matrix3f cov;
+        for (int c = 0; c < 3; c++)
+          for (int r = 0; r < 3; r++) cov(r, c) = q[3 + 3 * c + r];
+        cloud.gaussians()[i] = Gaussian3f(mean, cov, false);
+      }
+    }
     _context->stamp(&cloud);
   }
 

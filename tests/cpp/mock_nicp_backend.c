@@ -111,7 +111,8 @@ int nicp_voxelize(nicp_context *ctx, nicp_cloud *c, float res, int *reps, int *n
   if (reps) memcpy(reps, rep, 4 * (size_t)k); c->n = k; if (newSize) *newSize = k; nicp_cloud_destroy(t); free(rep); return 0; }
 /* entry points the mock does not model: loud failures */
 int nicp_cloud_transform(nicp_context *c, nicp_cloud *d, const float T[16]) { return 1; }
-int nicp_cloud_download_gaussians(nicp_context *c, const nicp_cloud *d, float *g, int *f) { return 1; }
+int nicp_cloud_download_gaussians(nicp_context *c, const nicp_cloud *d, float *g, int *f) {
+  if (!d->has_gauss) return 1; if (g) memcpy(g, d->gauss, 96 * (size_t)d->n); if (f) memcpy(f, d->gflags, 4 * (size_t)d->n); return 0; }
 int nicp_cloud_upload_gaussians(nicp_context *c, nicp_cloud *d, const float *g, const int *f) { return 1; }
 int nicp_unproject(nicp_context *c, const float *d, int r, int co, const float *m, float a, float b, nicp_cloud *cl, int *i) { return 1; }
 int nicp_project_intervals(nicp_context *c, const float *d, const nicp_projector *p, float w, int *i) { return 1; }

@@ -915,8 +915,10 @@ def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
     out = json.loads(o.stdout)
     cpu, dev = out["reference_cpu"], out["b200"]
     assert dev["T"] == cpu["T"]
-    for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error"):
+    for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error", "gaussians",
+              "gaussian_sum"):
         assert dev[k] == cpu[k], k
+    assert cpu["gaussians"] == cpu["reference_points"] and cpu["gaussian_sum"] > 0
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(REF_MAP_CLI)), reason="reference CLI drivers not built")

@@ -139,6 +139,9 @@ def test_drop_in_demo_reference_classes_with_the_b200_backend(tmp_path):
         assert abs(gpu["num_correspondences"] - cpu["num_correspondences"]) <= 1e-3 * cpu["num_correspondences"] + 1
         assert abs(gpu["inliers"] - cpu["inliers"]) <= 1e-3 * cpu["inliers"] + 1
         assert abs(gpu["reference_pixels"] - cpu["reference_pixels"]) <= 1e-2 * cpu["reference_pixels"]
+        # the Gaussian3f sensor model the converter leaves in cloud.gaussians() (what a CPU Merger reads)
+        assert gpu["gaussians"] == cpu["gaussians"] == cpu["reference_points"]
+        assert abs(gpu["gaussian_sum"] - cpu["gaussian_sum"]) <= 1e-6 * cpu["gaussian_sum"]
         print("drop-in demo %dx%d: B200 align %.3f ms (second call), |dT| %.2e" %
               (s.rows, s.cols, out["b200_second_align_ms"], float(np.abs(Tg - Tc).max())))
 
