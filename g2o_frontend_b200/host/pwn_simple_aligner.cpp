@@ -135,11 +135,29 @@ int main(int argc, char **argv) {
     K.setIdentity();
     K(0, 0) = get(cfg, "fx", 525.0f); K(1, 1) = get(cfg, "fy", 525.0f);
     K(0, 2) = get(cfg, "cx", 319.5f); K(1, 2) = get(cfg, "cy", 239.5f);
+    // pwn_simple_aligner.cpp:62-75 / pwn_aligner.cpp:74-87: tx ty tz qx qy qz qw are the INITIAL GLOBAL POSE of the
+    // trajectory (a quaternion with its w, default (0,0,0,1), turned into a rotation matrix as it is, not normalised)
+    Isometry3f initialT;
+    {
+      const float qx = get(cfg, "qx", 0), qy = get(cfg, "qy", 0), qz = get(cfg, "qz", 0), qw = get(cfg, "qw", 1.0f);
+      // Eigen's QuaternionBase::toRotationMatrix
+      const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+      const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx;
+      const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+      Matrix3f R;
+      R(0, 0) = 1.0f - (tyy + tzz); R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+      R(1, 0) = txy + twz; R(1, 1) = 1.0f - (txx + tzz); R(1, 2) = tyz - twx;
+      R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1.0f - (txx + tyy);
+      initialT.setLinear(R);
+      initialT.setTranslation(get(cfg, "tx", 0), get(cfg, "ty", 0), get(cfg, "tz", 0));
+    }
+    // The reference's drivers run with an identity sensor offset (pwn_simple_aligner.cpp:126-127); the keys
+    // sensorOffset{Tx,Ty,Tz,Qx,Qy,Qz} (an extension, v2t order) set one.
     Isometry3f sensorOffset;
     {
       Vector6f v;
-      v(0) = get(cfg, "tx", 0); v(1) = get(cfg, "ty", 0); v(2) = get(cfg, "tz", 0);
-      v(3) = get(cfg, "qx", 0); v(4) = get(cfg, "qy", 0); v(5) = get(cfg, "qz", 0);
+      v(0) = get(cfg, "sensorOffsetTx", 0); v(1) = get(cfg, "sensorOffsetTy", 0); v(2) = get(cfg, "sensorOffsetTz", 0);
+      v(3) = get(cfg, "sensorOffsetQx", 0); v(4) = get(cfg, "sensorOffsetQy", 0); v(5) = get(cfg, "sensorOffsetQz", 0);
       sensorOffset = v2t(v);
     }
     PinholePointProjector projector;
@@ -253,7 +271,7 @@ int main(int argc, char **argv) {
       merger.setNormalThreshold(get(cfg, "mergerNormalThreshold", cosf(10 * M_PI / 180.0f)));
       merger.setMaxPointDepth(get(cfg, "mergerMaxPointDepth", 10.0f));
       Cloud referenceScene, subscene;
-      Isometry3f globalT, sceneT;
+      Isometry3f globalT = initialT, sceneT = initialT;  // pwn_aligner.cpp:137-140
       bool firstDepth = true;
       // pwn_aligner.cpp:72-73,194-205: after the first alignment and then every chunkStep frames the local map is closed
       // (the reference saves it as scene-%03d.pwn) and a new one is started from the current frame.  chunkStep 0 (where
@@ -361,7 +379,7 @@ int main(int argc, char **argv) {
       return 0;
     }
     Cloud *previous = 0;
-    Isometry3f globalT;
+    Isometry3f globalT = initialT;  // pwn_simple_aligner.cpp:128
     for (int a = 3; a < argc; a++) {
       RawDepthImage raw;
       if (!readPgm16(argv[a], raw)) throw std::runtime_error(std::string("cannot read ") + argv[a]);

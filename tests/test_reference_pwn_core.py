@@ -639,7 +639,7 @@ def test_real_kinect_frame_is_bit_identical(R):
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pwn_simple_aligner_ref")
 
 
-def run_reference_cli(tmp_path, raws, conf, image_scale, threads=1):
+def run_reference_cli(tmp_path, raws, conf, image_scale, threads=1, initial=None):
     """pwn_core/pwn_simple_aligner.cpp, compiled unmodified: config file, list of depth images, odometry file out.
     Returns the global poses (4x4) it wrote, one per frame."""
     import subprocess
@@ -655,7 +655,7 @@ def run_reference_cli(tmp_path, raws, conf, image_scale, threads=1):
             write_pgm16(p, r)
             f.write("%d.5 %s\n" % (100 + i, p))
     cfg = str(tmp_path / "ref_aligner.conf")
-    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0])
+    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=initial)
     odo = str(tmp_path / "ref_odometry.txt")
     subprocess.run([REF_CLI, cfg, lst, odo], check=True, capture_output=True, timeout=900,
                    env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
@@ -769,7 +769,7 @@ def oracle_scene_odometry(raws, conf, scale, chunk_step=10):
     return poses, sizes
 
 
-def run_reference_map_cli(tmp_path, raws, conf, image_scale, chunk_step=None):
+def run_reference_map_cli(tmp_path, raws, conf, image_scale, chunk_step=None, initial=None):
     """pwn_core/pwn_aligner.cpp compiled unmodified: global poses it wrote, one per frame"""
     import subprocess
     import sys
@@ -784,7 +784,10 @@ def run_reference_map_cli(tmp_path, raws, conf, image_scale, chunk_step=None):
             write_pgm16(p, r)
             f.write("%d.5 %s\n" % (100 + i, p))
     cfg = str(tmp_path / "map_aligner.conf")
-    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=None if chunk_step is None else {"chunkStep": chunk_step})
+    extra = dict(initial or {})
+    if chunk_step is not None:
+        extra["chunkStep"] = chunk_step
+    write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=extra)
     odo = str(tmp_path / "map_odometry.txt")
     subprocess.run([REF_MAP_CLI, cfg, lst, odo], check=True, capture_output=True, timeout=900, cwd=str(tmp_path),
                    env=dict(os.environ, OMP_NUM_THREADS="1"))

@@ -160,19 +160,28 @@ def test_cli_driver_against_the_reference_cli_driver(tmp_path):
         pytest.skip("oracle/_ref/pwn_simple_aligner_ref not built")
     poses = [synth.POSE_A, synth.POSE_B, synth.POSE_B @ synth.make_pose((-0.02, 0.01, 0.03), (1.0, 0.3, 0.2), 1.5)]
     raws = [synth.render_depth_u16(p, seed=3 + i) for i, p in enumerate(poses)]
-    for image_scale, conf in ((4, CONF_1_4), (1, CONF_1_1)):
-        ref = run_reference_cli(tmp_path, raws, conf, image_scale)
+    # the second case starts the trajectory at a non-identity initial pose (tx .. qw of the configuration file)
+    start = dict(tx=0.4, ty=-0.1, tz=0.25, qx=0.05, qy=-0.1, qz=0.02, qw=0.9935290634701167)
+    for image_scale, conf, initial in ((4, CONF_1_4, None), (4, CONF_1_4, start), (1, CONF_1_1, None)):
+        ref = run_reference_cli(tmp_path, raws, conf, image_scale, initial=initial)
         files = []
         for i, r in enumerate(raws):
             p = str(tmp_path / ("depth%d.pgm" % i))
             write_pgm16(p, r)
             files.append(p)
         cfg = str(tmp_path / "aligner.conf")
-        write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0])
+        write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=initial)
         out = str(tmp_path / "out.jsonl")
         subprocess.check_call([BIN, cfg, out] + files)
         lines = [json.loads(l) for l in open(out)]
-        G = np.eye(4)
+        G = ref[0].copy()  # both start from the configured initial pose (identity when none is given)
+        if initial is None:
+            assert np.abs(G - np.eye(4)).max() < 1e-6
+        else:
+            assert np.abs(G[:3, 3] - (0.4, -0.1, 0.25)).max() < 1e-6
+            from oracle import pwn_oracle as O
+            g = np.array(lines[2]["global"], np.float64)  # the driver's own global pose (t, qx, qy, qz) after the last frame
+            assert np.abs(O.v2t(g.astype(np.float32)) - ref[2]).max() <= 5e-4
         for i in (1, 2):
             G = G @ np.array(lines[i]["T"], np.float64).reshape(4, 4).T
             assert rot_angle(G[:3, :3], ref[i][:3, :3]) <= 3e-4, (image_scale, i)
@@ -192,20 +201,23 @@ def test_scene_odometry_driver_against_the_reference_driver(tmp_path):
     if not os.path.exists(REF_MAP_CLI):
         pytest.skip("oracle/_ref/pwn_aligner_ref not built")
     gt, raws = map_sequence(6)
-    ref = run_reference_map_cli(tmp_path, raws, CONF_1_4, 4, None)
     files = []
     for i, r in enumerate(raws):
         p = str(tmp_path / ("m%d.pgm" % i))
         write_pgm16(p, r)
         files.append(p)
-    cfg = str(tmp_path / "map.conf")
-    write_conf(cfg, CONF_1_4, 4, [0, 0, 0, 0, 0, 0], extra={"localmap": 1})
-    out = str(tmp_path / "map.jsonl")
-    subprocess.check_call([BIN, cfg, out] + files)
-    lines = [json.loads(l) for l in open(out)]
-    assert [l["new_map"] for l in lines[:6]] == [0, 1, 0, 0, 0, 0]
-    for i in range(6):
-        G = np.array(lines[i]["globalT"], np.float64).reshape(4, 4).T
-        # free-running through Merger::merge: a pose difference of 1e-6 moves points across pixel borders of the rendered
-        # map, so the trajectories drift apart by a few 1e-4 over the six frames
-        assert np.abs(G - ref[i]).max() <= 3e-3, (i, G, ref[i])
+    # identity start, and a trajectory (and first local map) that starts at a configured initial pose
+    start = dict(tx=0.4, ty=-0.1, tz=0.25, qx=0.05, qy=-0.1, qz=0.02, qw=0.9935290634701167)
+    for initial in (None, start):
+        ref = run_reference_map_cli(tmp_path, raws, CONF_1_4, 4, None, initial=initial)
+        cfg = str(tmp_path / "map.conf")
+        write_conf(cfg, CONF_1_4, 4, [0, 0, 0, 0, 0, 0], extra=dict(initial or {}, localmap=1))
+        out = str(tmp_path / "map.jsonl")
+        subprocess.check_call([BIN, cfg, out] + files)
+        lines = [json.loads(l) for l in open(out)]
+        assert [l["new_map"] for l in lines[:6]] == [0, 1, 0, 0, 0, 0]
+        for i in range(6):
+            G = np.array(lines[i]["globalT"], np.float64).reshape(4, 4).T
+            # free-running through Merger::merge: a pose difference of 1e-6 moves points across pixel borders of the
+            # rendered map, so the trajectories drift apart by a few 1e-4 over the six frames
+            assert np.abs(G - ref[i]).max() <= 3e-3, (initial is not None, i, G, ref[i])
