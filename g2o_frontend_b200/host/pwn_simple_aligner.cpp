@@ -122,10 +122,15 @@ int main(int argc, char **argv) {
       return 1;
     }
   }
-  if (argc < 5) {
-    fprintf(stderr, "usage: %s config.conf out.jsonl depth0.pgm depth1.pgm ...\n", argv[0]);
+  if (argc < 4) {
+    fprintf(stderr, "usage: %s config.conf out.jsonl depth0.pgm depth1.pgm ...\n"
+                    "       %s configurationFilename.txt depthImageListFilename.txt visualOdometryFilename.txt   (the reference's own)\n",
+            argv[0], argv[0]);
     return 2;
   }
+  // Exactly three arguments = the command line of the reference's pwn_simple_aligner (pwn_simple_aligner.cpp:33-40): a list of
+  // "timestamp depthFilename" lines in, "timestamp x y z qx qy qz qw" lines out, and <depthFilename>.pwn next to every frame.
+  const bool referenceCli = argc == 4;
   try {
     std::map<std::string, float> cfg = readConfig(argv[1]);
     // setInputParameters, pwn_simple_aligner.cpp:214-269
@@ -210,6 +215,75 @@ int main(int argc, char **argv) {
       sensorOffset = aligner.referenceSensorOffset();
       if (bp.hasMatcher) imageScale = bp.matcherScale;
       if (bp.hasTracker) cfg["newFrameInliersFraction"] = bp.newFrameCloudInliersFraction;
+    }
+    if (referenceCli) {
+      // pwn_simple_aligner.cpp:117-187
+      std::ifstream is(argv[2]);
+      if (!is) throw std::runtime_error(std::string("Impossible to open depth image list file: ") + argv[2]);
+      std::ofstream os(argv[3]);
+      if (!os) throw std::runtime_error(std::string("Impossible to open visual odometry file: ") + argv[3]);
+      converter.setKeepStats(true);  // the .pwn records carry the Stats
+      Cloud *cloud = 0, *previousCloud = 0;
+      bool firstDepth = true;
+      Isometry3f globalT = initialT;
+      while (is.good()) {
+        char buf[1024];
+        is.getline(buf, 1024);
+        std::istringstream iss(buf);
+        std::string timestamp, depthFilename;
+        if (!(iss >> timestamp >> depthFilename)) continue;
+        if (timestamp[0] == '#') continue;
+        RawDepthImage raw;
+        if (!readPgm16(depthFilename.c_str(), raw)) throw std::runtime_error("cannot read " + depthFilename);
+        DepthImage scaledDepth;
+        DepthImage_convertAndScale(scaledDepth, raw, imageScale, depthScale);
+        if (firstDepth) {
+          projector.setCameraMatrix(K);
+          projector.setImageSize(raw.rows, raw.cols);
+          projector.scale(1.0f / imageScale);
+          correspondenceFinder.setImageSize(scaledDepth.rows, scaledDepth.cols);
+        }
+        cloud = new Cloud();
+        converter.compute(*cloud, scaledDepth, sensorOffset);
+        if (!firstDepth) {
+          aligner.setReferenceCloud(previousCloud);
+          aligner.setCurrentCloud(cloud);
+          aligner.setInitialGuess(Isometry3f::Identity());
+          aligner.setSensorOffset(sensorOffset);
+          aligner.align();
+          globalT = globalT * aligner.T();
+          globalT.fixLastRow();
+          delete previousCloud;
+        }
+        cloud->save((depthFilename + ".pwn").c_str(), globalT, 1, true);
+        // Quaternionf(globalT.linear()), normalize(): Eigen's matrix -> quaternion
+        const Matrix3f R = globalT.linear();
+        float q[4];  // x y z w
+        float t = (R(0, 0) + R(1, 1)) + R(2, 2);
+        if (t > 0.0f) {
+          t = sqrtf(t + 1.0f);
+          q[3] = 0.5f * t;
+          t = 0.5f / t;
+          q[0] = (R(2, 1) - R(1, 2)) * t; q[1] = (R(0, 2) - R(2, 0)) * t; q[2] = (R(1, 0) - R(0, 1)) * t;
+        } else {
+          int i = 0;
+          if (R(1, 1) > R(0, 0)) i = 1;
+          if (R(2, 2) > R(i, i)) i = 2;
+          const int j = (i + 1) % 3, k = (j + 1) % 3;
+          t = sqrtf(R(i, i) - R(j, j) - R(k, k) + 1.0f);
+          q[i] = 0.5f * t;
+          t = 0.5f / t;
+          q[3] = (R(k, j) - R(j, k)) * t; q[j] = (R(j, i) + R(i, j)) * t; q[k] = (R(k, i) + R(i, k)) * t;
+        }
+        const float qn = sqrtf(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+        for (int i = 0; i < 4; i++) q[i] = q[i] / qn;
+        os << timestamp << " " << globalT.translation().x() << " " << globalT.translation().y() << " "
+           << globalT.translation().z() << " " << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << std::endl;
+        previousCloud = cloud;
+        firstDepth = false;
+      }
+      delete previousCloud;
+      return 0;
     }
     FILE *out = fopen(argv[2], "w");
     if (!out) throw std::runtime_error("cannot open output file");

@@ -958,3 +958,68 @@ def test_host_classes_with_a_mock_backend(tmp_path, monkeypatch):
         d = tmp_path / ("case%d" % i)
         d.mkdir()
         fn(d, *args)
+
+
+def run_both_drivers_with_the_reference_command_line(tmp_path, image_scale=4, initial=None):
+    """`driver config list odometry` -- the reference's own three-argument command line -- once with the reference's
+    pwn_simple_aligner (oracle/_ref) and once with this repository's driver.  Returns the two odometry texts and, per frame,
+    the two .pwn files they left next to the depth images."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import CONF_1_1, CONF_1_4
+    from g2o_frontend_b200 import synth
+    from test_host_cpp import BIN, write_conf, write_pgm16
+    conf = CONF_1_1 if image_scale == 1 else CONF_1_4
+    poses = [synth.POSE_A, synth.POSE_B, synth.POSE_B @ synth.make_pose((-0.02, 0.01, 0.03), (1.0, 0.3, 0.2), 1.5)]
+    raws = [synth.render_depth_u16(p, seed=3 + i) for i, p in enumerate(poses)]
+    out = {}
+    for who, exe in (("reference", REF_CLI), ("ours", BIN)):
+        d = tmp_path / who
+        d.mkdir()
+        lst = str(d / "frames.txt")
+        with open(lst, "w") as f:
+            f.write("# timestamp depthFilename\n")
+            for i, r in enumerate(raws):
+                p = str(d / ("depth%d.pgm" % i))
+                write_pgm16(p, r)
+                f.write("%d.25 %s\n" % (1000 + i, p))
+        cfg = str(d / "aligner.conf")
+        write_conf(cfg, conf, image_scale, [0, 0, 0, 0, 0, 0], extra=initial)
+        odo = str(d / "odometry.txt")
+        if not os.access(exe, os.X_OK):
+            os.chmod(exe, 0o755)
+        subprocess.run([exe, cfg, lst, odo], check=True, capture_output=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        out[who] = (open(odo).read(), [str(d / ("depth%d.pgm.pwn" % i)) for i in range(len(raws))])
+    return out
+
+
+def pwn_payload(path):
+    """points, normals, Stats matrix, n, eigenvalues of a binary .pwn file (the vptr / padding bytes of the raw object dump
+    are skipped: cloud.cpp:116-124, 32 + 32 + 112 bytes per point)"""
+    data = open(path, "rb").read()
+    head_end = data.index(b"\n", data.index(b"\n") + 1) + 1
+    n = int(data.split()[1])
+    rec = np.frombuffer(data, np.uint8, n * 176, head_end).reshape(n, 176)
+    f = lambda a, b: np.ascontiguousarray(rec[:, a:b]).view(np.float32)
+    return f(16, 32), f(48, 64), f(80, 144), np.ascontiguousarray(rec[:, 144:148]).view(np.int32)[:, 0], f(148, 160)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/pwn_simple_aligner_ref not built")
+def test_same_command_line_same_files_as_the_reference_driver(tmp_path, monkeypatch):
+    """Drop-in at the command line: `pwn_simple_aligner config list odometry` with the reference's binary and with this
+    repository's driver (behind the test double of the C-ABI, so that every number is the oracle's): the odometry files
+    are identical BYTE FOR BYTE and the .pwn clouds left next to the frames carry identical payloads."""
+    mock = build_mock_backend(tmp_path)
+    monkeypatch.setenv("LD_LIBRARY_PATH", str(mock))
+    start = dict(tx=0.4, ty=-0.1, tz=0.25, qx=0.05, qy=-0.1, qz=0.02, qw=0.9935290634701167)
+    for k, initial in enumerate((None, start)):
+        d = tmp_path / ("run%d" % k)
+        d.mkdir()
+        out = run_both_drivers_with_the_reference_command_line(d, 4, initial)
+        assert out["ours"][0] == out["reference"][0] and len(out["ours"][0].splitlines()) == 3
+        for a, b in zip(out["ours"][1], out["reference"][1]):
+            pa, pb = pwn_payload(a), pwn_payload(b)
+            assert open(a, "rb").read().split(b"\n")[:2] == open(b, "rb").read().split(b"\n")[:2]  # header + pose line
+            for x, y in zip(pa, pb):
+                assert np.array_equal(x, y, equal_nan=True)

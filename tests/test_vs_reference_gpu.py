@@ -221,3 +221,26 @@ def test_scene_odometry_driver_against_the_reference_driver(tmp_path):
             # free-running through Merger::merge: a pose difference of 1e-6 moves points across pixel borders of the
             # rendered map, so the trajectories drift apart by a few 1e-4 over the six frames
             assert np.abs(G - ref[i]).max() <= 3e-3, (initial is not None, i, G, ref[i])
+
+
+def test_same_command_line_as_the_reference_driver(tmp_path):
+    """Drop-in at the command line: `pwn_simple_aligner config list odometry`, the reference's own three arguments, with
+    the reference's binary (oracle/_ref/pwn_simple_aligner_ref) and with this repository's driver on the GPU: same odometry
+    file (numbers within the alignment tolerance; byte-identical through the test double on the CPU), same clouds in the
+    .pwn files left next to the frames (points and Stats::n bit-identical)."""
+    from test_reference_pwn_core import REF_CLI, pwn_payload, run_both_drivers_with_the_reference_command_line
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/pwn_simple_aligner_ref not built")
+    out = run_both_drivers_with_the_reference_command_line(tmp_path, 4, None)
+    ours, ref = out["ours"][0].splitlines(), out["reference"][0].splitlines()
+    assert len(ours) == len(ref) == 3
+    for a, b in zip(ours, ref):
+        fa, fb = a.split(), b.split()
+        assert fa[0] == fb[0]  # timestamp
+        va, vb = np.array(fa[1:], np.float64), np.array(fb[1:], np.float64)
+        assert np.abs(va - vb).max() <= 3e-4, (a, b)
+    for a, b in zip(out["ours"][1], out["reference"][1]):
+        pa, pb = pwn_payload(a), pwn_payload(b)
+        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[3], pb[3])
+        has_a, has_b = np.abs(pa[1][:, :3]).sum(1) > 0, np.abs(pb[1][:, :3]).sum(1) > 0
+        assert (has_a != has_b).mean() < 1e-4
