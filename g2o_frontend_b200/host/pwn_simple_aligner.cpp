@@ -223,6 +223,98 @@ int main(int argc, char **argv) {
       std::ofstream os(argv[3]);
       if (!os) throw std::runtime_error(std::string("Impossible to open visual odometry file: ") + argv[3]);
       converter.setKeepStats(true);  // the .pwn records carry the Stats
+      // "timestamp x y z qx qy qz qw" with Quaternionf(globalT.linear()), normalize(): Eigen's matrix -> quaternion
+      // (SURVEY.md Appendix A1), default ostream formatting like the reference
+      auto writeOdometryLine = [&os](const std::string &timestamp, const Isometry3f &G) {
+        const Matrix3f R = G.linear();
+        float q[4];  // x y z w
+        float t = (R(0, 0) + R(1, 1)) + R(2, 2);
+        if (t > 0.0f) {
+          t = sqrtf(t + 1.0f);
+          q[3] = 0.5f * t;
+          t = 0.5f / t;
+          q[0] = (R(2, 1) - R(1, 2)) * t; q[1] = (R(0, 2) - R(2, 0)) * t; q[2] = (R(1, 0) - R(0, 1)) * t;
+        } else {
+          int i = 0;
+          if (R(1, 1) > R(0, 0)) i = 1;
+          if (R(2, 2) > R(i, i)) i = 2;
+          const int j = (i + 1) % 3, k = (j + 1) % 3;
+          t = sqrtf(R(i, i) - R(j, j) - R(k, k) + 1.0f);
+          q[i] = 0.5f * t;
+          t = 0.5f / t;
+          q[3] = (R(k, j) - R(j, k)) * t; q[j] = (R(j, i) + R(i, j)) * t; q[k] = (R(k, i) + R(i, k)) * t;
+        }
+        const float qn = sqrtf(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+        for (int i = 0; i < 4; i++) q[i] = q[i] / qn;
+        os << timestamp << " " << G.translation().x() << " " << G.translation().y() << " " << G.translation().z() << " "
+           << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << std::endl;
+      };
+      if (get(cfg, "localmap", 0) != 0) {
+        // the reference's OTHER driver with the same command line, pwn_core/pwn_aligner.cpp:129-236: scene-based odometry
+        // with the local map (the scene-NNN.pwn snapshots of :196-198,233-235 are not written: the device map does not
+        // carry the per-point Stats those records hold)
+        converter.setKeepGaussians(true);
+        Merger merger;
+        merger.setDepthImageConverter(&converter);
+        merger.setDistanceThreshold(get(cfg, "mergerDistanceThreshold", 0.1f));
+        merger.setNormalThreshold(get(cfg, "mergerNormalThreshold", cosf(10 * M_PI / 180.0f)));
+        merger.setMaxPointDepth(get(cfg, "mergerMaxPointDepth", 10.0f));
+        Cloud referenceScene, subscene;
+        Isometry3f globalT = initialT, sceneT = initialT;
+        const int chunkStep = (int)get(cfg, "chunkStep", 10);
+        int counter = 0;
+        bool firstDepth = true;
+        while (is.good()) {
+          char buf[1024];
+          is.getline(buf, 1024);
+          std::istringstream iss(buf);
+          std::string timestamp, depthFilename;
+          if (!(iss >> timestamp >> depthFilename)) continue;
+          if (timestamp[0] == '#') continue;
+          RawDepthImage raw;
+          if (!readPgm16(depthFilename.c_str(), raw)) throw std::runtime_error("cannot read " + depthFilename);
+          DepthImage scaledDepth;
+          DepthImage_convertAndScale(scaledDepth, raw, imageScale, depthScale);
+          if (firstDepth) {
+            projector.setCameraMatrix(K);
+            projector.setImageSize(raw.rows, raw.cols);
+            projector.scale(1.0f / imageScale);
+            correspondenceFinder.setImageSize(scaledDepth.rows, scaledDepth.cols);
+            merger.setImageSize(scaledDepth.rows, scaledDepth.cols);
+          }
+          Cloud cloud;
+          converter.compute(cloud, scaledDepth, sensorOffset);
+          if (!firstDepth) {
+            IntImage scaledIndexImage;
+            projector.setTransform(sceneT * sensorOffset);
+            projector.project(scaledIndexImage, scaledDepth, referenceScene);
+            converter.setKeepGaussians(false);
+            converter.compute(subscene, scaledDepth, sensorOffset);
+            converter.setKeepGaussians(true);
+            projector.setTransform(Isometry3f::Identity());
+            aligner.setReferenceCloud(&subscene);
+            aligner.setCurrentCloud(&cloud);
+            aligner.setInitialGuess(Isometry3f::Identity());
+            aligner.setSensorOffset(sensorOffset);
+            aligner.align();
+            globalT = globalT * aligner.T();
+            globalT.fixLastRow();
+            sceneT = sceneT * aligner.T();
+            sceneT.fixLastRow();
+          }
+          if (!firstDepth && chunkStep > 0 && counter++ % chunkStep == 0) {
+            sceneT = Isometry3f::Identity();
+            referenceScene.clear();
+          }
+          referenceScene.add(cloud, sceneT);
+          merger.merge(&referenceScene, sceneT * sensorOffset);
+          projector.setTransform(Isometry3f::Identity());
+          cloud.save((depthFilename + ".pwn").c_str(), globalT, 1, true);
+          writeOdometryLine(timestamp, globalT);
+          firstDepth = false;
+        }
+        return 0;
+      }
       Cloud *cloud = 0, *previousCloud = 0;
       bool firstDepth = true;
       Isometry3f globalT = initialT;
@@ -256,29 +348,7 @@ int main(int argc, char **argv) {
           delete previousCloud;
         }
         cloud->save((depthFilename + ".pwn").c_str(), globalT, 1, true);
-        // Quaternionf(globalT.linear()), normalize(): Eigen's matrix -> quaternion
-        const Matrix3f R = globalT.linear();
-        float q[4];  // x y z w
-        float t = (R(0, 0) + R(1, 1)) + R(2, 2);
-        if (t > 0.0f) {
-          t = sqrtf(t + 1.0f);
-          q[3] = 0.5f * t;
-          t = 0.5f / t;
-          q[0] = (R(2, 1) - R(1, 2)) * t; q[1] = (R(0, 2) - R(2, 0)) * t; q[2] = (R(1, 0) - R(0, 1)) * t;
-        } else {
-          int i = 0;
-          if (R(1, 1) > R(0, 0)) i = 1;
-          if (R(2, 2) > R(i, i)) i = 2;
-          const int j = (i + 1) % 3, k = (j + 1) % 3;
-          t = sqrtf(R(i, i) - R(j, j) - R(k, k) + 1.0f);
-          q[i] = 0.5f * t;
-          t = 0.5f / t;
-          q[3] = (R(k, j) - R(j, k)) * t; q[j] = (R(j, i) + R(i, j)) * t; q[k] = (R(k, i) + R(i, k)) * t;
-        }
-        const float qn = sqrtf(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
-        for (int i = 0; i < 4; i++) q[i] = q[i] / qn;
-        os << timestamp << " " << globalT.translation().x() << " " << globalT.translation().y() << " "
-           << globalT.translation().z() << " " << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << std::endl;
+        writeOdometryLine(timestamp, globalT);
         previousCloud = cloud;
         firstDepth = false;
       }

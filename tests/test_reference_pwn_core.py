@@ -1023,3 +1023,43 @@ def test_same_command_line_same_files_as_the_reference_driver(tmp_path, monkeypa
             assert open(a, "rb").read().split(b"\n")[:2] == open(b, "rb").read().split(b"\n")[:2]  # header + pose line
             for x, y in zip(pa, pb):
                 assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MAP_CLI), reason="oracle/_ref/pwn_aligner_ref not built")
+def test_same_command_line_same_odometry_as_the_reference_scene_driver(tmp_path, monkeypatch):
+    """`pwn_aligner config list odometry` (the reference's scene-based odometry driver: local map, Merger, chunkStep) and
+    this repository's driver with the same three arguments and `localmap 1` in the configuration, behind the test double
+    of the C-ABI: byte-identical odometry files, identical per-frame .pwn payloads."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import CONF_1_4
+    from test_host_cpp import BIN, write_conf, write_pgm16
+    mock = build_mock_backend(tmp_path)
+    monkeypatch.setenv("LD_LIBRARY_PATH", str(mock))
+    gt, raws = map_sequence(6)
+    start = dict(tx=0.4, ty=-0.1, tz=0.25, qx=0.05, qy=-0.1, qz=0.02, qw=0.9935290634701167)
+    for k, extra in enumerate((dict(), dict(start, chunkStep=2))):
+        texts, clouds = {}, {}
+        for who, exe in (("reference", REF_MAP_CLI), ("ours", BIN)):
+            d = tmp_path / ("%s%d" % (who, k))
+            d.mkdir()
+            lst = str(d / "frames.txt")
+            with open(lst, "w") as f:
+                for i, r in enumerate(raws):
+                    p = str(d / ("depth%d.pgm" % i))
+                    write_pgm16(p, r)
+                    f.write("%d.5 %s\n" % (100 + i, p))
+            cfg = str(d / "aligner.conf")
+            write_conf(cfg, CONF_1_4, 4, [0, 0, 0, 0, 0, 0], extra=dict(extra, localmap=1))
+            odo = str(d / "odometry.txt")
+            if not os.access(exe, os.X_OK):
+                os.chmod(exe, 0o755)
+            subprocess.run([exe, cfg, lst, odo], check=True, capture_output=True, timeout=900, cwd=str(d),
+                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+            texts[who] = open(odo).read()
+            clouds[who] = [str(d / ("depth%d.pgm.pwn" % i)) for i in range(len(raws))]
+        assert texts["ours"] == texts["reference"] and len(texts["ours"].splitlines()) == 6, k
+        for a, b in zip(clouds["ours"], clouds["reference"]):
+            for x, y in zip(pwn_payload(a), pwn_payload(b)):
+                assert np.array_equal(x, y, equal_nan=True)
