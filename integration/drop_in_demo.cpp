@@ -5,7 +5,7 @@
 // code, compiled from /root/reference), once with B200DepthImageConverter + B200Aligner (integration/pwn_b200/b200_pwn.h
 // -> C-ABI -> CUDA) plugged into the SAME pointers -- and prints both results as one JSON object.
 //
-//   drop_in_demo depthA.f32 depthB.f32 rows cols fx fy cx cy [minImageRadius maxImageRadius minPoints inlierDistance [cpu|gpu|both]]
+//   drop_in_demo depthA.f32 depthB.f32 rows cols fx fy cx cy [minImageRadius maxImageRadius minPoints inlierDistance [cpu|gpu|both [priors]]]
 //
 // depth files: rows*cols float32, metres.  Built by oracle/build_ref_pwn_core.sh into oracle/_ref/drop_in_demo (it contains
 // reference code, so it lives with the other compiled reference artefacts); run by tests/test_vs_reference_gpu.py.
@@ -45,6 +45,23 @@ static bool readDepth(const char *path, int rows, int cols, DepthImage &d) {
   return true;
 }
 
+// odometry / IMU style priors as pwn_tracker2 adds them (pwn_tracker.cpp:150-160): one relative, one absolute
+static void addPriors(Aligner *aligner) {
+  Vector6f v;
+  v << 0.03f, -0.02f, 0.05f, 0.002f, 0.017f, 0.001f;
+  Eigen::Isometry3f mean = v2t(v);
+  Matrix6f info = Matrix6f::Identity() * 2000.0f;
+  info(0, 1) = info(1, 0) = 150.0f;  // not diagonal, not symmetric-by-accident: a transposed copy would show
+  info(3, 5) = info(5, 3) = -300.0f;
+  aligner->addRelativePrior(mean, info);
+  Vector6f w;
+  w << 0.5f, 0.1f, -0.2f, 0.0f, 0.0871557f, 0.0f;
+  Eigen::Isometry3f reference = v2t(w);
+  aligner->addAbsolutePrior(reference, reference * mean, info * 0.5f);
+}
+
+static bool g_withPriors = false;
+
 // everything below only sees the base-class pointers, like a tracker does
 static Result run(DepthImageConverter *converter, Aligner *aligner, PinholePointProjector *projector, const DepthImage &dA,
                   const DepthImage &dB) {
@@ -57,6 +74,7 @@ static Result run(DepthImageConverter *converter, Aligner *aligner, PinholePoint
   aligner->setCurrentCloud(&current);
   aligner->setInitialGuess(Eigen::Isometry3f::Identity());
   aligner->setSensorOffset(Eigen::Isometry3f::Identity());
+  if (g_withPriors) addPriors(aligner);  // after setReferenceCloud / setCurrentCloud, which clear them (aligner.h:60-80)
   aligner->align();
   Result r;
   r.T = aligner->T();
@@ -104,7 +122,9 @@ int main(int argc, char **argv) {
   const int minR = argc > 9 ? std::atoi(argv[9]) : 10, maxR = argc > 10 ? std::atoi(argv[10]) : 30, minPts = argc > 11 ? std::atoi(argv[11]) : 50;
   const float inlierDistance = argc > 12 ? (float)std::atof(argv[12]) : 1.0f;
   const std::string which = argc > 13 ? argv[13] : "both";
+  const bool withPriors = argc > 14 && std::string(argv[14]) == "priors";
   omp_set_num_threads(1);  // the reference drops rows % threads rows and correspondences % threads terms; 1 = none
+  g_withPriors = withPriors;
 
   // the reference's objects, configured as pwn_simple_aligner.cpp does from pwn_aligner_1_1.conf
   PinholePointProjector projector;

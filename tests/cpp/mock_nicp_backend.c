@@ -50,6 +50,9 @@ int nicp_align(nicp_context *ctx, const nicp_cloud *r, const nicp_cloud *c, cons
   memcpy(q.refSensorOffset, ro, 64); memcpy(q.curSensorOffset, co, 64); memcpy(q.initialGuess, g, 64);
   q.corr.inlierDistanceThreshold = a->inlier_distance_threshold; q.corr.inlierNormalAngularThreshold = a->inlier_normal_angular_threshold; q.corr.flatCurvatureThreshold = a->flat_curvature_threshold; q.corr.inlierCurvatureRatioThreshold = a->inlier_curvature_ratio_threshold;
   q.inlierMaxChi2 = a->inlier_max_chi2; q.robustKernel = a->robust_kernel; q.numThreads = 1;
+  orc_prior priors[8]; if (np > 8) return 1;
+  for (int j = 0; j < np; j++) { priors[j].kind = pr[j].kind; memcpy(priors[j].mean, pr[j].mean, 64); orc_iso_inverse(pr[j].reference, priors[j].refInv); memcpy(priors[j].info, pr[j].information, 144); }
+  q.numPriors = np; q.priors = np ? priors : 0;
   int P = p->rows * p->cols; ctx->P = P; free(ctx->refIndex); free(ctx->curIndex); free(ctx->corr); free(ctx->refDepth); free(ctx->curDepth);
   ctx->refIndex = malloc(4*P); ctx->curIndex = malloc(4*P); ctx->corr = malloc(8*P); ctx->refDepth = malloc(4*P); ctx->curDepth = malloc(4*P);
   orc_align_result o; orc_align(r->n, r->points, r->normals, r->curv, c->n, c->points, c->normals, c->curv, c->oP, c->oN, &q, &o, ctx->refIndex, ctx->refDepth, ctx->curIndex, ctx->curDepth, ctx->corr, 0);

@@ -539,7 +539,7 @@ def test_randomised_differential(R, seed):
 DEMO = os.path.join(ROOT, "oracle", "_ref", "drop_in_demo")
 
 
-def run_drop_in_demo(S, which, tmp_path):
+def run_drop_in_demo(S, which, tmp_path, priors=False):
     """oracle/_ref/drop_in_demo: one program on the reference's own classes, reference CPU arm and / or B200 arm"""
     import json
     import subprocess
@@ -550,7 +550,8 @@ def run_drop_in_demo(S, which, tmp_path):
     np.ascontiguousarray(S.depthB, np.float32).tofile(b)
     c = S.conf
     args = [DEMO, a, b, str(S.rows), str(S.cols)] + [repr(float(S.K[i, j])) for i, j in ((0, 0), (1, 1), (0, 2), (1, 2))] + \
-           [str(c["minImageRadius"]), str(c["maxImageRadius"]), str(c["minPoints"]), repr(float(c["inlierDistanceThreshold"])), which]
+           [str(c["minImageRadius"]), str(c["maxImageRadius"]), str(c["minPoints"]), repr(float(c["inlierDistanceThreshold"])), which] + \
+           (["priors"] if priors else [])
     o = subprocess.run(args, capture_output=True, text=True, timeout=600)
     return o.returncode, json.loads(o.stdout), o.stderr
 
@@ -913,15 +914,20 @@ def test_drop_in_binding_logic_with_a_mock_backend(tmp_path):
     c = S.conf
     args = [DEMO, a, b, str(S.rows), str(S.cols)] + [repr(float(S.K[i, j])) for i, j in ((0, 0), (1, 1), (0, 2), (1, 2))] + \
            [str(c["minImageRadius"]), str(c["maxImageRadius"]), str(c["minPoints"]), repr(float(c["inlierDistanceThreshold"])), "both"]
-    o = subprocess.run(args, capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_LIBRARY_PATH=str(mock)))
-    assert o.returncode == 0, o.stdout + o.stderr
-    out = json.loads(o.stdout)
-    cpu, dev = out["reference_cpu"], out["b200"]
-    assert dev["T"] == cpu["T"]
-    for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error", "gaussians",
-              "gaussian_sum"):
-        assert dev[k] == cpu[k], k
-    assert cpu["gaussians"] == cpu["reference_points"] and cpu["gaussian_sum"] > 0
+    plain = None
+    for extra in ([], ["priors"]):  # without and with SE(3) priors (Aligner::addRelativePrior / addAbsolutePrior -> nicp_prior[])
+        o = subprocess.run(args + extra, capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_LIBRARY_PATH=str(mock)))
+        assert o.returncode == 0, o.stdout + o.stderr
+        out = json.loads(o.stdout)
+        cpu, dev = out["reference_cpu"], out["b200"]
+        assert dev["T"] == cpu["T"], extra
+        for k in ("reference_points", "current_points", "inliers", "num_correspondences", "reference_pixels", "error", "gaussians",
+                  "gaussian_sum"):
+            assert dev[k] == cpu[k], (k, extra)
+        assert cpu["gaussians"] == cpu["reference_points"] and cpu["gaussian_sum"] > 0
+        if not extra:
+            plain = cpu["T"]
+    assert plain != cpu["T"]  # the priors really changed the solution
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(REF_MAP_CLI)), reason="reference CLI drivers not built")

@@ -144,6 +144,12 @@ def test_drop_in_demo_reference_classes_with_the_b200_backend(tmp_path):
         assert abs(gpu["gaussian_sum"] - cpu["gaussian_sum"]) <= 1e-6 * cpu["gaussian_sum"]
         print("drop-in demo %dx%d: B200 align %.3f ms (second call), |dT| %.2e" %
               (s.rows, s.cols, out["b200_second_align_ms"], float(np.abs(Tg - Tc).max())))
+    # with SE(3) priors added through the reference's own Aligner::addRelativePrior / addAbsolutePrior
+    s = get_scene(4)
+    rc, out, err = run_drop_in_demo(s, "both", tmp_path, priors=True)
+    assert rc == 0, (out, err)
+    Tp, Tq = np.array(out["reference_cpu"]["T"]).reshape(4, 4), np.array(out["b200"]["T"]).reshape(4, 4)
+    assert rot_angle(Tq[:3, :3], Tp[:3, :3]) <= 2e-4 and np.abs(Tq[:3, 3] - Tp[:3, 3]).max() <= 2e-4
 
 
 def test_cli_driver_against_the_reference_cli_driver(tmp_path):
