@@ -149,7 +149,9 @@ def cpu_reference_run(steps, warmup, sample_pairs, n_threads=None):
     # the finder drops rows % numThreads (correspondencefinder.cpp:38): use a divisor of 480
     while ROWS % cores:
         cores -= 1
-    os.environ["OMP_NUM_THREADS"] = str(cores)
+    # through the library (omp_set_num_threads), not the environment: libgomp reads OMP_NUM_THREADS once, when it is
+    # loaded, and torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; `cores` is what the team really has
+    cores = O.set_threads(cores, fast=True)
     raws_cur, raws_cand, pairs, guesses = make_workload(1, sample_pairs, 0)
     K = synth.K_KINECT
     sp = O.default_stats_params(minImageRadius=CONF["minImageRadius"], maxImageRadius=CONF["maxImageRadius"],

@@ -995,12 +995,8 @@ int partial_rows_for(const nicp_context *ctx, size_t pixels) {
 template <int MODE, int NT, int TK, int MINB, bool INPLACE = false>
 static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac, int P,
                          int imgStats, float imgThr, int curEpoch) {
-  size_t smem = INPLACE ? sizeof(TileSmemInplace<NT, TK>) : sizeof(TileSmem<NT, TK>);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  constexpr size_t smem = INPLACE ? sizeof(TileSmemInplace<NT, TK>) : sizeof(TileSmem<NT, TK>);
+  static_assert(smem <= 48 * 1024, "below the default dynamic shared-memory limit: no per-device opt-in needed");
   static const int pairFast = getenv("NICP_PAIR_FAST") ? atoi(getenv("NICP_PAIR_FAST")) : 1;
   const bool swap = pairFast && grid.x <= 65535;
   const dim3 g = swap ? dim3(grid.y, grid.x) : grid;

@@ -543,9 +543,10 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
   compute_iKRt(proj->K, I4, iKRt);
   Affine a = affine_from(iKRt);
   size_t smem = (size_t)kIntegralCh * (cols + 1) * sizeof(float);
-  if (smem > 48 * 1024) {
+  if (smem > 48 * 1024 && smem > ctx->rowsSmemCfg) {
     NICP_CUDA(cudaFuncSetAttribute(k_integral_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NICP_CUDA(cudaFuncSetAttribute(k_integral_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->rowsSmemCfg = smem;
   }
   if (multi)
     k_integral_rows<true><<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
@@ -556,10 +557,10 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
   NICP_CHECK_LAUNCH(ctx);
   const size_t stripBytes = (size_t)rows * 32 * sizeof(float);
   if (stripBytes <= 200 * 1024) {
-    static size_t configured = 0;
-    if (stripBytes > 48 * 1024 && stripBytes > configured) {
+    // per context = per device: the attribute is a per-device property of the kernel
+    if (stripBytes > 48 * 1024 && stripBytes > ctx->colsSmemCfg) {
       NICP_CUDA(cudaFuncSetAttribute(k_integral_cols_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stripBytes));
-      configured = stripBytes;
+      ctx->colsSmemCfg = stripBytes;
     }
     dim3 gc((cols + 31) / 32, kIntegralCh);
     k_integral_cols_smem<<<gc, 256, stripBytes, ctx->stream>>>(rows, cols, ctx->d_integral);

@@ -69,7 +69,18 @@ static int ensure_raw(nicp_context *ctx, size_t pixels) {
   return NICP_OK;
 }
 
+// The captured single-pair graphs bake in device AND pinned host addresses (descriptor staging, result / statistics
+// buffers, trace, z-buffers): every reallocation of one of them drops all cached graphs.
+static void invalidate_graphs(nicp_context *ctx) {
+  for (int g = 0; g < nicp_context::kGraphCache; g++)
+    if (ctx->graphValid[g]) {
+      cudaGraphExecDestroy(ctx->graphExec[g]);
+      ctx->graphValid[g] = false;
+    }
+}
+
 static void free_align(nicp_context *ctx) {
+  invalidate_graphs(ctx);
   dev_free(ctx->d_refZ);
   dev_free(ctx->d_curZ);
   dev_free(ctx->d_curIndex);
@@ -119,6 +130,7 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
 }
 static int ensure_results(nicp_context *ctx, int n) {
   if (n <= ctx->resultCap) return NICP_OK;
+  invalidate_graphs(ctx);
   dev_free(ctx->d_results);
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
@@ -139,6 +151,7 @@ static int ensure_results(nicp_context *ctx, int n) {
 }
 static int ensure_trace(nicp_context *ctx, int iters) {
   if (iters <= ctx->traceIters) return NICP_OK;
+  invalidate_graphs(ctx);
   dev_free(ctx->d_trace);
   int rc;
   if ((rc = dev_alloc(&ctx->d_trace, (size_t)iters * 61))) return rc;
@@ -149,6 +162,7 @@ static int ensure_trace(nicp_context *ctx, int iters) {
 static int cloud_sync_n(nicp_context *ctx, const nicp_cloud *cloud) {
   nicp_cloud *c = const_cast<nicp_cloud *>(cloud);
   if (c->n_known) return NICP_OK;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   NICP_CUDA(cudaMemcpyAsync(&c->n_host, c->d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   c->n_known = true;
@@ -540,8 +554,7 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_statHb);
   if (ctx->h_results) cudaFreeHost(ctx->h_results);
   if (ctx->h_statHb) cudaFreeHost(ctx->h_statHb);
-  for (int g = 0; g < nicp_context::kGraphCache; g++)
-    if (ctx->graphValid[g]) cudaGraphExecDestroy(ctx->graphExec[g]);
+  invalidate_graphs(ctx);
   for (cudaEvent_t e : *ctx->evCorr) cudaEventDestroy(e);
   for (cudaEvent_t e : *ctx->evProj) cudaEventDestroy(e);
   delete ctx->evCorr;
@@ -559,6 +572,7 @@ void nicp_destroy(nicp_context *ctx) {
 
 int nicp_synchronize(nicp_context *ctx) {
   if (!ctx) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   return NICP_OK;
 }
@@ -567,6 +581,7 @@ long long nicp_launch_count(const nicp_context *ctx) { return ctx ? ctx->launche
 
 int nicp_set_kernel_timing(nicp_context *ctx, int enable) {
   if (!ctx) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   ctx->timing = enable != 0;
   ctx->msCorr = ctx->msProj = 0.0;
   ctx->nCorr = ctx->nProj = 0;
@@ -577,6 +592,7 @@ int nicp_set_kernel_timing(nicp_context *ctx, int enable) {
 int nicp_get_kernel_timing(const nicp_context *ctx, double *corr_lin_ms, long long *corr_lin_launches, double *project_ms,
                            long long *project_launches) {
   if (!ctx) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (corr_lin_ms) *corr_lin_ms = ctx->msCorr;
   if (corr_lin_launches) *corr_lin_launches = ctx->nCorr;
   if (project_ms) *project_ms = ctx->msProj;
@@ -640,6 +656,7 @@ int nicp_cloud_size(const nicp_cloud *c) {
 int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *points4, const float *normals4,
                       const float *curvature, const float *omega_p6, const float *omega_n6) {
   if (!ctx || !c || n < 0 || !points4) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (n > c->capacity) {
     set_error("cloud upload of %d points exceeds capacity %d", n, c->capacity);
     return NICP_ERR_INVALID;
@@ -668,6 +685,7 @@ int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *poin
 int nicp_cloud_download(nicp_context *ctx, const nicp_cloud *c, float *points4, float *normals4, float *curvature,
                         float *omega_p6, float *omega_n6) {
   if (!ctx || !c) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   int rc = cloud_sync_n(ctx, c);
   if (rc) return rc;
   const int n = c->n_host;
@@ -699,6 +717,7 @@ int nicp_cloud_download(nicp_context *ctx, const nicp_cloud *c, float *points4, 
 
 int nicp_cloud_download_stats(nicp_context *ctx, const nicp_cloud *c, float *stats16, float *eigenvalues3, int *n_points) {
   if (!ctx || !c) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (!c->has_stats) {
     set_error("cloud was built without keep_stats");
     return NICP_ERR_INVALID;
@@ -715,11 +734,13 @@ int nicp_cloud_download_stats(nicp_context *ctx, const nicp_cloud *c, float *sta
 
 int nicp_cloud_transform(nicp_context *ctx, nicp_cloud *c, const float T[16]) {
   if (!ctx || !c || !T) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   return launch_cloud_transform(ctx, c, T);
 }
 
 int nicp_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]) {
   if (!ctx || !dst || !src || !T || dst == src) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = cloud_sync_n(ctx, dst))) return rc;
   if ((rc = cloud_sync_n(ctx, src))) return rc;
@@ -743,6 +764,7 @@ int nicp_cloud_compute_gaussians(nicp_context *ctx, nicp_cloud *c, const float *
 int nicp_cloud_has_gaussians(const nicp_cloud *c) { return c && c->has_gauss ? 1 : 0; }
 int nicp_cloud_download_gaussians(nicp_context *ctx, const nicp_cloud *c, float *gauss24, int *flags) {
   if (!ctx || !c) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (!c->has_gauss) {
     set_error("the cloud carries no gaussians (nicp_cloud_compute_gaussians / nicp_cloud_upload_gaussians first)");
     return NICP_ERR_INVALID;
@@ -757,6 +779,7 @@ int nicp_cloud_download_gaussians(nicp_context *ctx, const nicp_cloud *c, float 
 }
 int nicp_cloud_upload_gaussians(nicp_context *ctx, nicp_cloud *c, const float *gauss24, const int *flags) {
   if (!ctx || !c || !gauss24 || !flags) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = cloud_sync_n(ctx, c))) return rc;
   if ((rc = cloud_ensure_gaussians(ctx, c))) return rc;
@@ -801,6 +824,7 @@ int nicp_voxelize(nicp_context *ctx, nicp_cloud *c, float resolution, int *repre
 int nicp_depth_prepare(nicp_context *ctx, const uint16_t *raw, int rows, int cols, float depth_scale, int step,
                        float max_depth_cov, float *out) {
   if (!ctx || !raw || !out || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (step < 1) step = 1;
   int rc;
   size_t px = (size_t)rows * cols;
@@ -818,6 +842,7 @@ int nicp_depth_prepare(nicp_context *ctx, const uint16_t *raw, int rows, int col
 int nicp_unproject(nicp_context *ctx, const float *depth, int rows, int cols, const float iKRt[16], float min_distance,
                    float max_distance, nicp_cloud *cloud, int *index) {
   if (!ctx || !depth || !iKRt || !cloud || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)rows * cols;
   if ((size_t)cloud->capacity < px) {
     set_error("cloud capacity %d smaller than the image (%zu pixels)", cloud->capacity, px);
@@ -838,6 +863,7 @@ int nicp_unproject(nicp_context *ctx, const float *depth, int rows, int cols, co
 int nicp_project_intervals(nicp_context *ctx, const float *depth, const nicp_projector *proj, float world_radius,
                            int *interval) {
   if (!ctx || !depth || !proj || !interval || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)proj->rows * proj->cols;
   int rc;
   if ((rc = ensure_prep(ctx, px))) return rc;
@@ -868,6 +894,7 @@ static int depth_to_cloud_device(nicp_context *ctx, const nicp_projector *proj, 
 int nicp_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_projector *proj, const nicp_stats_params *sp,
                         const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
   if (!ctx || !depth || !proj || !sp || !cloud || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)proj->rows * proj->cols;
   if ((size_t)cloud->capacity < px) {
     set_error("cloud capacity %d smaller than the image (%zu pixels)", cloud->capacity, px);
@@ -883,6 +910,7 @@ int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows
                             float max_depth_cov, const nicp_projector *proj, const nicp_stats_params *sp,
                             const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
   if (!ctx || !raw || !proj || !sp || !cloud || raw_rows <= 0 || raw_cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (step < 1) step = 1;
   if (proj->rows != raw_rows / step || proj->cols != raw_cols / step) {
     set_error("projector image size %dx%d does not match the scaled raw image %dx%d", proj->rows, proj->cols,
@@ -913,6 +941,7 @@ int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows
 
 int nicp_last_integral_image(nicp_context *ctx, float *integral10) {
   if (!ctx || !integral10 || ctx->lastRows <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)ctx->lastRows * ctx->lastCols;
   std::vector<float> planar(px * kIntegralCh);
   NICP_CUDA(cudaMemcpyAsync(planar.data(), ctx->d_integral, planar.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -924,6 +953,7 @@ int nicp_last_integral_image(nicp_context *ctx, float *integral10) {
 
 int nicp_last_interval_image(nicp_context *ctx, int *interval) {
   if (!ctx || !interval || ctx->lastRows <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)ctx->lastRows * ctx->lastCols;
   NICP_CUDA(cudaMemcpyAsync(interval, ctx->d_interval, px * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -934,6 +964,7 @@ int nicp_last_interval_image(nicp_context *ctx, int *interval) {
 int nicp_project(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols, float min_distance,
                  float max_distance, int *index, float *depth) {
   if (!ctx || !cloud || !KRt || rows <= 0 || cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)rows * cols;
   int rc;
   if ((rc = ensure_align(ctx, 1, px))) return rc;
@@ -976,6 +1007,7 @@ int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, co
                               int *num_correspondences, int *corr_image) {
   if (!ctx || !reference || !current || !reference_index || !current_index || !T || !ap || rows <= 0 || cols <= 0)
     return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = (size_t)rows * cols;
   int rc;
   if ((rc = ensure_align(ctx, 1, px))) return rc;
@@ -1003,6 +1035,7 @@ int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cl
                    int n, const float T[16], const nicp_align_params *ap, float H[36], float b[6], float *error,
                    int *inliers) {
   if (!ctx || !reference || !current || (!correspondences && n > 0) || n < 0 || !T || !ap) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   size_t px = n > 0 ? (size_t)n : 1;
   int rc;
   if ((rc = ensure_align(ctx, 1, px))) return rc;
@@ -1071,6 +1104,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       for (int i = 0; i < 36; i++) hp[j].info[i] = priors[j].information[i];
     }
     if (numPriors > ctx->priorCap) {
+      invalidate_graphs(ctx);
       if (ctx->d_priors) cudaFree(ctx->d_priors);
       ctx->d_priors = nullptr;
       NICP_CUDA(cudaMalloc(&ctx->d_priors, sizeof(HostPrior) * numPriors));
@@ -1228,6 +1262,7 @@ int nicp_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_cloud 
                const float initial_guess[16], const nicp_prior *priors, int num_priors, float frame_inlier_depth_threshold,
                nicp_align_result *result) {
   if (!ctx || !reference || !current || !proj || !ap || !result || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (num_priors < 0 || (num_priors > 0 && !priors)) return NICP_ERR_INVALID;
   return align_common(ctx, 1, &reference, &current, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guess,
                       frame_inlier_depth_threshold, result, true, priors, num_priors);
@@ -1238,6 +1273,7 @@ int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *referenc
                      const float current_sensor_offset[16], const float *initial_guesses, float frame_inlier_depth_threshold,
                      nicp_align_result *results) {
   if (!ctx || n < 0 || !proj || !ap || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return NICP_OK;
   if (!references || !currents || !results) return NICP_ERR_INVALID;
   return align_common(ctx, n, references, currents, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guesses,
@@ -1255,6 +1291,7 @@ void nicp_multi_image_size(const nicp_multi_projector *mp, int *rows, int *cols)
 int nicp_multi_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_multi_projector *mp, const nicp_stats_params *sp,
                               const float sensor_offset[16], int keep_stats, nicp_cloud *cloud, int *index) {
   if (!ctx || !depth || !mp || !sp || !cloud) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   CamSet cams;
   int rows, cols, rc;
   if ((rc = camset_multi(mp, cams, rows, cols))) return rc;
@@ -1283,6 +1320,7 @@ int nicp_multi_depth_to_cloud(nicp_context *ctx, const float *depth, const nicp_
 int nicp_multi_project(nicp_context *ctx, const nicp_cloud *cloud, const nicp_multi_projector *mp, const float T[16],
                        int *index, float *depth) {
   if (!ctx || !cloud || !mp || !T) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   CamSet cams;
   int rows, cols, rc;
   if ((rc = camset_multi(mp, cams, rows, cols))) return rc;
@@ -1307,6 +1345,7 @@ int nicp_multi_align(nicp_context *ctx, const nicp_cloud *reference, const nicp_
                      const float initial_guess[16], const nicp_prior *priors, int num_priors, float frame_inlier_depth_threshold,
                      nicp_align_result *result) {
   if (!ctx || !reference || !current || !mp || !ap || !result) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   if (num_priors < 0 || (num_priors > 0 && !priors)) return NICP_ERR_INVALID;
   CamSet cams;
   int rows, cols, rc;
@@ -1324,6 +1363,7 @@ int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *referen
     set_error("no single nicp_align state available on this context");
     return NICP_ERR_INVALID;
   }
+  NICP_CUDA(cudaSetDevice(ctx->device));
   const size_t P = (size_t)ctx->lastAlignRows * ctx->lastAlignCols;
   int rc;
   if ((rc = ensure_prep(ctx, P))) return rc;
@@ -1364,6 +1404,7 @@ int nicp_align_get_state(nicp_context *ctx, int *reference_index, float *referen
 
 int nicp_align_get_trace(nicp_context *ctx, float *trace61, int max_iterations) {
   if (!ctx || !trace61 || !ctx->lastAlignValid) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
   int it = ctx->lastAlignIters < max_iterations ? ctx->lastAlignIters : max_iterations;
   if (it <= 0) return NICP_OK;
   NICP_CUDA(cudaMemcpyAsync(trace61, ctx->d_trace, sizeof(float) * 61 * it, cudaMemcpyDeviceToHost, ctx->stream));

@@ -208,6 +208,8 @@ struct nicp_context {
   int *d_interval;
   int *d_index;
   int lastRows, lastCols;
+  // dynamic shared memory opted into on THIS context's device (cudaFuncAttributeMaxDynamicSharedMemorySize is per device)
+  size_t rowsSmemCfg, colsSmemCfg;
   void *h_stage;      // pinned staging
   size_t stageBytes;
 

@@ -404,6 +404,60 @@ int main(int argc, char **argv) {
       fclose(out);
       return 0;
     }
+    if (get(cfg, "cloudcopy", 0) != 0) {
+      // value semantics of pwn::Cloud and the host mirror: the same pair aligned (a) untouched, (b) after the current
+      // cloud's host vectors were touched through a non-const accessor (host mirror -> re-upload, default keepStats = false),
+      // (c) with by-value copies of both clouds (cloud.cpp:145, manifold_voronoi_extractor.cpp:82 copy clouds by value)
+      if (argc < 5) throw std::runtime_error("cloudcopy needs two frames");
+      Cloud clouds[2];
+      for (int f = 0; f < 2; f++) {
+        RawDepthImage raw;
+        if (!readPgm16(argv[3 + f], raw)) throw std::runtime_error("cannot read frame");
+        DepthImage depth;
+        DepthImage_convertAndScale(depth, raw, imageScale, depthScale);
+        if (f == 0) {
+          projector.setCameraMatrix(K);
+          projector.setImageSize(raw.rows, raw.cols);
+          projector.scale(1.0f / imageScale);
+          correspondenceFinder.setImageSize(depth.rows, depth.cols);
+        }
+        converter.compute(clouds[f], depth, sensorOffset);
+      }
+      Isometry3f Ts[3];
+      int inl[3];
+      double maxCurv = 0;
+      for (int variant = 0; variant < 3; variant++) {
+        Cloud copyRef, copyCur;
+        const Cloud *ref = &clouds[0], *cur = &clouds[1];
+        if (variant == 1) {
+          Cloud &touched = clouds[1];
+          const size_t n = touched.points().size();  // non-const accessor: the host mirror becomes the truth
+          for (size_t i = 0; i < n; i++) maxCurv = std::max(maxCurv, (double)((const Cloud &)touched).stats()[i].curvature());
+        } else if (variant == 2) {
+          copyRef = clouds[0];        // host-valid source (copied vectors, uploaded on demand) or device-to-device
+          Cloud byValue(clouds[1]);
+          copyCur = byValue;
+          ref = &copyRef;
+          cur = &copyCur;
+        }
+        aligner.setReferenceCloud(const_cast<Cloud *>(ref));
+        aligner.setCurrentCloud(const_cast<Cloud *>(cur));
+        aligner.setInitialGuess(Isometry3f::Identity());
+        aligner.setSensorOffset(sensorOffset);
+        aligner.align();
+        Ts[variant] = aligner.T();
+        inl[variant] = aligner.inliers();
+      }
+      double d01 = 0, d02 = 0;
+      for (int k = 0; k < 16; k++) {
+        d01 = std::max(d01, (double)std::fabs(Ts[0].data()[k] - Ts[1].data()[k]));
+        d02 = std::max(d02, (double)std::fabs(Ts[0].data()[k] - Ts[2].data()[k]));
+      }
+      fprintf(out, "{\"inliers\": [%d, %d, %d], \"dT_touched\": %.9g, \"dT_copied\": %.9g, \"max_mirror_curvature\": %.9g}\n",
+              inl[0], inl[1], inl[2], d01, d02, maxCurv);
+      fclose(out);
+      return 0;
+    }
     if (get(cfg, "localmap", 0) != 0) {
       // the scene-based odometry of pwn_core/pwn_aligner.cpp:140-215: every frame is aligned against the local map
       // re-rendered at the predicted pose, added to the map (Cloud::add) and fused into it (Merger::merge); the map is

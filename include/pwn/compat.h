@@ -188,7 +188,11 @@ typedef std::vector<InformationMatrix> InformationMatrixVector;
 struct Stats : Matrix4f {
   int _n;
   Vector3f _eigenValues;
-  Stats() : _n(0) { setIdentity(); }
+  // stats.h:98-119: the curvature is cached (and settable); a cloud that was downloaded without its Stats still
+  // carries the per-point curvature the CorrespondenceFinder gates on
+  mutable bool _curvatureComputed;
+  mutable float _curvature;
+  Stats() : _n(0), _curvatureComputed(false), _curvature(0.0f) { setIdentity(); }
   int n() const { return _n; }
   Vector3f eigenValues() const { return _eigenValues; }
   Matrix3f eigenVectors() const {
@@ -199,8 +203,14 @@ struct Stats : Matrix4f {
   }
   Point mean() const { return Point((*this)(0, 3), (*this)(1, 3), (*this)(2, 3)); }
   float curvature() const {
-    return (float)((double)_eigenValues(0) / ((double)((_eigenValues(0) + _eigenValues(1)) + _eigenValues(2)) + 1e-9));
+    if (!_curvatureComputed)
+      _curvature = (float)((double)_eigenValues(0) / ((double)((_eigenValues(0) + _eigenValues(1)) + _eigenValues(2)) + 1e-9));
+    _curvatureComputed = true;
+    return _curvature;
   }
+  void setCurvature(float curvature_) { _curvature = curvature_; _curvatureComputed = true; }
+  void setN(int n_) { _n = n_; }
+  void setEigenValues(const Vector3f &eigenValues_) { _eigenValues = eigenValues_; }
 };
 typedef std::vector<Stats> StatsVector;
 

@@ -98,6 +98,14 @@ class Cloud {
  public:
   Cloud() : _dev(0), _capacity(0), _deviceValid(false), _hostValid(true), _hasStats(false) {}
   virtual ~Cloud() { release(); }
+  // The reference copies clouds by value (Cloud::add(Cloud cloud, ...), cloud.cpp:145; `pwn::Cloud cloud = *cloud_;`,
+  // pwn_tracker2/manifold_voronoi_extractor.cpp:82): a copy owns its own device cloud (device-to-device append with the
+  // identity; Stats and gaussians are carried through the host mirror / are not carried, like Cloud::add).
+  Cloud(const Cloud &o) : _dev(0), _capacity(0), _deviceValid(false), _hostValid(true), _hasStats(false) { copyFrom(o); }
+  Cloud &operator=(const Cloud &o) {
+    if (this != &o) copyFrom(o);
+    return *this;
+  }
 
   const PointVector &points() const { ensureHost(); return _points; }
   PointVector &points() { ensureHost(); _deviceValid = false; return _points; }
@@ -240,6 +248,11 @@ class Cloud {
         std::memcpy(stats.m, rec + 64 + 16, 64);
         std::memcpy(&stats._n, rec + 64 + 80, 4);
         std::memcpy(stats._eigenValues.m, rec + 64 + 84, 12);
+        if (rec[64 + 96]) {  // _curvatureComputed, _curvature (stats.h:117-118)
+          float curv;
+          std::memcpy(&curv, rec + 64 + 100, 4);
+          stats.setCurvature(curv);
+        }
       }
       point[3] = 1.0f;
       normal[3] = 0.0f;
@@ -309,6 +322,33 @@ class Cloud {
     _dev = 0;
     _capacity = 0;
   }
+  void copyFrom(const Cloud &o) {
+    _traversabilityVector = o._traversabilityVector;
+    if (o._hostValid) {  // the host vectors are the truth (or as good as the device): copy them, upload on demand
+      _points = o._points; _normals = o._normals; _stats = o._stats;
+      _pointInformationMatrix = o._pointInformationMatrix; _normalInformationMatrix = o._normalInformationMatrix;
+      _hostValid = true;
+      _deviceValid = false;
+      _hasStats = false;
+      return;
+    }
+    // device-resident source: a device-to-device copy into a cloud of our own
+    nicp_context *ctx = Context::current().handle();
+    const int n = (int)o.size();
+    nicp_cloud *fresh = 0;
+    nicpCheck(nicp_cloud_create(ctx, n > 0 ? n : 1, &fresh), "nicp_cloud_create");
+    Isometry3f I;
+    int rc = nicp_cloud_append(ctx, fresh, o._dev, I.data());
+    if (rc != NICP_OK) { nicp_cloud_destroy(fresh); nicpCheck(rc, "Cloud copy"); }
+    release();
+    _dev = fresh;
+    _capacity = n > 0 ? n : 1;
+    _points.clear(); _normals.clear(); _stats.clear();
+    _pointInformationMatrix.clear(); _normalInformationMatrix.clear();
+    _deviceValid = true;
+    _hostValid = false;
+    _hasStats = false;
+  }
   void upload() {
     const int n = (int)_points.size();
     if (!_dev || _capacity < n || _capacity == 0) {
@@ -367,6 +407,8 @@ class Cloud {
         for (int k = 0; k < 3; k++) self->_stats[i]._eigenValues(k) = ev[3 * (size_t)i + k];
         self->_stats[i]._n = cnt[i];
       }
+      // the curvature lives with the normals on the device and is always mirrored (stats.h:98-119 caches it in Stats)
+      self->_stats[i].setCurvature(cv[i]);
     }
     self->_hostValid = true;
   }

@@ -11,7 +11,9 @@
 # InformationMatrixVector::transformInPlace, informationmatrix.h:98-112).
 # Flags: -DNDEBUG like the reference's release build (pwn_static.cpp:40,55 carry inverted asserts that fire on every valid
 # input), -ffp-contract=off and no -march so that float32 arithmetic is evaluated as written, OpenMP on.
+# Usage: build_ref_pwn_core.sh [all|demo]   (demo: only oracle/_ref/drop_in_demo, which also needs the CUDA library)
 set -e
+MODE=${1:-all}
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 OUT="$HERE/_ref/libpwn_core_ref.so"
@@ -30,6 +32,7 @@ SRCS="$S/pwn_static.cpp $S/pointprojector.cpp $S/pinholepointprojector.cpp $S/ga
  $S/statscalculator.cpp $S/statscalculatorintegralimage.cpp $S/informationmatrixcalculator.cpp $S/cloud.cpp
  $S/depthimageconverter.cpp $S/depthimageconverterintegralimage.cpp $S/correspondencefinder.cpp $S/linearizer.cpp
  $S/se3_prior.cpp $S/aligner.cpp $S/merger.cpp $S/voxelcalculator.cpp $S/multipointprojector.cpp"
+if [ "$MODE" != demo ]; then
 $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC \
   -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -o "$OUT" $SRCS "$HERE/ref_pwn_core.cpp" \
   -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
@@ -48,10 +51,13 @@ for drv in pwn_simple_aligner pwn_aligner; do
     -L"$HERE/build" -loracle -Wl,-rpath,'$ORIGIN/../build' -lm
   echo "built $HERE/_ref/${drv}_ref"
 done
+fi
 # the drop-in demonstration (integration/drop_in_demo.cpp): the same reference sources + the option-A binding of
 # integration/pwn_b200/b200_pwn.h + this repository's CUDA library, in one executable
 REPO=$(cd "$HERE/.." && pwd)
-if [ -f "$REPO/g2o_frontend_b200/lib/libnicp_b200.so" ]; then
+if [ ! -f "$REPO/g2o_frontend_b200/lib/libnicp_b200.so" ]; then
+  [ "$MODE" = demo ] && { echo "drop_in_demo needs g2o_frontend_b200/lib/libnicp_b200.so (make -C g2o_frontend_b200/csrc first)" >&2; exit 1; }
+else
   $CXX -std=gnu++11 -fpermissive -w -O2 -DNDEBUG -ffp-contract=off -fno-fast-math -fopenmp \
     -I"$HERE/shim" -I"$SCRATCH" -I"$SCRATCH/g2o_frontend" -I"$REPO/include" -I"$REPO/integration" \
     -o "$HERE/_ref/drop_in_demo" $SRCS "$REPO/integration/drop_in_demo.cpp" \

@@ -1214,6 +1214,14 @@ static void compute_statistics(const float *H_lin, const float *T, float *mean, 
    summation noise.  0 = reference behaviour. */
 static int g_accumulate_f64 = 0;
 void orc_set_accumulate_f64(int on) { g_accumulate_f64 = on; }
+/* OpenMP team size of every parallel region of this library (the reference runs its `#pragma omp parallel for` loops with
+ * the runtime's default team; OMP_NUM_THREADS is only read when libgomp initialises, so callers that choose the thread
+ * count later -- bench.py under torch.distributed.run, which exports OMP_NUM_THREADS=1 -- must call this).  Returns the
+ * team size now in force (omp_get_max_threads). */
+int orc_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
 static void align_linearize(const int *corr, int numCorr, const float *refPoints, const float *refNormals,
                             const float *curPoints, const float *curNormals, const float *curOmegaP,
                             const float *curOmegaN, const float *invT, const orc_align_params *p, float *H, float *b,

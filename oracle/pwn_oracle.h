@@ -187,6 +187,7 @@ void orc_align(int nRef, const float *refPoints, const float *refNormals, const 
 
 /* test knob: float64 accumulation of the Linearizer sums inside orc_align (0 = reference behaviour) */
 void orc_set_accumulate_f64(int on);
+int orc_set_threads(int n); /* omp_set_num_threads(n) if n > 0; returns omp_get_max_threads() */
 
 /* PwnMatcherBase::matchClouds image statistics (pwn_tracker2/pwn_matcher_base.cpp:156-196) */
 void orc_image_stats(const float *curDepth, const float *refDepth, int n, float inlierDepthThreshold,

@@ -552,6 +552,14 @@ def voxelize(points, resolution=0.01, strict=True):
     return rep[:m].copy()
 
 
+def set_threads(n, fast=False):
+    """omp_set_num_threads(n) inside the oracle library (OMP_NUM_THREADS is only read when libgomp initialises);
+    returns the OpenMP team size actually in force"""
+    f = lib(fast).orc_set_threads
+    f.restype = C.c_int
+    return int(f(int(n)))
+
+
 # restype declarations that are not int
 def _declare():
     for fast in (False, True):

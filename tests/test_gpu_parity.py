@@ -16,6 +16,12 @@ pytestmark = pytest.mark.gpu
 H_RTOL = 1e-4     # ||dH||_F / ||H||_F
 T_ROT_TOL = 1e-4  # rad
 T_TRA_TOL = 1e-4  # m
+# Aligner::omega() / eigen-ratios given identical correspondences (teacher-forced): the float32 sigma-point round trip of
+# aligner.cpp:172-198 amplifies the ~1e-6 difference of the two H summation orders; measured values are printed by the test
+OMEGA_RTOL = 2e-3
+RATIO_RTOL = 2e-3
+# free-running agreement after 10 iterations (index image / correspondence set), measured 0.995-0.9999
+FREE_AGREE = 0.995
 
 
 @pytest.fixture(scope="module", params=["verify", "default"])
@@ -206,14 +212,14 @@ def test_align_end_to_end(ctx, step, seed, dropout, offset):
     # boundary.  (Teacher-forced, i.e. restarted from the oracle's T, the images are bit-exact: see
     # test_align_teacher_forced_iterations.)
     agree_idx = (st["ref_index"] == out.refIndex).mean()
-    assert agree_idx >= 0.99, agree_idx
+    assert agree_idx >= FREE_AGREE, agree_idx
     assert np.array_equal(st["cur_index"], out.curIndex)
     assert np.array_equal(st["cur_depth"].view(np.uint32), out.curDepth.view(np.uint32))
     # correspondences of the last iteration (raster order on both sides)
     a = set(map(tuple, st["corr"].tolist()))
     o = set(map(tuple, out.corr.tolist()))
     agree = len(a & o) / max(len(a | o), 1)
-    assert agree >= 0.99, agree
+    assert agree >= FREE_AGREE, agree
     print("free-running agreement after 10 iterations: index image %.4f, correspondences %.4f" % (agree_idx, agree))
     assert abs(res.num_correspondences - out.numCorrespondences) <= 1e-3 * out.numCorrespondences
     # inliers: the oracle (8 threads) drops numCorr % 8 correspondences (linearizer.cpp:32-39)
@@ -228,20 +234,27 @@ def test_align_end_to_end(ctx, step, seed, dropout, offset):
         assert np.abs(Ti[:3, 3] - out.trace_T[i][:3, 3]).max() <= T_TRA_TOL
     # Aligner::omega(): tolerance-level (float64 Jacobi stands in for JacobiSVD on both sides)
     om = capi.result_omega(res)
-    assert frob_rel(om, out.omega) <= 2e-2
+    assert frob_rel(om, out.omega) <= 2e-2  # free-running: different correspondence sets; 2e-3 teacher-forced (below)
+    for mine, theirs in ((res.translational_eigen_ratio, out.translationalRatio), (res.rotational_eigen_ratio, out.rotationalRatio)):
+        assert abs(mine - theirs) <= 2e-2 * abs(theirs), (mine, theirs)
     # matchClouds image statistics
     nz, inl, outl, rd = O.image_stats(out.curDepth, st["ref_depth"])
     assert res.image_non_zeros == nz and res.image_inliers == inl and res.image_outliers == outl
     assert abs(res.image_reprojection_distance - rd) <= 1e-4 * abs(rd) + 1e-6
 
 
-def test_align_teacher_forced_iterations(ctx):
-    """every iteration restarted from the ORACLE's T: index + correspondence images bit-exact"""
+@pytest.mark.parametrize("step,seed,dropout", [(4, 0, 0.05), (1, 2, 0.05), (1, None, 0.0)])
+def test_align_teacher_forced_iterations(ctx, step, seed, dropout):
+    """The whole iteration composed (project -> correspond -> linearise -> statistics), restarted from the ORACLE's T at
+    iterations 0, 3 and 9, at 160x120 and at the full 640x480: index + depth + correspondence images bit-exact in both
+    builds, H / b within 1e-4, and -- the correspondences being identical -- Aligner::omega() and the two eigen-ratios of
+    _computeStatistics (aligner.cpp:152-199) at tolerance level."""
+    from g2o_frontend_b200 import capi
     from oracle import pwn_oracle as O
-    s = get_scene(4, 0, 0.05)
+    s = get_scene(step, seed, dropout)
     ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
     out = O.align(s.cloudA, s.cloudB, s.oracle_align_params(num_threads=8))
-    c = s.conf
+    worst_om = worst_ratio = 0.0
     for i in (0, 3, 9):
         Ti = out.trace_T[i]
         o1 = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=1, guess=Ti, num_threads=1))
@@ -249,13 +262,23 @@ def test_align_teacher_forced_iterations(ctx):
         st = ctx.align_state(s.rows, s.cols)
         assert np.array_equal(st["ref_index"], o1.refIndex)
         assert np.array_equal(st["ref_depth"].view(np.uint32), o1.refDepth.view(np.uint32))
+        assert np.array_equal(st["cur_index"], o1.curIndex)
         assert np.array_equal(st["corr"], o1.corr)
         assert r1.num_correspondences == o1.numCorrespondences
         tr = ctx.align_trace(1)
-        from g2o_frontend_b200 import capi
         assert frob_rel(capi.from_colmajor(tr[0, 16:52], 6), o1.trace_H[0]) <= H_RTOL
         assert frob_rel(tr[0, 52:58], o1.trace_b[0]) <= H_RTOL
         assert int(tr[0, 59]) == o1.trace_inliers[0]
+        # _computeStatistics on identical correspondences
+        assert frob_rel(st["H"], o1.H) <= H_RTOL
+        om = frob_rel(capi.result_omega(r1), o1.omega)
+        rt = max(abs(r1.translational_eigen_ratio - o1.translationalRatio) / abs(o1.translationalRatio),
+                 abs(r1.rotational_eigen_ratio - o1.rotationalRatio) / abs(o1.rotationalRatio))
+        worst_om, worst_ratio = max(worst_om, om), max(worst_ratio, rt)
+        assert om <= OMEGA_RTOL, (i, om)
+        assert rt <= RATIO_RTOL, (i, rt, r1.translational_eigen_ratio, o1.translationalRatio,
+                                  r1.rotational_eigen_ratio, o1.rotationalRatio)
+    print("teacher-forced %dx%d: omega rel %.2e, eigen-ratio rel %.2e" % (s.cols, s.rows, worst_om, worst_ratio))
 
 
 def test_inner_iterations(ctx):

@@ -960,6 +960,7 @@ def test_host_classes_with_a_mock_backend(tmp_path, monkeypatch):
                                     (TH.test_pyramid_matches_oracle_composition, ()),
                                     (TH.test_sequential_tracker_matches_oracle_loop, ()),
                                     (TH.test_cloud_file_io_and_add, ()),
+                                    (TH.test_cloud_value_semantics_and_host_mirror, ()),
                                     (TH.test_cli_driver_accepts_boss_configuration, ())]):
         d = tmp_path / ("case%d" % i)
         d.mkdir()
