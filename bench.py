@@ -304,9 +304,11 @@ def run_ours(args):
                                 CONF["inlierMaxChi2"], True, CONF["outerIterations"], CONF["innerIterations"])
     clouds = [ctx.new_cloud(ROWS * COLS) for _ in range(n_frames)]
 
+    frames = [host_raw[i] for i in range(n_frames)]  # views of the pinned buffer: uploaded in place, no host copy
+
     def build_clouds():
-        for i in range(n_frames):
-            ctx.raw_depth_to_cloud(host_raw[i], proj, sp, cloud=clouds[i])
+        # one launch set per sub-batch of 8 frames (nicp_raw_depth_to_cloud_batch); asynchronous
+        ctx.raw_depth_to_cloud_batch(frames, proj, sp, clouds=clouds)
 
     refs = [clouds[n_cur + ri] for ri, ci in pairs]
     curs = [clouds[ci] for ri, ci in pairs]

@@ -22,7 +22,7 @@ SYMBOLS = [
     "nicp_cloud_create", "nicp_cloud_destroy", "nicp_cloud_size", "nicp_cloud_upload", "nicp_cloud_download",
     "nicp_cloud_download_stats", "nicp_cloud_transform", "nicp_cloud_append",
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
-    "nicp_raw_depth_to_cloud", "nicp_last_integral_image", "nicp_last_interval_image",
+    "nicp_raw_depth_to_cloud", "nicp_raw_depth_to_cloud_batch", "nicp_last_integral_image", "nicp_last_interval_image",
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
     "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch",
     "nicp_multi_image_size", "nicp_multi_depth_to_cloud", "nicp_multi_project", "nicp_multi_align",
@@ -422,6 +422,24 @@ class Context:
                                                       C.byref(proj), C.byref(sp), _fptr(so), int(keep_stats),
                                                       cloud.handle, _iptr(index) if want_index else None))
         return cloud, index
+
+    def raw_depth_to_cloud_batch(self, raws, proj, sp, depth_scale=0.001, step=1, max_depth_cov=0.01, sensor_offset=None,
+                                 keep_stats=False, clouds=None):
+        """n raw frames (uint16 arrays of one shape, or rows of one 3-D array -- e.g. a pinned staging buffer) -> n clouds
+        with one launch set per sub-batch (nicp_raw_depth_to_cloud_batch).  Asynchronous like raw_depth_to_cloud."""
+        n = len(raws)
+        frames = [r if (isinstance(r, np.ndarray) and r.dtype == np.uint16 and r.flags.c_contiguous)
+                  else np.ascontiguousarray(r, np.uint16) for r in raws]
+        rows, cols = frames[0].shape
+        clouds = clouds or [self.new_cloud(proj.rows * proj.cols) for _ in range(n)]
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        RA = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        CA = (C.c_void_p * n)(*[c.handle for c in clouds])
+        _check(self.L, self.L.nicp_raw_depth_to_cloud_batch(self.handle, n, RA, rows, cols, C.c_float(depth_scale), int(step),
+                                                            C.c_float(max_depth_cov), C.byref(proj), C.byref(sp), _fptr(so),
+                                                            int(keep_stats), CA))
+        self._keepalive = frames  # the copies are asynchronous: keep the host frames alive until the next call
+        return clouds
 
     def last_integral_image(self, rows, cols):
         out = np.zeros((rows, cols, 10), np.float32)

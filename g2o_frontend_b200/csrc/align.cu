@@ -349,9 +349,9 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[kAccum], int l
 __device__ __forceinline__ void accumulate_term(float (&acc)[kAccum], float rpx, float rpy, float rpz, float rnx,
                                                 float rny, float rnz, float4 cp, float4 cn, float4 o0, float4 o1,
                                                 float4 o2, float maxChi2, int robust) {
-  // Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l]
-  const float a = o0.x, b = o0.y, c = o0.z, d = o0.w, e = o1.x, f = o1.y;
-  const float g = o1.z, h = o1.w, i = o2.x, j = o2.y, k = o2.z, l = o2.w;
+  // Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l], interleaved in memory (Omega3)
+  const float a = o0.x, b = o0.z, c = o1.x, d = o1.z, e = o2.x, f = o2.z;
+  const float g = o0.y, h = o0.w, i = o1.y, j = o1.w, k = o2.y, l = o2.w;
   const float pe0 = rpx - cp.x, pe1 = rpy - cp.y, pe2 = rpz - cp.z;
   const float ne0 = rnx - cn.x, ne1 = rny - cn.y, ne2 = rnz - cn.z;
   const float ep0 = (a * pe0 + b * pe1) + c * pe2;
@@ -426,6 +426,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+
+}  // namespace nicp
+#include "corr_lin.cuh"
+namespace nicp {
 
 template <int NT, int TK>
 struct TileSmem {
@@ -978,7 +982,7 @@ __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *_
 //   2  {64, 3} in-place Linearizer stage, 10 CTAs/SM                              299 us
 //   3  {64, 2} shared-memory compaction of the accepted terms (round-1 structure) 355 us
 struct TileCfg { int nt, tk; };
-static const TileCfg kTileCfgs[] = {{32, 3}, {64, 3}, {64, 2}};
+static const TileCfg kTileCfgs[] = {{32, 3}, {64, 3}, {64, 2}, {32, 3}};
 static int tile_px(const nicp_context *ctx) { return kTileCfgs[ctx->tileConfig].nt * kTileCfgs[ctx->tileConfig].tk; }
 
 static int pixels_per_block(const nicp_context *ctx, int /*P*/) { return tile_px(ctx); }
@@ -1003,20 +1007,40 @@ static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, in
   k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<g, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
                                                                                imgThr, swap ? 1 : 0, curEpoch);
 }
-// MODE 0 / 1 launch of the fused kernel in the context's tile configuration
-static void launch_corr_lin(nicp_context *ctx, int mode, dim3 grid, int parity, int epoch, int writeCorr, const AlignConsts &ac,
-                            int P, int imgStats, float imgThr, int curEpoch = kEpochFresh) {
+// grouped kernel (corr_lin.cuh): grid = groups x tiles, group-fastest when the group count fits gridDim.x
+template <int MODE, int MINB>
+static void launch_group(nicp_context *ctx, int nGroups, int tiles, int parity, int epoch, int writeCorr, const AlignConsts &ac,
+                         int P, int imgStats, float imgThr, int curEpoch) {
+  const PairGroup *d_groups = reinterpret_cast<const PairGroup *>(reinterpret_cast<const int *>(ctx->d_desc + ctx->slots) + ctx->slots);
+  const bool groupFast = tiles <= 65535;
+  const dim3 g = groupFast ? dim3(nGroups, tiles) : dim3(tiles, nGroups);
+  k_corr_lin_group<MODE, MINB><<<g, 32, 0, ctx->stream>>>(ctx->d_desc, d_groups, parity, epoch, writeCorr, ac, P, imgStats, imgThr,
+                                                           groupFast ? 1 : 0, curEpoch);
+}
+// MODE 0 / 1 launch of the fused kernel in the context's tile configuration.  Configuration 0 (default) is the grouped
+// kernel; 1..3 are the round-1 per-pair kernels kept for comparison (tools/tune_corr.py), which ignore the grouping.
+static void launch_corr_lin(nicp_context *ctx, int mode, int nPairs, int nGroups, int nb, int parity, int epoch, int writeCorr,
+                            const AlignConsts &ac, int P, int imgStats, float imgThr, int curEpoch = kEpochFresh) {
+  const dim3 grid(nb, nPairs);
   if (mode == 0) {
     switch (ctx->tileConfig) {
       case 1: launch_tiled<0, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       case 2: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
-      default: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      case 3: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      default:
+        if (ctx->groupMinBlocks >= 20) launch_group<0, 20>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        else launch_group<0, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        break;
     }
   } else {
     switch (ctx->tileConfig) {
       case 1: launch_tiled<1, 64, 3, 10, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       case 2: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
-      default: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      case 3: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
+      default:
+        if (ctx->groupMinBlocks >= 20) launch_group<1, 20>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        else launch_group<1, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        break;
     }
   }
 }
@@ -1037,7 +1061,7 @@ static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used) {
 // runs Aligner::align for the nPairs descriptors staged in ctx->h_desc (one lock-step chunk).
 // ownsCur: per pair, 1 if the pair's curZ/curIndex buffers must be produced by it.
 int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const CamSet &cams, const float curOffset[16],
-                    int outerIters, int innerIters, float imgThreshold, int /*nUniqueCur*/, const int *h_ownsCur,
+                    int outerIters, int innerIters, float imgThreshold, int nGroups, const int *h_ownsCur,
                     bool fresh, int resultOffset) {
   cudaStream_t st = ctx->stream;
   const int P = ac.rows * ac.cols;
@@ -1047,7 +1071,8 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   int *d_flags = reinterpret_cast<int *>(ctx->d_desc + ctx->slots);
   for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
-  NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * nPairs, cudaMemcpyHostToDevice, st));
+  // flags and the pair groups (staged by the caller right behind the flags) in one copy
+  NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * ctx->slots + sizeof(PairGroup) * nGroups, cudaMemcpyHostToDevice, st));
   // z-buffer words carry an epoch tag instead of being cleared per iteration (z_encode in nicp_internal.cuh).
   // (slot buffers are contiguous: refZ is laid out [2][slots][slotPixels], curZ [slots][slotPixels])
   //  fresh (single-pair nicp_align, the CUDA-graph path): this call clears its own slots and counts its iterations
@@ -1103,7 +1128,6 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags, curEpoch);
   NICP_CHECK_LAUNCH(ctx);
   const Affine dummy = curMats.M[0];
-  dim3 cg(nb, nPairs);
   int parity = (int)(iterBase & 1), epoch = epoch_of_iteration((int)(iterBase & 1023));
   for (int it = 0; it < outerIters; it++) {
     const long long G = iterBase + it;
@@ -1123,10 +1147,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     for (int k = 0; k < innerIters; k++) {
       if (k == 0) {
         NICP_TIME_BEGIN(evCorr, evCorrUsed);
-        launch_corr_lin(ctx, 0, cg, parity, epoch, writeCorr, ac, P, 0, 0.0f);
+        launch_corr_lin(ctx, 0, nPairs, nGroups, nb, parity, epoch, writeCorr, ac, P, 0, 0.0f);
         NICP_TIME_END(evCorr, evCorrUsed);
       } else {
-        launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 0, 0.0f, curEpoch);
+        launch_corr_lin(ctx, 1, nPairs, nGroups, nb, parity, epoch, 0, ac, P, 0, 0.0f, curEpoch);
       }
       NICP_CHECK_LAUNCH(ctx);
       if (ctx->h_desc[0].numPriors > 0)
@@ -1142,7 +1166,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
       NICP_CUDA(cudaMemsetAsync(ctx->h_desc[i].corrImage, 0xFF, sizeof(int) * P, st));
   }
   // _computeStatistics linearisation at the final T over the last correspondences + image statistics
-  launch_corr_lin(ctx, 1, cg, parity, epoch, 0, ac, P, 1, imgThreshold, curEpoch);
+  launch_corr_lin(ctx, 1, nPairs, nGroups, nb, parity, epoch, 0, ac, P, 1, imgThreshold, curEpoch);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
@@ -1156,8 +1180,7 @@ int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool from
   cudaStream_t st = ctx->stream;
   const int ppb = pixels_per_block(ctx, numPixels);
   const int nb = (numPixels + ppb - 1) / ppb;
-  dim3 cg(nb, 1);
-  launch_corr_lin(ctx, fromCorrImage ? 1 : 0, cg, 0, kEpochFresh, 1, ac, numPixels, 0, 0.0f);
+  launch_corr_lin(ctx, fromCorrImage ? 1 : 0, 1, 1, nb, 0, kEpochFresh, 1, ac, numPixels, 0, 0.0f);
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<false><<<dim3(kRowGroups, 1), 256, 0, st>>>(ctx->d_desc, nb, 2, 0, 1, 0, ac);
   NICP_CHECK_LAUNCH(ctx);

@@ -27,8 +27,22 @@ namespace nicp {
 // ---------------------------------------------------------------------------------------------
 // DepthImage_convert_16UC1_to_32FC1 (pwn_static.cpp:54-68) + DepthImage_scale (:5-36)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_depth_convert(const uint16_t *__restrict__ raw, int rows, int cols, float scale, int step,
-                                float maxCov, float *__restrict__ out) {
+// Frames of one launch set (kernel parameter, no device-side descriptor array): frame f = blockIdx.y (depth convert, row
+// pass), blockIdx.z (column pass, statistics).  A single frame is a batch of one.
+struct PrepBatch {
+  int n;
+  const uint16_t *raw[kMaxPrepBatch];
+  float *depth[kMaxPrepBatch];
+  float *integral[kMaxPrepBatch];     // planar [10][rows][cols]
+  float4 *points[kMaxPrepBatch], *normals[kMaxPrepBatch], *omega[kMaxPrepBatch];
+  float *stats16[kMaxPrepBatch], *eigvals[kMaxPrepBatch];
+  int *statsN[kMaxPrepBatch];
+  int *count[kMaxPrepBatch];
+};
+
+__global__ void k_depth_convert(PrepBatch B, int rows, int cols, float scale, int step, float maxCov) {
+  const uint16_t *__restrict__ raw = B.raw[blockIdx.y];
+  float *__restrict__ out = B.depth[blockIdx.y];
   int drows = rows / step, dcols = cols / step;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= drows * dcols) return;
@@ -64,7 +78,12 @@ int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int
                          float maxCov, float *d_out) {
   if (step < 1) step = 1;
   int n = (rows / step) * (cols / step);
-  k_depth_convert<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_raw, rows, cols, scale, step, maxCov, d_out);
+  PrepBatch B;
+  memset(&B, 0, sizeof B);
+  B.n = 1;
+  B.raw[0] = d_raw;
+  B.depth[0] = d_out;
+  k_depth_convert<<<(n + 255) / 256, 256, 0, ctx->stream>>>(B, rows, cols, scale, step, maxCov);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }
@@ -105,10 +124,11 @@ __device__ __forceinline__ bool pixel_point(const Affine &iKRt, float minD, floa
 // PointIntegralImage::compute, pass 1 (scatter + prefix along image-x)
 // ---------------------------------------------------------------------------------------------
 template <bool MULTI>
-__global__ void __launch_bounds__(256) k_integral_rows(const float *__restrict__ depth, int rows, int cols, Affine iKRt,
-                                                       float minD, float maxD, const PrepCams *__restrict__ pc,
-                                                       float *__restrict__ I) {
+__global__ void __launch_bounds__(256) k_integral_rows(PrepBatch B, int rows, int cols, Affine iKRt,
+                                                       float minD, float maxD, const PrepCams *__restrict__ pc) {
   extern __shared__ float sm[];  // [10][stride]
+  const float *__restrict__ depth = B.depth[blockIdx.y];
+  float *__restrict__ I = B.integral[blockIdx.y];
   const int stride = cols + 1;   // +1: the 10 scanning lanes hit 10 different banks
   const int r = blockIdx.x;
   const float *drow = depth + (size_t)r * cols;
@@ -153,10 +173,10 @@ __global__ void __launch_bounds__(256) k_integral_rows(const float *__restrict__
 // ---------------------------------------------------------------------------------------------
 // PointIntegralImage::compute, pass 2 (prefix along image-y)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_integral_cols(int rows, int cols, float *__restrict__ I) {
+__global__ void __launch_bounds__(64) k_integral_cols(PrepBatch B, int rows, int cols) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= cols) return;
-  float *p = I + (size_t)blockIdx.y * rows * cols + x;
+  float *p = B.integral[blockIdx.z] + (size_t)blockIdx.y * rows * cols + x;
   float v = p[0];
   int y = 1;
   constexpr int U = 16;
@@ -319,13 +339,20 @@ __device__ __forceinline__ void rotate_sym(const float *M, const float *Om /*3x3
 }
 
 template <bool MULTI>
-__global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, const float *__restrict__ I, int rows,
-                                               int cols, StatsConsts sc, const PrepCams *__restrict__ pc,
-                                               float4 *__restrict__ points,
-                                               float4 *__restrict__ normals, float4 *__restrict__ omega,
-                                               int *__restrict__ index, int *__restrict__ interval,
-                                               float *__restrict__ stats16, float *__restrict__ eigvalsOut,
-                                               int *__restrict__ statsN, int *__restrict__ countOut) {
+__global__ void __launch_bounds__(256) k_stats(PrepBatch B, int rows, int cols, StatsConsts sc,
+                                               const PrepCams *__restrict__ pc, int *__restrict__ index,
+                                               int *__restrict__ interval) {
+  // index / interval images (single-frame calls that asked for them) may be null: a batch does not materialise them
+  const int f = blockIdx.z;
+  const float *__restrict__ depth = B.depth[f];
+  const float *__restrict__ I = B.integral[f];
+  float4 *__restrict__ points = B.points[f];
+  float4 *__restrict__ normals = B.normals[f];
+  float4 *__restrict__ omega = B.omega[f];
+  float *__restrict__ stats16 = B.stats16[f];
+  float *__restrict__ eigvalsOut = B.eigvals[f];
+  int *__restrict__ statsN = B.statsN[f];
+  int *__restrict__ countOut = B.count[f];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y * blockDim.y + threadIdx.y;
   if (c >= cols || r >= rows) return;
@@ -336,8 +363,8 @@ __global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, 
   float px, py, pz, ivx, ivy;
   int cam;
   if (!pixel_point<MULTI>(sc.iKRt, sc.minD, sc.maxD, sc.ivx, sc.ivy, pc, r, c, d, px, py, pz, ivx, ivy, cam)) {
-    index[pix] = -1;
-    interval[pix] = -1;
+    if (index) index[pix] = -1;
+    if (interval) interval[pix] = -1;
     return;
   }
   // compacted index from channel 0 of the integral image (exact integer counts in float32)
@@ -358,13 +385,13 @@ __global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, 
     float rowUpTo = (Ir[c] - (Ip ? Ip[c] : 0.0f)) - (off > 0 ? (Ir[off - 1] - (Ip ? Ip[off - 1] : 0.0f)) : 0.0f);
     idx = (int)before + (int)aboveBlock + (int)rowUpTo - 1;
   }
-  index[pix] = idx;
+  if (index) index[pix] = idx;
 
   // _projectInterval (pinholepointprojector.h:264-274)
   float invd = fdiv(1.0f, d);
   float ia = fmul(ivx, invd), ib = fmul(ivy, invd);
   int k = (ia > ib) ? (int)ia : (int)ib;
-  interval[pix] = k;
+  if (interval) interval[pix] = k;
 
   float nx = 0.f, ny = 0.f, nz = 0.f, curv = 0.f;
   float OP[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -462,9 +489,14 @@ __global__ void __launch_bounds__(256) k_stats(const float *__restrict__ depth, 
 
   points[idx] = make_float4(px, py, pz, 1.0f);
   normals[idx] = make_float4(nx, ny, nz, curv);
-  omega[3 * (size_t)idx + 0] = make_float4(NM3(OP, 0, 0), NM3(OP, 0, 1), NM3(OP, 0, 2), NM3(OP, 1, 1));
-  omega[3 * (size_t)idx + 1] = make_float4(NM3(OP, 1, 2), NM3(OP, 2, 2), NM3(ON, 0, 0), NM3(ON, 0, 1));
-  omega[3 * (size_t)idx + 2] = make_float4(NM3(ON, 0, 2), NM3(ON, 1, 1), NM3(ON, 1, 2), NM3(ON, 2, 2));
+  {
+    const float P6[6] = {NM3(OP, 0, 0), NM3(OP, 0, 1), NM3(OP, 0, 2), NM3(OP, 1, 1), NM3(OP, 1, 2), NM3(OP, 2, 2)};
+    const float N6[6] = {NM3(ON, 0, 0), NM3(ON, 0, 1), NM3(ON, 0, 2), NM3(ON, 1, 1), NM3(ON, 1, 2), NM3(ON, 2, 2)};
+    const Omega3 w = omega_pack(P6, N6);
+    omega[3 * (size_t)idx + 0] = w.o0;
+    omega[3 * (size_t)idx + 1] = w.o1;
+    omega[3 * (size_t)idx + 2] = w.o2;
+  }
   if (stats16) {
     float4 *so = reinterpret_cast<float4 *>(stats16 + 16 * (size_t)idx);
     so[0] = make_float4(S[0], S[1], S[2], S[3]);
@@ -489,10 +521,10 @@ static bool is_identity16(const float *m) {
 // strip (rows x 32 floats) into shared memory with coalesced loads from all its threads, lets 32 threads walk
 // their column sequentially (the reference's order) at shared-memory latency, and writes the strip back
 // coalesced.  ~8x faster than the register-prefetch version, which is kept for images too tall for 227 KB.
-__global__ void __launch_bounds__(256) k_integral_cols_smem(int rows, int cols, float *__restrict__ I) {
+__global__ void __launch_bounds__(256) k_integral_cols_smem(PrepBatch B, int rows, int cols) {
   extern __shared__ float strip[];  // [rows][32]
   const int x0 = blockIdx.x * 32;
-  float *plane = I + (size_t)blockIdx.y * rows * cols;
+  float *plane = B.integral[blockIdx.z] + (size_t)blockIdx.y * rows * cols;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const bool inside = x0 + lx < cols;
 #pragma unroll 8
@@ -517,10 +549,50 @@ __global__ void __launch_bounds__(256) k_integral_cols_smem(int rows, int cols, 
   }
 }
 
-int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
-                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index, const CamSet *cams) {
-  cloud->points3_valid = false;
-  const int rows = proj->rows, cols = proj->cols;
+// Streaming version of pass 2 for batches: one thread per (column, channel, frame) walks its column in the reference's
+// order with the next 16 rows already in flight while the current 16 are added (32 independent loads per thread); a warp
+// covers 32 adjacent columns, so every load / store is one full 128-byte line and nothing is staged in shared memory.
+// With F frames there are F * 6400 such threads: enough bytes in flight to run at memory speed, which a single frame
+// (6400 threads) is not -- that case keeps the shared-memory strips above.
+__global__ void __launch_bounds__(128) k_integral_cols_stream(PrepBatch B, int rows, int cols) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= cols) return;
+  float *p = B.integral[blockIdx.z] + (size_t)blockIdx.y * rows * cols + x;
+  constexpr int U = 16;
+  float cur[U], nxt[U];
+  float v = 0.0f;
+  int y = 0;
+  if (rows >= U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) cur[u] = p[(size_t)u * cols];
+  }
+  for (; y + U <= rows; y += U) {
+    const bool more = y + 2 * U <= rows;
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) nxt[u] = p[(size_t)(y + U + u) * cols];
+    }
+    if (y == 0) {
+      v = cur[0];  // row 0 is its own prefix (no 0 + x: -0.0f must stay -0.0f like in the reference)
+#pragma unroll
+      for (int u = 1; u < U; u++) { v = fadd(cur[u], v); p[(size_t)(y + u) * cols] = v; }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; u++) { v = fadd(cur[u], v); p[(size_t)(y + u) * cols] = v; }
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) cur[u] = nxt[u];
+    }
+  }
+  if (y == 0) { v = p[0]; y = 1; }
+  for (; y < rows; y++) { v = fadd(p[(size_t)y * cols], v); p[(size_t)y * cols] = v; }
+}
+
+// one launch set (row pass, column pass, statistics) for the B.n frames of `B`: depth images already on the device
+static int launch_prep_set(nicp_context *ctx, const PrepBatch &B, const nicp_projector *proj, const nicp_stats_params *sp,
+                           const float sensorOffset[16], int *d_index, int *d_interval, const CamSet *cams) {
+  const int rows = proj->rows, cols = proj->cols, F = B.n;
   const bool multi = cams && cams->multi;
   const PrepCams *d_pc = nullptr;
   if (multi) {
@@ -549,24 +621,24 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
     ctx->rowsSmemCfg = smem;
   }
   if (multi)
-    k_integral_rows<true><<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
-                                                            d_pc, ctx->d_integral);
+    k_integral_rows<true><<<dim3(rows, F), 256, smem, ctx->stream>>>(B, rows, cols, a, proj->min_distance, proj->max_distance, d_pc);
   else
-    k_integral_rows<false><<<rows, 256, smem, ctx->stream>>>(d_depth, rows, cols, a, proj->min_distance, proj->max_distance,
-                                                             d_pc, ctx->d_integral);
+    k_integral_rows<false><<<dim3(rows, F), 256, smem, ctx->stream>>>(B, rows, cols, a, proj->min_distance, proj->max_distance, d_pc);
   NICP_CHECK_LAUNCH(ctx);
   const size_t stripBytes = (size_t)rows * 32 * sizeof(float);
-  if (stripBytes <= 200 * 1024) {
+  // batches stream the columns (enough threads to cover the memory latency); a lone frame stages strips in shared memory
+  static const int streamFrom = getenv("NICP_PREP_STREAM_FROM") ? atoi(getenv("NICP_PREP_STREAM_FROM")) : 4;
+  if (F >= streamFrom) {
+    k_integral_cols_stream<<<dim3((cols + 127) / 128, kIntegralCh, F), 128, 0, ctx->stream>>>(B, rows, cols);
+  } else if (stripBytes <= 200 * 1024) {
     // per context = per device: the attribute is a per-device property of the kernel
     if (stripBytes > 48 * 1024 && stripBytes > ctx->colsSmemCfg) {
       NICP_CUDA(cudaFuncSetAttribute(k_integral_cols_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stripBytes));
       ctx->colsSmemCfg = stripBytes;
     }
-    dim3 gc((cols + 31) / 32, kIntegralCh);
-    k_integral_cols_smem<<<gc, 256, stripBytes, ctx->stream>>>(rows, cols, ctx->d_integral);
+    k_integral_cols_smem<<<dim3((cols + 31) / 32, kIntegralCh, F), 256, stripBytes, ctx->stream>>>(B, rows, cols);
   } else {
-    dim3 gc((cols + 63) / 64, kIntegralCh);
-    k_integral_cols<<<gc, 64, 0, ctx->stream>>>(rows, cols, ctx->d_integral);
+    k_integral_cols<<<dim3((cols + 63) / 64, kIntegralCh, F), 64, 0, ctx->stream>>>(B, rows, cols);
   }
   NICP_CHECK_LAUNCH(ctx);
 
@@ -591,22 +663,65 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
   fix_last_row(sc.M);
   sc.applyOffset = is_identity16(sc.M) ? 0 : 1;
   dim3 bs(32, 8);
-  dim3 gs((cols + 31) / 32, (rows + 7) / 8);
-  bool ks = keepStats && cloud->stats16;
+  dim3 gs((cols + 31) / 32, (rows + 7) / 8, F);
   if (multi)
-    k_stats<true><<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, d_pc, cloud->points, cloud->normals,
-                                              cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
-                                              ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
+    k_stats<true><<<gs, bs, 0, ctx->stream>>>(B, rows, cols, sc, d_pc, d_index, d_interval);
   else
-    k_stats<false><<<gs, bs, 0, ctx->stream>>>(d_depth, ctx->d_integral, rows, cols, sc, d_pc, cloud->points, cloud->normals,
-                                               cloud->omega, d_index, ctx->d_interval, ks ? cloud->stats16 : nullptr,
-                                               ks ? cloud->eigvals : nullptr, ks ? cloud->statsN : nullptr, cloud->d_n);
+    k_stats<false><<<gs, bs, 0, ctx->stream>>>(B, rows, cols, sc, d_pc, d_index, d_interval);
   NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+static void prep_batch_add(PrepBatch &B, float *d_depth, float *d_integral, nicp_cloud *cloud, bool keepStats) {
+  const int f = B.n++;
+  B.depth[f] = d_depth;
+  B.integral[f] = d_integral;
+  B.points[f] = cloud->points;
+  B.normals[f] = cloud->normals;
+  B.omega[f] = cloud->omega;
+  const bool ks = keepStats && cloud->stats16;
+  B.stats16[f] = ks ? cloud->stats16 : nullptr;
+  B.eigvals[f] = ks ? cloud->eigvals : nullptr;
+  B.statsN[f] = ks ? cloud->statsN : nullptr;
+  B.count[f] = cloud->d_n;
+  cloud->points3_valid = false;
   cloud->n_known = false;
   cloud->has_stats = ks;
-  ctx->lastRows = rows;
-  ctx->lastCols = cols;
+}
+
+int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
+                      const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index, const CamSet *cams) {
+  PrepBatch B;
+  memset(&B, 0, sizeof B);
+  prep_batch_add(B, const_cast<float *>(d_depth), ctx->d_integral, cloud, keepStats != 0);
+  int rc = launch_prep_set(ctx, B, proj, sp, sensorOffset, d_index, ctx->d_interval, cams);
+  if (rc) return rc;
+  ctx->lastRows = proj->rows;
+  ctx->lastCols = proj->cols;
   return NICP_OK;
+}
+
+// n raw 16-bit frames already on the device (d_raw[f]) -> n clouds: depth conversion + the launch set above, in
+// sub-batches of at most kMaxPrepBatch frames whose scratch (depth + integral image, 44 B/pixel/frame) stays L2 resident
+int launch_raw_prep_batch(nicp_context *ctx, int n, const uint16_t *const *d_raw, int rawRows, int rawCols, float scale, int step,
+                          float maxCov, const nicp_projector *proj, const nicp_stats_params *sp, const float sensorOffset[16],
+                          int keepStats, nicp_cloud *const *clouds) {
+  const size_t px = (size_t)proj->rows * proj->cols;
+  if (n > ctx->batchSlots || px > ctx->batchPixels) {
+    set_error("internal: batch prep scratch too small");
+    return NICP_ERR_INVALID;
+  }
+  PrepBatch B;
+  memset(&B, 0, sizeof B);
+  for (int f = 0; f < n; f++) {
+    prep_batch_add(B, ctx->d_bDepth + (size_t)f * ctx->batchPixels, ctx->d_bIntegral + (size_t)f * ctx->batchPixels * kIntegralCh,
+                   clouds[f], keepStats != 0);
+    B.raw[f] = d_raw[f];
+  }
+  const int outPx = (rawRows / step) * (rawCols / step);
+  k_depth_convert<<<dim3((outPx + 255) / 256, n), 256, 0, ctx->stream>>>(B, rawRows, rawCols, scale, step, maxCov);
+  NICP_CHECK_LAUNCH(ctx);
+  return launch_prep_set(ctx, B, proj, sp, sensorOffset, nullptr, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -727,14 +842,21 @@ __global__ void k_cloud_transform(int capacity, const int *__restrict__ nPtr, Af
   xform_normal(M, nn.x, nn.y, nn.z, x, y, z);
   normals[i] = make_float4(x, y, z, nn.w);
   float4 o0 = omega[3 * (size_t)i], o1 = omega[3 * (size_t)i + 1], o2 = omega[3 * (size_t)i + 2];
-  float OP[9] = {o0.x, o0.y, o0.z, o0.y, o0.w, o1.x, o0.z, o1.x, o1.y};
-  float ON[9] = {o1.z, o1.w, o2.x, o1.w, o2.y, o2.z, o2.x, o2.z, o2.w};
+  float P6[6], N6[6];
+  omega_unpack(o0, o1, o2, P6, N6);
+  float OP[9] = {P6[0], P6[1], P6[2], P6[1], P6[3], P6[4], P6[2], P6[4], P6[5]};
+  float ON[9] = {N6[0], N6[1], N6[2], N6[1], N6[3], N6[4], N6[2], N6[4], N6[5]};
   float tp[9], tn[9];
   rotate_sym(M16, OP, tp);
   rotate_sym(M16, ON, tn);
-  omega[3 * (size_t)i + 0] = make_float4(NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1));
-  omega[3 * (size_t)i + 1] = make_float4(NM3(tp, 1, 2), NM3(tp, 2, 2), NM3(tn, 0, 0), NM3(tn, 0, 1));
-  omega[3 * (size_t)i + 2] = make_float4(NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2));
+  {
+    const float Q6[6] = {NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1), NM3(tp, 1, 2), NM3(tp, 2, 2)};
+    const float R6[6] = {NM3(tn, 0, 0), NM3(tn, 0, 1), NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2)};
+    const Omega3 w = omega_pack(Q6, R6);
+    omega[3 * (size_t)i + 0] = w.o0;
+    omega[3 * (size_t)i + 1] = w.o1;
+    omega[3 * (size_t)i + 2] = w.o2;
+  }
   if (stats16) {
     float *S = stats16 + 16 * (size_t)i;
     float o[16];
@@ -767,14 +889,19 @@ __global__ void k_cloud_append(int srcCapacity, const int *__restrict__ srcN, co
     p = make_float4(x, y, z, 1.0f);
     xform_normal(M, nn.x, nn.y, nn.z, x, y, z);
     nn = make_float4(x, y, z, nn.w);
-    float OP[9] = {o0.x, o0.y, o0.z, o0.y, o0.w, o1.x, o0.z, o1.x, o1.y};
-    float ON[9] = {o1.z, o1.w, o2.x, o1.w, o2.y, o2.z, o2.x, o2.z, o2.w};
+    float P6[6], N6[6];
+    omega_unpack(o0, o1, o2, P6, N6);
+    float OP[9] = {P6[0], P6[1], P6[2], P6[1], P6[3], P6[4], P6[2], P6[4], P6[5]};
+    float ON[9] = {N6[0], N6[1], N6[2], N6[1], N6[3], N6[4], N6[2], N6[4], N6[5]};
     float tp[9], tn[9];
     rotate_sym(M16, OP, tp);
     rotate_sym(M16, ON, tn);
-    o0 = make_float4(NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1));
-    o1 = make_float4(NM3(tp, 1, 2), NM3(tp, 2, 2), NM3(tn, 0, 0), NM3(tn, 0, 1));
-    o2 = make_float4(NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2));
+    const float Q6[6] = {NM3(tp, 0, 0), NM3(tp, 0, 1), NM3(tp, 0, 2), NM3(tp, 1, 1), NM3(tp, 1, 2), NM3(tp, 2, 2)};
+    const float R6[6] = {NM3(tn, 0, 0), NM3(tn, 0, 1), NM3(tn, 0, 2), NM3(tn, 1, 1), NM3(tn, 1, 2), NM3(tn, 2, 2)};
+    const Omega3 w = omega_pack(Q6, R6);
+    o0 = w.o0;
+    o1 = w.o1;
+    o2 = w.o2;
   }
   dp[o] = p;
   dn[o] = nn;

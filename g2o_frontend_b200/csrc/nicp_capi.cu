@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -79,6 +80,29 @@ static void invalidate_graphs(nicp_context *ctx) {
     }
 }
 
+// scratch of the batched frame preparation: `slots` frames of depth + integral image, raw staging for two sub-batches
+static int ensure_batch_prep(nicp_context *ctx, int slots, size_t pixels, size_t rawPixels) {
+  if (slots <= ctx->batchSlots && pixels <= ctx->batchPixels && rawPixels <= ctx->batchRawPixels) return NICP_OK;
+  if (slots < ctx->batchSlots) slots = ctx->batchSlots;
+  if (pixels < ctx->batchPixels) pixels = ctx->batchPixels;
+  if (rawPixels < ctx->batchRawPixels) rawPixels = ctx->batchRawPixels;
+  NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->copyStream));
+  dev_free(ctx->d_bDepth);
+  dev_free(ctx->d_bIntegral);
+  dev_free(ctx->d_bRaw);
+  ctx->batchSlots = 0;
+  ctx->batchPixels = ctx->batchRawPixels = 0;
+  int rc;
+  if ((rc = dev_alloc(&ctx->d_bDepth, (size_t)slots * pixels))) return rc;
+  if ((rc = dev_alloc(&ctx->d_bIntegral, (size_t)slots * pixels * kIntegralCh))) return rc;
+  if ((rc = dev_alloc(&ctx->d_bRaw, 2 * (size_t)slots * rawPixels))) return rc;
+  ctx->batchSlots = slots;
+  ctx->batchPixels = pixels;
+  ctx->batchRawPixels = rawPixels;
+  return NICP_OK;
+}
+
 static void free_align(nicp_context *ctx) {
   invalidate_graphs(ctx);
   dev_free(ctx->d_refZ);
@@ -111,8 +135,8 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_partials2, (size_t)slots * 16 * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   NICP_CUDA(cudaMemset(ctx->d_state, 0, sizeof(PairState) * (size_t)slots));  // the reduction tickets start at 0
-  // two sets of: descriptors followed by one int flag per slot
-  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots;
+  // two sets of: descriptors, one int flag per slot, one pair group per slot
+  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots + sizeof(PairGroup) * slots;
   descBytes = (descBytes + 255) & ~(size_t)255;
   void *p = nullptr;
   NICP_CUDA(cudaMalloc(&p, 2 * descBytes));
@@ -246,6 +270,34 @@ static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_para
   ac.maxChi2 = ap->inlier_max_chi2;
   ac.robust = ap->robust_kernel;
   return ac;
+}
+
+// pair groups of the chunk staged in ctx->h_desc: descriptors [0, m) are ordered so that pairs sharing a current cloud are
+// adjacent (curSlotOf[i] = descriptor that owns pair i's current z-buffer); groups of at most ctx->groupSize pairs.
+static PairGroup *staged_groups(nicp_context *ctx) {
+  return reinterpret_cast<PairGroup *>(reinterpret_cast<int *>(ctx->h_desc + ctx->slots) + ctx->slots);
+}
+static int stage_groups(nicp_context *ctx, int m, const int *curSlotOf) {
+  PairGroup *g = staged_groups(ctx);
+  int n = 0;
+  for (int i = 0; i < m;) {
+    int j = i + 1;
+    while (j < m && j - i < ctx->groupSize && curSlotOf[j] == curSlotOf[i]) j++;
+    g[n].first = i;
+    g[n].count = j - i;
+    n++;
+    i = j;
+  }
+  return n;
+}
+// stage-level calls: one pair, one group
+static int upload_single_group(nicp_context *ctx) {
+  PairGroup *g = staged_groups(ctx);
+  g[0].first = 0;
+  g[0].count = 1;
+  PairGroup *d = reinterpret_cast<PairGroup *>(reinterpret_cast<int *>(ctx->d_desc + ctx->slots) + ctx->slots);
+  NICP_CUDA(cudaMemcpyAsync(d, g, sizeof(PairGroup), cudaMemcpyHostToDevice, ctx->stream));
+  return NICP_OK;
 }
 
 static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud *ref, const nicp_cloud *cur,
@@ -508,6 +560,8 @@ int nicp_create(int device, nicp_context **out) {
   for (int i = 0; i < 2; i++) {
     NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawCopied[i], cudaEventDisableTiming));
     NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawUsed[i], cudaEventDisableTiming));
+    NICP_CUDA(cudaEventCreateWithFlags(&ctx->evBRawCopied[i], cudaEventDisableTiming));
+    NICP_CUDA(cudaEventCreateWithFlags(&ctx->evBRawUsed[i], cudaEventDisableTiming));
   }
   cudaDeviceProp prop;
   NICP_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -516,7 +570,9 @@ int nicp_create(int device, nicp_context **out) {
   ctx->corrVariant = 1;
   // fixed per context (not per batch) so that a pair's H/b never depend on batch size or GPU count
   ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
-  if (ctx->tileConfig < 0 || ctx->tileConfig > 2) ctx->tileConfig = 0;
+  if (ctx->tileConfig < 0 || ctx->tileConfig > 3) ctx->tileConfig = 0;
+  ctx->groupSize = env_int("NICP_GROUP", 4);
+  ctx->groupMinBlocks = env_int("NICP_GROUP_MINB", 16);
   {
     void *p = nullptr;
     NICP_CUDA(cudaMalloc(&p, sizeof(DeviceCams)));
@@ -564,7 +620,12 @@ void nicp_destroy(nicp_context *ctx) {
   for (int i = 0; i < 2; i++) {
     cudaEventDestroy(ctx->evRawCopied[i]);
     cudaEventDestroy(ctx->evRawUsed[i]);
+    cudaEventDestroy(ctx->evBRawCopied[i]);
+    cudaEventDestroy(ctx->evBRawUsed[i]);
   }
+  dev_free(ctx->d_bDepth);
+  dev_free(ctx->d_bIntegral);
+  dev_free(ctx->d_bRaw);
   cudaStreamDestroy(ctx->copyStream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -665,10 +726,11 @@ int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *poin
   for (int i = 0; i < n; i++) {
     if (normals4) { nrm[4 * i] = normals4[4 * i]; nrm[4 * i + 1] = normals4[4 * i + 1]; nrm[4 * i + 2] = normals4[4 * i + 2]; }
     nrm[4 * i + 3] = curvature ? curvature[i] : 0.0f;
+    // device layout: the two upper triangles interleaved (Omega3, nicp_internal.cuh)
     if (omega_p6)
-      for (int k = 0; k < 6; k++) om[12 * (size_t)i + k] = omega_p6[6 * (size_t)i + k];
+      for (int k = 0; k < 6; k++) om[12 * (size_t)i + 2 * k] = omega_p6[6 * (size_t)i + k];
     if (omega_n6)
-      for (int k = 0; k < 6; k++) om[12 * (size_t)i + 6 + k] = omega_n6[6 * (size_t)i + k];
+      for (int k = 0; k < 6; k++) om[12 * (size_t)i + 2 * k + 1] = omega_n6[6 * (size_t)i + k];
   }
   c->points3_valid = false;
   NICP_CUDA(cudaMemcpyAsync(c->points, points4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -708,9 +770,9 @@ int nicp_cloud_download(nicp_context *ctx, const nicp_cloud *c, float *points4, 
     }
     if (curvature) curvature[i] = nrm[4 * i + 3];
     if (omega_p6)
-      for (int k = 0; k < 6; k++) omega_p6[6 * (size_t)i + k] = om[12 * (size_t)i + k];
+      for (int k = 0; k < 6; k++) omega_p6[6 * (size_t)i + k] = om[12 * (size_t)i + 2 * k];
     if (omega_n6)
-      for (int k = 0; k < 6; k++) omega_n6[6 * (size_t)i + k] = om[12 * (size_t)i + 6 + k];
+      for (int k = 0; k < 6; k++) omega_n6[6 * (size_t)i + k] = om[12 * (size_t)i + 2 * k + 1];
   }
   return NICP_OK;
 }
@@ -939,6 +1001,72 @@ int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows
   return depth_to_cloud_device(ctx, proj, sp, sensor_offset, keep_stats, cloud, index);
 }
 
+int nicp_raw_depth_to_cloud_batch(nicp_context *ctx, int n, const uint16_t *const *raws, int raw_rows, int raw_cols,
+                                  float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
+                                  const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
+                                  nicp_cloud *const *clouds) {
+  if (!ctx || n < 0 || !proj || !sp || raw_rows <= 0 || raw_cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return NICP_OK;
+  if (!raws || !clouds) return NICP_ERR_INVALID;
+  if (step < 1) step = 1;
+  if (proj->rows != raw_rows / step || proj->cols != raw_cols / step) {
+    set_error("projector image size %dx%d does not match the scaled raw image %dx%d", proj->rows, proj->cols,
+              raw_rows / step, raw_cols / step);
+    return NICP_ERR_INVALID;
+  }
+  const size_t rpx = (size_t)raw_rows * raw_cols, px = (size_t)proj->rows * proj->cols;
+  for (int i = 0; i < n; i++) {
+    if (!raws[i] || !clouds[i]) {
+      set_error("null frame or cloud at index %d", i);
+      return NICP_ERR_INVALID;
+    }
+    if ((size_t)clouds[i]->capacity < px) {
+      set_error("cloud %d: capacity %d smaller than the image (%zu pixels)", i, clouds[i]->capacity, px);
+      return NICP_ERR_INVALID;
+    }
+    if (clouds[i]->device != ctx->device) {
+      set_error("cloud %d lives on GPU %d, the context on GPU %d", i, clouds[i]->device, ctx->device);
+      return NICP_ERR_INVALID;
+    }
+    for (int j = 0; j < i; j++)
+      if (clouds[j] == clouds[i]) {
+        set_error("cloud %d and cloud %d are the same object", j, i);
+        return NICP_ERR_INVALID;
+      }
+  }
+  int sub = env_int("NICP_PREP_BATCH", kMaxPrepBatch);
+  if (sub > kMaxPrepBatch) sub = kMaxPrepBatch;
+  if (sub > n) sub = n;
+  int rc;
+  if ((rc = ensure_batch_prep(ctx, sub, px, rpx))) return rc;
+  float eye[16];
+  mat4_identity(eye);
+  for (int base = 0; base < n; base += sub) {
+    const int m = n - base < sub ? n - base : sub;
+    // raw frames of sub-batch k are uploaded on the copy stream into staging set k & 1 while sub-batch k - 1 computes
+    const int b = (ctx->bRawToggle ^= 1);
+    uint16_t *stage = ctx->d_bRaw + (size_t)b * ctx->batchSlots * ctx->batchRawPixels;
+    const uint16_t *d_raw[kMaxPrepBatch];
+    NICP_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evBRawUsed[b], 0));
+    for (int f = 0; f < m; f++) {
+      uint16_t *dst = stage + (size_t)f * ctx->batchRawPixels;
+      NICP_CUDA(cudaMemcpyAsync(dst, raws[base + f], rpx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copyStream));
+      d_raw[f] = dst;
+    }
+    NICP_CUDA(cudaEventRecord(ctx->evBRawCopied[b], ctx->copyStream));
+    NICP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evBRawCopied[b], 0));
+    for (int f = 0; f < m; f++)
+      if (keep_stats && (rc = ensure_stats(clouds[base + f]))) return rc;
+    if ((rc = launch_raw_prep_batch(ctx, m, d_raw, raw_rows, raw_cols, depth_scale, step, max_depth_cov, proj, sp,
+                                    sensor_offset ? sensor_offset : eye, keep_stats, clouds + base)))
+      return rc;
+    NICP_CUDA(cudaEventRecord(ctx->evBRawUsed[b], ctx->stream));
+  }
+  ctx->lastRows = 0;  // the single-frame test hooks (integral / interval image) describe no frame of a batch
+  return NICP_OK;
+}
+
 int nicp_last_integral_image(nicp_context *ctx, float *integral10) {
   if (!ctx || !integral10 || ctx->lastRows <= 0) return NICP_ERR_INVALID;
   NICP_CUDA(cudaSetDevice(ctx->device));
@@ -1023,6 +1151,7 @@ int nicp_correspond_linearize(nicp_context *ctx, const nicp_cloud *reference, co
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].refZ[0], z.data(), px * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, current_index, px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = stage_set_T(ctx, T))) return rc;
+  if ((rc = upload_single_group(ctx))) return rc;
   ctx->zIter = ctx->zCurGen = -1;  // slot 0 was staged by hand
   if ((rc = run_correspond_linearize(ctx, ac, false, (int)px))) return rc;
   if (corr_image)
@@ -1054,6 +1183,7 @@ int nicp_linearize(nicp_context *ctx, const nicp_cloud *reference, const nicp_cl
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].corrImage, ri.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(ctx->h_desc[0].curIndex, ci.data(), px * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = stage_set_T(ctx, T))) return rc;
+  if ((rc = upload_single_group(ctx))) return rc;
   ctx->zIter = ctx->zCurGen = -1;
   if ((rc = run_correspond_linearize(ctx, ac, true, (int)px))) return rc;
   ctx->lastAlignValid = false;
@@ -1129,7 +1259,11 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     // chunk c stages into descriptor set c&1; the event of chunk c-2 (same set) was waited for when the
     // host post-processed that chunk, so the set is free
     select_desc_set(ctx, chunk & 1);
-    std::map<const nicp_cloud *, int> curSlot;
+    // descriptor order inside the chunk: pairs that share a current cloud adjacent (stable, by first appearance), so that
+    // the grouped kernel can walk them with the current side of a tile held in registers; the result of descriptor i
+    // still goes to the record of the pair it came from
+    std::map<const nicp_cloud *, int> curRank;
+    std::vector<int> order(m), rankOf(m);
     for (int i = 0; i < m; i++) {
       const nicp_cloud *r = refs[base + i], *c = curs[base + i];
       if (!r || !c) {
@@ -1140,17 +1274,21 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         set_error("pair %d: cloud lives on GPU %d / %d, the context on GPU %d", base + i, r->device, c->device, ctx->device);
         return NICP_ERR_INVALID;
       }
-      auto it = curSlot.find(c);
-      int cs;
-      if (it == curSlot.end()) {
-        cs = i;
-        curSlot[c] = i;
-        owns[i] = 1;
-      } else {
-        cs = it->second;
-        owns[i] = 0;
-      }
-      fill_desc(ctx, i, cs, r, c, guesses ? guesses + 16 * (size_t)(base + i) : nullptr, ctx->d_results + base + i,
+      auto it = curRank.find(c);
+      if (it == curRank.end()) it = curRank.insert(std::make_pair(c, (int)curRank.size())).first;
+      rankOf[i] = it->second;
+      order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rankOf[a] < rankOf[b]; });
+    std::vector<int> curSlotOf(m);
+    for (int i = 0; i < m; i++) {
+      const int src = base + order[i];
+      const nicp_cloud *r = refs[src], *c = curs[src];
+      const bool first = i == 0 || rankOf[order[i]] != rankOf[order[i - 1]];
+      const int cs = first ? i : curSlotOf[i - 1];
+      curSlotOf[i] = cs;
+      owns[i] = first ? 1 : 0;
+      fill_desc(ctx, i, cs, r, c, guesses ? guesses + 16 * (size_t)src : nullptr, ctx->d_results + src,
                 single ? ctx->d_trace : nullptr);
       // big chunks are DRAM bound: the pinhole projection kernel streams the reference points from the packed copy
       // (a lone pair is latency bound and keeps the direct float4 loads)
@@ -1163,6 +1301,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         ctx->h_desc[i].numPriors = numPriors;
       }
     }
+    const int nGroups = stage_groups(ctx, m, curSlotOf.data());
     const bool useGraph = single && ctx->graphsEnabled && !cams.multi && !ctx->timing;
     bool replayed = false;
     if (useGraph) {
@@ -1202,7 +1341,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         cudaGraph_t graph = nullptr;
         const long long launchesBefore = ctx->launches;
         NICP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+        rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, nGroups,
                              owns.data(), single, base);
         cudaError_t e1 = cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
                                          cudaMemcpyDeviceToHost, ctx->stream);
@@ -1225,7 +1364,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       }
     }
     if (!replayed) {
-      if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, (int)curSlot.size(),
+      if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, nGroups,
                                 owns.data(), single, base)))
         return rc;
       NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,

@@ -32,6 +32,7 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 constexpr int kMaxCams = 8;       // NICP_MAX_CAMERAS
+constexpr int kMaxPrepBatch = 8;  // frames per frame-preparation launch set (their scratch stays L2 resident)
 constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
 constexpr int kIntegralCh = 10;   // n,x,y,z,xx,xy,xz,yy,yz,zz
 constexpr unsigned long long kEmptyZ = 0xFFFFFFFFFFFFFFFFull;
@@ -65,6 +66,27 @@ __device__ __forceinline__ float z_depth(unsigned long long v, int epoch, float 
 #endif
 inline int epoch_of_iteration(int it) { return kEpochFresh - ((it >> 1) & 15); }
 
+// Device layout of a point's two information matrices: 3 float4 holding the upper triangles of Omega_P and Omega_N
+// INTERLEAVED element by element,
+//   (Pxx, Nxx, Pxy, Nxy)  (Pxz, Nxz, Pyy, Nyy)  (Pyz, Nyz, Pzz, Nzz),
+// so that a 128-bit load leaves (P_ij, N_ij) in an aligned register pair: the Linearizer term of the fused kernel runs
+// its point half and its normal half in the two lanes of the packed FP32 instructions (fma.rn.f32x2) without a move.
+struct Omega3 {
+  float4 o0, o1, o2;
+};
+__host__ __device__ inline Omega3 omega_pack(const float *P6, const float *N6) {
+  Omega3 w;
+  w.o0 = make_float4(P6[0], N6[0], P6[1], N6[1]);
+  w.o1 = make_float4(P6[2], N6[2], P6[3], N6[3]);
+  w.o2 = make_float4(P6[4], N6[4], P6[5], N6[5]);
+  return w;
+}
+__host__ __device__ inline void omega_unpack(const float4 &o0, const float4 &o1, const float4 &o2, float *P6, float *N6) {
+  P6[0] = o0.x; N6[0] = o0.y; P6[1] = o0.z; N6[1] = o0.w;
+  P6[2] = o1.x; N6[2] = o1.y; P6[3] = o1.z; N6[3] = o1.w;
+  P6[4] = o2.x; N6[4] = o2.y; P6[5] = o2.z; N6[5] = o2.w;
+}
+
 // accumulator slot layout of the fused correspondence+linearise reduction
 enum {
   A_HTT = 0,   // 6: xx xy xz yy yz zz
@@ -95,6 +117,13 @@ struct PairState {
   float sumMidx;   // sum over outer iterations of pixels with both indices valid (roofline accounting)
   float sumMacc;   // sum over outer iterations of accepted correspondences
   int ticket;      // k_reduce_solve: how many of the kRowGroups first-level CTAs are done (0 between launches)
+  int pad[3];      // sizeof % 16 == 0: T / invT of every slot can be fetched with 128-bit loads
+};
+static_assert(sizeof(PairState) % 16 == 0, "PairState slots must keep T / invT 16-byte aligned");
+
+// pairs [first, first + count) of a chunk's descriptor array share their current cloud (corr_lin.cuh)
+struct PairGroup {
+  int first, count;
 };
 
 // per-pair descriptor for the batched kernels (device memory, filled by the host per chunk)
@@ -105,7 +134,7 @@ struct PairDesc {
   const int *refN;
   const float4 *curPoints;
   const float4 *curNormals;  // w = curvature
-  const float4 *curOmega;    // 3 float4 per point: (Pxx,Pxy,Pxz,Pyy) (Pyz,Pzz,Nxx,Nxy) (Nxz,Nyy,Nyz,Nzz)
+  const float4 *curOmega;    // 3 float4 per point, Omega_P / Omega_N interleaved (Omega3 above)
   const int *curN;
   unsigned long long *refZ[2];  // double-buffered reference z-buffer (packed depth|index)
   unsigned long long *curZ;     // current z-buffer (shared by pairs with the same current cloud)
@@ -175,7 +204,7 @@ struct nicp_cloud {
   int capacity;
   float4 *points;
   float4 *normals;  // w = curvature
-  float4 *omega;    // 3 per point
+  float4 *omega;    // 3 per point (Omega3 layout)
   float *stats16;   // optional
   float *eigvals;
   int *statsN;
@@ -208,6 +237,14 @@ struct nicp_context {
   int *d_interval;
   int *d_index;
   int lastRows, lastCols;
+  // batched frame prep (nicp_raw_depth_to_cloud_batch): scratch of batchSlots frames, raw staging of 2 x batchSlots frames
+  int batchSlots;
+  size_t batchPixels, batchRawPixels;
+  float *d_bDepth;      // [batchSlots][batchPixels]
+  float *d_bIntegral;   // [batchSlots][10][batchPixels]
+  uint16_t *d_bRaw;     // [2][batchSlots][batchRawPixels]
+  cudaEvent_t evBRawCopied[2], evBRawUsed[2];
+  int bRawToggle;
   // dynamic shared memory opted into on THIS context's device (cudaFuncAttributeMaxDynamicSharedMemorySize is per device)
   size_t rowsSmemCfg, colsSmemCfg;
   void *h_stage;      // pinned staging
@@ -218,7 +255,9 @@ struct nicp_context {
   size_t slotPixels;  // pixels per slot
   int blocksPerPair;            // lower bound of the partial-row allocation
   int corrVariant;              // reserved (one fused-kernel variant is compiled)
-  int tileConfig;               // index into the tiled kernel's (threads, pixels/thread) table
+  int tileConfig;               // fused-kernel variant: 0 = grouped kernel (default), 1..3 = round-1 per-pair kernels
+  int groupSize;                // pairs per group of the grouped kernel (pairs of a group share their current cloud)
+  int groupMinBlocks;           // its __launch_bounds__ min-blocks instantiation (16 or 20 one-warp CTAs per SM)
   int partialRows;              // rows of d_partials per slot
   unsigned long long *d_refZ;   // [slots][2][P]
   unsigned long long *d_curZ;   // [slots][P]
@@ -287,6 +326,9 @@ int launch_depth_convert(nicp_context *ctx, const uint16_t *d_raw, int rows, int
 int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, const nicp_stats_params *sp,
                       const float sensorOffset[16], int keepStats, nicp_cloud *cloud, int *d_index,
                       const CamSet *cams = nullptr);
+int launch_raw_prep_batch(nicp_context *ctx, int n, const uint16_t *const *d_raw, int rawRows, int rawCols, float scale, int step,
+                          float maxCov, const nicp_projector *proj, const nicp_stats_params *sp, const float sensorOffset[16],
+                          int keepStats, nicp_cloud *const *clouds);
 int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
                      float maxD, nicp_cloud *cloud, int *d_index);
 int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius, int *d_interval);

@@ -235,6 +235,17 @@ int nicp_raw_depth_to_cloud(nicp_context *ctx, const uint16_t *raw, int raw_rows
                             float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
                             const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
                             nicp_cloud *cloud, int *index);
+/* The same for n frames with one launch set per sub-batch of up to 8 frames (grid.z = frame): what a tracker's cloud
+ * cache or a loop closer does frame by frame (pwn_tracker2/pwn_cloud_cache.cpp:60-102 -> PwnMatcherBase::makeCloud,
+ * pwn_matcher_base.cpp:46-75) when it (re)builds the clouds of many frames.  One frame does not fill a B200 -- its two
+ * order-preserving prefix-sum passes are bound by latency -- a batch does.  All frames share the raw size, step,
+ * projector, statistics parameters and sensor offset; clouds[i] receives frame i (distinct clouds, capacity >= pixels).
+ * Results are bit-identical to n calls of nicp_raw_depth_to_cloud.  ASYNCHRONOUS like it (no index images are returned);
+ * pinned raw buffers must stay unchanged until the next synchronous call on this context returns. */
+int nicp_raw_depth_to_cloud_batch(nicp_context *ctx, int n, const uint16_t *const *raws, int raw_rows, int raw_cols,
+                                  float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
+                                  const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
+                                  nicp_cloud *const *clouds);
 /* PointIntegralImage::compute (pointintegralimage.cpp:7-44) of the last nicp_depth_to_cloud call:
  * 10 channels per pixel, interleaved [rows][cols][10] = n,x,y,z,xx,xy,xz,yy,yz,zz (test hook) */
 int nicp_last_integral_image(nicp_context *ctx, float *integral10);

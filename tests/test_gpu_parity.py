@@ -9,7 +9,7 @@ relative, final transform within 1e-4 rad / 1e-4 m.
 import numpy as np
 import pytest
 
-from conftest import get_scene
+from conftest import get_scene, CONF_1_1, CONF_1_4
 
 pytestmark = pytest.mark.gpu
 
@@ -626,6 +626,49 @@ def test_raw_depth_to_cloud_matches_two_step(ctx):
 
 
 # ---- edge cases -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("step,n,offset", [(4, 11, True), (1, 5, False), (2, 9, False)])
+def test_frame_prep_batch_is_bit_identical_to_single_calls(ctx, step, n, offset):
+    """nicp_raw_depth_to_cloud_batch (one launch set per sub-batch of up to 8 frames, streaming column pass) against n
+    single-frame calls (shared-memory column strips): every cloud array bit-identical, ragged last sub-batch included;
+    frame 0 also against the oracle."""
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    conf = {4: CONF_1_4, 2: CONF_1_4, 1: CONF_1_1}[step]
+    rows, cols = 480 // step, 640 // step
+    K = synth.scaled_K(synth.K_KINECT, 1.0 / step)
+    rng = np.random.default_rng(7)
+    raws = [synth.render_depth_u16(synth.perturbed_pose(rng, np.eye(4), 0.2, 5.0), seed=20 + i, dropout=0.03 * (i % 3))
+            for i in range(n)]
+    raws[-1] = np.zeros_like(raws[-1])          # an empty frame inside a batch
+    so = synth.make_pose((0.05, -0.02, 0.1), (0.2, 1.0, 0.1), 4.0).astype(np.float32) if offset else np.eye(4, dtype=np.float32)
+    proj = capi.make_projector(K, rows, cols, conf["minD"], conf["maxD"])
+    sp = capi.make_stats_params(conf["worldRadius"], conf["minImageRadius"], conf["maxImageRadius"], conf["minPoints"],
+                                conf["curvatureThreshold"], conf["omegaCurvatureThreshold"])
+    single = [ctx.raw_depth_to_cloud(r, proj, sp, step=step, sensor_offset=so, keep_stats=(step == 4))[0] for r in raws]
+    batch = ctx.raw_depth_to_cloud_batch(raws, proj, sp, step=step, sensor_offset=so, keep_stats=(step == 4))
+    ctx.synchronize()
+    for i, (a, b) in enumerate(zip(single, batch)):
+        assert a.size() == b.size(), i
+        da, db = a.download(), b.download()
+        for k in da:
+            assert np.array_equal(da[k].view(np.uint32), db[k].view(np.uint32)), (i, k)
+        if step == 4 and a.size():
+            sa, sb = a.download_stats(), b.download_stats()
+            for x, y in zip(sa, sb):
+                assert np.array_equal(np.asarray(x).view(np.uint32), np.asarray(y).view(np.uint32)), i
+    assert batch[-1].size() == 0
+    # frame 0 against the oracle (points / index-derived size exact, normals statistically identical: test_depth_to_cloud)
+    d0 = O.depth_u16_to_f32(raws[0])
+    if step > 1:
+        d0 = O.depth_scale(d0, step)
+    osp = O.default_stats_params(minImageRadius=conf["minImageRadius"], maxImageRadius=conf["maxImageRadius"],
+                                 minPoints=conf["minPoints"], curvatureThreshold=conf["curvatureThreshold"],
+                                 worldRadius=conf["worldRadius"], omegaCurvatureThreshold=conf["omegaCurvatureThreshold"])
+    oc, _ = O.depth_to_cloud(d0, K, conf["minD"], conf["maxD"], osp, so)
+    assert oc.n == batch[0].size()
+    assert np.array_equal(batch[0].download()["points"], oc.points)
+
+
 def test_empty_depth_image(ctx):
     s = get_scene(4)
     z = np.zeros((s.rows, s.cols), np.float32)
