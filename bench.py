@@ -233,6 +233,60 @@ def cpu_reference_sources_run(sample_pairs, n_threads=None):
                     "(-O3 -march=x86-64-v3 -fopenmp), 1 cloud build + %d alignments" % sample_pairs}
 
 
+class CpuLeg:
+    """The CPU oracle (performance build, all host threads) as the baseline of the secondary configurations
+    (tools/bench_configs.py): cloud builds, alignments, pyramids, rig alignments.  Part of the cpu_baseline leg."""
+
+    def __init__(self, threads=None):
+        from oracle import pwn_oracle as O
+        from g2o_frontend_b200 import synth
+        self.O, self.synth = O, synth
+        cores = threads or os.cpu_count() or 1
+        while ROWS % cores:  # the finder drops rows % numThreads (correspondencefinder.cpp:38)
+            cores -= 1
+        self.cores = O.set_threads(cores, fast=True)
+
+    def sp(self, minr, maxr, minp):
+        return self.O.default_stats_params(minImageRadius=minr, maxImageRadius=maxr, minPoints=minp,
+                                           curvatureThreshold=CONF["curvatureThreshold"], worldRadius=CONF["worldRadius"],
+                                           omegaCurvatureThreshold=CONF["omegaCurvatureThreshold"])
+
+    def cp(self, dist):
+        return self.O.default_corr_params(inlierDistanceThreshold=dist,
+                                          inlierNormalAngularThreshold=CONF["inlierNormalAngularThreshold"],
+                                          flatCurvatureThreshold=CONF["flatCurvatureThreshold"],
+                                          inlierCurvatureRatioThreshold=CONF["inlierCurvatureRatioThreshold"])
+
+    def K(self, step):
+        return self.synth.scaled_K(self.synth.K_KINECT, np.float32(1.0) / np.float32(step))
+
+    def cloud(self, raw, step, minr, maxr, minp):
+        O = self.O
+        d = O.depth_u16_to_f32(raw, fast=True)
+        if step > 1:
+            d = O.depth_scale(d, step, fast=True)
+        return O.depth_to_cloud(d, self.K(step), CONF["minD"], CONF["maxD"], self.sp(minr, maxr, minp), fast=True)[0]
+
+    def align(self, ref, cur, step, dist, guess=None):
+        O = self.O
+        ap = O.make_align_params(self.K(step), ROWS // step, COLS // step, CONF["minD"], CONF["maxD"], self.cp(dist), guess=guess,
+                                 max_chi2=CONF["inlierMaxChi2"], num_threads=self.cores)
+        return O.align(ref, cur, ap, fast=True, want_trace=False)
+
+    def multi_pair_align_seconds(self, cams, depthA, depthB):
+        """one alignment of a MultiPointProjector rig pair (clouds prebuilt, not timed)"""
+        O = self.O
+        om = O.make_multi(cams)
+        osp = self.sp(10, 30, 50)
+        oA, oB = O.multi_depth_to_cloud(om, depthA, osp)[0], O.multi_depth_to_cloud(om, depthB, osp)[0]
+        rows, cols = O.multi_image_size(om)
+        oap = O.make_align_params(cams[0]["K"], rows, cols, CONF["minD"], CONF["maxD"], self.cp(1.0),
+                                  max_chi2=CONF["inlierMaxChi2"], num_threads=self.cores, multi=om)
+        t0 = time.perf_counter()
+        O.align(oA, oB, oap, fast=True, want_trace=False)
+        return time.perf_counter() - t0
+
+
 def workload_config(n_cur, n_cand, world):
     """the `config` object both arms report (same workload name; the reference arm times a bounded sample of it)"""
     n_pairs = n_cur * n_cand

@@ -607,7 +607,9 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
 
   float acc[kAccum];
   if constexpr (INPLACE) {
-    // ---- in-place stage 2: the thread that owns the pixel accumulates its term; Omega through its own smem slot ----
+    // ---- in-place stage 2: the thread that owns the pixel accumulates its term; Omega through its own smem slot.  The
+    // term is the packed-FP32 formulation of corr_lin.cuh, operation for operation, so a (pair, tile) row has the same bits
+    // whether this kernel or the grouped one produced it ----
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       if (!kSpeculativeOmega && ok[k]) {
@@ -618,19 +620,26 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
       }
     }
     cp_async_wait_all();
-#pragma unroll
-    for (int s = 0; s < kAccum; s++) acc[s] = 0.0f;
+    TermAcc tacc;
+    term_clear<false>(tacc);
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       if (__any_sync(0xffffffffu, ok[k])) {
         if (ok[k]) {
-          const float4 o0 = S.om[0][k * NT + threadIdx.x], o1 = S.om[1][k * NT + threadIdx.x],
-                       o2 = S.om[2][k * NT + threadIdx.x];
-          accumulate_term(acc, rp0[k].x, rp0[k].y, rp0[k].z, rn0[k].x, rn0[k].y, rn0[k].z, cp[k], cn[k], o0, o1, o2,
-                          ac.maxChi2, ac.robust);
+          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2 *>(&S.om[0][k * NT + threadIdx.x]);
+          const ulonglong2 w1 = *reinterpret_cast<const ulonglong2 *>(&S.om[1][k * NT + threadIdx.x]);
+          const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&S.om[2][k * NT + threadIdx.x]);
+          const f32x2 Rx = pk(rp0[k].x, rn0[k].x), Ry = pk(rp0[k].y, rn0[k].y), Rz = pk(rp0[k].z, rn0[k].z);
+          if (ac.robust)
+            term_add<true>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 1);
+          else
+            term_add<false>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 0);
         }
       }
     }
+    term_slots(tacc, acc);
+    acc[30] = 0.0f;
+    acc[31] = 0.0f;
   } else {
   // ---- compaction (fixed order: pixel slot k, then warp, then lane) ----
   unsigned int bal[TK];
@@ -967,10 +976,14 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
   solve_step<PRIORS>(D, tot, mode, lastInner, firstInner, iter, ac);
 }
 
-__global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, float *__restrict__ statHb) {
+// H / b of the _computeStatistics linearisation, to the slot of the pair's RESULT record (descriptors are ordered by
+// current cloud inside a chunk, results by the caller's pair index)
+__global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, const nicp_align_result *__restrict__ results,
+                              float *__restrict__ statHb) {
   int i = blockIdx.x;
   const PairState *st = desc[i].state;
-  for (int k = threadIdx.x; k < 42; k += blockDim.x) statHb[(size_t)i * 42 + k] = k < 36 ? st->statH[k] : st->statb[k - 36];
+  const size_t slot = (size_t)(desc[i].result - results);
+  for (int k = threadIdx.x; k < 42; k += blockDim.x) statHb[slot * 42 + k] = k < 36 ? st->statH[k] : st->statb[k - 36];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1007,15 +1020,53 @@ static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, in
   k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<g, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
                                                                                imgThr, swap ? 1 : 0, curEpoch);
 }
+// the pair groups live behind the flags in the descriptor staging area, 16-byte aligned
+static size_t groups_offset(const nicp_context *ctx) {
+  size_t off = sizeof(PairDesc) * (size_t)ctx->slots + sizeof(int) * (size_t)ctx->slots;
+  return (off + 15) & ~(size_t)15;
+}
+const PairGroup *device_groups(const nicp_context *ctx) {
+  return reinterpret_cast<const PairGroup *>(reinterpret_cast<const unsigned char *>(ctx->d_desc) + groups_offset(ctx));
+}
+PairGroup *host_groups(nicp_context *ctx) {
+  return reinterpret_cast<PairGroup *>(reinterpret_cast<unsigned char *>(ctx->h_desc) + groups_offset(ctx));
+}
 // grouped kernel (corr_lin.cuh): grid = groups x tiles, group-fastest when the group count fits gridDim.x
-template <int MODE, int MINB>
+template <int MODE, int MINB, bool PACKED = true>
 static void launch_group(nicp_context *ctx, int nGroups, int tiles, int parity, int epoch, int writeCorr, const AlignConsts &ac,
                          int P, int imgStats, float imgThr, int curEpoch) {
-  const PairGroup *d_groups = reinterpret_cast<const PairGroup *>(reinterpret_cast<const int *>(ctx->d_desc + ctx->slots) + ctx->slots);
+  const PairGroup *d_groups = device_groups(ctx);
   const bool groupFast = tiles <= 65535;
   const dim3 g = groupFast ? dim3(nGroups, tiles) : dim3(tiles, nGroups);
-  k_corr_lin_group<MODE, MINB><<<g, 32, 0, ctx->stream>>>(ctx->d_desc, d_groups, parity, epoch, writeCorr, ac, P, imgStats, imgThr,
-                                                           groupFast ? 1 : 0, curEpoch);
+  SlotBases B;
+  B.refZ = ctx->d_refZ + (size_t)parity * ctx->slots * ctx->slotPixels;
+  B.curZ = ctx->d_curZ;
+  B.curIndex = ctx->d_curIndex;
+  B.corrImage = ctx->d_corrImage;
+  B.partials = ctx->d_partials;
+  B.state = ctx->d_state;
+  B.slotPixels = (long long)ctx->slotPixels;
+  B.partialStride = (long long)ctx->partialRows * kAccum;
+  const int var = ctx->corrVariant & 3;
+#define NICP_LAUNCH_GROUP(MB, ROB, VARI, WARPS)                                                                                  \
+  k_corr_lin_group<MODE, MB, PACKED, ROB, VARI, WARPS><<<g, 32 * WARPS, 0, ctx->stream>>>(ctx->d_desc, d_groups, B, epoch, writeCorr, \
+                                                                                          ac, P, imgStats, imgThr, groupFast ? 1 : 0, \
+                                                                                          curEpoch)
+  (void)MINB;
+  if (!ac.robust) {
+    NICP_LAUNCH_GROUP(16, false, 0, 1);
+  } else if (ctx->groupWarps >= 2) {
+    if (ctx->groupMinBlocks >= 20) NICP_LAUNCH_GROUP(10, true, 0, 2);  // 10 two-warp CTAs = 20 warps per SM (96 registers)
+    else NICP_LAUNCH_GROUP(8, true, 0, 2);                             // 16 warps per SM (128 registers)
+  } else {
+    switch (var) {
+      case 0: NICP_LAUNCH_GROUP(16, true, 0, 1); break;
+      case 1: NICP_LAUNCH_GROUP(16, true, 1, 1); break;
+      case 2: NICP_LAUNCH_GROUP(16, true, 2, 1); break;
+      default: NICP_LAUNCH_GROUP(16, true, 3, 1); break;
+    }
+  }
+#undef NICP_LAUNCH_GROUP
 }
 // MODE 0 / 1 launch of the fused kernel in the context's tile configuration.  Configuration 0 (default) is the grouped
 // kernel; 1..3 are the round-1 per-pair kernels kept for comparison (tools/tune_corr.py), which ignore the grouping.
@@ -1028,8 +1079,13 @@ static void launch_corr_lin(nicp_context *ctx, int mode, int nPairs, int nGroups
       case 2: launch_tiled<0, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       case 3: launch_tiled<0, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       default:
-        if (ctx->groupMinBlocks >= 20) launch_group<0, 20>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
-        else launch_group<0, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        // pairs that share their current cloud with at least a few others go through the grouped kernel; lone pairs
+        // (a single alignment, a batch of unrelated pairs) through the per-pair kernel, whose prologue is shorter.
+        // The rows they produce are bit-identical (same term, same lane / pixel mapping, same butterfly).
+        if (nPairs >= ctx->groupMinAvg * nGroups)
+          launch_group<0, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        else
+          launch_tiled<0, 32, 3, 18, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
         break;
     }
   } else {
@@ -1038,8 +1094,10 @@ static void launch_corr_lin(nicp_context *ctx, int mode, int nPairs, int nGroups
       case 2: launch_tiled<1, 64, 2, 12>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       case 3: launch_tiled<1, 32, 3, 20, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch); break;
       default:
-        if (ctx->groupMinBlocks >= 20) launch_group<1, 20>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
-        else launch_group<1, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        if (nPairs >= ctx->groupMinAvg * nGroups)
+          launch_group<1, 16>(ctx, nGroups, nb, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
+        else
+          launch_tiled<1, 32, 3, 18, true>(ctx, grid, parity, epoch, writeCorr, ac, P, imgStats, imgThr, curEpoch);
         break;
     }
   }
@@ -1071,8 +1129,9 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   int *d_flags = reinterpret_cast<int *>(ctx->d_desc + ctx->slots);
   for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
-  // flags and the pair groups (staged by the caller right behind the flags) in one copy
-  NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, sizeof(int) * ctx->slots + sizeof(PairGroup) * nGroups, cudaMemcpyHostToDevice, st));
+  // flags and the pair groups (staged by the caller behind the flags) in one copy
+  NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, (groups_offset(ctx) - sizeof(PairDesc) * (size_t)ctx->slots) + sizeof(PairGroup) * nGroups,
+                            cudaMemcpyHostToDevice, st));
   // z-buffer words carry an epoch tag instead of being cleared per iteration (z_encode in nicp_internal.cuh).
   // (slot buffers are contiguous: refZ is laid out [2][slots][slotPixels], curZ [slots][slotPixels])
   //  fresh (single-pair nicp_align, the CUDA-graph path): this call clears its own slots and counts its iterations
@@ -1170,7 +1229,8 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   NICP_CHECK_LAUNCH(ctx);
   k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
-  k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_statHb + (size_t)resultOffset * 42);
+  (void)resultOffset;
+  k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_results, ctx->d_statHb);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }

@@ -65,38 +65,60 @@ struct TermAcc {
   f32x2 br[3];
   float err, inl;
 };
+// OPAQUE: the zeros come out of an asm statement, so the compiler cannot fold "0 + term" of the first pixel slot into a
+// move and every slot updates the sums in place (used where the slots sit behind warp-uniform branches)
+template <bool OPAQUE>
 __device__ __forceinline__ void term_clear(TermAcc &A) {
+  float z = 0.0f;
+  f32x2 z2 = 0ull;
+  if (OPAQUE) {
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(z));
+    asm volatile("mov.b64 %0, 0;" : "=l"(z2));
+  }
 #pragma unroll
-  for (int i = 0; i < 6; i++) { A.htt[i] = 0.0f; A.hrr[i] = 0ull; }
+  for (int i = 0; i < 6; i++) { A.htt[i] = z; A.hrr[i] = z2; }
 #pragma unroll
-  for (int i = 0; i < 9; i++) A.htr[i] = 0.0f;
+  for (int i = 0; i < 9; i++) A.htr[i] = z;
 #pragma unroll
-  for (int i = 0; i < 3; i++) { A.bt[i] = 0.0f; A.br[i] = 0ull; }
-  A.err = 0.0f;
-  A.inl = 0.0f;
+  for (int i = 0; i < 3; i++) { A.bt[i] = z; A.br[i] = z2; }
+  A.err = z;
+  A.inl = z;
 }
 
-// one correspondence (linearizer.cpp:56-89).  R = transformed reference (point, normal) per axis, packed; cp / cn the
-// current point / normal; w0..w2 the interleaved information matrices: A=(a,g) B=(b,h) C=(c,i) D=(d,j) E=(e,k) F=(f,l)
-// with Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l].
-__device__ __forceinline__ void term_add(TermAcc &acc, f32x2 Rx, f32x2 Ry, f32x2 Rz, float4 cp, float4 cn, f32x2 A, f32x2 B,
+// one correspondence (linearizer.cpp:56-89), executed by every lane of the warp: `w` is 1 for the lanes whose pixel was
+// accepted and 0 for the others, whose Omega is multiplied away (everything below is linear in Omega, and every input is
+// finite -- the shared-memory slots are zero-filled at kernel start), so there is no divergent control flow around the
+// accumulators.  R = transformed reference (point, normal) per axis, packed; cp / cn the current point / normal;
+// A=(a,g) B=(b,h) C=(c,i) D=(d,j) E=(e,k) F=(f,l) with Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l].
+template <bool ROBUST>
+__device__ __forceinline__ void term_add(TermAcc &acc, float w, f32x2 Rx, f32x2 Ry, f32x2 Rz, float4 cp, float4 cn, f32x2 A, f32x2 B,
                                          f32x2 C, f32x2 D, f32x2 E, f32x2 F, float maxChi2, int robust) {
+  const f32x2 W = pk(w, w);
+  A = mul2(A, W); B = mul2(B, W); C = mul2(C, W); D = mul2(D, W); E = mul2(E, W); F = mul2(F, W);
   // errors (rp - cp, rn - cn)
   const f32x2 E0 = pk(__fsub_rn(lo_of(Rx), cp.x), __fsub_rn(hi_of(Rx), cn.x));
   const f32x2 E1 = pk(__fsub_rn(lo_of(Ry), cp.y), __fsub_rn(hi_of(Ry), cn.y));
   const f32x2 E2 = pk(__fsub_rn(lo_of(Rz), cp.z), __fsub_rn(hi_of(Rz), cn.z));
   // Omega e, rows: (a e0 + b e1) + c e2 ...
-  const f32x2 W0 = fma2(C, E2, fma2(B, E1, mul2(A, E0)));
-  const f32x2 W1 = fma2(E, E2, fma2(D, E1, mul2(B, E0)));
-  const f32x2 W2 = fma2(F, E2, fma2(E, E1, mul2(C, E0)));
+  f32x2 W0 = fma2(C, E2, fma2(B, E1, mul2(A, E0)));
+  f32x2 W1 = fma2(E, E2, fma2(D, E1, mul2(B, E0)));
+  f32x2 W2 = fma2(F, E2, fma2(E, E1, mul2(C, E0)));
   const f32x2 chi2 = fma2(E2, W2, fma2(E1, W1, mul2(E0, W0)));
-  const float chi = __fadd_rn(lo_of(chi2), hi_of(chi2));
+  float chi = __fadd_rn(lo_of(chi2), hi_of(chi2));
   float ks = 1.0f;
-  if (chi > maxChi2) {
-    if (!robust) return;
-    ks = sqrtf(__fdividef(maxChi2, chi));
+  if (ROBUST) {
+    if (chi > maxChi2) ks = sqrtf(__fdividef(maxChi2, chi));  // one predicated value, no control flow around the sums
+  } else {
+    // without the robust kernel such a correspondence is skipped altogether (linearizer.cpp:66-71): multiplied away
+    const float keep = chi > maxChi2 ? 0.0f : 1.0f;
+    const f32x2 K2 = pk(keep, keep);
+    A = mul2(A, K2); B = mul2(B, K2); C = mul2(C, K2); D = mul2(D, K2); E = mul2(E, K2); F = mul2(F, K2);
+    W0 = mul2(W0, K2); W1 = mul2(W1, K2); W2 = mul2(W2, K2);
+    chi = __fmul_rn(chi, keep);
+    w = __fmul_rn(w, keep);
   }
-  acc.inl = __fadd_rn(acc.inl, 1.0f);
+  (void)robust;
+  acc.inl = __fadd_rn(acc.inl, w);
   acc.err = __fmaf_rn(ks, chi, acc.err);
   // skew(v) = -2 [v]x (bm_se3.h:54-66): P = 2 v, NP = -2 v
   const f32x2 two = pk(2.0f, 2.0f), mtwo = pk(-2.0f, -2.0f);
@@ -146,48 +168,192 @@ __device__ __forceinline__ void term_slots(const TermAcc &A, float (&v)[kAccum])
   v[A_INL] = A.inl;
 }
 
-// per-lane slots (lane l, pixel slot k -> [k * 32 + l]): nothing here is shared between lanes, shared memory is used as
-// a register file extension for what must survive the walk over the pairs of the group
-struct GroupSmem {
-  float4 om[3][96];  // Omega_P / Omega_N of the current point (Omega3 layout), written by cp.async
-  float4 cp[96];     // current point (w unused)
-  float4 cn[96];     // current normal; w = curvature clamped to flatCurvatureThreshold, or -1 for a zero normal (MODE 0)
+// per-lane slots (lane l, pixel slot k -> [k * 32 + l]): nothing here is shared between lanes except T; shared memory is
+// used as a register file extension -- for what must survive the walk over the pairs of the group, and as the landing
+// zone of the reference gathers, which are issued with cp.async one pair AHEAD of the pair being computed (no registers
+// are held while they are in flight)
+template <int MAXG>
+struct GroupSmem {  // shared by the warps of a CTA: the current side of the tile and T of every pair
+  float4 om[3][96];     // Omega_P / Omega_N of the current point (Omega3 layout), cp.async
+  float4 cp[96];        // current point (w unused)
+  float4 cn[96];        // current normal; w = curvature clamped to flatCurvatureThreshold, or -1 for a zero normal (MODE 0)
+  float4 T[MAXG][4];  // state->invT of every pair of the group (column-major), fetched by lane g in the prologue
 };
+struct GatherStage {
+  float4 rp[96];        // reference point of the pair being computed / the next pair, cp.async
+  float4 rn[96];        // reference normal (w = curvature)
+};                      // (a consumed stage doubles as the scratch of the shared-memory reduction)
+static_assert(sizeof(GatherStage) >= 32 * 20 * sizeof(float), "reduction scratch fits a gather stage");
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ const float4 *shfl_ptr(const float4 *p, int src) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)v, src), hi = __shfl_sync(0xffffffffu, (unsigned int)(v >> 32), src);
+  return reinterpret_cast<const float4 *>(((unsigned long long)hi << 32) | lo);
+}
 
 // MODE 0: correspondence gates + linearise at state->invT; the correspondence image is written only when asked for.
 // MODE 1: linearise over the stored correspondence image (inner iterations > 0, _computeStatistics) and, if imgStats,
 //         accumulate the matchClouds image statistics (slots 29..31).
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(32, MINB) k_corr_lin_group(const PairDesc *__restrict__ desc, const PairGroup *__restrict__ groups,
-                                                             int parity, int epoch, int writeCorr, AlignConsts ac, int numPixels,
+// Software pipeline over the pairs of the group (one exposed memory round trip per GROUP, not per pair):
+//   while pair g is computed out of shared memory, the point / normal gathers of pair g + 1 are landing there (cp.async)
+//   and the z-buffer words of pair g + 2 are on their way into registers.  No address is loaded inside the loop: the
+//   slot buffers are affine in the slot index (SlotBases), the cloud pointers and T of all pairs are fetched by lane g
+//   in the prologue and handed out with shuffles / shared memory.
+// Deterministic cross-lane sums through shared memory, in two rounds of 16 values so that the scratch (32 rows x 20
+// floats = 2560 bytes) fits into the gather stage the pair has just consumed: lane l parks 16 values as row l (padded
+// rows: conflict-free 128-bit stores); lane j adds rows 0..15 of column j & 15 if j < 16, rows 16..31 otherwise, top to
+// bottom, and one shuffle joins the halves.  After the two rounds lane j holds the total of value j.
+// 8 STS.128 + 32 LDS + 32 FADD + 2 SHFL instead of the register butterfly's 31 SHFL + 62 FSEL + 31 FADD.
+__device__ __forceinline__ float warp_transpose_reduce_smem(const float (&v)[kAccum], int lane, float *scratch) {
+  float result = 0.0f;
+  const int col = lane & 15, rowBase = lane & 16;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    float4 *row = reinterpret_cast<float4 *>(scratch + lane * 20);
+#pragma unroll
+    for (int q = 0; q < 4; q++) row[q] = make_float4(v[16 * r + 4 * q], v[16 * r + 4 * q + 1], v[16 * r + 4 * q + 2], v[16 * r + 4 * q + 3]);
+    __syncwarp();
+    float t[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) t[l] = scratch[(rowBase + l) * 20 + col];
+    float sum = t[0];
+#pragma unroll
+    for (int l = 1; l < 16; l++) sum = __fadd_rn(sum, t[l]);
+    const float other = __shfl_xor_sync(0xffffffffu, sum, 16);
+    // rows 0..15 first, then rows 16..31, on both halves of the warp
+    const float total = (lane & 16) ? __fadd_rn(other, sum) : __fadd_rn(sum, other);
+    if ((lane >> 4) == r) result = total;
+    __syncwarp();
+  }
+  return result;
+}
+
+// VAR bit 0: 1 = every pixel slot of a non-empty tile runs straight-line, 0 = a slot no lane needs is skipped behind a
+//            warp-uniform branch;  bit 1: 1 = cross-lane sums through shared memory, 0 = register butterfly.
+// NW warps per CTA share the current side of the tile and split the pairs of the group (warp w takes pairs w, w + NW, ...):
+// less shared memory per warp, so more warps fit an SM.
+template <int MODE, int MINB, bool PACKED, bool ROBUST, int VAR, int NW>
+__global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc *__restrict__ desc, const PairGroup *__restrict__ groups,
+                                                             SlotBases B, int epoch, int writeCorr, AlignConsts ac, int numPixels,
                                                              int imgStats, float imgThreshold, int groupFast, int curEpoch) {
   constexpr int TK = 3, NT = 32, TILE = NT * TK;
-  __shared__ GroupSmem S;
+  constexpr bool STRAIGHT = (VAR & 1) != 0, SMEMRED = (VAR & 2) != 0;
+  __shared__ GroupSmem<(NW > 1 ? kMaxGroup : kMaxGroup / 2)> S;  // one-warp CTAs walk at most kMaxGroup / 2 pairs
+  __shared__ GatherStage stages[NW][2];
+  const int warp = NW > 1 ? (int)(threadIdx.x >> 5) : 0;
+  GatherStage *const stage = stages[warp];
   // group-fastest block order: the CTAs resident together work on the same tile of different groups, so the reference
   // z-buffer rows and the tile's current-cloud lines they touch stay close in L2
   const int groupId = groupFast ? blockIdx.x : blockIdx.y;
   const int tileId = groupFast ? blockIdx.y : blockIdx.x;
-  const PairGroup G = groups[groupId];
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int base = tileId * TILE;
+  const bool wantZ = MODE == 0 || imgStats;  // the reference z-buffer words are needed (index / depth)
+  PairGroup G;
+  {
+    const uint4 *gp = reinterpret_cast<const uint4 *>(groups + groupId);
+    const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+    G.first = (int)g0.x; G.count = (int)g0.y; G.curSlot = (int)g0.z; G.pad = 0;
+    G.curPoints = reinterpret_cast<const float4 *>(((unsigned long long)g1.y << 32) | g1.x);
+    G.curNormals = reinterpret_cast<const float4 *>(((unsigned long long)g1.w << 32) | g1.z);
+    G.curOmega = reinterpret_cast<const float4 *>(((unsigned long long)g2.y << 32) | g2.x);
+    G.pad2 = nullptr;
+  }
 
-  // ---- the current side of the tile, once per group ----
-  const PairDesc &D0 = desc[G.first];
-  const int *__restrict__ curIndex = D0.curIndex;
-  const float4 *__restrict__ curPoints = D0.curPoints;
-  const float4 *__restrict__ curNormals = D0.curNormals;
-  const float4 *__restrict__ curOmega = D0.curOmega;
-  // (read-only global loads spelled __ldg: the pointers come out of the descriptor, where the compiler cannot see their
-  // address space and would emit generic loads)
+  // what identifies the reference side of a pixel for one pair: the z-buffer word (MODE 0: index + epoch; MODE 1 with
+  // image statistics: depth) and / or the stored correspondence (MODE 1)
+  struct RefKey {
+    unsigned long long z[TK];
+    int ri[TK];
+  };
+  auto load_key = [&](int g, RefKey &key) {
+    const size_t off = (size_t)(G.first + g) * (size_t)B.slotPixels;
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      const int pix = base + k * NT + lane;
+      key.z[k] = kEmptyZ;
+      key.ri[k] = -1;
+      if (pix < numPixels) {
+        if (wantZ) key.z[k] = __ldg(B.refZ + off + pix);
+        if (MODE == 1) key.ri[k] = __ldg(B.corrImage + off + pix);
+      }
+    }
+  };
+  auto issue_gathers = [&](const float4 *refPoints, const float4 *refNormals, const int (&ri)[TK], const bool (&curOk)[TK], int st) {
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      if (ri[k] >= 0 && curOk[k]) {
+        cp_async16(&stage[st].rn[k * NT + lane], refNormals + ri[k]);
+        cp_async16(&stage[st].rp[k * NT + lane], refPoints + ri[k]);
+      }
+    }
+  };
+
+  // every shared-memory slot of this lane holds finite values from the start (the per-pixel code below is branch free
+  // and multiplies what a rejected lane read by zero)
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      if (warp == 0) { S.om[0][k * NT + lane] = z4; S.om[1][k * NT + lane] = z4; S.om[2][k * NT + lane] = z4; }
+      stage[0].rp[k * NT + lane] = z4; stage[1].rp[k * NT + lane] = z4;
+      stage[0].rn[k * NT + lane] = z4; stage[1].rn[k * NT + lane] = z4;
+    }
+  }
+  // ---- prologue: current side of the tile (once per group), keys of pairs 0 and 1, pointers and T of every pair ----
+  const int *__restrict__ curIndex = B.curIndex + (size_t)G.curSlot * (size_t)B.slotPixels;
   int ci[TK];
 #pragma unroll
   for (int k = 0; k < TK; k++) {
     const int pix = base + k * NT + lane;
     ci[k] = pix < numPixels ? __ldg(curIndex + pix) : -1;
   }
+  RefKey keyNext;  // keys of the pair whose gathers are issued next
+  const bool mine = warp < G.count;  // this warp has at least one pair
+  if (mine) load_key(warp, keyNext);
+  else {
+#pragma unroll
+    for (int k = 0; k < TK; k++) { keyNext.z[k] = kEmptyZ; keyNext.ri[k] = -1; }
+  }
+  // lane g fetches what pair g of the group needs: its cloud pointers (kept, handed out by shuffle) and its T (to shared
+  // memory); count <= kMaxGroup
+  const float4 *myRefPoints = nullptr, *myRefNormals = nullptr;
+  if (lane < G.count) {
+    const PairDesc &Dl = desc[G.first + lane];
+    myRefPoints = Dl.refPoints;
+    myRefNormals = Dl.refNormals;
+    if (warp == 0) {
+      const float4 *tp = reinterpret_cast<const float4 *>(B.state[G.first + lane].invT);
+      S.T[lane][0] = __ldg(tp);
+      S.T[lane][1] = __ldg(tp + 1);
+      S.T[lane][2] = __ldg(tp + 2);
+      S.T[lane][3] = __ldg(tp + 3);
+    }
+  }
+  // nothing of the current cloud projects into this tile: every pair of the group gets a row of zeros (MODE 1 with image
+  // statistics still has to look at the reference z-buffer)
+  if (!(MODE == 1 && imgStats) && !__any_sync(0xffffffffu, ci[0] >= 0 || ci[1] >= 0 || ci[2] >= 0)) {
+    for (int g = warp; g < G.count; g += NW) {
+      B.partials[(size_t)(G.first + g) * (size_t)B.partialStride + (size_t)tileId * kAccum + lane] = 0.0f;
+      if (MODE == 0 && writeCorr) {
+        int *__restrict__ corrImage = B.corrImage + (size_t)(G.first + g) * (size_t)B.slotPixels;
+#pragma unroll
+        for (int k = 0; k < TK; k++) {
+          const int pix = base + k * NT + lane;
+          if (pix < numPixels) corrImage[pix] = -1;
+        }
+      }
+    }
+    return;
+  }
   unsigned long long zc[TK];
   if (MODE == 1 && imgStats) {
-    const unsigned long long *__restrict__ zcur = D0.curZ;
+    const unsigned long long *__restrict__ zcur = B.curZ + (size_t)G.curSlot * (size_t)B.slotPixels;
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       const int pix = base + k * NT + lane;
@@ -195,6 +361,8 @@ __global__ void __launch_bounds__(32, MINB) k_corr_lin_group(const PairDesc *__r
     }
   }
   bool curOk[TK];
+  int riCur[TK];                 // reference indices of the pair being computed
+  unsigned long long zCur[TK];   // its z-buffer words (image statistics)
   {
     float4 cpl[TK], cnl[TK];
 #pragma unroll
@@ -202,15 +370,24 @@ __global__ void __launch_bounds__(32, MINB) k_corr_lin_group(const PairDesc *__r
       curOk[k] = ci[k] >= 0;
       cpl[k] = make_float4(0.f, 0.f, 0.f, 1.f);
       cnl[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (curOk[k]) {
-        const float4 *om = curOmega + 3 * (size_t)ci[k];
+      if (curOk[k] && warp == 0) {
+        const float4 *om = G.curOmega + 3 * (size_t)ci[k];
         cp_async16(&S.om[0][k * NT + lane], om);
         cp_async16(&S.om[1][k * NT + lane], om + 1);
         cp_async16(&S.om[2][k * NT + lane], om + 2);
-        cnl[k] = __ldg(curNormals + ci[k]);
-        cpl[k] = __ldg(curPoints + ci[k]);
+        cnl[k] = __ldg(G.curNormals + ci[k]);
+        cpl[k] = __ldg(G.curPoints + ci[k]);
       }
     }
+    // gathers of pair 0 ride in the same cp.async group as Omega
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      riCur[k] = MODE == 0 ? z_index(keyNext.z[k], epoch) : keyNext.ri[k];
+      zCur[k] = keyNext.z[k];
+    }
+    issue_gathers(shfl_ptr(myRefPoints, warp), shfl_ptr(myRefNormals, warp), riCur, curOk, 0);
+    cp_async_commit();
+    if (warp + NW < G.count) load_key(warp + NW, keyNext);
     // what the gates need from the current side (correspondencefinder.cpp:69, :87-93), prepared once per group
 #pragma unroll
     for (int k = 0; k < TK; k++) {
@@ -219,8 +396,10 @@ __global__ void __launch_bounds__(32, MINB) k_corr_lin_group(const PairDesc *__r
         if (dot3(cnl[k].x, cnl[k].y, cnl[k].z, cnl[k].x, cnl[k].y, cnl[k].z) == 0.0f) cnl[k].w = -1.0f;  // curvature >= 0
         else if (cnl[k].w < ac.flatCurvature) cnl[k].w = ac.flatCurvature;
       }
-      S.cp[k * NT + lane] = cpl[k];
-      S.cn[k * NT + lane] = cnl[k];
+      if (warp == 0) {
+        S.cp[k * NT + lane] = cpl[k];
+        S.cn[k * NT + lane] = cnl[k];
+      }
     }
   }
   unsigned short c16[TK];
@@ -232,149 +411,177 @@ __global__ void __launch_bounds__(32, MINB) k_corr_lin_group(const PairDesc *__r
       c16[k] = dc < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dc) : 0;
     }
   }
-  bool omegaReady = false;
+  if (NW > 1) {
+    // the shared current side (cp / cn stores, Omega cp.async of warp 0) and T become visible to the other warps
+    if (warp == 0) cp_async_wait_group<0>();
+    __syncthreads();
+  } else {
+    __syncwarp();  // S.T of every pair visible to every lane
+  }
 
   // ---- the pairs of the group ----
-  for (int g = 0; g < G.count; g++) {
-    const PairDesc &D = desc[G.first + g];
-    Affine T;  // state->invT (column-major), four 128-bit read-only loads
+  for (int g = warp, it = 0; g < G.count; g += NW, it++) {
+    const int st = it & 1;
+    // pair g + 1: decode its keys (loaded one iteration ago), send its gathers into the other stage; pair g + 2: keys
+    int riNext[TK];
+    unsigned long long zNext[TK];
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      riNext[k] = -1;
+      zNext[k] = kEmptyZ;
+    }
+    if (g + NW < G.count) {
+#pragma unroll
+      for (int k = 0; k < TK; k++) {
+        riNext[k] = MODE == 0 ? z_index(keyNext.z[k], epoch) : keyNext.ri[k];
+        zNext[k] = keyNext.z[k];
+      }
+      issue_gathers(shfl_ptr(myRefPoints, g + NW), shfl_ptr(myRefNormals, g + NW), riNext, curOk, st ^ 1);
+      if (g + 2 * NW < G.count) load_key(g + 2 * NW, keyNext);
+    }
+    cp_async_commit();         // (an empty group when there is no next pair)
+    cp_async_wait_group<1>();  // everything but the group just committed has landed: Omega and the gathers of pair g
+
+    Affine T;  // state->invT of pair g (column-major), broadcast reads from shared memory
     {
-      const float4 *tp = reinterpret_cast<const float4 *>(D.state->invT);
-      const float4 c0 = __ldg(tp), c1 = __ldg(tp + 1), c2 = __ldg(tp + 2), c3 = __ldg(tp + 3);
+      const float4 c0 = S.T[g][0], c1 = S.T[g][1], c2 = S.T[g][2], c3 = S.T[g][3];
       T.r[0][0] = c0.x; T.r[1][0] = c0.y; T.r[2][0] = c0.z;
       T.r[0][1] = c1.x; T.r[1][1] = c1.y; T.r[2][1] = c1.z;
       T.r[0][2] = c2.x; T.r[1][2] = c2.y; T.r[2][2] = c2.z;
       T.r[0][3] = c3.x; T.r[1][3] = c3.y; T.r[2][3] = c3.z;
     }
-    const float4 *__restrict__ refPoints = D.refPoints;
-    const float4 *__restrict__ refNormals = D.refNormals;
-    const unsigned long long *__restrict__ zref = D.refZ[parity];
-    int *__restrict__ corrImage = D.corrImage;
+    int *__restrict__ corrImage = B.corrImage + (size_t)(G.first + g) * (size_t)B.slotPixels;
 
-    int ri[TK];
-    unsigned long long zr[TK];
+    // a tile where no lane has a pixel of this pair contributes a row of zeros (decided before any sum is live)
+    bool ok0[TK];
 #pragma unroll
-    for (int k = 0; k < TK; k++) {
-      const int pix = base + k * NT + lane;
-      ri[k] = -1;
-      zr[k] = kEmptyZ;
-      if (pix < numPixels) {
-        if (MODE == 0) {
-          ri[k] = z_index(__ldg(zref + pix), epoch);
-        } else {
-          ri[k] = __ldg(corrImage + pix);
-          if (imgStats) zr[k] = __ldg(zref + pix);
+    for (int k = 0; k < TK; k++) ok0[k] = riCur[k] >= 0 && curOk[k];
+    const bool tileAny = __any_sync(0xffffffffu, ok0[0] || ok0[1] || ok0[2]) || (MODE == 1 && imgStats);
+    float tot = 0.0f;
+    if (tileAny) {
+      float midx = 0.0f, imgSum = 0.0f, imgNz = 0.0f, imgInl = 0.0f;
+      if (MODE == 1 && imgStats) {
+#pragma unroll
+        for (int k = 0; k < TK; k++) {
+          // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
+          const float dr = z_depth(zCur[k], epoch, FLT_MAX);
+          const unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
+          if (c16[k] > 0 && r16 > 0) {
+            const float df = fabsf(fsub((float)c16[k], (float)r16));
+            const float dm = __uint_as_float(__float_as_uint(df) & 0x437F0000u);
+            imgNz += 1.0f;
+            if (dm < imgThreshold) imgInl += 1.0f;
+            imgSum += dm;
+          }
         }
       }
-    }
-    float4 rp0[TK], rn0[TK];
-    bool ok[TK];
+      // ---- per pixel, STRAIGHT-LINE for every lane: transform, gates in the reference's order, Linearizer term weighted
+      // by 1 (accepted) or 0.  No branch surrounds the sums, so they stay in place in their registers; a lane without a
+      // pixel works on the zeros / stale finite values of its slots and its Omega is multiplied away. ----
+      TermAcc acc;
+      term_clear<!STRAIGHT>(acc);
+      float sacc[kAccum];  // scalar formulation of the term (comparison variant, PACKED = false)
+      if (!PACKED) {
 #pragma unroll
-    for (int k = 0; k < TK; k++) {
-      ok[k] = ri[k] >= 0 && curOk[k];
-      if (ok[k]) {
-        rn0[k] = __ldg(refNormals + ri[k]);
-        rp0[k] = __ldg(refPoints + ri[k]);
+        for (int i = 0; i < kAccum; i++) sacc[i] = 0.0f;
       }
-    }
-    float midx = 0.0f, imgSum = 0.0f, imgNz = 0.0f, imgInl = 0.0f;
-    if (MODE == 1 && imgStats) {
+      float nc = 0.0f;
 #pragma unroll
       for (int k = 0; k < TK; k++) {
-        // DepthImage_convert_32FC1_to_16UC1 + mask + bitwise (abs diff & 255.0f) (pwn_matcher_base.cpp:167-190)
-        const float dr = z_depth(zr[k], epoch, FLT_MAX);
-        const unsigned short r16 = dr < FLT_MAX ? (unsigned short)(int)fmul(1000.0f, dr) : 0;
-        if (c16[k] > 0 && r16 > 0) {
-          const float df = fabsf(fsub((float)c16[k], (float)r16));
-          const float dm = __uint_as_float(__float_as_uint(df) & 0x437F0000u);
-          imgNz += 1.0f;
-          if (dm < imgThreshold) imgInl += 1.0f;
-          imgSum += dm;
-        }
-      }
-    }
-
-    // ---- per pixel: transform, gates in the reference's order, then the Linearizer term of an accepted pixel in place
-    // (the thread that owns the pixel accumulates it; a pixel slot nobody in the warp accepted is skipped warp-wide) ----
-    if (!omegaReady) {
-      cp_async_wait_all();
-      omegaReady = true;
-    }
-    TermAcc acc;
-    term_clear(acc);
-    float nc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < TK; k++) {
-      bool good = ok[k];
-      f32x2 Rx = 0ull, Ry = 0ull, Rz = 0ull;
-      float4 cpk = make_float4(0.f, 0.f, 0.f, 1.f), cnk = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (good) {
-        cpk = S.cp[k * NT + lane];
-        cnk = S.cn[k * NT + lane];
-        float rpx, rpy, rpz, rnx, rny, rnz;
-        xform_point(T, rp0[k].x, rp0[k].y, rp0[k].z, rpx, rpy, rpz);
-        xform_normal(T, rn0[k].x, rn0[k].y, rn0[k].z, rnx, rny, rnz);
-        if (MODE == 0) {
-          midx += 1.0f;
-          // correspondencefinder.cpp:69 zero normals, :78 normal angle, :84 distance, :87-99 curvature ratio
-          if (cnk.w < 0.0f || dot3(rn0[k].x, rn0[k].y, rn0[k].z, rn0[k].x, rn0[k].y, rn0[k].z) == 0.0f) good = false;
-          if (good && dot3(cnk.x, cnk.y, cnk.z, rnx, rny, rnz) < ac.normalThreshold) good = false;
-          if (good) {
-            const float dx = fsub(cpk.x, rpx), dy = fsub(cpk.y, rpy), dz = fsub(cpk.z, rpz);
-            if (dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold) good = false;
-          }
-          if (good) {
-            float rc = rn0[k].w;
-            const float cc = cnk.w;  // already clamped
-            if (rc < ac.flatCurvature) rc = ac.flatCurvature;
-            // (rc + 1e-5) / (cc + 1e-5) in double, rounded to float; identical operands give exactly 1.  A float32
-            // pre-test decides unless the quotient lies within 1e-4 (relative) of a threshold.
-            if (rc != cc) {
-              const float q = __fdividef(rc + 1e-5f, cc + 1e-5f);
-              const float lo = ac.minRatio * (1.0f - 1e-4f), hi = ac.maxRatio * (1.0f + 1e-4f);
-              const float loIn = ac.minRatio * (1.0f + 1e-4f), hiIn = ac.maxRatio * (1.0f - 1e-4f);
-              if (q < lo || q > hi) {
-                good = false;
-              } else if (!(q > loIn && q < hiIn)) {
-                const float ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
-                if (ratio < ac.minRatio || ratio > ac.maxRatio) good = false;
-              }
+        if (!STRAIGHT) {
+          if (!__any_sync(0xffffffffu, ok0[k])) {  // warp-uniform: no lane has a pixel in this slot
+            if (MODE == 0 && writeCorr) {
+              const int pix = base + k * NT + lane;
+              if (pix < numPixels) corrImage[pix] = -1;
             }
+            continue;
           }
         }
-        Rx = pk(rpx, rnx);
-        Ry = pk(rpy, rny);
-        Rz = pk(rpz, rnz);
-      }
-      if (MODE == 0 && writeCorr) {
-        const int pix = base + k * NT + lane;
-        if (pix < numPixels) corrImage[pix] = good ? ri[k] : -1;
-      }
-      if (__any_sync(0xffffffffu, good)) {
-        if (good) {
+        const float4 rp0 = stage[st].rp[k * NT + lane], rn0 = stage[st].rn[k * NT + lane];
+        const float4 cpk = S.cp[k * NT + lane], cnk = S.cn[k * NT + lane];
+        float rpx, rpy, rpz, rnx, rny, rnz;
+        xform_point(T, rp0.x, rp0.y, rp0.z, rpx, rpy, rpz);
+        xform_normal(T, rn0.x, rn0.y, rn0.z, rnx, rny, rnz);
+        bool good = ok0[k];
+        if (MODE == 0) {
+          midx += ok0[k] ? 1.0f : 0.0f;
+          // correspondencefinder.cpp:69 zero normals, :78 normal angle, :84 distance, :87-99 curvature ratio
+          good = good && !(cnk.w < 0.0f) && dot3(rn0.x, rn0.y, rn0.z, rn0.x, rn0.y, rn0.z) != 0.0f;
+          good = good && !(dot3(cnk.x, cnk.y, cnk.z, rnx, rny, rnz) < ac.normalThreshold);
+          const float dx = fsub(cpk.x, rpx), dy = fsub(cpk.y, rpy), dz = fsub(cpk.z, rpz);
+          good = good && !(dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold);
+          float rc = rn0.w;
+          const float cc = cnk.w;  // already clamped
+          if (rc < ac.flatCurvature) rc = ac.flatCurvature;
+          // (rc + 1e-5) / (cc + 1e-5) in double, rounded to float; identical operands give exactly 1.  A float32
+          // pre-test decides unless the quotient lies within 1e-4 (relative) of a threshold.
+          const float q = __fdividef(rc + 1e-5f, cc + 1e-5f);
+          const float lo = ac.minRatio * (1.0f - 1e-4f), hi = ac.maxRatio * (1.0f + 1e-4f);
+          const float loIn = ac.minRatio * (1.0f + 1e-4f), hiIn = ac.maxRatio * (1.0f - 1e-4f);
+          const bool differ = rc != cc;
+          good = good && !(differ && (q < lo || q > hi));
+          if (good && differ && !(q > loIn && q < hiIn)) {  // rare: the exact quotient decides
+            const float ratio = (float)(((double)rc + 1e-5) / ((double)cc + 1e-5));
+            if (ratio < ac.minRatio || ratio > ac.maxRatio) good = false;
+          }
+        }
+        if (MODE == 0 && writeCorr) {
+          const int pix = base + k * NT + lane;
+          if (pix < numPixels) corrImage[pix] = good ? riCur[k] : -1;
+        }
+        const float w = good ? 1.0f : 0.0f;
+        nc += w;
+        if (!STRAIGHT) {
+          if (!__any_sync(0xffffffffu, good)) continue;  // warp-uniform: every lane of this slot was rejected
+        }
+        if (PACKED) {
           const ulonglong2 w0 = *reinterpret_cast<const ulonglong2 *>(&S.om[0][k * NT + lane]);
           const ulonglong2 w1 = *reinterpret_cast<const ulonglong2 *>(&S.om[1][k * NT + lane]);
           const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&S.om[2][k * NT + lane]);
-          term_add(acc, Rx, Ry, Rz, cpk, cnk, w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, ac.robust);
-          nc += 1.0f;
+          term_add<ROBUST>(acc, w, pk(rpx, rnx), pk(rpy, rny), pk(rpz, rnz), cpk, cnk, w0.x, w0.y, w1.x, w1.y, w2.x, w2.y,
+                           ac.maxChi2, ac.robust);
+        } else if (good) {
+          accumulate_term(sacc, rpx, rpy, rpz, rnx, rny, rnz, cpk, cnk, S.om[0][k * NT + lane], S.om[1][k * NT + lane],
+                          S.om[2][k * NT + lane], ac.maxChi2, ac.robust);
         }
       }
+      float v[kAccum];
+      if (PACKED) {
+        term_slots(acc, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kAccum; i++) v[i] = sacc[i];
+      }
+      if (MODE == 0) {
+        v[A_NCORR] = nc;
+        v[A_MIDX] = midx;
+        v[31] = 0.0f;
+      } else {
+        v[29] = imgSum;
+        v[30] = imgNz;
+        v[31] = imgInl;
+      }
+      if (SMEMRED) {
+        tot = warp_transpose_reduce_smem(v, lane, reinterpret_cast<float *>(&stage[st]));
+        // the scratch goes back to being a gather stage: finite values everywhere (rejected lanes read their slots)
+      } else {
+        tot = warp_transpose_reduce(v, lane);
+      }
+    } else if (MODE == 0 && writeCorr) {
+#pragma unroll
+      for (int k = 0; k < TK; k++) {
+        const int pix = base + k * NT + lane;
+        if (pix < numPixels) corrImage[pix] = -1;
+      }
     }
-    float v[kAccum];
-    term_slots(acc, v);
-    if (MODE == 0) {
-      v[A_NCORR] = nc;
-      v[A_MIDX] = midx;
-      v[31] = 0.0f;
-    } else {
-      v[29] = imgSum;
-      v[30] = imgNz;
-      v[31] = imgInl;
+    B.partials[(size_t)(G.first + g) * (size_t)B.partialStride + (size_t)tileId * kAccum + lane] = tot;
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      riCur[k] = riNext[k];
+      zCur[k] = zNext[k];
     }
-    const float tot = warp_transpose_reduce(v, lane);
-    D.partials[(size_t)tileId * kAccum + lane] = tot;
   }
-  if (!omegaReady) cp_async_wait_all();
+  cp_async_wait_group<0>();
 }
 
 }  // namespace nicp

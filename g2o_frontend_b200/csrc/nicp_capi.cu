@@ -136,7 +136,7 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   NICP_CUDA(cudaMemset(ctx->d_state, 0, sizeof(PairState) * (size_t)slots));  // the reduction tickets start at 0
   // two sets of: descriptors, one int flag per slot, one pair group per slot
-  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots + sizeof(PairGroup) * slots;
+  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots + 16 + sizeof(PairGroup) * slots;
   descBytes = (descBytes + 255) & ~(size_t)255;
   void *p = nullptr;
   NICP_CUDA(cudaMalloc(&p, 2 * descBytes));
@@ -272,31 +272,35 @@ static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_para
   return ac;
 }
 
-// pair groups of the chunk staged in ctx->h_desc: descriptors [0, m) are ordered so that pairs sharing a current cloud are
-// adjacent (curSlotOf[i] = descriptor that owns pair i's current z-buffer); groups of at most ctx->groupSize pairs.
-static PairGroup *staged_groups(nicp_context *ctx) {
-  return reinterpret_cast<PairGroup *>(reinterpret_cast<int *>(ctx->h_desc + ctx->slots) + ctx->slots);
-}
+// pair groups of the chunk staged in ctx->h_desc (descriptors already filled): descriptors [0, m) are ordered so that
+// pairs sharing a current cloud are adjacent (curSlotOf[i] = descriptor that owns pair i's current z-buffer); groups of at
+// most ctx->groupSize (<= kMaxGroup) pairs.
 static int stage_groups(nicp_context *ctx, int m, const int *curSlotOf) {
-  PairGroup *g = staged_groups(ctx);
+  PairGroup *g = host_groups(ctx);
+  const int cap = ctx->groupWarps >= 2 ? kMaxGroup : kMaxGroup / 2;  // shared-memory T slots of the kernel instantiation
+  const int maxCount = ctx->groupSize < 1 ? 1 : (ctx->groupSize > cap ? cap : ctx->groupSize);
   int n = 0;
   for (int i = 0; i < m;) {
     int j = i + 1;
-    while (j < m && j - i < ctx->groupSize && curSlotOf[j] == curSlotOf[i]) j++;
+    while (j < m && j - i < maxCount && curSlotOf[j] == curSlotOf[i]) j++;
+    memset(&g[n], 0, sizeof(PairGroup));
     g[n].first = i;
     g[n].count = j - i;
+    g[n].curSlot = curSlotOf[i];
+    g[n].curPoints = ctx->h_desc[i].curPoints;
+    g[n].curNormals = ctx->h_desc[i].curNormals;
+    g[n].curOmega = ctx->h_desc[i].curOmega;
     n++;
     i = j;
   }
   return n;
 }
-// stage-level calls: one pair, one group
+// stage-level calls: one pair (descriptor 0 staged), one group
 static int upload_single_group(nicp_context *ctx) {
-  PairGroup *g = staged_groups(ctx);
-  g[0].first = 0;
-  g[0].count = 1;
-  PairGroup *d = reinterpret_cast<PairGroup *>(reinterpret_cast<int *>(ctx->d_desc + ctx->slots) + ctx->slots);
-  NICP_CUDA(cudaMemcpyAsync(d, g, sizeof(PairGroup), cudaMemcpyHostToDevice, ctx->stream));
+  const int zero = 0;
+  stage_groups(ctx, 1, &zero);
+  NICP_CUDA(cudaMemcpyAsync(const_cast<PairGroup *>(device_groups(ctx)), host_groups(ctx), sizeof(PairGroup), cudaMemcpyHostToDevice,
+                            ctx->stream));
   return NICP_OK;
 }
 
@@ -567,12 +571,18 @@ int nicp_create(int device, nicp_context **out) {
   NICP_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->smCount = prop.multiProcessorCount;
   ctx->blocksPerPair = 296;  // lower bound of the partial-row allocation
-  ctx->corrVariant = 1;
+  ctx->corrVariant = env_int("NICP_CORR_VARIANT", 1) - 1;  // grouped-kernel variant (corr_lin.cuh VAR), 1-based in the environment
   // fixed per context (not per batch) so that a pair's H/b never depend on batch size or GPU count
   ctx->tileConfig = env_int("NICP_TILE_CONFIG", 1) - 1;
   if (ctx->tileConfig < 0 || ctx->tileConfig > 3) ctx->tileConfig = 0;
-  ctx->groupSize = env_int("NICP_GROUP", 4);
+  ctx->groupSize = env_int("NICP_GROUP", 16);
   ctx->groupMinBlocks = env_int("NICP_GROUP_MINB", 16);
+  ctx->groupWarps = env_int("NICP_GROUP_WARPS", 1);
+  {
+    const char *v = getenv("NICP_GROUP_MIN_AVG");  // 0 = always the grouped kernel (tests)
+    ctx->groupMinAvg = (v && *v) ? atoi(v) : 3;
+    if (ctx->groupMinAvg < 0) ctx->groupMinAvg = 0;
+  }
   {
     void *p = nullptr;
     NICP_CUDA(cudaMalloc(&p, sizeof(DeviceCams)));

@@ -32,6 +32,7 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 constexpr int kMaxCams = 8;       // NICP_MAX_CAMERAS
+constexpr int kMaxGroup = 32;     // pairs per group of the grouped fused kernel (corr_lin.cuh)
 constexpr int kMaxPrepBatch = 8;  // frames per frame-preparation launch set (their scratch stays L2 resident)
 constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
 constexpr int kIntegralCh = 10;   // n,x,y,z,xx,xy,xz,yy,yz,zz
@@ -121,9 +122,28 @@ struct PairState {
 };
 static_assert(sizeof(PairState) % 16 == 0, "PairState slots must keep T / invT 16-byte aligned");
 
-// pairs [first, first + count) of a chunk's descriptor array share their current cloud (corr_lin.cuh)
+// pairs [first, first + count) of a chunk's descriptor array share their current cloud (corr_lin.cuh); count <= kMaxGroup.
+// Everything the grouped kernel needs of the current side sits in the group record itself (one 48-byte load instead
+// of a pointer chase through the descriptor); curSlot = the slot whose curZ / curIndex buffers the group reads.
 struct PairGroup {
-  int first, count;
+  int first, count, curSlot, pad;
+  const float4 *curPoints;
+  const float4 *curNormals;  // w = curvature
+  const float4 *curOmega;    // Omega3 layout
+  const void *pad2;
+};
+static_assert(sizeof(PairGroup) == 48, "PairGroup is fetched with three 128-bit loads");
+// slot-indexed scratch of a chunk: buffer of slot i = base + i * stride (what fill_desc puts into the descriptors,
+// passed by value so the grouped kernel computes the addresses instead of loading them)
+struct SlotBases {
+  const unsigned long long *refZ;  // reference z-buffers of the parity in use
+  const unsigned long long *curZ;
+  const int *curIndex;
+  int *corrImage;
+  float *partials;
+  const PairState *state;
+  long long slotPixels;            // stride of the image buffers
+  long long partialStride;         // floats per slot in `partials`
 };
 
 // per-pair descriptor for the batched kernels (device memory, filled by the host per chunk)
@@ -257,7 +277,9 @@ struct nicp_context {
   int corrVariant;              // reserved (one fused-kernel variant is compiled)
   int tileConfig;               // fused-kernel variant: 0 = grouped kernel (default), 1..3 = round-1 per-pair kernels
   int groupSize;                // pairs per group of the grouped kernel (pairs of a group share their current cloud)
-  int groupMinBlocks;           // its __launch_bounds__ min-blocks instantiation (16 or 20 one-warp CTAs per SM)
+  int groupMinBlocks;           // its __launch_bounds__ min-blocks instantiation (16 or 20 warps per SM)
+  int groupMinAvg;              // mean pairs per group from which a chunk takes the grouped kernel (else the per-pair one)
+  int groupWarps;               // warps per CTA of the grouped kernel (1 or 2; they share the current side of the tile)
   int partialRows;              // rows of d_partials per slot
   unsigned long long *d_refZ;   // [slots][2][P]
   unsigned long long *d_curZ;   // [slots][P]
@@ -349,6 +371,8 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
                     int resultOffset);
 int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);
 int partial_rows_for(const nicp_context *ctx, size_t pixels);
+const PairGroup *device_groups(const nicp_context *ctx);
+PairGroup *host_groups(nicp_context *ctx);
 // map_ops.cu
 int cloud_ensure_gaussians(nicp_context *ctx, nicp_cloud *cloud);
 int launch_gauss_transform(nicp_context *ctx, nicp_cloud *cloud, const int *d_first, int first, const int *d_count,

@@ -60,10 +60,11 @@ NICP_HD Affine affine_from(const float *m) {
   return a;
 }
 // rows 0..2 of M * (x,y,z,1)
+// (the product with the homogeneous 1 is exact, so the translation entry is added as it is)
 NICP_HD void xform_point(const Affine &a, float x, float y, float z, float &ox, float &oy, float &oz) {
-  ox = dot4(a.r[0][0], a.r[0][1], a.r[0][2], a.r[0][3], x, y, z, 1.0f);
-  oy = dot4(a.r[1][0], a.r[1][1], a.r[1][2], a.r[1][3], x, y, z, 1.0f);
-  oz = dot4(a.r[2][0], a.r[2][1], a.r[2][2], a.r[2][3], x, y, z, 1.0f);
+  ox = fadd(dot3(a.r[0][0], a.r[0][1], a.r[0][2], x, y, z), a.r[0][3]);
+  oy = fadd(dot3(a.r[1][0], a.r[1][1], a.r[1][2], x, y, z), a.r[1][3]);
+  oz = fadd(dot3(a.r[2][0], a.r[2][1], a.r[2][2], x, y, z), a.r[2][3]);
 }
 // rows 0..2 of M * (x,y,z,0): the translation column contributes an exact zero
 NICP_HD void xform_normal(const Affine &a, float x, float y, float z, float &ox, float &oy, float &oz) {

@@ -63,7 +63,45 @@ static void run(const char *name, int opsPerInstr, int instrPerIter) {
   cudaFree(out);
 }
 
+// dependent-issue latency: one warp, one chain
+template <int MODE>
+__global__ void klat(float *out, int iters, float a, float b, long long *cycles) {
+  float x = threadIdx.x * 0.001f;
+  unsigned long long p = ((unsigned long long)__float_as_uint(x) << 32) | __float_as_uint(x + 0.5f);
+  const unsigned long long pa = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+  const unsigned long long pb = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(b);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (MODE == 0) x = fmaf(x, a, b);
+      if (MODE == 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p) : "l"(pa), "l"(pb));
+      if (MODE == 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(pb));
+    }
+  }
+  long long t1 = clock64();
+  out[threadIdx.x] = x + __uint_as_float((unsigned)p) + __uint_as_float((unsigned)(p >> 32));
+  if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+template <int MODE>
+static void lat(const char *name) {
+  float *out;
+  long long *cyc, h = 0;
+  cudaMalloc(&out, 32 * sizeof(float));
+  cudaMalloc(&cyc, sizeof(long long));
+  const int iters = 4096;
+  klat<MODE><<<1, 32>>>(out, iters, 1.0001f, 0.001f, cyc);
+  klat<MODE><<<1, 32>>>(out, iters, 1.0001f, 0.001f, cyc);
+  cudaMemcpy(&h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+  printf("%-28s dependent-chain latency %.2f cycles\n", name, (double)h / (iters * 16.0));
+  cudaFree(out);
+  cudaFree(cyc);
+}
+
 int main() {
+  lat<0>("FFMA");
+  lat<1>("FFMA2");
+  lat<2>("FADD2");
   run<0>("FFMA (scalar, 3-reg)", 1, 1);
   run<1>("FADD (scalar)", 1, 1);
   run<2>("FFMA2 (fma.rn.f32x2)", 2, 1);
