@@ -2,17 +2,19 @@
 """bench.py -- NICP 640x480 alignments/s on 1/2/4/8 B200 (BASELINE.json metric).
 
 Workload (config 4 of BASELINE.json, the one the metric's multi-GPU numbers are quoted on):
-batched loop-closure candidate verification -- every rank aligns PAIRS = 1024 independent
-640x480 frame pairs per step (16 "current" frames x 64 candidate "reference" frames, guesses
-perturbed by U(+-5 cm, +-3 deg), 10 outer iterations, parameters of pwn_core/conf/pwn_aligner_1_1.conf).
-At 8 GPUs that is exactly the 8192 pairs of config 4; scaling is weak (per-GPU work fixed).
+batched loop-closure candidate verification of 8192 independent 640x480 frame pairs per step
+(64 "current" frames x 128 candidate "reference" frames, guesses perturbed by U(+-5 cm, +-3 deg),
+10 outer iterations, parameters of pwn_core/conf/pwn_aligner_1_1.conf).  The pair list is sharded
+pair-wise over the ranks, current-major (rank r takes the currents [r 64/N, (r+1) 64/N) with all 128
+candidates): the total work is fixed, scaling is strong.
 
 One JSON line on rank 0:
   value     whole-job alignments/s with the clouds already resident in HBM (device-timed, CUDA events
             on the library's stream, max over ranks)
-  e2e       the same metric through the C-ABI with HOST buffers: every step uploads the 80 raw
-            16-bit depth frames from pinned memory, builds the 80 clouds, aligns the 1024 pairs and
-            reads the 256-byte result records back
+  e2e       the same metric through the C-ABI with HOST buffers: every step uploads the raw 16-bit
+            depth frames the rank needs from pinned memory (192 at N = 1), builds their clouds, aligns
+            its pairs and reads the 256-byte result records back
+  configs   (N = 1) BASELINE configs 1, 2, 3, 5 through tools/bench_configs.py, each with its own CPU sample
   roofline  the fused correspondence+linearise kernel: algorithmic bytes / live CUDA-event time
   cpu_baseline  the CPU oracle (restatement of pwn_core; the reference itself cannot be built here)
             timed on this box's host cores on a bounded sample of the same workload
@@ -47,8 +49,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--currents", type=int, default=16)
-    ap.add_argument("--candidates", type=int, default=64)
+    ap.add_argument("--currents", type=int, default=64, help="current frames of the whole job (sharded over the ranks)")
+    ap.add_argument("--candidates", type=int, default=128, help="candidate frames every current is verified against")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs block (BASELINE configs 1, 2, 3, 5)")
+    ap.add_argument("--tracking-frames", type=int, default=2000)
     ap.add_argument("--cpu-sample-pairs", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
@@ -56,20 +60,42 @@ def parse_args():
 
 
 # ---------------------------------------------------------------------------------------------------
-def make_workload(n_cur, n_cand, rank):
-    """poses + raw frames + pair list + guesses (deterministic, different per rank)"""
+def _render(args):
+    from g2o_frontend_b200 import synth
+    pose, seed = args
+    return synth.render_depth_u16(pose, ROWS, COLS, seed=seed)
+
+
+def render_frames(jobs, procs=None):
+    """(pose, seed) -> raw 16-bit frames; a process pool when there are many (0.1 s per frame in numpy)"""
+    procs = procs or min(os.cpu_count() or 1, 32)
+    if procs > 1 and len(jobs) >= 32:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(_render, jobs, chunksize=4)
+    return [_render(j) for j in jobs]
+
+
+def make_workload(n_cur, n_cand, rank, cur_slice=None, procs=None):
+    """poses + raw frames + pair list + guesses (deterministic in `rank`, the seed of the job).  cur_slice = (lo, hi):
+    only the currents [lo, hi) are rendered and paired (a rank's shard of the current-major pair list); the candidate
+    frames, which every rank needs, are all rendered."""
     from g2o_frontend_b200 import synth
     rng = np.random.default_rng(1000 + rank)
     cur_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cur)]
     cand_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cand)]
-    raws_cur = [synth.render_depth_u16(p, ROWS, COLS, seed=10 * rank + i) for i, p in enumerate(cur_poses)]
-    raws_cand = [synth.render_depth_u16(p, ROWS, COLS, seed=5000 + 10 * rank + i) for i, p in enumerate(cand_poses)]
+    lo, hi = cur_slice if cur_slice else (0, n_cur)
+    frames = render_frames([(cur_poses[i], 10 * rank + i) for i in range(lo, hi)] +
+                           [(p, 5000 + 10 * rank + i) for i, p in enumerate(cand_poses)], procs)
+    raws_cur, raws_cand = frames[:hi - lo], frames[hi - lo:]
     pairs, guesses = [], []
     for ci, cp in enumerate(cur_poses):
         for ri, rp in enumerate(cand_poses):
             T_true = np.linalg.inv(rp) @ cp  # reference <- current
-            guesses.append(synth.perturbed_pose(rng, T_true, 0.05, 3.0))
-            pairs.append((ri, ci))
+            g = synth.perturbed_pose(rng, T_true, 0.05, 3.0)  # drawn for every pair so that a shard sees the job's guesses
+            if lo <= ci < hi:
+                guesses.append(g)
+                pairs.append((ri, ci - lo))
     return raws_cur, raws_cand, np.array(pairs), np.stack(guesses).astype(np.float32)
 
 
@@ -291,13 +317,14 @@ def workload_config(n_cur, n_cand, world):
     """the `config` object both arms report (same workload name; the reference arm times a bounded sample of it)"""
     n_pairs = n_cur * n_cand
     P = ROWS * COLS
-    return {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/GPU/step = "
+    return {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/step = "
                         "%d current x %d candidate 640x480 frames, 10 outer iterations, "
                         "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
-            "pairs_per_gpu_per_step": n_pairs, "rows": ROWS, "cols": COLS,
-            "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per step)" %
-                         ((n_cur + n_cand) * P * 80 / 1e9, 256 * P * 32 / 1e9),
-            "parallelism": "pair-sharded x%d" % world}
+            "pairs_total_per_step": n_pairs, "pairs_per_gpu_per_step": n_pairs // world, "rows": ROWS, "cols": COLS,
+            "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per GPU and step)" %
+                         ((n_cur // world + n_cand) * P * 92 / 1e9, 256 * P * 32 / 1e9),
+            "parallelism": "pair-sharded x%d (current-major blocks, no data-path collective; one all-gather of the "
+                           "256-byte records)" % world}
 
 
 def run_reference(args):
@@ -313,7 +340,7 @@ def run_reference(args):
     except Exception as e:  # the baseline is the port; this figure is informative
         ref_src = {"value": None, "note": "failed: %s" % e}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.currents, args.candidates, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -338,9 +365,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_cur, n_cand = args.currents, args.candidates
+    n_cur_total, n_cand = args.currents, args.candidates
+    if n_cur_total % world:
+        raise SystemExit("--currents (%d) must be divisible by the number of ranks (%d)" % (n_cur_total, world))
+    # this rank's block of the current-major pair list: its currents x all candidates
+    n_cur = n_cur_total // world
     n_pairs = n_cur * n_cand
-    raws_cur, raws_cand, pairs, guesses = make_workload(n_cur, n_cand, rank)
+    n_pairs_total = n_cur_total * n_cand
+    raws_cur, raws_cand, pairs, guesses = make_workload(n_cur_total, n_cand, 0, (rank * n_cur, (rank + 1) * n_cur),
+                                                        procs=max(1, min(32, (os.cpu_count() or 1) // world)))
     n_frames = n_cur + n_cand
     # pinned host staging of the raw frames (what a tracker would hand over)
     pinned = torch.empty((n_frames, ROWS, COLS), dtype=torch.int16).pin_memory()
@@ -371,7 +404,7 @@ def run_ours(args):
     def align_step():
         ctx.align_batch(refs, curs, proj, ap, guesses, results=results)
         if world > 1:
-            return sharding.gather_records(results, n_pairs * world, device=dev)
+            return sharding.gather_records(results, n_pairs_total, device=dev)
         return results
 
     def barrier():
@@ -411,7 +444,7 @@ def run_ours(args):
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     kt = ctx.kernel_timing()
     ctx.set_kernel_timing(False)
-    value = world * n_pairs * args.steps / (dev_ms * 1e-3)
+    value = n_pairs_total * args.steps / (dev_ms * 1e-3)
     ok_pairs = int((allrec["status"] == 0).sum())
     mean_inliers = float(results["inliers"].mean())
 
@@ -425,7 +458,7 @@ def run_ours(args):
     # launch, 640x480); null if the launch shape differs
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         pairs_per_launch = n_pairs * args.steps * CONF["outerIterations"] / n_launch
         if abs(pairs_per_launch - tj["pairs_per_launch"]) < 0.5 and (tj["rows"], tj["cols"]) == (ROWS, COLS):
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
@@ -471,20 +504,20 @@ def run_ours(args):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall_ms))
-    e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
+    e2e_value = n_pairs_total * args.steps / (e2e_ms * 1e-3)
     h2d = n_frames * ROWS * COLS * 2 + n_pairs * 64 + n_pairs * 0
     d2h = n_pairs * 256 + n_pairs * 42 * 4
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": workload_config(n_cur, n_cand, world),
+                "config": workload_config(n_cur_total, n_cand, world),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps},
                 "roofline": roofline,
-                "checks": {"pairs_ok": ok_pairs, "pairs_total": int(world * n_pairs), "mean_inliers": mean_inliers}}
+                "checks": {"pairs_ok": ok_pairs, "pairs_total": int(n_pairs_total), "mean_inliers": mean_inliers}}
         if not args.no_cpu_baseline and world == 1:
             v, cores, ms = cpu_reference_run(1, 1, args.cpu_sample_pairs)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -502,6 +535,17 @@ def run_ours(args):
                 line["cpu_baseline"]["value_1_thread"] = json.loads(o.stdout.strip().splitlines()[-1])["value"]
             except Exception:
                 line["cpu_baseline"]["value_1_thread"] = None
+        if world == 1 and not args.no_configs:
+            # BASELINE configs 1, 2, 3 and 5 on the same context (tools/bench_configs.py), each beside its CPU sample
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_configs
+                for c in clouds:
+                    c.close()
+                line["configs"] = bench_configs.run_all(ctx, None if args.no_cpu_baseline else CpuLeg(),
+                                                        tracking_frames=args.tracking_frames)
+            except Exception as e:
+                line["configs"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -24,10 +24,11 @@ SYMBOLS = [
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
     "nicp_raw_depth_to_cloud", "nicp_raw_depth_to_cloud_batch", "nicp_last_integral_image", "nicp_last_interval_image",
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
-    "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch",
+    "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch", "nicp_align_batch_priors",
     "nicp_multi_image_size", "nicp_multi_depth_to_cloud", "nicp_multi_project", "nicp_multi_align",
     "nicp_cloud_compute_gaussians", "nicp_cloud_has_gaussians", "nicp_cloud_download_gaussians",
     "nicp_cloud_upload_gaussians", "nicp_merge", "nicp_voxelize",
+    "nicp_shard_pool_create", "nicp_shard_pool_destroy", "nicp_shard_pool_size", "nicp_align_frames_sharded",
 ]
 
 GAUSS_FLOATS = 24
@@ -549,9 +550,9 @@ class Context:
         return tr
 
     def align_batch(self, refs, curs, proj, ap, guesses=None, ref_offset=None, cur_offset=None, img_threshold=50.0,
-                    results=None):
-        """refs/curs: sequences of Cloud.  guesses: (n,4,4) row/col matrices or None.  Returns a
-        numpy structured array (RESULT_DTYPE) of n 256-byte records."""
+                    results=None, priors=None):
+        """refs/curs: sequences of Cloud.  guesses: (n,4,4) row/col matrices or None.  priors: None or a sequence of
+        n lists of Prior (nicp_align_batch_priors).  Returns a numpy structured array (RESULT_DTYPE) of n 256-byte records."""
         n = len(refs)
         assert len(curs) == n
         eye = np.eye(4, dtype=np.float32)
@@ -566,6 +567,16 @@ class Context:
         CA = (C.c_void_p * n)(*[c.handle for c in curs])
         if results is None:
             results = np.zeros(n, RESULT_DTYPE)
+        if priors is not None:
+            assert len(priors) == n
+            flat = [p for ps in priors for p in ps]
+            offs = np.zeros(n + 1, np.int32)
+            offs[1:] = np.cumsum([len(ps) for ps in priors])
+            parr = (Prior * max(len(flat), 1))(*flat)
+            _check(self.L, self.L.nicp_align_batch_priors(self.handle, n, RA, CA, C.byref(proj), C.byref(ap), _fptr(ro),
+                                                          _fptr(co), _fptr(g), parr, _iptr(offs), C.c_float(img_threshold),
+                                                          results.ctypes.data_as(C.POINTER(AlignResult))))
+            return results
         _check(self.L, self.L.nicp_align_batch(self.handle, n, RA, CA, C.byref(proj), C.byref(ap), _fptr(ro), _fptr(co),
                                                _fptr(g), C.c_float(img_threshold),
                                                results.ctypes.data_as(C.POINTER(AlignResult))))
@@ -587,3 +598,47 @@ def result_T(res):
 
 def result_omega(res):
     return from_colmajor(np.array(res.omega[:], np.float32), 6)
+
+
+class ShardPool:
+    """nicp_shard_pool: one worker thread + context per listed device (a device may be listed twice)"""
+
+    def __init__(self, devices, verify=False):
+        self.L = load(verify)
+        self.handle = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self.L.nicp_shard_pool_create(arr, len(devices), C.byref(self.handle))
+        if rc != NICP_OK:
+            raise NicpError("nicp_shard_pool_create failed (%d): %s" % (rc, self.L.nicp_last_error().decode()))
+
+    def size(self):
+        return int(self.L.nicp_shard_pool_size(self.handle))
+
+    def align_frames(self, raws, proj, sp, ref_frame, cur_frame, guesses, ap, depth_scale=0.001, step=1, max_depth_cov=0.01,
+                     sensor_offset=None, img_threshold=50.0):
+        """raws: list of uint16 frames; pair i = (ref_frame[i], cur_frame[i]); returns RESULT_DTYPE records"""
+        frames = [np.ascontiguousarray(r, np.uint16) for r in raws]
+        rows, cols = frames[0].shape
+        n = len(ref_frame)
+        RA = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+        rf = np.ascontiguousarray(ref_frame, np.int32)
+        cf = np.ascontiguousarray(cur_frame, np.int32)
+        g = np.ascontiguousarray(np.asarray(guesses, np.float32).transpose(0, 2, 1)).reshape(n, 16)
+        so = colmajor(np.eye(4) if sensor_offset is None else sensor_offset)
+        results = np.zeros(n, RESULT_DTYPE)
+        _check(self.L, self.L.nicp_align_frames_sharded(self.handle, len(frames), RA, rows, cols, C.c_float(depth_scale), int(step),
+                                                        C.c_float(max_depth_cov), C.byref(proj), C.byref(sp), _fptr(so), n,
+                                                        _iptr(rf), _iptr(cf), _fptr(g), C.byref(ap), C.c_float(img_threshold),
+                                                        results.ctypes.data_as(C.POINTER(AlignResult))))
+        return results
+
+    def close(self):
+        if self.handle:
+            self.L.nicp_shard_pool_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

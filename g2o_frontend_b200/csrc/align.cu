@@ -1124,6 +1124,8 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   cudaStream_t st = ctx->stream;
   const int P = ac.rows * ac.cols;
   const int nb = num_blocks_for(ctx, P);
+  bool anyPriors = false;  // the solve kernel carrying the SE(3)-prior code is only launched when a pair of the chunk needs it
+  for (int i = 0; i < nPairs; i++) anyPriors = anyPriors || ctx->h_desc[i].numPriors > 0;
   // descriptors + ownership flags (flags live right after the descriptors in the staging buffer)
   int *h_flags = reinterpret_cast<int *>(ctx->h_desc + ctx->slots);
   int *d_flags = reinterpret_cast<int *>(ctx->d_desc + ctx->slots);
@@ -1212,7 +1214,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
         launch_corr_lin(ctx, 1, nPairs, nGroups, nb, parity, epoch, 0, ac, P, 0, 0.0f, curEpoch);
       }
       NICP_CHECK_LAUNCH(ctx);
-      if (ctx->h_desc[0].numPriors > 0)
+      if (anyPriors)
         k_reduce_solve<true><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);
       else
         k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 0, k == innerIters - 1, k == 0, it, ac);

@@ -1223,7 +1223,10 @@ static_assert(sizeof(GraphKey) <= 512, "graph key fits the context buffer");
 static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs, const nicp_cloud *const *curs,
                         const nicp_projector *proj, const nicp_align_params *ap, const float *refOffset,
                         const float *curOffset, const float *guesses, float imgThr, nicp_align_result *results,
-                        bool single, const nicp_prior *priors = nullptr, int numPriors = 0, const CamSet *multiCams = nullptr) {
+                        bool single, const nicp_prior *priors = nullptr, int numPriors = 0, const CamSet *multiCams = nullptr,
+                        const int *priorOffsets = nullptr) {
+  // priorOffsets (batch): pair i owns priors[priorOffsets[i] .. priorOffsets[i + 1]); null: every pair gets all numPriors
+  if (priorOffsets) numPriors = priorOffsets[n];
   const size_t P = (size_t)proj->rows * proj->cols;
   int maxSlots = single ? 1 : env_int("NICP_BATCH_SLOTS", 256);
   if (maxSlots > n) maxSlots = n;
@@ -1307,8 +1310,9 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
         ctx->h_desc[i].refPoints3 = r->points3;
       }
       if (numPriors > 0) {
-        ctx->h_desc[i].priors = ctx->d_priors;
-        ctx->h_desc[i].numPriors = numPriors;
+        const int p0 = priorOffsets ? priorOffsets[src] : 0, p1 = priorOffsets ? priorOffsets[src + 1] : numPriors;
+        ctx->h_desc[i].priors = p1 > p0 ? reinterpret_cast<const HostPrior *>(ctx->d_priors) + p0 : nullptr;
+        ctx->h_desc[i].numPriors = p1 - p0;
       }
     }
     const int nGroups = stage_groups(ctx, m, curSlotOf.data());
@@ -1427,6 +1431,24 @@ int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *referenc
   if (!references || !currents || !results) return NICP_ERR_INVALID;
   return align_common(ctx, n, references, currents, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guesses,
                       frame_inlier_depth_threshold, results, false);
+}
+
+int nicp_align_batch_priors(nicp_context *ctx, int n, const nicp_cloud *const *references, const nicp_cloud *const *currents,
+                            const nicp_projector *proj, const nicp_align_params *ap, const float reference_sensor_offset[16],
+                            const float current_sensor_offset[16], const float *initial_guesses, const nicp_prior *priors,
+                            const int *prior_offsets, float frame_inlier_depth_threshold, nicp_align_result *results) {
+  if (!ctx || n < 0 || !proj || !ap || proj->rows <= 0 || proj->cols <= 0) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return NICP_OK;
+  if (!references || !currents || !results) return NICP_ERR_INVALID;
+  if (prior_offsets) {
+    if (prior_offsets[0] != 0) return NICP_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+      if (prior_offsets[i + 1] < prior_offsets[i]) return NICP_ERR_INVALID;
+    if (prior_offsets[n] > 0 && !priors) return NICP_ERR_INVALID;
+  }
+  return align_common(ctx, n, references, currents, proj, ap, reference_sensor_offset, current_sensor_offset, initial_guesses,
+                      frame_inlier_depth_threshold, results, false, priors, 0, nullptr, prior_offsets);
 }
 
 void nicp_multi_image_size(const nicp_multi_projector *mp, int *rows, int *cols) {

@@ -289,12 +289,45 @@ int nicp_align_get_trace(nicp_context *ctx, float *trace61, int max_iterations);
 
 /* Batched alignment of n independent pairs (loop-closure candidate verification,
  * pwn_tracker2/pwn_closer.cpp:83-182).  initial_guesses = n x 16 floats.  Results of pair i are
- * identical to nicp_align on pair i.  No priors. */
+ * identical to nicp_align on pair i.  (Priors per pair: nicp_align_batch_priors below.) */
 int nicp_align_batch(nicp_context *ctx, int n, const nicp_cloud *const *references,
                      const nicp_cloud *const *currents, const nicp_projector *proj,
                      const nicp_align_params *ap, const float reference_sensor_offset[16],
                      const float current_sensor_offset[16], const float *initial_guesses,
                      float frame_inlier_depth_threshold, nicp_align_result *results);
+
+/* The same with SE(3) priors per pair, as the trackers add them before every match (odometry / IMU priors,
+ * pwn_tracker2/pwn_tracker.cpp:150-160 -> Aligner::addRelativePrior / addAbsolutePrior, aligner.cpp:97-108): pair i owns
+ * priors[prior_offsets[i] .. prior_offsets[i + 1]) (prior_offsets has n + 1 entries, prior_offsets[0] = 0; NULL = no
+ * priors).  Results of pair i are identical to nicp_align on pair i with its priors. */
+int nicp_align_batch_priors(nicp_context *ctx, int n, const nicp_cloud *const *references,
+                            const nicp_cloud *const *currents, const nicp_projector *proj,
+                            const nicp_align_params *ap, const float reference_sensor_offset[16],
+                            const float current_sensor_offset[16], const float *initial_guesses,
+                            const nicp_prior *priors, const int *prior_offsets,
+                            float frame_inlier_depth_threshold, nicp_align_result *results);
+
+/* ---- multi-GPU: pair-wise sharding over the devices of ONE process ---------------------------
+ * The reference's loop closer walks the candidate pairs of a partition serially, building the clouds of both frames and
+ * matching them (PwnCloser::processPartition, pwn_tracker2/pwn_closer.cpp:83-182).  Here the pair list is cut into
+ * contiguous blocks, one per device (block g = pairs [g n / G, (g + 1) n / G): order the list so that pairs sharing a
+ * current frame are adjacent); every device prepares the clouds of the frames its block references from the raw images
+ * and aligns its block on its own stream, one worker thread and one context per device.  Pairs are independent, so there
+ * is no data-path exchange; the records land in the caller's array.  A pair's record does not depend on the number of
+ * devices, on the block it fell into or on its neighbours (same bits as nicp_align on that pair).
+ * devices may name a GPU more than once (two workers sharing a device). */
+typedef struct nicp_shard_pool nicp_shard_pool;
+int nicp_shard_pool_create(const int *devices, int n_devices, nicp_shard_pool **pool);
+void nicp_shard_pool_destroy(nicp_shard_pool *pool);
+int nicp_shard_pool_size(const nicp_shard_pool *pool);
+/* frames in, records out: raws[f] = raw 16-bit image of frame f (all raw_rows x raw_cols, converted like
+ * nicp_raw_depth_to_cloud; sensor_offset is the sensor pose used for the frame preparation and for both sides of every
+ * alignment, as PwnMatcherBase does), pair i = (reference_frame[i], current_frame[i]) with initial_guesses + 16 i. */
+int nicp_align_frames_sharded(nicp_shard_pool *pool, int n_frames, const uint16_t *const *raws, int raw_rows, int raw_cols,
+                              float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
+                              const nicp_stats_params *sp, const float sensor_offset[16], int n_pairs,
+                              const int *reference_frame, const int *current_frame, const float *initial_guesses,
+                              const nicp_align_params *ap, float frame_inlier_depth_threshold, nicp_align_result *results);
 
 /* ---- MultiPointProjector (BASELINE config 5) -------------------------------------------------------- */
 /* MultiPointProjector::computeImageSize (multipointprojector.cpp:7-18) */

@@ -115,9 +115,14 @@ def test_null_handles_are_rejected_not_dereferenced(verify):
     assert L.nicp_align_get_state(N, N, N, N, N, N, N, N) == 1
     assert L.nicp_align_get_trace(N, N, 0) == 1
     assert L.nicp_align_batch(N, 0, N, N, N, N, N, N, N, f0, N) == 1
+    assert L.nicp_align_batch_priors(N, 0, N, N, N, N, N, N, N, N, N, f0, N) == 1
     assert L.nicp_multi_depth_to_cloud(N, N, N, N, N, 0, N, N) == 1
     assert L.nicp_multi_project(N, N, N, N, N, N) == 1
     assert L.nicp_multi_align(N, N, N, N, N, N, N, N, N, 0, f0, N) == 1
+    assert L.nicp_shard_pool_create(N, 0, N) == 1
+    assert L.nicp_shard_pool_size(N) == 0
+    assert L.nicp_align_frames_sharded(N, 0, N, 4, 4, C.c_float(0.001), 1, C.c_float(0.01), N, N, N, 0, N, N, N, N, f0, N) == 1
+    L.nicp_shard_pool_destroy(N)
     L.nicp_destroy(N)
     L.nicp_cloud_destroy(N)
     rows, cols = C.c_int(7), C.c_int(7)

@@ -353,6 +353,28 @@ def test_priors(ctx):
         assert np.abs(T - base).max() > 1e-3
 
 
+def test_priors_in_a_batch(ctx):
+    """nicp_align_batch_priors: every pair with its own list of SE(3) priors (none, one, two), as the tracker adds them
+    before every match (pwn_tracker2/pwn_tracker.cpp:150-160): record for record the single-pair call with those priors"""
+    from g2o_frontend_b200 import capi, synth
+    s = get_scene(4)
+    ref, cur = upload(ctx, s.cloudA), upload(ctx, s.cloudB)
+    mean = synth.make_pose((0.05, -0.03, 0.08), (0.1, 1.0, 0.3), 3.0).astype(np.float32)
+    refT = synth.make_pose((0.2, 0.1, -0.1), (1.0, 0.2, 0.1), 5.0).astype(np.float32)
+    info = (np.diag([2e5, 1e5, 3e5, 5e6, 4e6, 6e6]) + 1e3).astype(np.float32)
+    lists = [[], [capi.make_prior(0, mean, info, None)], [capi.make_prior(1, mean, info, refT)],
+             [capi.make_prior(0, mean, info, None), capi.make_prior(1, mean, info * 0.5, refT)], []]
+    rng = np.random.default_rng(1)
+    guesses = np.stack([synth.perturbed_pose(rng, np.eye(4), 0.02, 1.0) for _ in lists]).astype(np.float32)
+    singles = [bytes(ctx.align(ref, cur, s.projector(), s.align_params(), guess=g, priors=pl)) for g, pl in zip(guesses, lists)]
+    batch = ctx.align_batch([ref] * 5, [cur] * 5, s.projector(), s.align_params(), guesses, priors=lists)
+    for i in range(5):
+        assert batch[i].tobytes() == singles[i], i
+    assert singles[0] != singles[1]
+    plain = ctx.align_batch([ref] * 5, [cur] * 5, s.projector(), s.align_params(), guesses)
+    assert plain[0].tobytes() == singles[0] and plain[1].tobytes() != singles[1]
+
+
 @pytest.mark.parametrize("width,height,ncam", [(160, 120, 4), (64, 48, 3)])
 def test_multi_point_projector(ctx, width, height, ncam):
     """MultiPointProjector (BASELINE config 5 layout, scaled down): composite frame prep, base-class z-buffer
@@ -823,3 +845,66 @@ def test_packed_point_stream_is_invalidated(ctx):
     assert batch(big) == alone(big)
     big.append(cur, T)                                         # Cloud::add grows the cloud behind the cache
     assert batch(big) == alone(big)
+
+
+def _sharded_case(verify, device_lists):
+    """loop-closure verification of 3 currents x 5 candidates at 160x120 through nicp_align_frames_sharded for several
+    device lists; returns the records per device list and the same pairs aligned one by one on a plain context"""
+    from g2o_frontend_b200 import capi, synth
+    step = 4
+    rows, cols = 480 // step, 640 // step
+    K = synth.scaled_K(synth.K_KINECT, 1.0 / step)
+    rng = np.random.default_rng(11)
+    poses = [synth.perturbed_pose(rng, np.eye(4), 0.15, 4.0) for _ in range(8)]
+    raws = [synth.render_depth_u16(p, seed=40 + i) for i, p in enumerate(poses)]
+    cur_frames, cand_frames = [0, 1, 2], [3, 4, 5, 6, 7]
+    ref_frame, cur_frame, guesses = [], [], []
+    for c in cur_frames:          # current-major: pairs sharing a current frame are adjacent
+        for r in cand_frames:
+            ref_frame.append(r)
+            cur_frame.append(c)
+            guesses.append(synth.perturbed_pose(rng, np.linalg.inv(poses[r]) @ poses[c], 0.02, 1.0))
+    guesses = np.stack(guesses).astype(np.float32)
+    conf = CONF_1_4
+    proj = capi.make_projector(K, rows, cols, conf["minD"], conf["maxD"])
+    sp = capi.make_stats_params(conf["worldRadius"], conf["minImageRadius"], conf["maxImageRadius"], conf["minPoints"],
+                                conf["curvatureThreshold"], conf["omegaCurvatureThreshold"])
+    ap = capi.make_align_params(conf["inlierDistanceThreshold"], conf["inlierNormalAngularThreshold"],
+                                conf["flatCurvatureThreshold"], conf["inlierCurvatureRatioThreshold"], conf["inlierMaxChi2"],
+                                True, 10, 1)
+    out = []
+    for devs in device_lists:
+        pool = capi.ShardPool(devs, verify=verify)
+        assert pool.size() == len(devs)
+        out.append(pool.align_frames(raws, proj, sp, ref_frame, cur_frame, guesses, ap, step=step))
+        again = pool.align_frames(raws, proj, sp, ref_frame, cur_frame, guesses, ap, step=step)  # the cloud cache is reused
+        assert again.tobytes() == out[-1].tobytes()
+        pool.close()
+    c = capi.Context(0, verify=verify)
+    clouds = [c.raw_depth_to_cloud(r, proj, sp, step=step)[0] for r in raws]
+    singles = [bytes(c.align(clouds[r], clouds[k], proj, ap, guess=g)) for r, k, g in zip(ref_frame, cur_frame, guesses)]
+    c.close()
+    return out, singles
+
+
+@pytest.mark.parametrize("verify", [True, False])
+def test_sharded_alignment_is_independent_of_the_device_count(verify):
+    """nicp_align_frames_sharded (the C-ABI entry of the pair-sharded path): one, two and three workers (contexts on the
+    same GPU when the box has one) give every pair the record it gets alone -- 'pair i alone = in a batch = on another
+    device count', bit for bit"""
+    out, singles = _sharded_case(verify, [[0], [0, 0], [0, 0, 0]])
+    for recs in out:
+        assert (recs["status"] == 0).all() and (recs["inliers"] > 3000).all()
+        for i, sgl in enumerate(singles):
+            assert recs[i].tobytes() == sgl, i
+
+
+def test_sharded_alignment_over_the_visible_gpus():
+    """the same over every GPU the box has (two workers on GPU 0 when it has one; `gpurun --gpus 2` runs it on two)"""
+    import torch
+    n = torch.cuda.device_count()
+    lists = [list(range(n)), list(range(n))[::-1] + [0]] if n >= 2 else [[0, 0]]
+    out, singles = _sharded_case(False, lists)
+    for recs in out:
+        for i, sgl in enumerate(singles):
+            assert recs[i].tobytes() == sgl, i
