@@ -23,6 +23,7 @@ SYMBOLS = [
     "nicp_cloud_download_stats", "nicp_cloud_transform", "nicp_cloud_append",
     "nicp_depth_prepare", "nicp_unproject", "nicp_project_intervals", "nicp_depth_to_cloud",
     "nicp_raw_depth_to_cloud", "nicp_raw_depth_to_cloud_batch", "nicp_last_integral_image", "nicp_last_interval_image",
+    "nicp_stats_compute", "nicp_information_compute",
     "nicp_project", "nicp_correspond_linearize", "nicp_linearize",
     "nicp_align", "nicp_align_get_state", "nicp_align_get_trace", "nicp_align_batch", "nicp_align_batch_priors",
     "nicp_multi_image_size", "nicp_multi_depth_to_cloud", "nicp_multi_project", "nicp_multi_align",
@@ -441,6 +442,31 @@ class Context:
                                                             int(keep_stats), CA))
         self._keepalive = frames  # the copies are asynchronous: keep the host frames alive until the next call
         return clouds
+
+    def stats_compute(self, points, index, interval, sp):
+        """StatsCalculatorIntegralImage::compute(normals, stats, points, indexImage) with its interval image"""
+        pts = np.ascontiguousarray(points, np.float32)
+        n = pts.shape[0]
+        idx = np.ascontiguousarray(index, np.int32)
+        itv = np.ascontiguousarray(interval, np.int32)
+        rows, cols = idx.shape
+        out = {"normals": np.zeros((n, 4), np.float32), "stats16": np.zeros((n, 16), np.float32),
+               "eigenvalues": np.zeros((n, 3), np.float32), "n": np.zeros(n, np.int32), "curvature": np.zeros(n, np.float32)}
+        _check(self.L, self.L.nicp_stats_compute(self.handle, _fptr(pts), n, _iptr(idx), _iptr(itv), rows, cols, C.byref(sp),
+                                                 _fptr(out["normals"]), _fptr(out["stats16"]), _fptr(out["eigenvalues"]),
+                                                 _iptr(out["n"]), _fptr(out["curvature"])))
+        return out
+
+    def information_compute(self, normals, stats16, eigenvalues, curvature, sp):
+        """Point / NormalInformationMatrixCalculator::compute: (n, 6) upper triangles"""
+        n = normals.shape[0]
+        op, on = np.zeros((n, 6), np.float32), np.zeros((n, 6), np.float32)
+        _check(self.L, self.L.nicp_information_compute(self.handle, n, _fptr(np.ascontiguousarray(normals, np.float32)),
+                                                       _fptr(np.ascontiguousarray(stats16, np.float32)),
+                                                       _fptr(np.ascontiguousarray(eigenvalues, np.float32)),
+                                                       _fptr(np.ascontiguousarray(curvature, np.float32)), C.byref(sp),
+                                                       _fptr(op), _fptr(on)))
+        return op, on
 
     def last_integral_image(self, rows, cols):
         out = np.zeros((rows, cols, 10), np.float32)

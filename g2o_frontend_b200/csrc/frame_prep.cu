@@ -338,8 +338,70 @@ __device__ __forceinline__ void rotate_sym(const float *M, const float *Om /*3x3
       NM3(out, r, c) = dot3(NM3(t, r, 0), NM3(t, r, 1), NM3(t, r, 2), NM4(M, c, 0), NM4(M, c, 1), NM4(M, c, 2));
 }
 
+// StatsCalculatorIntegralImage::compute for one pixel (statscalculatorintegralimage.cpp:41-78): region sums of the window
+// of radius clamp(k), mean / covariance (pointaccumulator.h:65-86), computeDirect, curvature, normal orientation.
+// Returns false when the window holds fewer than minPoints points (outputs untouched).
+__device__ __forceinline__ bool stats_core(const float *__restrict__ I, size_t plane, int rows, int cols, int r, int c, int k,
+                                           const StatsConsts &sc, float px, float py, float pz, float &nx, float &ny, float &nz,
+                                           float &curv, float *U, float *ev, float *mu, int &npts) {
+  k = clampi(k, sc.minR, sc.maxR);
+  // getRegion(c-k, c+k, r-k, r+k) (pointintegralimage.cpp:53-66)
+  int x0 = clampi(c - k - 1, 0, cols - 1), x1 = clampi(c + k - 1, 0, cols - 1);
+  int y0 = clampi(r - k - 1, 0, rows - 1), y1 = clampi(r + k - 1, 0, rows - 1);
+  size_t o11 = (size_t)y1 * cols + x1, o00 = (size_t)y0 * cols + x0;
+  size_t o10 = (size_t)y1 * cols + x0, o01 = (size_t)y0 * cols + x1;
+  float acc[kIntegralCh];
+#pragma unroll
+  for (int ch = 0; ch < kIntegralCh; ch++) {
+    const float *P = I + ch * plane;
+    acc[ch] = fsub(fsub(fadd(P[o11], P[o00]), P[o10]), P[o01]);
+  }
+  if ((int)acc[0] < sc.minPoints) return false;
+  npts = (int)acc[0];
+  float dd = fdiv(1.0f, acc[0]);
+  mu[0] = fmul(acc[1], dd); mu[1] = fmul(acc[2], dd); mu[2] = fmul(acc[3], dd);
+  float c00 = fsub(fmul(acc[4], dd), fmul(mu[0], mu[0]));
+  float c10 = fsub(fmul(acc[5], dd), fmul(mu[0], mu[1]));
+  float c20 = fsub(fmul(acc[6], dd), fmul(mu[0], mu[2]));
+  float c11 = fsub(fmul(acc[7], dd), fmul(mu[1], mu[1]));
+  float c21 = fsub(fmul(acc[8], dd), fmul(mu[1], mu[2]));
+  float c22 = fsub(fmul(acc[9], dd), fmul(mu[2], mu[2]));
+  eigen3(c00, c10, c20, c11, c21, c22, ev, U);
+  if (ev[0] < 0.0f) ev[0] = 0.0f;
+  // Stats::curvature (stats.h:98-103): float sum, double divide
+  curv = (float)((double)ev[0] / ((double)fadd(fadd(ev[0], ev[1]), ev[2]) + 1e-9));
+  nx = U[0]; ny = U[1]; nz = U[2];
+  if (curv < sc.curvThr) {
+    if (dot4(nx, ny, nz, 0.0f, px, py, pz, 1.0f) > 0) { nx = -nx; ny = -ny; nz = -nz; }
+  } else {
+    nx = ny = nz = 0.0f;
+  }
+  return true;
+}
+
+// Point / NormalInformationMatrixCalculator::compute for one point (informationmatrixcalculator.cpp:17-35, 46-57):
+// OP / ON stay zero for a zero normal
+__device__ __forceinline__ void information_core(float nx, float ny, float nz, float curv, const float *U, const float *ev,
+                                                 const StatsConsts &sc, float *OP, float *ON) {
+  float sq = fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz));
+  if (sq > 0) {
+    bool flat = curv < sc.omegaCurvThr;
+    float dg[3];
+    if (flat) { dg[0] = sc.flatP[0]; dg[1] = sc.flatP[1]; dg[2] = sc.flatP[2]; }
+    else { dg[0] = fdiv(1.0f, ev[0]); dg[1] = fdiv(1.0f, ev[1]); dg[2] = fdiv(1.0f, ev[2]); }
+    float UD[9];
+    for (int rr = 0; rr < 3; rr++)
+      for (int cc = 0; cc < 3; cc++) NM3(UD, rr, cc) = fmul(NM3(U, rr, cc), dg[cc]);
+    for (int rr = 0; rr < 3; rr++)
+      for (int cc = 0; cc < 3; cc++)
+        NM3(OP, rr, cc) = dot3(NM3(UD, rr, 0), NM3(UD, rr, 1), NM3(UD, rr, 2), NM3(U, cc, 0), NM3(U, cc, 1), NM3(U, cc, 2));
+    const float *dn = flat ? sc.flatN : sc.nonflatN;
+    ON[0] = dn[0]; ON[4] = dn[1]; ON[8] = dn[2];
+  }
+}
+
 template <bool MULTI>
-__global__ void __launch_bounds__(256) k_stats(PrepBatch B, int rows, int cols, StatsConsts sc,
+__global__ void __launch_bounds__(256, 4) k_stats(PrepBatch B, int rows, int cols, StatsConsts sc,
                                                const PrepCams *__restrict__ pc, int *__restrict__ index,
                                                int *__restrict__ interval) {
   // index / interval images (single-frame calls that asked for them) may be null: a batch does not materialise them
@@ -403,56 +465,8 @@ __global__ void __launch_bounds__(256) k_stats(PrepBatch B, int rows, int cols, 
   bool computed = false;
 
   if (k >= 0) {
-    k = clampi(k, sc.minR, sc.maxR);
-    // getRegion(c-k, c+k, r-k, r+k) (pointintegralimage.cpp:53-66)
-    int x0 = clampi(c - k - 1, 0, cols - 1), x1 = clampi(c + k - 1, 0, cols - 1);
-    int y0 = clampi(r - k - 1, 0, rows - 1), y1 = clampi(r + k - 1, 0, rows - 1);
-    size_t o11 = (size_t)y1 * cols + x1, o00 = (size_t)y0 * cols + x0;
-    size_t o10 = (size_t)y1 * cols + x0, o01 = (size_t)y0 * cols + x1;
-    float acc[kIntegralCh];
-#pragma unroll
-    for (int ch = 0; ch < kIntegralCh; ch++) {
-      const float *P = I + ch * plane;
-      acc[ch] = fsub(fsub(fadd(P[o11], P[o00]), P[o10]), P[o01]);
-    }
-    if ((int)acc[0] >= sc.minPoints) {
-      computed = true;
-      npts = (int)acc[0];
-      float dd = fdiv(1.0f, acc[0]);
-      mu[0] = fmul(acc[1], dd); mu[1] = fmul(acc[2], dd); mu[2] = fmul(acc[3], dd);
-      float c00 = fsub(fmul(acc[4], dd), fmul(mu[0], mu[0]));
-      float c10 = fsub(fmul(acc[5], dd), fmul(mu[0], mu[1]));
-      float c20 = fsub(fmul(acc[6], dd), fmul(mu[0], mu[2]));
-      float c11 = fsub(fmul(acc[7], dd), fmul(mu[1], mu[1]));
-      float c21 = fsub(fmul(acc[8], dd), fmul(mu[1], mu[2]));
-      float c22 = fsub(fmul(acc[9], dd), fmul(mu[2], mu[2]));
-      eigen3(c00, c10, c20, c11, c21, c22, ev, U);
-      if (ev[0] < 0.0f) ev[0] = 0.0f;
-      // Stats::curvature (stats.h:98-103): float sum, double divide
-      curv = (float)((double)ev[0] / ((double)fadd(fadd(ev[0], ev[1]), ev[2]) + 1e-9));
-      nx = U[0]; ny = U[1]; nz = U[2];
-      if (curv < sc.curvThr) {
-        if (dot4(nx, ny, nz, 0.0f, px, py, pz, 1.0f) > 0) { nx = -nx; ny = -ny; nz = -nz; }
-      } else {
-        nx = ny = nz = 0.0f;
-      }
-      // information matrices (informationmatrixcalculator.cpp:17-35, 46-57)
-      float sq = fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz));
-      if (sq > 0) {
-        bool flat = curv < sc.omegaCurvThr;
-        float dg[3];
-        if (flat) { dg[0] = sc.flatP[0]; dg[1] = sc.flatP[1]; dg[2] = sc.flatP[2]; }
-        else { dg[0] = fdiv(1.0f, ev[0]); dg[1] = fdiv(1.0f, ev[1]); dg[2] = fdiv(1.0f, ev[2]); }
-        float UD[9];
-        for (int rr = 0; rr < 3; rr++)
-          for (int cc = 0; cc < 3; cc++) NM3(UD, rr, cc) = fmul(NM3(U, rr, cc), dg[cc]);
-        for (int rr = 0; rr < 3; rr++)
-          for (int cc = 0; cc < 3; cc++)
-            NM3(OP, rr, cc) = dot3(NM3(UD, rr, 0), NM3(UD, rr, 1), NM3(UD, rr, 2), NM3(U, cc, 0), NM3(U, cc, 1), NM3(U, cc, 2));
-        const float *dn = flat ? sc.flatN : sc.nonflatN;
-        ON[0] = dn[0]; ON[4] = dn[1]; ON[8] = dn[2];
-      }
-    }
+    computed = stats_core(I, plane, rows, cols, r, c, k, sc, px, py, pz, nx, ny, nz, curv, U, ev, mu, npts);
+    if (computed) information_core(nx, ny, nz, curv, U, ev, sc, OP, ON);
   }
 
   float S[16];
@@ -722,6 +736,167 @@ int launch_raw_prep_batch(nicp_context *ctx, int n, const uint16_t *const *d_raw
   k_depth_convert<<<dim3((outPx + 255) / 256, n), 256, 0, ctx->stream>>>(B, rawRows, rawCols, scale, step, maxCov);
   NICP_CHECK_LAUNCH(ctx);
   return launch_prep_set(ctx, B, proj, sp, sensorOffset, nullptr, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-level StatsCalculatorIntegralImage::compute(normals, stats, points, indexImage) with its _intervalImage
+// (statscalculatorintegralimage.cpp:14-82) and Point / NormalInformationMatrixCalculator::compute
+// (informationmatrixcalculator.cpp:9-58): the virtuals of the boundary that take an arbitrary point vector + index
+// image (any projector pose, merged clouds, ...), not a depth image.
+// ---------------------------------------------------------------------------------------------
+// PointIntegralImage::compute pass 1 from (index image, points): same row staging / sequential scan as k_integral_rows
+__global__ void __launch_bounds__(256) k_integral_rows_indexed(const int *__restrict__ index, const float4 *__restrict__ points,
+                                                               int rows, int cols, float *__restrict__ I) {
+  extern __shared__ float sm[];  // [10][stride]
+  const int stride = cols + 1;
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const int idx = index[(size_t)r * cols + c];
+    float ch[kIntegralCh];
+    if (idx < 0) {
+#pragma unroll
+      for (int k = 0; k < kIntegralCh; k++) ch[k] = 0.0f;
+    } else {
+      const float4 p = points[idx];
+      ch[0] = 1.0f; ch[1] = p.x; ch[2] = p.y; ch[3] = p.z;
+      ch[4] = fmul(p.x, p.x); ch[5] = fmul(p.x, p.y); ch[6] = fmul(p.x, p.z);
+      ch[7] = fmul(p.y, p.y); ch[8] = fmul(p.y, p.z); ch[9] = fmul(p.z, p.z);
+    }
+#pragma unroll
+    for (int k = 0; k < kIntegralCh; k++) sm[k * stride + c] = ch[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kIntegralCh) {
+    float *p = sm + threadIdx.x * stride;
+    float v = p[0];
+    for (int c = 1; c < cols; c++) { v = fadd(p[c], v); p[c] = v; }
+  }
+  __syncthreads();
+  const size_t plane = (size_t)rows * cols;
+  for (int k = 0; k < kIntegralCh; k++) {
+    float *orow = I + k * plane + (size_t)r * cols;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) orow[c] = sm[k * stride + c];
+  }
+}
+
+// Stats() / Normal::Zero() defaults of every point (statscalculatorintegralimage.cpp:22-28)
+__global__ void k_stats_defaults(int n, float4 *__restrict__ normals, float *__restrict__ stats16, float *__restrict__ eigvals,
+                                 int *__restrict__ statsN, float *__restrict__ curvature) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  normals[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 *so = reinterpret_cast<float4 *>(stats16 + 16 * (size_t)i);
+  so[0] = make_float4(1.f, 0.f, 0.f, 0.f);
+  so[1] = make_float4(0.f, 1.f, 0.f, 0.f);
+  so[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+  so[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+  eigvals[3 * (size_t)i] = eigvals[3 * (size_t)i + 1] = eigvals[3 * (size_t)i + 2] = 0.0f;
+  statsN[i] = 0;
+  curvature[i] = 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_stats_stage(const float *__restrict__ I, const int *__restrict__ index,
+                                                     const int *__restrict__ interval, const float4 *__restrict__ points,
+                                                     int rows, int cols, int n, StatsConsts sc, float4 *__restrict__ normals,
+                                                     float *__restrict__ stats16, float *__restrict__ eigvals,
+                                                     int *__restrict__ statsN, float *__restrict__ curvature) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= cols || r >= rows) return;
+  const size_t pix = (size_t)r * cols + c;
+  const int idx = index[pix], k = interval[pix];
+  if (idx < 0 || idx >= n || k < 0) return;
+  const float4 p = points[idx];
+  float nx = 0.f, ny = 0.f, nz = 0.f, curv = 0.f, U[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ev[3] = {0, 0, 0}, mu[3] = {0, 0, 0};
+  int npts = 0;
+  if (!stats_core(I, (size_t)rows * cols, rows, cols, r, c, k, sc, p.x, p.y, p.z, nx, ny, nz, curv, U, ev, mu, npts)) return;
+  normals[idx] = make_float4(nx, ny, nz, 0.0f);
+  float4 *so = reinterpret_cast<float4 *>(stats16 + 16 * (size_t)idx);
+  so[0] = make_float4(U[0], U[1], U[2], 0.0f);
+  so[1] = make_float4(U[3], U[4], U[5], 0.0f);
+  so[2] = make_float4(U[6], U[7], U[8], 0.0f);
+  so[3] = make_float4(mu[0], mu[1], mu[2], 1.0f);
+  eigvals[3 * (size_t)idx] = ev[0];
+  eigvals[3 * (size_t)idx + 1] = ev[1];
+  eigvals[3 * (size_t)idx + 2] = ev[2];
+  statsN[idx] = npts;
+  curvature[idx] = curv;
+}
+
+__global__ void k_information_stage(int n, const float4 *__restrict__ normals, const float *__restrict__ stats16,
+                                    const float *__restrict__ eigvals, const float *__restrict__ curvature, StatsConsts sc,
+                                    float *__restrict__ omegaP6, float *__restrict__ omegaN6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 nn = normals[i];
+  const float *S = stats16 + 16 * (size_t)i;
+  const float U[9] = {S[0], S[1], S[2], S[4], S[5], S[6], S[8], S[9], S[10]};
+  const float ev[3] = {eigvals[3 * (size_t)i], eigvals[3 * (size_t)i + 1], eigvals[3 * (size_t)i + 2]};
+  float OP[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ON[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  information_core(nn.x, nn.y, nn.z, curvature[i], U, ev, sc, OP, ON);
+  if (omegaP6) {
+    float *o = omegaP6 + 6 * (size_t)i;
+    o[0] = NM3(OP, 0, 0); o[1] = NM3(OP, 0, 1); o[2] = NM3(OP, 0, 2); o[3] = NM3(OP, 1, 1); o[4] = NM3(OP, 1, 2); o[5] = NM3(OP, 2, 2);
+  }
+  if (omegaN6) {
+    float *o = omegaN6 + 6 * (size_t)i;
+    o[0] = NM3(ON, 0, 0); o[1] = NM3(ON, 0, 1); o[2] = NM3(ON, 0, 2); o[3] = NM3(ON, 1, 1); o[4] = NM3(ON, 1, 2); o[5] = NM3(ON, 2, 2);
+  }
+}
+
+static StatsConsts stage_consts(const nicp_stats_params *sp) {
+  StatsConsts sc;
+  memset(&sc, 0, sizeof sc);
+  sc.minR = sp->min_image_radius;
+  sc.maxR = sp->max_image_radius;
+  sc.minPoints = sp->min_points;
+  sc.curvThr = sp->curvature_threshold;
+  sc.omegaCurvThr = sp->omega_curvature_threshold;
+  for (int i = 0; i < 3; i++) {
+    sc.flatP[i] = sp->flat_omega_p[i];
+    sc.flatN[i] = sp->flat_omega_n[i];
+    sc.nonflatN[i] = sp->nonflat_omega_n[i];
+  }
+  return sc;
+}
+
+// device buffers in, device buffers out; d_integral = [10][rows][cols] scratch
+int launch_stats_stage(nicp_context *ctx, const float4 *d_points, int n, const int *d_index, const int *d_interval, int rows,
+                       int cols, const nicp_stats_params *sp, float *d_integral, float4 *d_normals, float *d_stats16,
+                       float *d_eigvals, int *d_statsN, float *d_curvature) {
+  const size_t smem = (size_t)kIntegralCh * (cols + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("image too wide for the row pass (%d columns)", cols);
+    return NICP_ERR_INVALID;
+  }
+  if (smem > 48 * 1024) NICP_CUDA(cudaFuncSetAttribute(k_integral_rows_indexed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_integral_rows_indexed<<<rows, 256, smem, ctx->stream>>>(d_index, d_points, rows, cols, d_integral);
+  NICP_CHECK_LAUNCH(ctx);
+  PrepBatch B;
+  memset(&B, 0, sizeof B);
+  B.n = 1;
+  B.integral[0] = d_integral;
+  k_integral_cols<<<dim3((cols + 63) / 64, kIntegralCh, 1), 64, 0, ctx->stream>>>(B, rows, cols);
+  NICP_CHECK_LAUNCH(ctx);
+  if (n > 0) {
+    k_stats_defaults<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_normals, d_stats16, d_eigvals, d_statsN, d_curvature);
+    NICP_CHECK_LAUNCH(ctx);
+  }
+  const StatsConsts sc = stage_consts(sp);
+  k_stats_stage<<<dim3((cols + 31) / 32, (rows + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(d_integral, d_index, d_interval, d_points, rows,
+                                                                                         cols, n, sc, d_normals, d_stats16, d_eigvals,
+                                                                                         d_statsN, d_curvature);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+int launch_information_stage(nicp_context *ctx, int n, const float4 *d_normals, const float *d_stats16, const float *d_eigvals,
+                             const float *d_curvature, const nicp_stats_params *sp, float *d_omegaP6, float *d_omegaN6) {
+  if (n <= 0) return NICP_OK;
+  k_information_stage<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_normals, d_stats16, d_eigvals, d_curvature, stage_consts(sp),
+                                                                d_omegaP6, d_omegaN6);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

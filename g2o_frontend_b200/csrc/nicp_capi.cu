@@ -528,6 +528,27 @@ static void finish_results(nicp_context *ctx, int base, int n, nicp_align_result
 
 using namespace nicp;
 
+namespace {
+struct DevBufs {  // temporaries of a stage-level call, freed on every exit path
+  std::vector<void *> p;
+  ~DevBufs() {
+    for (void *q : p) cudaFree(q);
+  }
+  template <typename T>
+  int alloc(T **out, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return NICP_ERR_ALLOC;
+    }
+    p.push_back(q);
+    *out = reinterpret_cast<T *>(q);
+    return NICP_OK;
+  }
+};
+}  // namespace
+
 // =============================================================================================
 extern "C" {
 
@@ -1074,6 +1095,66 @@ int nicp_raw_depth_to_cloud_batch(nicp_context *ctx, int n, const uint16_t *cons
     NICP_CUDA(cudaEventRecord(ctx->evBRawUsed[b], ctx->stream));
   }
   ctx->lastRows = 0;  // the single-frame test hooks (integral / interval image) describe no frame of a batch
+  return NICP_OK;
+}
+
+// ---- stage-level statistics / information matrices (host buffers in, host buffers out) -----------------------------
+int nicp_stats_compute(nicp_context *ctx, const float *points4, int n, const int *index_image, const int *interval_image,
+                       int rows, int cols, const nicp_stats_params *sp, float *normals4, float *stats16, float *eigenvalues3,
+                       int *n_points, float *curvature) {
+  if (!ctx || !points4 || n < 0 || !index_image || !interval_image || rows <= 0 || cols <= 0 || !sp) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  const size_t px = (size_t)rows * cols;
+  DevBufs bufs;
+  float4 *d_points, *d_normals;
+  int *d_index, *d_interval, *d_cnt;
+  float *d_integral, *d_stats, *d_eig, *d_curv;
+  int rc;
+  if ((rc = bufs.alloc(&d_points, (size_t)n)) || (rc = bufs.alloc(&d_normals, (size_t)n)) || (rc = bufs.alloc(&d_index, px)) ||
+      (rc = bufs.alloc(&d_interval, px)) || (rc = bufs.alloc(&d_cnt, (size_t)n)) || (rc = bufs.alloc(&d_integral, px * kIntegralCh)) ||
+      (rc = bufs.alloc(&d_stats, (size_t)n * 16)) || (rc = bufs.alloc(&d_eig, (size_t)n * 3)) || (rc = bufs.alloc(&d_curv, (size_t)n)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  if (n) NICP_CUDA(cudaMemcpyAsync(d_points, points4, sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_index, index_image, sizeof(int) * px, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_interval, interval_image, sizeof(int) * px, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_stats_stage(ctx, d_points, n, d_index, d_interval, rows, cols, sp, d_integral, d_normals, d_stats, d_eig, d_cnt,
+                               d_curv)))
+    return rc;
+  if (n) {
+    if (normals4) NICP_CUDA(cudaMemcpyAsync(normals4, d_normals, sizeof(float4) * n, cudaMemcpyDeviceToHost, st));
+    if (stats16) NICP_CUDA(cudaMemcpyAsync(stats16, d_stats, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, st));
+    if (eigenvalues3) NICP_CUDA(cudaMemcpyAsync(eigenvalues3, d_eig, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    if (n_points) NICP_CUDA(cudaMemcpyAsync(n_points, d_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (curvature) NICP_CUDA(cudaMemcpyAsync(curvature, d_curv, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  }
+  NICP_CUDA(cudaStreamSynchronize(st));
+  return NICP_OK;
+}
+
+int nicp_information_compute(nicp_context *ctx, int n, const float *normals4, const float *stats16, const float *eigenvalues3,
+                             const float *curvature, const nicp_stats_params *sp, float *omega_p6, float *omega_n6) {
+  if (!ctx || n < 0 || !sp || (n > 0 && (!normals4 || !stats16 || !eigenvalues3 || !curvature))) return NICP_ERR_INVALID;
+  NICP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return NICP_OK;
+  DevBufs bufs;
+  float4 *d_normals;
+  float *d_stats, *d_eig, *d_curv, *d_op = nullptr, *d_on = nullptr;
+  int rc;
+  if ((rc = bufs.alloc(&d_normals, (size_t)n)) || (rc = bufs.alloc(&d_stats, (size_t)n * 16)) || (rc = bufs.alloc(&d_eig, (size_t)n * 3)) ||
+      (rc = bufs.alloc(&d_curv, (size_t)n)))
+    return rc;
+  if (omega_p6 && (rc = bufs.alloc(&d_op, (size_t)n * 6))) return rc;
+  if (omega_n6 && (rc = bufs.alloc(&d_on, (size_t)n * 6))) return rc;
+  cudaStream_t st = ctx->stream;
+  NICP_CUDA(cudaMemcpyAsync(d_normals, normals4, sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_stats, stats16, sizeof(float) * 16 * n, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_eig, eigenvalues3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
+  NICP_CUDA(cudaMemcpyAsync(d_curv, curvature, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_information_stage(ctx, n, d_normals, d_stats, d_eig, d_curv, sp, d_op, d_on))) return rc;
+  if (omega_p6) NICP_CUDA(cudaMemcpyAsync(omega_p6, d_op, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, st));
+  if (omega_n6) NICP_CUDA(cudaMemcpyAsync(omega_n6, d_on, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, st));
+  NICP_CUDA(cudaStreamSynchronize(st));
   return NICP_OK;
 }
 

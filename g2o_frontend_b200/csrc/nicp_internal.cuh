@@ -351,6 +351,11 @@ int launch_frame_prep(nicp_context *ctx, const float *d_depth, const nicp_projec
 int launch_raw_prep_batch(nicp_context *ctx, int n, const uint16_t *const *d_raw, int rawRows, int rawCols, float scale, int step,
                           float maxCov, const nicp_projector *proj, const nicp_stats_params *sp, const float sensorOffset[16],
                           int keepStats, nicp_cloud *const *clouds);
+int launch_stats_stage(nicp_context *ctx, const float4 *d_points, int n, const int *d_index, const int *d_interval, int rows,
+                       int cols, const nicp_stats_params *sp, float *d_integral, float4 *d_normals, float *d_stats16,
+                       float *d_eigvals, int *d_statsN, float *d_curvature);
+int launch_information_stage(nicp_context *ctx, int n, const float4 *d_normals, const float *d_stats16, const float *d_eigvals,
+                             const float *d_curvature, const nicp_stats_params *sp, float *d_omegaP6, float *d_omegaN6);
 int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
                      float maxD, nicp_cloud *cloud, int *d_index);
 int launch_intervals(nicp_context *ctx, const float *d_depth, const nicp_projector *proj, float worldRadius, int *d_interval);

@@ -404,6 +404,51 @@ int main(int argc, char **argv) {
       fclose(out);
       return 0;
     }
+    if (get(cfg, "stages", 0) != 0) {
+      // the stage-level virtuals of the converter (StatsCalculator::compute, InformationMatrixCalculator::compute,
+      // statscalculator.h:36, informationmatrixcalculator.h:83) chained by hand like
+      // DepthImageConverterIntegralImage::compute does (depthimageconverterintegralimage.cpp:35-52), against the fused call
+      RawDepthImage raw;
+      if (!readPgm16(argv[3], raw)) throw std::runtime_error("cannot read frame");
+      DepthImage depth;
+      DepthImage_convertAndScale(depth, raw, imageScale, depthScale);
+      projector.setCameraMatrix(K);
+      projector.setImageSize(raw.rows, raw.cols);
+      projector.scale(1.0f / imageScale);
+      converter.setKeepStats(true);
+      Cloud fused;
+      converter.compute(fused, depth, Isometry3f::Identity());
+      Cloud staged;
+      IntImage indexImage;
+      projector.setTransform(Isometry3f::Identity());
+      projector.unProject(staged, indexImage, depth);
+      projector.projectIntervals(statsCalculator.intervalImage(), depth, statsCalculator.worldRadius());
+      NormalVector normals;
+      StatsVector stats;
+      statsCalculator.compute(normals, stats, ((const Cloud &)staged).points(), indexImage);
+      InformationMatrixVector omegaP, omegaN;
+      pointInformationMatrixCalculator.compute(omegaP, stats, normals);
+      normalInformationMatrixCalculator.compute(omegaN, stats, normals);
+      const Cloud &F = fused;
+      double dN = 0, dC = 0, dP = 0, dNN = 0, dS = 0;
+      size_t nonzero = 0;
+      if (F.size() != normals.size()) throw std::runtime_error("stage-level point count differs");
+      for (size_t i = 0; i < F.size(); i++) {
+        for (int k = 0; k < 3; k++) dN = std::max(dN, (double)std::fabs(F.normals()[i][k] - normals[i][k]));
+        if (normals[i][0] != 0 || normals[i][1] != 0 || normals[i][2] != 0) nonzero++;
+        dC = std::max(dC, (double)std::fabs(F.stats()[i].curvature() - stats[i].curvature()));
+        for (int k = 0; k < 16; k++) dS = std::max(dS, (double)std::fabs(F.stats()[i].m[k] - stats[i].m[k]));
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            dP = std::max(dP, (double)std::fabs(F.pointInformationMatrix()[i](r, c) - omegaP[i](r, c)));
+            dNN = std::max(dNN, (double)std::fabs(F.normalInformationMatrix()[i](r, c) - omegaN[i](r, c)));
+          }
+      }
+      fprintf(out, "{\"points\": %zu, \"nonzero_normals\": %zu, \"d_normals\": %.9g, \"d_curvature\": %.9g, \"d_stats\": %.9g, "
+                   "\"d_omega_p\": %.9g, \"d_omega_n\": %.9g}\n", F.size(), nonzero, dN, dC, dS, dP, dNN);
+      fclose(out);
+      return 0;
+    }
     if (get(cfg, "cloudcopy", 0) != 0) {
       // value semantics of pwn::Cloud and the host mirror: the same pair aligned (a) untouched, (b) after the current
       // cloud's host vectors were touched through a non-const accessor (host mirror -> re-upload, default keepStats = false),

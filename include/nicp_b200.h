@@ -246,6 +246,21 @@ int nicp_raw_depth_to_cloud_batch(nicp_context *ctx, int n, const uint16_t *cons
                                   float depth_scale, int step, float max_depth_cov, const nicp_projector *proj,
                                   const nicp_stats_params *sp, const float sensor_offset[16], int keep_stats,
                                   nicp_cloud *const *clouds);
+/* ---- stage-level virtuals of the converter ------------------------------------------------
+ * StatsCalculatorIntegralImage::compute(normals, statsVector, points, indexImage) with the calculator's _intervalImage
+ * (statscalculator.h:36, statscalculatorintegralimage.h:37 / .cpp:14-82): PointIntegralImage::compute over
+ * (index_image, points), then per pixel the window statistics.  points4 = n x 4 floats; index_image / interval_image =
+ * rows x cols (index -1 / interval -1 = skip).  Outputs (n entries each, any may be NULL): normals4 (w = 0), stats16
+ * (column-major 4x4: eigenvectors + mean, identity where nothing was computed), eigenvalues3, n_points, curvature
+ * (Stats::curvature(), stats.h:98-103). */
+int nicp_stats_compute(nicp_context *ctx, const float *points4, int n, const int *index_image, const int *interval_image,
+                       int rows, int cols, const nicp_stats_params *sp, float *normals4, float *stats16, float *eigenvalues3,
+                       int *n_points, float *curvature);
+/* PointInformationMatrixCalculator::compute / NormalInformationMatrixCalculator::compute(informationMatrix, statsVector,
+ * imageNormals) (informationmatrixcalculator.h:83,123,158 / .cpp:9-58): 6 floats per point (upper triangle), zero where
+ * the normal is zero.  Either output may be NULL. */
+int nicp_information_compute(nicp_context *ctx, int n, const float *normals4, const float *stats16, const float *eigenvalues3,
+                             const float *curvature, const nicp_stats_params *sp, float *omega_p6, float *omega_n6);
 /* PointIntegralImage::compute (pointintegralimage.cpp:7-44) of the last nicp_depth_to_cloud call:
  * 10 channels per pixel, interleaved [rows][cols][10] = n,x,y,z,xx,xy,xz,yy,yz,zz (test hook) */
 int nicp_last_integral_image(nicp_context *ctx, float *integral10);

@@ -648,6 +648,8 @@ class MultiPointProjector : public PointProjector {
 class StatsCalculator {
  public:
   virtual ~StatsCalculator() {}
+  // statscalculator.h:36: the base class computes nothing
+  virtual void compute(NormalVector &, StatsVector &, const PointVector &, const IntImage &) {}
 };
 class StatsCalculatorIntegralImage : public StatsCalculator {
  public:
@@ -664,6 +666,44 @@ class StatsCalculatorIntegralImage : public StatsCalculator {
   int minPoints() const { return _minPoints; }
   float curvatureThreshold() const { return _curvatureThreshold; }
   IntImage &intervalImage() { return _intervalImage; }
+
+  // statscalculatorintegralimage.h:37 / .cpp:14-82: normals and Stats of `points` from the integral image over
+  // (indexImage, points) and the interval image set through intervalImage() (nicp_stats_compute)
+  virtual void compute(NormalVector &normals, StatsVector &statsVector, const PointVector &points, const IntImage &indexImage) {
+    const int n = (int)points.size();
+    if (_intervalImage.rows != indexImage.rows || _intervalImage.cols != indexImage.cols)
+      throw std::runtime_error("StatsCalculatorIntegralImage::compute: the interval image does not match the index image");
+    std::vector<float> p(4 * (size_t)n), nr(4 * (size_t)n), s16(16 * (size_t)n), ev(3 * (size_t)n), cv(n);
+    std::vector<int> cnt(n);
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 4; k++) p[4 * (size_t)i + k] = points[i][k];
+    nicp_stats_params sp = abiParams();
+    nicpCheck(nicp_stats_compute(Context::current().handle(), p.data(), n, indexImage.data(), _intervalImage.data(), indexImage.rows,
+                                 indexImage.cols, &sp, nr.data(), s16.data(), ev.data(), cnt.data(), cv.data()),
+              "StatsCalculatorIntegralImage::compute");
+    normals.resize(n);
+    statsVector.assign(n, Stats());
+    for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 4; k++) normals[i][k] = nr[4 * (size_t)i + k];
+      for (int k = 0; k < 16; k++) statsVector[i].m[k] = s16[16 * (size_t)i + k];
+      for (int k = 0; k < 3; k++) statsVector[i]._eigenValues(k) = ev[3 * (size_t)i + k];
+      statsVector[i]._n = cnt[i];
+      statsVector[i].setCurvature(cv[i]);
+    }
+  }
+  // the statistics half of nicp_stats_params (the information-matrix half keeps its defaults)
+  nicp_stats_params abiParams() const {
+    nicp_stats_params sp;
+    sp.world_radius = _worldRadius;
+    sp.min_image_radius = _minImageRadius;
+    sp.max_image_radius = _maxImageRadius;
+    sp.min_points = _minPoints;
+    sp.curvature_threshold = _curvatureThreshold;
+    sp.omega_curvature_threshold = 0.02f;
+    const float fp[3] = {1000.0f, 1.0f, 1.0f}, fn[3] = {100.0f, 100.0f, 100.0f}, nn[3] = {1.0f, 1.0f, 1.0f};
+    for (int i = 0; i < 3; i++) { sp.flat_omega_p[i] = fp[i]; sp.flat_omega_n[i] = fn[i]; sp.nonflat_omega_n[i] = nn[i]; }
+    return sp;
+  }
 
  protected:
   float _worldRadius;
@@ -687,8 +727,42 @@ class InformationMatrixCalculator {
   void setNonFlatInformationMatrix(const InformationMatrix nonFlatInformationMatrix_) { _nonFlatInformationMatrix = nonFlatInformationMatrix_; }
   float curvatureThreshold() const { return _curvatureThreshold; }
   void setCurvatureThreshold(const float curvatureThreshold_) { _curvatureThreshold = curvatureThreshold_; }
+  // informationmatrixcalculator.h:83: pure virtual in the reference
+  virtual void compute(InformationMatrixVector &informationMatrix, const StatsVector &statsVector,
+                       const NormalVector &imageNormals) = 0;
 
  protected:
+  // nicp_information_compute with this calculator's matrices in the point (which = 0) or the normal (1) slot
+  void computeOnDevice(int which, InformationMatrixVector &informationMatrix, const StatsVector &statsVector,
+                       const NormalVector &imageNormals) const {
+    const int n = (int)statsVector.size();
+    if ((int)imageNormals.size() != n) throw std::runtime_error("InformationMatrixCalculator::compute: size mismatch");
+    std::vector<float> nr(4 * (size_t)n), s16(16 * (size_t)n), ev(3 * (size_t)n), cv(n), out(6 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+      for (int k = 0; k < 4; k++) nr[4 * (size_t)i + k] = imageNormals[i][k];
+      for (int k = 0; k < 16; k++) s16[16 * (size_t)i + k] = statsVector[i].m[k];
+      for (int k = 0; k < 3; k++) ev[3 * (size_t)i + k] = statsVector[i]._eigenValues(k);
+      cv[i] = statsVector[i].curvature();
+    }
+    nicp_stats_params sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.omega_curvature_threshold = _curvatureThreshold;
+    for (int i = 0; i < 3; i++) {
+      sp.flat_omega_p[i] = sp.flat_omega_n[i] = _flatInformationMatrix(i, i);
+      sp.nonflat_omega_n[i] = _nonFlatInformationMatrix(i, i);
+    }
+    nicpCheck(nicp_information_compute(Context::current().handle(), n, nr.data(), s16.data(), ev.data(), cv.data(), &sp,
+                                       which == 0 ? out.data() : 0, which == 1 ? out.data() : 0),
+              "InformationMatrixCalculator::compute");
+    informationMatrix.resize(n);
+    for (int i = 0; i < n; i++) {
+      const float *o = &out[6 * (size_t)i];
+      InformationMatrix &m = informationMatrix[i];
+      m.setZero();
+      m(0, 0) = o[0]; m(0, 1) = m(1, 0) = o[1]; m(0, 2) = m(2, 0) = o[2];
+      m(1, 1) = o[3]; m(1, 2) = m(2, 1) = o[4]; m(2, 2) = o[5];
+    }
+  }
   InformationMatrix _flatInformationMatrix, _nonFlatInformationMatrix;
   float _curvatureThreshold;
 };
@@ -699,6 +773,10 @@ class PointInformationMatrixCalculator : public InformationMatrixCalculator {
     _nonFlatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
     _curvatureThreshold = 0.02f;
   }
+  // informationmatrixcalculator.h:123 / .cpp:9-36: flat -> U diag(flat) U^T, else U diag(1 / eigenvalues) U^T
+  virtual void compute(InformationMatrixVector &informationMatrix, const StatsVector &statsVector, const NormalVector &imageNormals) {
+    computeOnDevice(0, informationMatrix, statsVector, imageNormals);
+  }
 };
 class NormalInformationMatrixCalculator : public InformationMatrixCalculator {
  public:
@@ -706,6 +784,10 @@ class NormalInformationMatrixCalculator : public InformationMatrixCalculator {
     _flatInformationMatrix.setDiagonal(100.0f, 100.0f, 100.0f);
     _nonFlatInformationMatrix.setDiagonal(1.0f, 1.0f, 1.0f);
     _curvatureThreshold = 0.02f;
+  }
+  // informationmatrixcalculator.h:158 / .cpp:38-58
+  virtual void compute(InformationMatrixVector &informationMatrix, const StatsVector &statsVector, const NormalVector &imageNormals) {
+    computeOnDevice(1, informationMatrix, statsVector, imageNormals);
   }
 };
 

@@ -552,6 +552,38 @@ def voxelize(points, resolution=0.01, strict=True):
     return rep[:m].copy()
 
 
+def stats_stage(integral, index, interval, points, sp):
+    """StatsCalculatorIntegralImage::compute given the integral image (orc_stats): normals, statsM, eigvals, statsN, curvature"""
+    rows, cols = index.shape
+    pts, pp = _f(points)
+    n = pts.shape[0]
+    integ, ip_ = _f(integral)
+    idx = np.ascontiguousarray(index, np.int32)
+    itv = np.ascontiguousarray(interval, np.int32)
+    normals = np.zeros((n, 4), np.float32)
+    statsM = np.zeros((n, 16), np.float32)
+    eig = np.zeros((n, 3), np.float32)
+    cnt = np.zeros(n, np.int32)
+    curv = np.zeros(n, np.float32)
+    f = lib().orc_stats
+    f.restype = None
+    f(ip_, _ip(idx), _ip(itv), pp, rows, cols, n, C.byref(sp), _fp(normals), _fp(statsM), _fp(eig), _ip(cnt), _fp(curv))
+    return normals, statsM, eig, cnt, curv
+
+
+def information_stage(normals, statsM, eigvals, curvature, sp):
+    """Point / NormalInformationMatrixCalculator::compute (orc_information): full 4x4 per point"""
+    n = normals.shape[0]
+    oP = np.zeros((n, 16), np.float32)
+    oN = np.zeros((n, 16), np.float32)
+    f = lib().orc_information
+    f.restype = None
+    f(_fp(np.ascontiguousarray(normals, np.float32)), _fp(np.ascontiguousarray(statsM, np.float32)),
+      _fp(np.ascontiguousarray(eigvals, np.float32)), _fp(np.ascontiguousarray(curvature, np.float32)), n, C.byref(sp),
+      _fp(oP), _fp(oN))
+    return oP, oN
+
+
 def set_threads(n, fast=False):
     """omp_set_num_threads(n) inside the oracle library (OMP_NUM_THREADS is only read when libgomp initialises);
     returns the OpenMP team size actually in force"""

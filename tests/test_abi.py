@@ -106,6 +106,8 @@ def test_null_handles_are_rejected_not_dereferenced(verify):
     assert L.nicp_depth_to_cloud(N, N, N, N, N, 0, N, N) == 1
     assert L.nicp_raw_depth_to_cloud(N, N, 4, 4, C.c_float(0.001), 1, C.c_float(0.01), N, N, N, 0, N, N) == 1
     assert L.nicp_raw_depth_to_cloud_batch(N, 2, N, 4, 4, C.c_float(0.001), 1, C.c_float(0.01), N, N, N, 0, N) == 1
+    assert L.nicp_stats_compute(N, N, 0, N, N, 4, 4, N, N, N, N, N, N) == 1
+    assert L.nicp_information_compute(N, 0, N, N, N, N, N, N, N) == 1
     assert L.nicp_last_integral_image(N, N) == 1
     assert L.nicp_last_interval_image(N, N) == 1
     assert L.nicp_project(N, N, N, 4, 4, f0, f0, N, N) == 1

@@ -724,6 +724,46 @@ def test_frame_prep_batch_is_bit_identical_to_single_calls(ctx, step, n, offset)
     assert np.array_equal(batch[0].download()["points"], oc.points)
 
 
+@pytest.mark.parametrize("step,seed,dropout", [(4, 0, 0.05), (1, 1, 0.05)])
+def test_stage_level_stats_and_information(ctx, step, seed, dropout):
+    """The stage virtuals of the boundary: StatsCalculatorIntegralImage::compute(normals, stats, points, indexImage) and
+    Point / NormalInformationMatrixCalculator::compute (statscalculator.h:36, informationmatrixcalculator.h:83) fed the
+    oracle's points / index / interval images, with the points in a SHUFFLED order (the stage takes any index image, not
+    only the raster-compacted one of the converter).  Stats n exact; normals / curvature / information matrices at the
+    tolerance of the fused converter path (the closed-form eigen-solver differs from the oracle's libm in the last ulp)."""
+    from oracle import pwn_oracle as O
+    s = get_scene(step, seed, dropout)
+    n = s.cloudA.n
+    perm = np.random.default_rng(5).permutation(n).astype(np.int32)   # new position of old point i
+    points = np.zeros_like(s.cloudA.points)
+    points[perm] = s.cloudA.points
+    index = np.where(s.indexA >= 0, perm[np.maximum(s.indexA, 0)], -1).astype(np.int32)
+    integral = O.integral_image(index, points)
+    on, oS, oe, ocnt, ocurv = O.stats_stage(integral, index, s.intervalA, points, s.sp)
+    g = ctx.stats_compute(points, index, s.intervalA, s.stats_params())
+    assert np.array_equal(g["n"], ocnt)
+    # the same values the converter produced for the unshuffled cloud (bit for bit on the oracle side)
+    assert np.array_equal(on[perm], s.cloudA.normals) and np.array_equal(ocurv[perm], s.cloudA.curvature)
+    valid = ocnt > 0
+    assert np.array_equal(g["stats16"][~valid], oS[~valid]) and not g["normals"][~valid].any()
+    same = (g["normals"].view(np.uint32) == on.view(np.uint32)).all(axis=1)
+    assert same.mean() > 0.99, same.mean()
+    dots = np.clip((g["normals"][:, :3] * on[:, :3]).sum(axis=1), -1, 1)
+    nz = (np.abs(on[:, :3]).sum(axis=1) > 0) & (np.abs(g["normals"][:, :3]).sum(axis=1) > 0)
+    assert np.arccos(dots[nz]).max() <= 1e-3
+    assert (np.abs(on[:, :3]).sum(axis=1) > 0).sum() == (np.abs(g["normals"][:, :3]).sum(axis=1) > 0).sum() or \
+        abs(int(nz.sum()) - int((np.abs(on[:, :3]).sum(axis=1) > 0).sum())) <= 3   # curvature threshold ties
+    assert np.abs(g["curvature"] - ocurv).max() <= 1e-4 * max(ocurv.max(), 1e-6) + 1e-7
+    assert np.abs(g["stats16"][valid][:, 12:15] - oS[valid][:, 12:15]).max() == 0.0   # the mean is exact
+    # information matrices from the ORACLE's stats (stage isolated): exact inputs -> bit-exact outputs
+    oP, oN = O.information_stage(on, oS, oe, ocurv, s.sp)
+    gp, gn = ctx.information_compute(on, oS, oe, ocurv, s.stats_params())
+    sym = lambda M: M.reshape(-1, 4, 4)[:, [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]]
+    assert np.array_equal(gn, sym(oN))
+    rel = np.abs(gp - sym(oP)).max(axis=1) / np.maximum(np.abs(sym(oP)).max(axis=1), 1e-20)
+    assert rel.max() <= 1e-6, rel.max()
+
+
 def test_empty_depth_image(ctx):
     s = get_scene(4)
     z = np.zeros((s.rows, s.cols), np.float32)
