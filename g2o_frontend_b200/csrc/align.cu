@@ -1171,7 +1171,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   NICP_CHECK_LAUNCH(ctx);
   // grid-stride, 8 points per thread at full density (two rounds of four loads in flight).  The kernel is DRAM bound
   // (16-byte points + read-modify-write of the z-buffer sectors): 64/128/256 threads x 4/8/16 points all land on 82-86 us
-  constexpr int projThreads = 256, projPerThread = 8;
+  // A lone pair (or a handful) is latency bound instead: 150 CTAs would leave most SMs with one CTA, so the grid is sized
+  // for two points per thread there.
+  constexpr int projThreads = 256;
+  const int projPerThread = nPairs >= 8 ? 8 : 2;
   const int projBlocks = (P + projThreads * projPerThread - 1) / (projThreads * projPerThread);
   dim3 pg(projBlocks, nPairs);
   // aligner.cpp:60-63: the current cloud is projected once with projector->setTransform(_currentSensorOffset)

@@ -128,3 +128,28 @@ int nicp_multi_project(nicp_context *c, const nicp_cloud *cl, const nicp_multi_p
 int nicp_multi_align(nicp_context *c, const nicp_cloud *r, const nicp_cloud *cu, const nicp_multi_projector *m, const nicp_align_params *a, const float *ro, const float *co, const float *g, const nicp_prior *p, int n, float t, nicp_align_result *res) { return 1; }
 int nicp_align_get_trace(nicp_context *c, float *t, int n) { return 1; }
 int nicp_align_batch(nicp_context *c, int n, const nicp_cloud *const *r, const nicp_cloud *const *cu, const nicp_projector *p, const nicp_align_params *a, const float *ro, const float *co, const float *g, float t, nicp_align_result *res) { return 1; }
+/* stage-level virtuals (pwn.h references them from the vtables of the statistics / information-matrix calculators) */
+static void mock_stats_params(const nicp_stats_params *sp, orc_stats_params *q) {
+  memset(q, 0, sizeof *q);
+  q->worldRadius = sp->world_radius; q->minImageRadius = sp->min_image_radius; q->maxImageRadius = sp->max_image_radius; q->minPoints = sp->min_points;
+  q->curvatureThreshold = sp->curvature_threshold; q->omegaCurvatureThreshold = sp->omega_curvature_threshold;
+  for (int i = 0; i < 3; i++) { q->flatOmegaP[i] = sp->flat_omega_p[i]; q->nonFlatOmegaP[i] = 1; q->flatOmegaN[i] = sp->flat_omega_n[i]; q->nonFlatOmegaN[i] = sp->nonflat_omega_n[i]; }
+}
+int nicp_stats_compute(nicp_context *ctx, const float *points4, int n, const int *index, const int *interval, int rows, int cols, const nicp_stats_params *sp, float *normals4, float *stats16, float *eig3, int *cnt, float *curv) {
+  orc_stats_params q; mock_stats_params(sp, &q);
+  float *integ = malloc(40 * (size_t)rows * cols);
+  float *nr = normals4 ? normals4 : malloc(16 * (size_t)(n + 1)), *s = stats16 ? stats16 : malloc(64 * (size_t)(n + 1)), *e = eig3 ? eig3 : malloc(12 * (size_t)(n + 1)), *cv = curv ? curv : malloc(4 * (size_t)(n + 1));
+  int *c = cnt ? cnt : malloc(4 * (size_t)(n + 1));
+  orc_integral_image(index, points4, rows, cols, integ);
+  orc_stats(integ, index, interval, points4, rows, cols, n, &q, nr, s, e, c, cv);
+  free(integ); if (!normals4) free(nr); if (!stats16) free(s); if (!eig3) free(e); if (!curv) free(cv); if (!cnt) free(c);
+  return 0; }
+int nicp_information_compute(nicp_context *ctx, int n, const float *normals4, const float *stats16, const float *eig3, const float *curv, const nicp_stats_params *sp, float *op6, float *on6) {
+  orc_stats_params q; mock_stats_params(sp, &q);
+  float *oP = malloc(64 * (size_t)(n + 1)), *oN = malloc(64 * (size_t)(n + 1));
+  orc_information(normals4, stats16, eig3, curv, n, &q, oP, oN);
+  static const int at[6] = {0, 4, 8, 5, 9, 10}; /* (0,0) (0,1) (0,2) (1,1) (1,2) (2,2) of a column-major 4x4 */
+  for (int i = 0; i < n; i++) for (int k = 0; k < 6; k++) { if (op6) op6[6 * (size_t)i + k] = oP[16 * (size_t)i + at[k]]; if (on6) on6[6 * (size_t)i + k] = oN[16 * (size_t)i + at[k]]; }
+  free(oP); free(oN); return 0; }
+int nicp_raw_depth_to_cloud_batch(nicp_context *c, int n, const uint16_t *const *r, int a, int b, float s, int st, float m, const nicp_projector *p, const nicp_stats_params *sp, const float *so, int k, nicp_cloud *const *cl) { return 1; }
+int nicp_align_batch_priors(nicp_context *c, int n, const nicp_cloud *const *r, const nicp_cloud *const *cu, const nicp_projector *p, const nicp_align_params *a, const float *ro, const float *co, const float *g, const nicp_prior *pr, const int *po, float t, nicp_align_result *res) { return 1; }
