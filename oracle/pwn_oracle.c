@@ -431,6 +431,105 @@ void orc_eigen3(const float C[9], float evals[3], float evecs[9]) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * The same call as Eigen >= 3.3 implements it (recalled from Eigen/src/Eigenvalues/SelfAdjointEigenSolver.h of 3.3.x,
+ * direct_selfadjoint_eigenvalues<SolverType, 3, false>; UNPINNED like the 3.2 variant above: no Eigen in this image).
+ * Differences from 3.2: the matrix is shifted by trace / 3 before scaling, the roots come out of computeRoots already
+ * sorted, and the eigenvectors are taken from the kernel of (A - lambda I) through the cross products of its most
+ * significant column (extract_kernel) instead of the row cross products with a safeNorm test.  The reference pins no
+ * Eigen version (CMakeLists.txt:158 asks for >= 3.1.2), so which of the two its users run depends on their distribution;
+ * tests/test_oracle.py and DESIGN.md section 2 report how far apart the two are on the bench inputs.
+ * ---------------------------------------------------------------------------------------- */
+static void extract_kernel33(const float *mat /* column-major 3x3 */, float *res, float *representative) {
+  int i0 = 0;
+  float best = fabsf(M3(mat, 0, 0));
+  for (int i = 1; i < 3; i++)
+    if (fabsf(M3(mat, i, i)) > best) { best = fabsf(M3(mat, i, i)); i0 = i; }
+  const int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+  float col0[3] = {M3(mat, 0, i0), M3(mat, 1, i0), M3(mat, 2, i0)};
+  float col1[3] = {M3(mat, 0, i1), M3(mat, 1, i1), M3(mat, 2, i1)};
+  float col2[3] = {M3(mat, 0, i2), M3(mat, 1, i2), M3(mat, 2, i2)};
+  for (int i = 0; i < 3; i++) representative[i] = col0[i];
+  float c0[3], c1[3];
+  cross3(col0, col1, c0);
+  cross3(col0, col2, c1);
+  float n0 = sqnorm3(c0), n1 = sqnorm3(c1);
+  if (n0 > n1) { float sn = sqrtf(n0); for (int i = 0; i < 3; i++) res[i] = c0[i] / sn; }
+  else { float sn = sqrtf(n1); for (int i = 0; i < 3; i++) res[i] = c1[i] / sn; }
+}
+void orc_eigen3_v33(const float C[9], float evals[3], float evecs[9]) {
+  const float eps = FLT_EPSILON;
+  /* shift to the mean eigenvalue, scale the (lower-triangle view of the) matrix into [-1, 1] */
+  float shift = ((M3(C, 0, 0) + M3(C, 1, 1)) + M3(C, 2, 2)) / 3.0f;
+  float m[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) M3(m, r, c) = r >= c ? M3(C, r, c) : M3(C, c, r);
+  m[0] -= shift; m[4] -= shift; m[8] -= shift;
+  float scale = 0.0f;
+  for (int i = 0; i < 9; i++) { float a = fabsf(m[i]); if (a > scale) scale = a; }
+  if (scale > 0.0f)
+    for (int i = 0; i < 9; i++) m[i] = m[i] / scale;
+  /* computeRoots (3.3): roots sorted by construction */
+  const float s_inv3 = 1.0f / 3.0f;
+  const float s_sqrt3 = sqrtf(3.0f);
+  float m00 = M3(m, 0, 0), m11 = M3(m, 1, 1), m22 = M3(m, 2, 2);
+  float m10 = M3(m, 1, 0), m20 = M3(m, 2, 0), m21 = M3(m, 2, 1);
+  float c0 = m00 * m11 * m22 + 2.0f * m10 * m20 * m21 - m00 * m21 * m21 - m11 * m20 * m20 - m22 * m10 * m10;
+  float c1 = m00 * m11 - m10 * m10 + m00 * m22 - m20 * m20 + m11 * m22 - m21 * m21;
+  float c2 = m00 + m11 + m22;
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c2 * c2_over_3 - c1) * s_inv3;
+  if (a_over_3 < 0.0f) a_over_3 = 0.0f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = a_over_3 * a_over_3 * a_over_3 - half_b * half_b;
+  if (q < 0.0f) q = 0.0f;
+  float rho = sqrtf(a_over_3);
+  float theta = atan2f(sqrtf(q), half_b) * s_inv3;
+  float cos_theta = cosf(theta);
+  float sin_theta = sinf(theta);
+  float ev[3];
+  ev[0] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  ev[1] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  ev[2] = c2_over_3 + 2.0f * rho * cos_theta;
+  if ((ev[2] - ev[0]) <= eps) {
+    memset(evecs, 0, 9 * sizeof(float));
+    evecs[0] = evecs[4] = evecs[8] = 1.0f;
+  } else {
+    float d0 = ev[2] - ev[1];
+    float d1 = ev[1] - ev[0];
+    int k = 0, l = 2;
+    if (d0 > d1) { k = 2; l = 0; d0 = d1; }
+    float tmp[9], vk[3], vl[3], dummy[3];
+    memcpy(tmp, m, sizeof tmp);
+    tmp[0] -= ev[k]; tmp[4] -= ev[k]; tmp[8] -= ev[k];
+    extract_kernel33(tmp, vk, vl);
+    if (d0 <= 2.0f * eps * d1) {
+      /* the other two eigenvalues are numerically the same: ortho-normalise the representative saved above */
+      float dot = (vk[0] * vl[0] + vk[1] * vl[1]) + vk[2] * vl[2];
+      for (int i = 0; i < 3; i++) vl[i] = vl[i] - dot * vl[i];
+      float sn = sqrtf(sqnorm3(vl));
+      for (int i = 0; i < 3; i++) vl[i] = vl[i] / sn;
+    } else {
+      memcpy(tmp, m, sizeof tmp);
+      tmp[0] -= ev[l]; tmp[4] -= ev[l]; tmp[8] -= ev[l];
+      extract_kernel33(tmp, vl, dummy);
+    }
+    for (int i = 0; i < 3; i++) { M3(evecs, i, k) = vk[i]; M3(evecs, i, l) = vl[i]; }
+    /* col(1) = col(2).cross(col(0)).normalized() */
+    float a2[3] = {M3(evecs, 0, 2), M3(evecs, 1, 2), M3(evecs, 2, 2)}, a0[3] = {M3(evecs, 0, 0), M3(evecs, 1, 0), M3(evecs, 2, 0)}, t[3];
+    cross3(a2, a0, t);
+    float sn = sqrtf(sqnorm3(t));
+    for (int i = 0; i < 3; i++) M3(evecs, i, 1) = t[i] / sn;
+  }
+  for (int i = 0; i < 3; i++) evals[i] = ev[i] * scale + shift;
+}
+static int g_eigen_variant = 0; /* 0: Eigen 3.2.x (the variant the CUDA path follows), 1: Eigen >= 3.3 */
+void orc_set_eigen_variant(int v) { g_eigen_variant = v; }
+static void eigen3_dispatch(const float C[9], float evals[3], float evecs[9]) {
+  if (g_eigen_variant == 1) orc_eigen3_v33(C, evals, evecs);
+  else orc_eigen3(C, evals, evecs);
+}
+
+/* ------------------------------------------------------------------------------------------
  * StatsCalculatorIntegralImage::compute, statscalculatorintegralimage.cpp:14-82.
  * statsM: 16 floats/point (the Stats 4x4: eigenvectors in the 3x3 block, mean in column 3),
  * defaults Stats() = identity, eigenvalues 0, n 0 (stats.h:21-27); curvature as
@@ -470,7 +569,7 @@ void orc_stats(const float *I, const int *index, const int *interval, const floa
       M3(C, 2, 1) = M3(C, 1, 2) = acc[8] * d - mu[1] * mu[2];
       M3(C, 2, 2) = acc[9] * d - mu[2] * mu[2];
       float ev[3], U[9];
-      orc_eigen3(C, ev, U);
+      eigen3_dispatch(C, ev, U);
       if (ev[0] < 0.0f) ev[0] = 0.0f;
       float *S = statsM + 16 * idx;
       memset(S, 0, 16 * sizeof(float));

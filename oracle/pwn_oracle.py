@@ -584,6 +584,23 @@ def information_stage(normals, statsM, eigvals, curvature, sp):
     return oP, oN
 
 
+def set_eigen_variant(v, fast=False):
+    """0: Eigen 3.2.x computeDirect (default; what the CUDA path follows), 1: the Eigen >= 3.3 implementation"""
+    f = lib(fast).orc_set_eigen_variant
+    f.restype = None
+    f(int(v))
+
+
+def eigen3_v33(Cm):
+    Cm, cp = _f(colmajor(Cm))
+    ev = np.zeros(3, np.float32)
+    U = np.zeros(9, np.float32)
+    f = lib().orc_eigen3_v33
+    f.restype = None
+    f(cp, _fp(ev), _fp(U))
+    return ev, from_colmajor(U, 3)
+
+
 def set_threads(n, fast=False):
     """omp_set_num_threads(n) inside the oracle library (OMP_NUM_THREADS is only read when libgomp initialises);
     returns the OpenMP team size actually in force"""
