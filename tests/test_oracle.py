@@ -385,7 +385,7 @@ def test_eigen33_variant_of_compute_direct():
     twice: as Eigen 3.2.x has it (orc_eigen3, what the CUDA path follows) and as Eigen >= 3.3 has it (orc_eigen3_v33: trace
     shift, extract_kernel).  Both must be eigen-decompositions -- checked against numpy.linalg.eigh -- and switching the
     variant must change nothing but what comes out of the eigen-solver.  How far apart they are on the bench inputs is
-    measured by tools/eigen_variant_study.py (profiles/r2_eigen_variant_study.json)."""
+    measured by tests/eigen_variant_study.py (profiles/r2_eigen_variant_study.json)."""
     from oracle import pwn_oracle as O
     rng = np.random.default_rng(0)
     for i in range(500):
