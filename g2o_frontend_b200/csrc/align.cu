@@ -631,9 +631,9 @@ __global__ void __launch_bounds__(NT, MINB) k_corr_lin_tiled(const PairDesc *__r
           const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&S.om[2][k * NT + threadIdx.x]);
           const f32x2 Rx = pk(rp0[k].x, rn0[k].x), Ry = pk(rp0[k].y, rn0[k].y), Rz = pk(rp0[k].z, rn0[k].z);
           if (ac.robust)
-            term_add<true>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 1);
+            term_add<true, false>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 1);
           else
-            term_add<false>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 0);
+            term_add<false, false>(tacc, 1.0f, Rx, Ry, Rz, cp[k], cn[k], w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, 0);
         }
       }
     }

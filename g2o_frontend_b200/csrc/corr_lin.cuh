@@ -90,11 +90,13 @@ __device__ __forceinline__ void term_clear(TermAcc &A) {
 // finite -- the shared-memory slots are zero-filled at kernel start), so there is no divergent control flow around the
 // accumulators.  R = transformed reference (point, normal) per axis, packed; cp / cn the current point / normal;
 // A=(a,g) B=(b,h) C=(c,i) D=(d,j) E=(e,k) F=(f,l) with Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l].
-template <bool ROBUST>
+template <bool ROBUST, bool MASKED = true>
 __device__ __forceinline__ void term_add(TermAcc &acc, float w, f32x2 Rx, f32x2 Ry, f32x2 Rz, float4 cp, float4 cn, f32x2 A, f32x2 B,
                                          f32x2 C, f32x2 D, f32x2 E, f32x2 F, float maxChi2, int robust) {
-  const f32x2 W = pk(w, w);
-  A = mul2(A, W); B = mul2(B, W); C = mul2(C, W); D = mul2(D, W); E = mul2(E, W); F = mul2(F, W);
+  if (MASKED) {  // (w == 1 for every caller with MASKED = false: the product with 1 is exact, the bits do not change)
+    const f32x2 W = pk(w, w);
+    A = mul2(A, W); B = mul2(B, W); C = mul2(C, W); D = mul2(D, W); E = mul2(E, W); F = mul2(F, W);
+  }
   // errors (rp - cp, rn - cn)
   const f32x2 E0 = pk(__fsub_rn(lo_of(Rx), cp.x), __fsub_rn(hi_of(Rx), cn.x));
   const f32x2 E1 = pk(__fsub_rn(lo_of(Ry), cp.y), __fsub_rn(hi_of(Ry), cn.y));
