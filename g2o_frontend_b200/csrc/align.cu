@@ -20,6 +20,7 @@
 // k_reduce_solve adds the rows in fixed order, so H, b and the pose are bit-reproducible run to
 // run (no float atomics anywhere).
 #include "nicp_internal.cuh"
+#include "nicp_stats_tail.cuh"
 
 namespace nicp {
 
@@ -976,6 +977,23 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
   solve_step<PRIORS>(D, tot, mode, lastInner, firstInner, iter, ac);
 }
 
+// Aligner::_computeStatistics' dense tail for a batch: one thread per pair (sigma points, 6x6 pseudo-inverse and inverse,
+// eigen-ratios; nicp_stats_tail.cuh -- the function a single alignment runs on the host, bit for bit)
+__global__ void __launch_bounds__(32) k_statistics(const PairDesc *__restrict__ desc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PairState *st = desc[i].state;
+  nicp_align_result *res = desc[i].result;
+  if (!res) return;
+  float H[36], T[16], omega[36], tr, rr;
+  for (int k = 0; k < 36; k++) H[k] = st->statH[k];
+  for (int k = 0; k < 16; k++) T[k] = res->T[k];
+  compute_statistics_tail(H, T, omega, &tr, &rr);
+  for (int k = 0; k < 36; k++) res->omega[k] = omega[k];
+  res->translational_eigen_ratio = tr;
+  res->rotational_eigen_ratio = rr;
+}
+
 // H / b of the _computeStatistics linearisation, to the slot of the pair's RESULT record (descriptors are ordered by
 // current cloud inside a chunk, results by the caller's pair index)
 __global__ void k_gather_stat(const PairDesc *__restrict__ desc, int n, const nicp_align_result *__restrict__ results,
@@ -1235,6 +1253,10 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   (void)resultOffset;
+  if (!fresh) {  // a batch: the records leave the device complete (a single alignment finishes them on the host)
+    k_statistics<<<(nPairs + 31) / 32, 32, 0, st>>>(ctx->d_desc, nPairs);
+    NICP_CHECK_LAUNCH(ctx);
+  }
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_results, ctx->d_statHb);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "nicp_internal.cuh"
+#include "nicp_stats_tail.cuh"
 
 namespace nicp {
 
@@ -335,159 +336,9 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   }
 }
 
-// ---- Aligner::_computeStatistics tail (aligner.cpp:172-198, unscented.h:23-65), host, tiny ----
-static void jacobi_sym(int n, double *A, double *V, double *w) {
-  for (int i = 0; i < n * n; i++) V[i] = 0;
-  for (int i = 0; i < n; i++) V[i * n + i] = 1;
-  for (int sweep = 0; sweep < 60; sweep++) {
-    double off = 0, diag = 0;
-    for (int p = 0; p < n; p++) {
-      diag += A[p * n + p] * A[p * n + p];
-      for (int q = p + 1; q < n; q++) off += A[q * n + p] * A[q * n + p];
-    }
-    /* converged to double precision (the old absolute 1e-300 test never fired and all 60 sweeps ran) */
-    if (off <= 1e-32 * (diag + off)) break;
-    for (int p = 0; p < n; p++)
-      for (int q = p + 1; q < n; q++) {
-        double apq = A[q * n + p];
-        if (fabs(apq) < 1e-300) continue;
-        double app = A[p * n + p], aqq = A[q * n + q];
-        double tau = (aqq - app) / (2 * apq);
-        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1 + tau * tau));
-        double c = 1 / sqrt(1 + t * t), s = t * c;
-        for (int k = 0; k < n; k++) {
-          double akp = A[p * n + k], akq = A[q * n + k];
-          A[p * n + k] = c * akp - s * akq;
-          A[q * n + k] = s * akp + c * akq;
-        }
-        for (int k = 0; k < n; k++) {
-          double apk = A[k * n + p], aqk = A[k * n + q];
-          A[k * n + p] = c * apk - s * aqk;
-          A[k * n + q] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < n; k++) {
-          double vkp = V[p * n + k], vkq = V[q * n + k];
-          V[p * n + k] = c * vkp - s * vkq;
-          V[q * n + k] = s * vkp + c * vkq;
-        }
-      }
-  }
-  for (int i = 0; i < n; i++) w[i] = A[i * n + i];
-}
-static void sym_pinv6(const float *H, float *Hi) {
-  double A[36], V[36], w[6];
-  for (int r = 0; r < 6; r++)
-    for (int c = 0; c < 6; c++) A[c * 6 + r] = 0.5 * ((double)NM6(H, r, c) + (double)NM6(H, c, r));
-  jacobi_sym(6, A, V, w);
-  double wmax = 0;
-  for (int i = 0; i < 6; i++)
-    if (fabs(w[i]) > wmax) wmax = fabs(w[i]);
-  for (int r = 0; r < 6; r++)
-    for (int c = 0; c < 6; c++) {
-      double s = 0;
-      for (int k = 0; k < 6; k++)
-        if (fabs(w[k]) > wmax * 6 * (double)FLT_EPSILON) s += V[k * 6 + r] * V[k * 6 + c] / w[k];
-      NM6(Hi, r, c) = (float)s;
-    }
-}
-static void mat6_inverse(const float *A, float *Ai) {
-  double a[6][12];
-  for (int r = 0; r < 6; r++)
-    for (int c = 0; c < 6; c++) {
-      a[r][c] = NM6(A, r, c);
-      a[r][c + 6] = (r == c);
-    }
-  for (int k = 0; k < 6; k++) {
-    int piv = k;
-    for (int r = k + 1; r < 6; r++)
-      if (fabs(a[r][k]) > fabs(a[piv][k])) piv = r;
-    if (piv != k)
-      for (int c = 0; c < 12; c++) { double t = a[k][c]; a[k][c] = a[piv][c]; a[piv][c] = t; }
-    double d = a[k][k];
-    for (int c = 0; c < 12; c++) a[k][c] /= d;
-    for (int r = 0; r < 6; r++)
-      if (r != k) {
-        double f = a[r][k];
-        if (f != 0.0)
-          for (int c = 0; c < 12; c++) a[r][c] -= f * a[k][c];
-      }
-  }
-  for (int r = 0; r < 6; r++)
-    for (int c = 0; c < 6; c++) NM6(Ai, r, c) = (float)a[r][c + 6];
-}
-static float sym_eig_ratio3(const float *O, int off) {
-  double A[9], V[9], w[3];
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) A[c * 3 + r] = 0.5 * ((double)NM6(O, off + r, off + c) + (double)NM6(O, off + c, off + r));
-  jacobi_sym(3, A, V, w);
-  double mx = 0, mn = 1e300;
-  for (int i = 0; i < 3; i++) {
-    double a = fabs(w[i]);
-    if (a > mx) mx = a;
-    if (a < mn) mn = a;
-  }
-  return (float)(mx / mn);
-}
+// ---- Aligner::_computeStatistics tail (aligner.cpp:172-198, unscented.h:23-65): nicp_stats_tail.cuh, shared with the device ----
 static void compute_statistics(const float *H_lin, const float *T, float *Omega, float *tr, float *rr) {
-  float H[36], Sigma[36];
-  memcpy(H, H_lin, sizeof H);
-  for (int i = 0; i < 6; i++) NM6(H, i, i) += 1.0f;
-  sym_pinv6(H, Sigma);
-  const int dim = 6;
-  const double alpha = 1e-3, beta = 2.;
-  const double lambda = alpha * alpha * dim;
-  const double wi = 1. / (2. * (dim + lambda));
-  double wm[13], wc[13];
-  float samples[13][6];
-  memset(samples, 0, sizeof samples);
-  wm[0] = lambda / (dim + lambda);
-  wc[0] = lambda / (dim + lambda) + (1. - alpha * alpha + beta);
-  float A[36], L[36];
-  memset(L, 0, sizeof L);
-  float sc = (float)(dim + lambda);
-  for (int i = 0; i < 36; i++) A[i] = Sigma[i] * sc;
-  for (int j = 0; j < 6; j++) {
-    float s = NM6(A, j, j);
-    for (int k = 0; k < j; k++) s -= NM6(L, j, k) * NM6(L, j, k);
-    float d = sqrtf(s);
-    NM6(L, j, j) = d;
-    for (int i = j + 1; i < 6; i++) {
-      float t = NM6(A, i, j);
-      for (int k = 0; k < j; k++) t -= NM6(L, i, k) * NM6(L, j, k);
-      NM6(L, i, j) = t / d;
-    }
-  }
-  int k = 1;
-  for (int i = 0; i < dim; i++) {
-    for (int r = 0; r < 6; r++) {
-      samples[k][r] = NM6(L, r, i);
-      samples[k + 1][r] = -NM6(L, r, i);
-    }
-    wm[k] = wc[k] = wi;
-    wm[k + 1] = wc[k + 1] = wi;
-    k += 2;
-  }
-  for (int i = 0; i < 13; i++) {
-    float X[16], Xi[16], Y[16];
-    v2t(samples[i], X);
-    iso_inverse(X, Xi);
-    iso_mul(T, Xi, Y);
-    t2v(Y, samples[i]);
-  }
-  float mean[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 13; i++)
-    for (int r = 0; r < 6; r++) mean[r] += (float)(wm[i] * (double)samples[i][r]);
-  float cov[36];
-  memset(cov, 0, sizeof cov);
-  for (int i = 0; i < 13; i++) {
-    float dl[6];
-    for (int r = 0; r < 6; r++) dl[r] = samples[i][r] - mean[r];
-    for (int r = 0; r < 6; r++)
-      for (int c = 0; c < 6; c++) NM6(cov, r, c) += (float)(wc[i] * (double)(dl[r] * dl[c]));
-  }
-  mat6_inverse(cov, Omega);
-  *tr = sym_eig_ratio3(Omega, 0);
-  *rr = sym_eig_ratio3(Omega, 3);
+  compute_statistics_tail(H_lin, T, Omega, tr, rr);
 }
 
 // after a stream synchronisation: fold the recorded event pairs into the running totals
@@ -515,11 +366,15 @@ static void select_desc_set(nicp_context *ctx, int set) {
   ctx->h_desc = reinterpret_cast<PairDesc *>(ctx->h_descBase + (size_t)set * ctx->descStride);
 }
 
-static void finish_results(nicp_context *ctx, int base, int n, nicp_align_result *out) {
+// single alignment: the dense tail of _computeStatistics runs here (3.8 us, nothing extra on the GPU's critical path);
+// batches get it from k_statistics on the device (same function, same bits) and the records arrive complete
+static void finish_results(nicp_context *ctx, int base, int n, nicp_align_result *out, bool onDevice) {
   for (int i = base; i < base + n; i++) {
     nicp_align_result r = ctx->h_results[i];
-    const float *Hb = ctx->h_statHb + (size_t)i * 42;
-    compute_statistics(Hb, r.T, r.omega, &r.translational_eigen_ratio, &r.rotational_eigen_ratio);
+    if (!onDevice) {
+      const float *Hb = ctx->h_statHb + (size_t)i * 42;
+      compute_statistics(Hb, r.T, r.omega, &r.translational_eigen_ratio, &r.rotational_eigen_ratio);
+    }
     out[i] = r;
   }
 }
@@ -1471,14 +1326,14 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     // while this chunk runs on the GPU, finish the previous one on the host (Aligner::_computeStatistics tail)
     if (chunk > 0) {
       NICP_CUDA(cudaEventSynchronize(ctx->evChunk[(chunk - 1) & 1]));
-      finish_results(ctx, prevBase, prevM, results);
+      finish_results(ctx, prevBase, prevM, results, !single);
     }
     prevBase = base;
     prevM = m;
   }
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
   collect_timing(ctx);
-  finish_results(ctx, prevBase, prevM, results);
+  finish_results(ctx, prevBase, prevM, results, !single);
   ctx->lastAlignRows = proj->rows;
   ctx->lastAlignCols = proj->cols;
   ctx->lastAlignIters = ap->outer_iterations;
