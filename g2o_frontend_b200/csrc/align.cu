@@ -279,6 +279,35 @@ int ensure_points3(nicp_context *ctx, nicp_cloud *cloud) {
   return NICP_OK;
 }
 
+// point + normal interleaved, one 32-byte sector per point: (px, nx, py, ny) (pz, nz, 1, curvature)
+__global__ void k_pack_pn(const float4 *__restrict__ pts, const float4 *__restrict__ nrm, const int *__restrict__ nPtr, int capacity,
+                          float4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*nPtr, capacity);
+  if (i >= n) return;
+  const float4 p = pts[i], q = nrm[i];
+  out[2 * (size_t)i] = make_float4(p.x, q.x, p.y, q.y);
+  out[2 * (size_t)i + 1] = make_float4(p.z, q.z, 1.0f, q.w);
+}
+int ensure_pn(nicp_context *ctx, nicp_cloud *cloud) {
+#ifndef NICP_VERIFY_BUILD
+  if (cloud->pn && cloud->pn_valid) return NICP_OK;
+#endif  // the verification build never trusts the cache
+  if (!cloud->pn) {
+    NICP_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(&cloud->pn, 2 * (size_t)cloud->capacity * sizeof(float4));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of the interleaved point/normal cache (%zu bytes) failed: %s", 2 * (size_t)cloud->capacity * sizeof(float4),
+                cudaGetErrorString(e));
+      return NICP_ERR_ALLOC;
+    }
+  }
+  k_pack_pn<<<(cloud->capacity + 255) / 256, 256, 0, ctx->stream>>>(cloud->points, cloud->normals, cloud->d_n, cloud->capacity, cloud->pn);
+  NICP_CHECK_LAUNCH(ctx);
+  cloud->pn_valid = true;
+  return NICP_OK;
+}
+
 int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const float KRt[16], int rows, int cols,
                           float minD, float maxD, unsigned long long *d_z) {
   NICP_CUDA(cudaMemsetAsync(d_z, 0xFF, (size_t)rows * cols * sizeof(unsigned long long), ctx->stream));

@@ -56,6 +56,12 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   return r;
 }
 
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // accumulators of one (pair, tile): scalar sums for what only the point half feeds, packed (point, normal) sums for Hrr / br
 struct TermAcc {
   float htt[6];    // sum Omega_P (xx xy xz yy yz zz)
@@ -88,19 +94,16 @@ __device__ __forceinline__ void term_clear(TermAcc &A) {
 // one correspondence (linearizer.cpp:56-89), executed by every lane of the warp: `w` is 1 for the lanes whose pixel was
 // accepted and 0 for the others, whose Omega is multiplied away (everything below is linear in Omega, and every input is
 // finite -- the shared-memory slots are zero-filled at kernel start), so there is no divergent control flow around the
-// accumulators.  R = transformed reference (point, normal) per axis, packed; cp / cn the current point / normal;
+// accumulators.  R = transformed reference (point, normal) per axis, packed; E0..E2 = the errors (rp - cp, rn - cn) per
+// axis, packed;
 // A=(a,g) B=(b,h) C=(c,i) D=(d,j) E=(e,k) F=(f,l) with Omega_P = [a b c; b d e; c e f], Omega_N = [g h i; h j k; i k l].
 template <bool ROBUST, bool MASKED = true>
-__device__ __forceinline__ void term_add(TermAcc &acc, float w, f32x2 Rx, f32x2 Ry, f32x2 Rz, float4 cp, float4 cn, f32x2 A, f32x2 B,
-                                         f32x2 C, f32x2 D, f32x2 E, f32x2 F, float maxChi2, int robust) {
+__device__ __forceinline__ void term_add_e(TermAcc &acc, float w, f32x2 Rx, f32x2 Ry, f32x2 Rz, f32x2 E0, f32x2 E1, f32x2 E2,
+                                           f32x2 A, f32x2 B, f32x2 C, f32x2 D, f32x2 E, f32x2 F, float maxChi2, int robust) {
   if (MASKED) {  // (w == 1 for every caller with MASKED = false: the product with 1 is exact, the bits do not change)
     const f32x2 W = pk(w, w);
     A = mul2(A, W); B = mul2(B, W); C = mul2(C, W); D = mul2(D, W); E = mul2(E, W); F = mul2(F, W);
   }
-  // errors (rp - cp, rn - cn)
-  const f32x2 E0 = pk(__fsub_rn(lo_of(Rx), cp.x), __fsub_rn(hi_of(Rx), cn.x));
-  const f32x2 E1 = pk(__fsub_rn(lo_of(Ry), cp.y), __fsub_rn(hi_of(Ry), cn.y));
-  const f32x2 E2 = pk(__fsub_rn(lo_of(Rz), cp.z), __fsub_rn(hi_of(Rz), cn.z));
   // Omega e, rows: (a e0 + b e1) + c e2 ...
   f32x2 W0 = fma2(C, E2, fma2(B, E1, mul2(A, E0)));
   f32x2 W1 = fma2(E, E2, fma2(D, E1, mul2(B, E0)));
@@ -153,6 +156,13 @@ __device__ __forceinline__ void term_add(TermAcc &acc, float w, f32x2 Rx, f32x2 
   acc.br[1] = fma2(KS, fma2(PZ, W0, mul2(NX, W2)), acc.br[1]);
   acc.br[2] = fma2(KS, fma2(PX, W1, mul2(NY, W0)), acc.br[2]);
 }
+// the same from the current point / normal (per-pair kernel)
+template <bool ROBUST, bool MASKED = true>
+__device__ __forceinline__ void term_add(TermAcc &acc, float w, f32x2 Rx, f32x2 Ry, f32x2 Rz, float4 cp, float4 cn, f32x2 A, f32x2 B,
+                                         f32x2 C, f32x2 D, f32x2 E, f32x2 F, float maxChi2, int robust) {
+  term_add_e<ROBUST, MASKED>(acc, w, Rx, Ry, Rz, sub2(Rx, pk(cp.x, cn.x)), sub2(Ry, pk(cp.y, cn.y)), sub2(Rz, pk(cp.z, cn.z)), A, B, C,
+                             D, E, F, maxChi2, robust);
+}
 
 // the 32 reduction slots of a (pair, tile) from the accumulators (slot layout: A_* in nicp_internal.cuh)
 __device__ __forceinline__ void term_slots(const TermAcc &A, float (&v)[kAccum]) {
@@ -177,13 +187,13 @@ __device__ __forceinline__ void term_slots(const TermAcc &A, float (&v)[kAccum])
 template <int MAXG>
 struct GroupSmem {  // shared by the warps of a CTA: the current side of the tile and T of every pair
   float4 om[3][96];     // Omega_P / Omega_N of the current point (Omega3 layout), cp.async
-  float4 cp[96];        // current point (w unused)
-  float4 cn[96];        // current normal; w = curvature clamped to flatCurvatureThreshold, or -1 for a zero normal (MODE 0)
-  float4 T[MAXG][4];  // state->invT of every pair of the group (column-major), fetched by lane g in the prologue
+  float4 c0[96];        // current point / normal interleaved like nicp_cloud::pn: (px, nx, py, ny)
+  float4 c1[96];        // (pz, nz, 1, curvature clamped to flatCurvatureThreshold, or -1 for a zero normal (MODE 0))
+  float4 T[MAXG][4];    // state->invT of every pair of the group (column-major), fetched by lane g in the prologue
 };
-struct GatherStage {
-  float4 rp[96];        // reference point of the pair being computed / the next pair, cp.async
-  float4 rn[96];        // reference normal (w = curvature)
+struct GatherStage {    // nicp_cloud::pn records of the pair being computed / the next pair, cp.async
+  float4 p0[96];        // reference (px, nx, py, ny)
+  float4 p1[96];        // reference (pz, nz, 1, curvature)
 };                      // (a consumed stage doubles as the scratch of the shared-memory reduction)
 static_assert(sizeof(GatherStage) >= 32 * 20 * sizeof(float), "reduction scratch fits a gather stage");
 
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
     G.curPoints = reinterpret_cast<const float4 *>(((unsigned long long)g1.y << 32) | g1.x);
     G.curNormals = reinterpret_cast<const float4 *>(((unsigned long long)g1.w << 32) | g1.z);
     G.curOmega = reinterpret_cast<const float4 *>(((unsigned long long)g2.y << 32) | g2.x);
-    G.pad2 = nullptr;
+    G.curPN = reinterpret_cast<const float4 *>(((unsigned long long)g2.w << 32) | g2.z);
   }
 
   // what identifies the reference side of a pixel for one pair: the z-buffer word (MODE 0: index + epoch; MODE 1 with
@@ -286,12 +296,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
       }
     }
   };
-  auto issue_gathers = [&](const float4 *refPoints, const float4 *refNormals, const int (&ri)[TK], const bool (&curOk)[TK], int st) {
+  auto issue_gathers = [&](const float4 *refPN, const int (&ri)[TK], const bool (&curOk)[TK], int st) {
 #pragma unroll
     for (int k = 0; k < TK; k++) {
-      if (ri[k] >= 0 && curOk[k]) {
-        cp_async16(&stage[st].rn[k * NT + lane], refNormals + ri[k]);
-        cp_async16(&stage[st].rp[k * NT + lane], refPoints + ri[k]);
+      if (ri[k] >= 0 && curOk[k]) {  // the two halves of the point's 32-byte sector
+        cp_async16(&stage[st].p0[k * NT + lane], refPN + 2 * (size_t)ri[k]);
+        cp_async16(&stage[st].p1[k * NT + lane], refPN + 2 * (size_t)ri[k] + 1);
       }
     }
   };
@@ -303,8 +313,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       if (warp == 0) { S.om[0][k * NT + lane] = z4; S.om[1][k * NT + lane] = z4; S.om[2][k * NT + lane] = z4; }
-      stage[0].rp[k * NT + lane] = z4; stage[1].rp[k * NT + lane] = z4;
-      stage[0].rn[k * NT + lane] = z4; stage[1].rn[k * NT + lane] = z4;
+      stage[0].p0[k * NT + lane] = z4; stage[1].p0[k * NT + lane] = z4;
+      stage[0].p1[k * NT + lane] = z4; stage[1].p1[k * NT + lane] = z4;
     }
   }
   // ---- prologue: current side of the tile (once per group), keys of pairs 0 and 1, pointers and T of every pair ----
@@ -324,11 +334,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
   }
   // lane g fetches what pair g of the group needs: its cloud pointers (kept, handed out by shuffle) and its T (to shared
   // memory); count <= kMaxGroup
-  const float4 *myRefPoints = nullptr, *myRefNormals = nullptr;
+  const float4 *myRefPN = nullptr;
   if (lane < G.count) {
-    const PairDesc &Dl = desc[G.first + lane];
-    myRefPoints = Dl.refPoints;
-    myRefNormals = Dl.refNormals;
+    myRefPN = desc[G.first + lane].refPN;
     if (warp == 0) {
       const float4 *tp = reinterpret_cast<const float4 *>(B.state[G.first + lane].invT);
       S.T[lane][0] = __ldg(tp);
@@ -366,19 +374,19 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
   int riCur[TK];                 // reference indices of the pair being computed
   unsigned long long zCur[TK];   // its z-buffer words (image statistics)
   {
-    float4 cpl[TK], cnl[TK];
+    float4 c0l[TK], c1l[TK];
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       curOk[k] = ci[k] >= 0;
-      cpl[k] = make_float4(0.f, 0.f, 0.f, 1.f);
-      cnl[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      c0l[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      c1l[k] = make_float4(0.f, 0.f, 1.f, 0.f);
       if (curOk[k] && warp == 0) {
         const float4 *om = G.curOmega + 3 * (size_t)ci[k];
         cp_async16(&S.om[0][k * NT + lane], om);
         cp_async16(&S.om[1][k * NT + lane], om + 1);
         cp_async16(&S.om[2][k * NT + lane], om + 2);
-        cnl[k] = __ldg(G.curNormals + ci[k]);
-        cpl[k] = __ldg(G.curPoints + ci[k]);
+        c0l[k] = __ldg(G.curPN + 2 * (size_t)ci[k]);
+        c1l[k] = __ldg(G.curPN + 2 * (size_t)ci[k] + 1);
       }
     }
     // gathers of pair 0 ride in the same cp.async group as Omega
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
       riCur[k] = MODE == 0 ? z_index(keyNext.z[k], epoch) : keyNext.ri[k];
       zCur[k] = keyNext.z[k];
     }
-    issue_gathers(shfl_ptr(myRefPoints, warp), shfl_ptr(myRefNormals, warp), riCur, curOk, 0);
+    issue_gathers(shfl_ptr(myRefPN, warp), riCur, curOk, 0);
     cp_async_commit();
     if (warp + NW < G.count) load_key(warp + NW, keyNext);
     // what the gates need from the current side (correspondencefinder.cpp:69, :87-93), prepared once per group
@@ -395,12 +403,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
     for (int k = 0; k < TK; k++) {
       if (MODE == 0) {
         // a zero current normal rejects the pixel for every pair (the pixel still counts as "both indices valid")
-        if (dot3(cnl[k].x, cnl[k].y, cnl[k].z, cnl[k].x, cnl[k].y, cnl[k].z) == 0.0f) cnl[k].w = -1.0f;  // curvature >= 0
-        else if (cnl[k].w < ac.flatCurvature) cnl[k].w = ac.flatCurvature;
+        const float nx = c0l[k].y, ny = c0l[k].w, nz = c1l[k].y;
+        if (dot3(nx, ny, nz, nx, ny, nz) == 0.0f) c1l[k].w = -1.0f;  // curvature >= 0
+        else if (c1l[k].w < ac.flatCurvature) c1l[k].w = ac.flatCurvature;
       }
       if (warp == 0) {
-        S.cp[k * NT + lane] = cpl[k];
-        S.cn[k * NT + lane] = cnl[k];
+        S.c0[k * NT + lane] = c0l[k];
+        S.c1[k * NT + lane] = c1l[k];
       }
     }
   }
@@ -438,20 +447,21 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
         riNext[k] = MODE == 0 ? z_index(keyNext.z[k], epoch) : keyNext.ri[k];
         zNext[k] = keyNext.z[k];
       }
-      issue_gathers(shfl_ptr(myRefPoints, g + NW), shfl_ptr(myRefNormals, g + NW), riNext, curOk, st ^ 1);
+      issue_gathers(shfl_ptr(myRefPN, g + NW), riNext, curOk, st ^ 1);
       if (g + 2 * NW < G.count) load_key(g + 2 * NW, keyNext);
     }
     cp_async_commit();         // (an empty group when there is no next pair)
     cp_async_wait_group<1>();  // everything but the group just committed has landed: Omega and the gathers of pair g
 
-    Affine T;  // state->invT of pair g (column-major), broadcast reads from shared memory
-    {
-      const float4 c0 = S.T[g][0], c1 = S.T[g][1], c2 = S.T[g][2], c3 = S.T[g][3];
-      T.r[0][0] = c0.x; T.r[1][0] = c0.y; T.r[2][0] = c0.z;
-      T.r[0][1] = c1.x; T.r[1][1] = c1.y; T.r[2][1] = c1.z;
-      T.r[0][2] = c2.x; T.r[1][2] = c2.y; T.r[2][2] = c2.z;
-      T.r[0][3] = c3.x; T.r[1][3] = c3.y; T.r[2][3] = c3.z;
-    }
+    // state->invT of pair g (column-major, broadcast reads from shared memory), the rotation entries duplicated into both
+    // halves of a packed register
+    const float4 t0 = S.T[g][0], t1 = S.T[g][1], t2 = S.T[g][2], t3 = S.T[g][3];
+    const f32x2 T00 = pk(t0.x, t0.x), T01 = pk(t1.x, t1.x), T02 = pk(t2.x, t2.x);
+    const f32x2 T10 = pk(t0.y, t0.y), T11 = pk(t1.y, t1.y), T12 = pk(t2.y, t2.y);
+    const f32x2 T20 = pk(t0.z, t0.z), T21 = pk(t1.z, t1.z), T22 = pk(t2.z, t2.z);
+    const float T03 = t3.x, T13 = t3.y, T23 = t3.z;
+    const f32x2 ONE = pk(ac.one, ac.one);
+    auto sum2 = [&](f32x2 a, f32x2 b) { return fma2(b, ONE, a); };  // a + b, exactly rounded, never contracted
     int *__restrict__ corrImage = B.corrImage + (size_t)(G.first + g) * (size_t)B.slotPixels;
 
     // a tile where no lane has a pixel of this pair contributes a row of zeros (decided before any sum is live)
@@ -499,21 +509,34 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
             continue;
           }
         }
-        const float4 rp0 = stage[st].rp[k * NT + lane], rn0 = stage[st].rn[k * NT + lane];
-        const float4 cpk = S.cp[k * NT + lane], cnk = S.cn[k * NT + lane];
-        float rpx, rpy, rpz, rnx, rny, rnz;
-        xform_point(T, rp0.x, rp0.y, rp0.z, rpx, rpy, rpz);
-        xform_normal(T, rn0.x, rn0.y, rn0.z, rnx, rny, rnz);
+        // reference and current point + normal, interleaved: (px, nx, py, ny) (pz, nz, 1, curvature)
+        const ulonglong2 r0 = *reinterpret_cast<const ulonglong2 *>(&stage[st].p0[k * NT + lane]);
+        const ulonglong2 r1 = *reinterpret_cast<const ulonglong2 *>(&stage[st].p1[k * NT + lane]);
+        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2 *>(&S.c0[k * NT + lane]);
+        const ulonglong2 q1 = *reinterpret_cast<const ulonglong2 *>(&S.c1[k * NT + lane]);
+        const f32x2 Px = r0.x, Py = r0.y, Pz = r1.x, Cx = q0.x, Cy = q0.y, Cz = q1.x;
+        // T (p, 1) in the low halves and T (n, 0) in the high halves, row by row in the order of xform_point /
+        // xform_normal: ((m0 v0 + m1 v1) + m2 v2) [+ m3]; products and sums rounded separately, so each half is bit for
+        // bit what the scalar functions return.  The sums are written b * 1 + a with a run-time 1: ptxas contracts
+        // mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (unlike the scalar .rn forms), which rounds once.
+        f32x2 Rx = sum2(sum2(mul2(T00, Px), mul2(T01, Py)), mul2(T02, Pz));
+        f32x2 Ry = sum2(sum2(mul2(T10, Px), mul2(T11, Py)), mul2(T12, Pz));
+        f32x2 Rz = sum2(sum2(mul2(T20, Px), mul2(T21, Py)), mul2(T22, Pz));
+        Rx = pk(fadd(lo_of(Rx), T03), hi_of(Rx));
+        Ry = pk(fadd(lo_of(Ry), T13), hi_of(Ry));
+        Rz = pk(fadd(lo_of(Rz), T23), hi_of(Rz));
+        const f32x2 E0 = sub2(Rx, Cx), E1 = sub2(Ry, Cy), E2 = sub2(Rz, Cz);  // (rp - cp, rn - cn)
         bool good = ok0[k];
         if (MODE == 0) {
           midx += ok0[k] ? 1.0f : 0.0f;
+          const float rnx0 = hi_of(Px), rny0 = hi_of(Py), rnz0 = hi_of(Pz);
+          const float cc = hi_of(q1.y);  // current curvature, already clamped; -1 = zero current normal
           // correspondencefinder.cpp:69 zero normals, :78 normal angle, :84 distance, :87-99 curvature ratio
-          good = good && !(cnk.w < 0.0f) && dot3(rn0.x, rn0.y, rn0.z, rn0.x, rn0.y, rn0.z) != 0.0f;
-          good = good && !(dot3(cnk.x, cnk.y, cnk.z, rnx, rny, rnz) < ac.normalThreshold);
-          const float dx = fsub(cpk.x, rpx), dy = fsub(cpk.y, rpy), dz = fsub(cpk.z, rpz);
+          good = good && !(cc < 0.0f) && dot3(rnx0, rny0, rnz0, rnx0, rny0, rnz0) != 0.0f;
+          good = good && !(dot3(hi_of(Cx), hi_of(Cy), hi_of(Cz), hi_of(Rx), hi_of(Ry), hi_of(Rz)) < ac.normalThreshold);
+          const float dx = lo_of(E0), dy = lo_of(E1), dz = lo_of(E2);  // (rp - cp)^2 = (cp - rp)^2 bit for bit
           good = good && !(dot3(dx, dy, dz, dx, dy, dz) > ac.squaredThreshold);
-          float rc = rn0.w;
-          const float cc = cnk.w;  // already clamped
+          float rc = hi_of(r1.y);
           if (rc < ac.flatCurvature) rc = ac.flatCurvature;
           // (rc + 1e-5) / (cc + 1e-5) in double, rounded to float; identical operands give exactly 1.  A float32
           // pre-test decides unless the quotient lies within 1e-4 (relative) of a threshold.
@@ -540,11 +563,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_corr_lin_group(const PairDesc
           const ulonglong2 w0 = *reinterpret_cast<const ulonglong2 *>(&S.om[0][k * NT + lane]);
           const ulonglong2 w1 = *reinterpret_cast<const ulonglong2 *>(&S.om[1][k * NT + lane]);
           const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&S.om[2][k * NT + lane]);
-          term_add<ROBUST>(acc, w, pk(rpx, rnx), pk(rpy, rny), pk(rpz, rnz), cpk, cnk, w0.x, w0.y, w1.x, w1.y, w2.x, w2.y,
-                           ac.maxChi2, ac.robust);
+          term_add_e<ROBUST>(acc, w, Rx, Ry, Rz, E0, E1, E2, w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, ac.maxChi2, ac.robust);
         } else if (good) {
-          accumulate_term(sacc, rpx, rpy, rpz, rnx, rny, rnz, cpk, cnk, S.om[0][k * NT + lane], S.om[1][k * NT + lane],
-                          S.om[2][k * NT + lane], ac.maxChi2, ac.robust);
+          accumulate_term(sacc, lo_of(Rx), lo_of(Ry), lo_of(Rz), hi_of(Rx), hi_of(Ry), hi_of(Rz),
+                          make_float4(lo_of(Cx), lo_of(Cy), lo_of(Cz), 1.0f), make_float4(hi_of(Cx), hi_of(Cy), hi_of(Cz), 0.0f),
+                          S.om[0][k * NT + lane], S.om[1][k * NT + lane], S.om[2][k * NT + lane], ac.maxChi2, ac.robust);
         }
       }
       float v[kAccum];

@@ -698,7 +698,7 @@ static void prep_batch_add(PrepBatch &B, float *d_depth, float *d_integral, nicp
   B.eigvals[f] = ks ? cloud->eigvals : nullptr;
   B.statsN[f] = ks ? cloud->statsN : nullptr;
   B.count[f] = cloud->d_n;
-  cloud->points3_valid = false;
+  cloud->points3_valid = false; cloud->pn_valid = false;
   cloud->n_known = false;
   cloud->has_stats = ks;
 }
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(256) k_unproject_rows(const float *__restrict_
 
 int launch_unproject(nicp_context *ctx, const float *d_depth, int rows, int cols, const float iKRt[16], float minD,
                      float maxD, nicp_cloud *cloud, int *d_index) {
-  cloud->points3_valid = false;
+  cloud->points3_valid = false; cloud->pn_valid = false;
   int *rowCount = ctx->d_interval;  // scratch (rows ints)
   k_row_counts<<<rows, 256, 0, ctx->stream>>>(d_depth, rows, cols, minD, maxD, rowCount);
   NICP_CHECK_LAUNCH(ctx);
@@ -1090,7 +1090,7 @@ __global__ void k_add_count(int *dstN, const int *srcN, int dstCapacity) {
 }
 
 int launch_cloud_append(nicp_context *ctx, nicp_cloud *dst, const nicp_cloud *src, const float T[16]) {
-  dst->points3_valid = false;
+  dst->points3_valid = false; dst->pn_valid = false;
   float m[16];
   for (int i = 0; i < 16; i++) m[i] = T[i];
   fix_last_row(m);
@@ -1113,7 +1113,7 @@ int launch_cloud_transform(nicp_context *ctx, nicp_cloud *cloud, const float T[1
   for (int i = 0; i < 16; i++) m[i] = T[i];
   fix_last_row(m);
   if (is_identity16(m)) return NICP_OK;
-  cloud->points3_valid = false;
+  cloud->points3_valid = false; cloud->pn_valid = false;
   k_cloud_transform<<<(cloud->capacity + 255) / 256, 256, 0, ctx->stream>>>(
       cloud->capacity, cloud->d_n, affine_from(m), cloud->points, cloud->normals, cloud->omega,
       cloud->has_stats ? cloud->stats16 : nullptr);

@@ -393,7 +393,7 @@ __global__ void k_set_count(int *dst, const int *src) { *dst = *src; }
 
 // reorders every per-point array of the cloud so that new[j] = old[map[j]], j < *d_m (n = upper bound of *d_m)
 static int reorder_cloud(nicp_context *ctx, nicp_cloud *cloud, const int *d_map, const int *d_m, int n, void *tmp) {
-  cloud->points3_valid = false;
+  cloud->points3_valid = false; cloud->pn_valid = false;
   cudaStream_t st = ctx->stream;
   auto vec = [&](float4 *arr, int vecPerRow) -> int {
     const size_t threads = (size_t)n * vecPerRow;
@@ -567,7 +567,7 @@ int run_merge(nicp_context *ctx, nicp_cloud *cloud, const nicp_projector *proj, 
   NICP_CHECK_LAUNCH(ctx);
   k_merge_accumulate<<<(n + 127) / 128, 128, 0, st>>>(n, d_count, d_offset, d_list, cloud->gauss, cloud->gflags);
   NICP_CHECK_LAUNCH(ctx);
-  cloud->points3_valid = false;
+  cloud->points3_valid = false; cloud->pn_valid = false;
   k_merge_finalize<<<nb, 256, 0, st>>>(n, d_collapsed, cloud->points, cloud->gauss, cloud->gflags, d_keep);
   NICP_CHECK_LAUNCH(ctx);
   if ((rc = exclusive_scan(ctx, d_keep, d_pos, n, d_scan, d_total))) return rc;

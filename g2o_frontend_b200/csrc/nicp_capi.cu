@@ -270,6 +270,7 @@ static AlignConsts make_consts(const nicp_projector *proj, const nicp_align_para
   ac.maxRatio = ap->inlier_curvature_ratio_threshold;
   ac.maxChi2 = ap->inlier_max_chi2;
   ac.robust = ap->robust_kernel;
+  ac.one = 1.0f;
   return ac;
 }
 
@@ -291,6 +292,7 @@ static int stage_groups(nicp_context *ctx, int m, const int *curSlotOf) {
     g[n].curPoints = ctx->h_desc[i].curPoints;
     g[n].curNormals = ctx->h_desc[i].curNormals;
     g[n].curOmega = ctx->h_desc[i].curOmega;
+    g[n].curPN = ctx->h_desc[i].curPN;
     n++;
     i = j;
   }
@@ -316,6 +318,8 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   D.curPoints = cur->points;
   D.curNormals = cur->normals;
   D.curOmega = cur->omega;
+  D.refPN = ref->pn;  // (null until ensure_pn: the grouped kernel's chunks call it)
+  D.curPN = cur->pn;
   D.curN = cur->d_n;
   D.refZ[0] = ctx->d_refZ + (size_t)slot * P;
   D.refZ[1] = ctx->d_refZ + ((size_t)ctx->slots + slot) * P;
@@ -590,6 +594,7 @@ void nicp_cloud_destroy(nicp_cloud *c) {
   dev_free(c->gauss);
   dev_free(c->gflags);
   dev_free(c->points3);
+  dev_free(c->pn);
   dev_free(c->d_n);
   delete c;
 }
@@ -618,7 +623,7 @@ int nicp_cloud_upload(nicp_context *ctx, nicp_cloud *c, int n, const float *poin
     if (omega_n6)
       for (int k = 0; k < 6; k++) om[12 * (size_t)i + 2 * k + 1] = omega_n6[6 * (size_t)i + k];
   }
-  c->points3_valid = false;
+  c->points3_valid = false; c->pn_valid = false;
   NICP_CUDA(cudaMemcpyAsync(c->points, points4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(c->normals, nrm.data(), sizeof(float) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   NICP_CUDA(cudaMemcpyAsync(c->omega, om.data(), sizeof(float) * 12 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1244,6 +1249,11 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       if (!cams.multi && m >= 8) {
         if ((rc = ensure_points3(ctx, const_cast<nicp_cloud *>(r)))) return rc;
         ctx->h_desc[i].refPoints3 = r->points3;
+      }
+      if (m >= 3 || ctx->groupMinAvg == 0) {  // chunks that may take the grouped kernel gather from the interleaved point + normal caches
+        if ((rc = ensure_pn(ctx, const_cast<nicp_cloud *>(r))) || (rc = ensure_pn(ctx, const_cast<nicp_cloud *>(c)))) return rc;
+        ctx->h_desc[i].refPN = r->pn;
+        ctx->h_desc[i].curPN = c->pn;
       }
       if (numPriors > 0) {
         const int p0 = priorOffsets ? priorOffsets[src] : 0, p1 = priorOffsets ? priorOffsets[src + 1] : numPriors;

@@ -130,7 +130,7 @@ struct PairGroup {
   const float4 *curPoints;
   const float4 *curNormals;  // w = curvature
   const float4 *curOmega;    // Omega3 layout
-  const void *pad2;
+  const float4 *curPN;       // nicp_cloud::pn of the current cloud
 };
 static_assert(sizeof(PairGroup) == 48, "PairGroup is fetched with three 128-bit loads");
 // slot-indexed scratch of a chunk: buffer of slot i = base + i * stride (what fill_desc puts into the descriptors,
@@ -155,6 +155,7 @@ struct PairDesc {
   const float4 *curPoints;
   const float4 *curNormals;  // w = curvature
   const float4 *curOmega;    // 3 float4 per point, Omega_P / Omega_N interleaved (Omega3 above)
+  const float4 *refPN, *curPN;  // interleaved point + normal caches (nicp_cloud::pn), 2 float4 per point
   const int *curN;
   unsigned long long *refZ[2];  // double-buffered reference z-buffer (packed depth|index)
   unsigned long long *curZ;     // current z-buffer (shared by pairs with the same current cloud)
@@ -214,6 +215,8 @@ struct AlignConsts {
   float squaredThreshold, normalThreshold, flatCurvature, minRatio, maxRatio;
   float maxChi2;
   int robust;
+  float one;  // 1.0f as a run-time value: x * one + y is an exactly rounded sum that ptxas cannot contract with the product
+              // that made x (it does contract mul.rn.f32x2 + add.rn.f32x2 into FFMA2; corr_lin.cuh)
 };
 
 }  // namespace nicp
@@ -234,6 +237,10 @@ struct nicp_cloud {
   bool has_stats;
   float *points3;   // cache: x,y,z packed at 12 bytes per point, the stream k_project reads (ensure_points3)
   bool points3_valid;  // every writer of `points` clears it
+  float4 *pn;       // cache: point and normal of a point interleaved in one 32-byte sector, (px,nx,py,ny) (pz,nz,1,curvature):
+                    // what the fused kernels gather (one sector per point instead of two, and a 128-bit load leaves
+                    // (p_k, n_k) in an aligned register pair for the packed transform); ensure_pn
+  bool pn_valid;    // cleared with points3_valid
   float *gauss;     // optional: Gaussian3f per point, NICP_GAUSS_FLOATS floats each (map_ops.cu)
   int *gflags;      // NICP_GAUSS_MOMENTS | NICP_GAUSS_INFO
   bool has_gauss;
@@ -367,6 +374,7 @@ int launch_project_single(nicp_context *ctx, const nicp_cloud *cloud, const floa
 int launch_project_cams(nicp_context *ctx, const nicp_cloud *cloud, const CamSet &cams, const float T[16], int rows,
                         int cols, unsigned long long *d_z);
 int ensure_points3(nicp_context *ctx, nicp_cloud *cloud);
+int ensure_pn(nicp_context *ctx, nicp_cloud *cloud);
 int launch_decode_z(nicp_context *ctx, const unsigned long long *d_z, int n, int *d_index, float *d_depth,
                     float emptyDepth = FLT_MAX, int epoch = kEpochFresh);
 void cam_mats_KRt(const CamSet &cams, const float T[16], CamMats &out);
