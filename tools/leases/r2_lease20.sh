@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_corr_lin_group -s 22 -c 2 -o gpurun_out/r2l20_corr_bench \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-configs --currents 8 --candidates 128 > gpurun_out/r2l20_ncu_corr.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 500 --csv --log-file gpurun_out/r2l20_launches_bench.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-configs --currents 8 --candidates 128 > gpurun_out/r2l20_ncu_launches.log 2>&1
