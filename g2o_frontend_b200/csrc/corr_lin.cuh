@@ -112,7 +112,13 @@ __device__ __forceinline__ void term_add_e(TermAcc &acc, float w, f32x2 Rx, f32x
   float chi = __fadd_rn(lo_of(chi2), hi_of(chi2));
   float ks = 1.0f;
   if (ROBUST) {
-    if (chi > maxChi2) ks = sqrtf(__fdividef(maxChi2, chi));  // one predicated value, no control flow around the sums
+    // sqrt(maxChi2 / chi) (linearizer.cpp:66-71) as r * rsqrt(r): two special-function results and a select, where sqrtf
+    // brings a divergent region with its own slow-path call into every pixel slot; 2 ulp from the rounded square root
+    // (the scale only weighs outlier terms in b and the error; H / b tolerance 1e-4).  chi = 0: inf * 0 is selected away.
+    const float r = __fdividef(maxChi2, chi);
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(r));
+    ks = chi > maxChi2 ? __fmul_rn(r, rs) : 1.0f;
   } else {
     // without the robust kernel such a correspondence is skipped altogether (linearizer.cpp:66-71): multiplied away
     const float keep = chi > maxChi2 ? 0.0f : 1.0f;
