@@ -454,7 +454,7 @@ def run_ours(args):
     bytes_total = 8.0 * P * n_pairs * args.steps * CONF["outerIterations"] + 56.0 * sumMidx + 48.0 * sumMacc
     achieved = bytes_total / (kt["corr_lin_ms"] * 1e-3) / 1e9 if kt["corr_lin_ms"] > 0 else 0.0
     peak, peak_src = measured_peak()
-    # DRAM traffic per launch from the committed ncu capture of this kernel on this workload shape (64 pairs per
+    # DRAM traffic per launch from the committed ncu capture of this kernel on this workload shape (256 pairs per
     # launch, 640x480); null if the launch shape differs
     traffic, traffic_src = None, None
     try:
@@ -464,7 +464,8 @@ def run_ours(args):
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     except Exception:
         pass
-    roofline = {"kernel": "k_corr_lin_tiled<0> (CorrespondenceFinder::compute + Linearizer::update fused)", "bound": "hbm",
+    roofline = {"kernel": "k_corr_lin_group<0> (CorrespondenceFinder::compute + Linearizer::update fused; one warp walks the pairs "
+                          "of a group that share a current cloud)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": kt["corr_lin_ms"] / n_launch,
