@@ -29,6 +29,9 @@ import sys
 import threading
 import time
 
+# NCCL announces its version on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
