@@ -4,15 +4,16 @@
 Workload (config 4 of BASELINE.json, the one the metric's multi-GPU numbers are quoted on):
 batched loop-closure candidate verification of 8192 independent 640x480 frame pairs per step
 (64 "current" frames x 128 candidate "reference" frames, guesses perturbed by U(+-5 cm, +-3 deg),
-10 outer iterations, parameters of pwn_core/conf/pwn_aligner_1_1.conf).  The pair list is sharded
-pair-wise over the ranks, current-major (rank r takes the currents [r 64/N, (r+1) 64/N) with all 128
-candidates): the total work is fixed, scaling is strong.
+10 outer iterations, parameters of pwn_core/conf/pwn_aligner_1_1.conf).  The pairs are sharded over the
+ranks as rectangular blocks of the current x candidate grid (shard_grid: 1x2, 2x2, 2x4 blocks at 2, 4, 8
+ranks, so that a rank prepares as few frames as possible; current-major inside a block):
+the total work is fixed, scaling is strong.
 
 One JSON line on rank 0:
   value     whole-job alignments/s with the clouds already resident in HBM (device-timed, CUDA events
             on the library's stream, max over ranks)
   e2e       the same metric through the C-ABI with HOST buffers: every step uploads the raw 16-bit
-            depth frames the rank needs from pinned memory (192 at N = 1), builds their clouds, aligns
+            depth frames the rank needs from pinned memory (192 at N = 1, 64 at N = 8), builds their clouds, aligns
             its pairs and reads the 256-byte result records back
   configs   (N = 1) BASELINE configs 1, 2, 3, 5 through tools/bench_configs.py, each with its own CPU sample
   roofline  the fused correspondence+linearise kernel: algorithmic bytes / live CUDA-event time
@@ -28,9 +29,6 @@ import subprocess
 import sys
 import threading
 import time
-
-# NCCL announces its version on stdout when NCCL_DEBUG asks for it; stdout carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np
 
@@ -79,27 +77,47 @@ def render_frames(jobs, procs=None):
     return [_render(j) for j in jobs]
 
 
-def make_workload(n_cur, n_cand, rank, cur_slice=None, procs=None):
-    """poses + raw frames + pair list + guesses (deterministic in `rank`, the seed of the job).  cur_slice = (lo, hi):
-    only the currents [lo, hi) are rendered and paired (a rank's shard of the current-major pair list); the candidate
-    frames, which every rank needs, are all rendered."""
+def make_workload(n_cur, n_cand, rank, cur_slice=None, procs=None, cand_slice=None):
+    """poses + raw frames + pair list + guesses (deterministic in `rank`, the seed of the job).  cur_slice = (lo, hi) /
+    cand_slice = (lo, hi): only those currents / candidates are rendered and paired (a rank's block of the job's
+    current x candidate grid); pair indices are relative to the slices."""
     from g2o_frontend_b200 import synth
     rng = np.random.default_rng(1000 + rank)
     cur_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cur)]
     cand_poses = [synth.perturbed_pose(rng, np.eye(4), 0.25, 6.0) for _ in range(n_cand)]
     lo, hi = cur_slice if cur_slice else (0, n_cur)
+    clo, chi = cand_slice if cand_slice else (0, n_cand)
     frames = render_frames([(cur_poses[i], 10 * rank + i) for i in range(lo, hi)] +
-                           [(p, 5000 + 10 * rank + i) for i, p in enumerate(cand_poses)], procs)
+                           [(cand_poses[i], 5000 + 10 * rank + i) for i in range(clo, chi)], procs)
     raws_cur, raws_cand = frames[:hi - lo], frames[hi - lo:]
     pairs, guesses = [], []
     for ci, cp in enumerate(cur_poses):
         for ri, rp in enumerate(cand_poses):
             T_true = np.linalg.inv(rp) @ cp  # reference <- current
             g = synth.perturbed_pose(rng, T_true, 0.05, 3.0)  # drawn for every pair so that a shard sees the job's guesses
-            if lo <= ci < hi:
+            if lo <= ci < hi and clo <= ri < chi:
                 guesses.append(g)
-                pairs.append((ri, ci - lo))
+                pairs.append((ri - clo, ci - lo))
     return raws_cur, raws_cand, np.array(pairs), np.stack(guesses).astype(np.float32)
+
+
+def shard_grid(n_cur, n_cand, world):
+    """The job's current x candidate grid cut into `world` rectangular blocks (a splits of the currents x b of the
+    candidates, a b = world) so that a rank prepares as few frames as possible: its n_cur / a currents and n_cand / b
+    candidates.  Pairs that share a current cloud stay contiguous inside a block."""
+    best = None
+    for a in range(1, world + 1):
+        if world % a:
+            continue
+        b = world // a
+        if n_cur % a or n_cand % b:
+            continue
+        frames = n_cur // a + n_cand // b
+        if best is None or frames < best[0] or (frames == best[0] and a > best[1]):
+            best = (frames, a, b)
+    if best is None:
+        raise SystemExit("--currents (%d) x --candidates (%d) cannot be cut into %d equal blocks" % (n_cur, n_cand, world))
+    return best[1], best[2]
 
 
 class ClockSampler:
@@ -320,14 +338,15 @@ def workload_config(n_cur, n_cand, world):
     """the `config` object both arms report (same workload name; the reference arm times a bounded sample of it)"""
     n_pairs = n_cur * n_cand
     P = ROWS * COLS
+    split_cur, split_cand = shard_grid(n_cur, n_cand, world)
     return {"workload": "batched loop-closure candidate verification (BASELINE config 4): %d pairs/step = "
                         "%d current x %d candidate 640x480 frames, 10 outer iterations, "
                         "pwn_aligner_1_1.conf parameters" % (n_pairs, n_cur, n_cand),
             "pairs_total_per_step": n_pairs, "pairs_per_gpu_per_step": n_pairs // world, "rows": ROWS, "cols": COLS,
             "l2_policy": "inputs larger than L2 (%.1f GB of clouds + %.1f GB of z-buffers per GPU and step)" %
-                         ((n_cur // world + n_cand) * P * 92 / 1e9, 256 * P * 32 / 1e9),
-            "parallelism": "pair-sharded x%d (current-major blocks, no data-path collective; one all-gather of the "
-                           "256-byte records)" % world}
+                         ((n_cur // split_cur + n_cand // split_cand) * P * 124 / 1e9, 256 * P * 32 / 1e9),
+            "parallelism": "pair-sharded x%d (%d x %d blocks of the current x candidate grid, current-major inside a block; no "
+                           "data-path collective, one all-gather of the 256-byte records)" % (world, split_cur, split_cand)}
 
 
 def run_reference(args):
@@ -349,7 +368,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "reference_sources": ref_src},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -368,15 +387,17 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_cur_total, n_cand = args.currents, args.candidates
-    if n_cur_total % world:
-        raise SystemExit("--currents (%d) must be divisible by the number of ranks (%d)" % (n_cur_total, world))
-    # this rank's block of the current-major pair list: its currents x all candidates
-    n_cur = n_cur_total // world
+    n_cur_total, n_cand_total = args.currents, args.candidates
+    # this rank's block of the job: a rectangle of the current x candidate grid, so that it prepares
+    # n_cur + n_cand frames for n_cur x n_cand pairs (at 8 ranks: 32 + 32 frames instead of 8 + 128)
+    split_cur, split_cand = shard_grid(n_cur_total, n_cand_total, world)
+    n_cur, n_cand = n_cur_total // split_cur, n_cand_total // split_cand
+    rc, rk = rank // split_cand, rank % split_cand
     n_pairs = n_cur * n_cand
-    n_pairs_total = n_cur_total * n_cand
-    raws_cur, raws_cand, pairs, guesses = make_workload(n_cur_total, n_cand, 0, (rank * n_cur, (rank + 1) * n_cur),
-                                                        procs=max(1, min(32, (os.cpu_count() or 1) // world)))
+    n_pairs_total = n_cur_total * n_cand_total
+    raws_cur, raws_cand, pairs, guesses = make_workload(n_cur_total, n_cand_total, 0, (rc * n_cur, (rc + 1) * n_cur),
+                                                        procs=max(1, min(32, (os.cpu_count() or 1) // world)),
+                                                        cand_slice=(rk * n_cand, (rk + 1) * n_cand))
     n_frames = n_cur + n_cand
     # pinned host staging of the raw frames (what a tracker would hand over)
     pinned = torch.empty((n_frames, ROWS, COLS), dtype=torch.int16).pin_memory()
@@ -516,7 +537,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": workload_config(n_cur_total, n_cand, world),
+                "config": workload_config(n_cur_total, n_cand_total, world),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps},
@@ -550,14 +571,30 @@ def run_ours(args):
                                                         tracking_frames=args.tracking_frames)
             except Exception as e:
                 line["configs"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the one JSON line, on the process's original stdout"""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: anything else a library prints on file descriptor 1 (NCCL announces its
+    # version there under NCCL_DEBUG=VERSION) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

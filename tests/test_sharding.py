@@ -27,6 +27,39 @@ def test_order_pairs_groups_currents():
     assert list(cur) == sorted(cur)
 
 
+def test_bench_blocks_cover_the_job_once():
+    """bench.py cuts the current x candidate grid of the job into one rectangular block per rank (shard_grid): every pair
+    lands in exactly one block with the guess the unsharded job gives it, and a rank renders only its own frames"""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert [bench.shard_grid(64, 128, w) for w in (1, 2, 4, 8)] == [(1, 1), (1, 2), (2, 2), (2, 4)]
+    n_cur, n_cand = 2, 4
+    raws_cur, raws_cand, pairs, guesses = bench.make_workload(n_cur, n_cand, 3, procs=1)
+    whole = {(int(r), int(c)): g for (r, c), g in zip(pairs, guesses)}
+    assert len(whole) == n_cur * n_cand
+    for world in (2, 4, 8):
+        a, b = bench.shard_grid(n_cur, n_cand, world)
+        assert a * b == world
+        seen = {}
+        for rank in range(world):
+            rc, rk = rank // b, rank % b
+            nc, nk = n_cur // a, n_cand // b
+            rcur, rcand, p, g = bench.make_workload(n_cur, n_cand, 3, (rc * nc, (rc + 1) * nc), procs=1,
+                                                    cand_slice=(rk * nk, (rk + 1) * nk))
+            assert len(rcur) == nc and len(rcand) == nk and len(p) == nc * nk
+            for (r, c), gg in zip(p, g):
+                key = (int(r) + rk * nk, int(c) + rc * nc)
+                assert key not in seen
+                seen[key] = gg
+                assert np.array_equal(gg, whole[key])
+            # the frames are the job's frames
+            for i in range(nc):
+                assert np.array_equal(rcur[i], raws_cur[rc * nc + i])
+            for i in range(nk):
+                assert np.array_equal(rcand[i], raws_cand[rk * nk + i])
+        assert len(seen) == n_cur * n_cand
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
