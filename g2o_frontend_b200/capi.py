@@ -336,6 +336,7 @@ class Context:
     def __init__(self, device=0, verify=False):
         self.L = load(verify)
         self.verify = verify
+        self.device = int(device)
         self.handle = C.c_void_p()
         _check(self.L, self.L.nicp_create(int(device), C.byref(self.handle)))
 

@@ -121,6 +121,17 @@ def config3(ctx, cpu, n_frames=2000):
     per frame one cloud build from the raw image + one alignment against the key frame"""
     proj, sp, ap = params(1, 10, 30, 50, 1.0)
     poses, raws = render_sequence(n_frames)
+    try:
+        # the frames a camera driver hands over sit in pinned memory (like bench.py's main workload): the upload of a frame
+        # is then asynchronous instead of a blocking staged copy
+        import torch
+        pinned = torch.empty((n_frames, 480, 640), dtype=torch.int16).pin_memory()
+        host = pinned.numpy().view(np.uint16)
+        for i, r in enumerate(raws):
+            host[i] = r
+        raws = [host[i] for i in range(n_frames)]
+    except Exception:
+        pinned = None
     key, cur = ctx.new_cloud(480 * 640), ctx.new_cloud(480 * 640)
 
     def track(n):
@@ -141,14 +152,56 @@ def config3(ctx, cpu, n_frames=2000):
                 nkey += 1
         return globalT, nkey
 
+    # The same tracker with the cloud of frame i + 1 built (second context = second stream of the same GPU) while frame i
+    # is aligned: the frames are still processed in order with the same guesses, so the poses are the sequential ones bit
+    # for bit; three cloud buffers (key, current, next).
+    prep = capi.Context(ctx.device)
+    bufs = [prep.new_cloud(480 * 640) for _ in range(3)]
+
+    def track_pipelined(n):
+        globalT = np.eye(4)
+        keyT = np.eye(4)
+        key, cur, free = bufs[0], bufs[1], bufs[2]
+        prep.raw_depth_to_cloud(raws[0], proj, sp, cloud=key)
+        if n > 1:
+            prep.raw_depth_to_cloud(raws[1], proj, sp, cloud=cur)
+        nkey = 1
+        for i in range(1, n):
+            prep.synchronize()  # the cloud of frame i is complete
+            if i + 1 < n:
+                prep.raw_depth_to_cloud(raws[i + 1], proj, sp, cloud=free)
+            guess = (np.linalg.inv(keyT) @ globalT).astype(np.float32)
+            r = ctx.align(key, cur, proj, ap, guess=guess)
+            if r.inliers > 0:
+                globalT = keyT @ capi.result_T(r).astype(np.float64)
+            if r.inliers / float(480 * 640) < 0.4:
+                key, cur, free = cur, free, key
+                keyT = globalT.copy()
+                nkey += 1
+            else:
+                cur, free = free, cur
+        prep.synchronize()
+        return globalT, nkey
+
     track(min(100, n_frames))
     t0 = time.perf_counter()
     G, nkey = track(n_frames)
     dt = time.perf_counter() - t0
+    track_pipelined(min(100, n_frames))
+    t0 = time.perf_counter()
+    G2, nkey2 = track_pipelined(n_frames)
+    dt2 = time.perf_counter() - t0
+    for b in bufs:
+        b.close()
+    prep.close()
     gt = np.linalg.inv(poses[0]) @ poses[-1]
     out = {"workload": "sequential keyframe tracking, %d-frame synthetic 640x480 sequence" % n_frames,
-           "frames": n_frames, "value": (n_frames - 1) / dt, "unit": "frames/s", "sequence_s": dt, "keyframes": nkey,
-           "final_translation_error_m": float(np.abs(G[:3, 3] - gt[:3, 3]).max())}
+           "frames": n_frames, "value": (n_frames - 1) / dt2, "unit": "frames/s", "sequence_s": dt2, "keyframes": nkey2,
+           "schedule": "the cloud of frame i + 1 is built on a second stream while frame i is aligned (same poses as the "
+                       "strictly sequential schedule: poses_identical below)",
+           "strictly_sequential": {"value": (n_frames - 1) / dt, "unit": "frames/s", "sequence_s": dt, "keyframes": nkey},
+           "poses_identical": bool(np.array_equal(G, G2) and nkey == nkey2),
+           "final_translation_error_m": float(np.abs(G2[:3, 3] - gt[:3, 3]).max())}
     if cpu:
         m = min(6, n_frames)
         t0 = time.perf_counter()
