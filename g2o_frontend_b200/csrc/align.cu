@@ -1007,15 +1007,15 @@ __global__ void __launch_bounds__(256) k_reduce_solve(const PairDesc *__restrict
 }
 
 // Aligner::_computeStatistics' dense tail for a batch: one thread per pair (sigma points, 6x6 pseudo-inverse and inverse,
-// eigen-ratios; nicp_stats_tail.cuh -- the function a single alignment runs on the host, bit for bit)
-__global__ void __launch_bounds__(32) k_statistics(const PairDesc *__restrict__ desc, int n) {
+// eigen-ratios; nicp_stats_tail.cuh -- the function a single alignment runs on the host, bit for bit).  Works on the
+// result records and the gathered H of a chunk (both indexed by the caller's pair index), not on the slot state: it runs
+// on the tail stream while the next chunk already reuses the slots.
+__global__ void __launch_bounds__(32) k_statistics(nicp_align_result *__restrict__ results, const float *__restrict__ statHb, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const PairState *st = desc[i].state;
-  nicp_align_result *res = desc[i].result;
-  if (!res) return;
+  nicp_align_result *res = results + i;
   float H[36], T[16], omega[36], tr, rr;
-  for (int k = 0; k < 36; k++) H[k] = st->statH[k];
+  for (int k = 0; k < 36; k++) H[k] = statHb[(size_t)i * 42 + k];
   for (int k = 0; k < 16; k++) T[k] = res->T[k];
   compute_statistics_tail(H, T, omega, &tr, &rr);
   for (int k = 0; k < 36; k++) res->omega[k] = omega[k];
@@ -1283,11 +1283,14 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   k_reduce_solve<false><<<dim3(kRowGroups, nPairs), 256, 0, st>>>(ctx->d_desc, nb, 1, 0, 0, 0, ac);
   NICP_CHECK_LAUNCH(ctx);
   (void)resultOffset;
-  if (!fresh) {  // a batch: the records leave the device complete (a single alignment finishes them on the host)
-    k_statistics<<<(nPairs + 31) / 32, 32, 0, st>>>(ctx->d_desc, nPairs);
-    NICP_CHECK_LAUNCH(ctx);
-  }
   k_gather_stat<<<nPairs, 64, 0, st>>>(ctx->d_desc, nPairs, ctx->d_results, ctx->d_statHb);
+  NICP_CHECK_LAUNCH(ctx);
+  return NICP_OK;
+}
+
+// a batch: the records [base, base + n) leave the device complete (a single alignment finishes them on the host)
+int launch_statistics(nicp_context *ctx, cudaStream_t s, int base, int n) {
+  k_statistics<<<(n + 31) / 32, 32, 0, s>>>(ctx->d_results + base, ctx->d_statHb + (size_t)base * 42, n);
   NICP_CHECK_LAUNCH(ctx);
   return NICP_OK;
 }

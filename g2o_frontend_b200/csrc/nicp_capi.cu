@@ -441,6 +441,9 @@ int nicp_create(int device, nicp_context **out) {
   ctx->device = device;
   NICP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   NICP_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  NICP_CUDA(cudaStreamCreateWithFlags(&ctx->tailStream, cudaStreamNonBlocking));
+  NICP_CUDA(cudaEventCreateWithFlags(&ctx->evTail[0], cudaEventDisableTiming));
+  NICP_CUDA(cudaEventCreateWithFlags(&ctx->evTail[1], cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) {
     NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawCopied[i], cudaEventDisableTiming));
     NICP_CUDA(cudaEventCreateWithFlags(&ctx->evRawUsed[i], cudaEventDisableTiming));
@@ -517,6 +520,9 @@ void nicp_destroy(nicp_context *ctx) {
   dev_free(ctx->d_bIntegral);
   dev_free(ctx->d_bRaw);
   cudaStreamDestroy(ctx->copyStream);
+  if (ctx->tailStream) cudaStreamDestroy(ctx->tailStream);
+  if (ctx->evTail[0]) cudaEventDestroy(ctx->evTail[0]);
+  if (ctx->evTail[1]) cudaEventDestroy(ctx->evTail[1]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1264,6 +1270,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     const int nGroups = stage_groups(ctx, m, curSlotOf.data());
     const bool useGraph = single && ctx->graphsEnabled && !cams.multi && !ctx->timing;
     bool replayed = false;
+    cudaStream_t tail = ctx->stream;  // where this chunk's records are finished and copied out
     if (useGraph) {
       GraphKey key;
       memset(&key, 0, sizeof key);
@@ -1327,12 +1334,20 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
       if ((rc = run_align_chunk(ctx, m, ac, cams, co, ap->outer_iterations, ap->inner_iterations, imgThr, nGroups,
                                 owns.data(), single, base)))
         return rc;
+      // a batch finishes its records (Aligner::_computeStatistics tail, one thread per pair: 0.1 ms of a nearly idle GPU)
+      // and copies them out on the tail stream, beside the kernels of the next chunk
+      if (!single) {
+        NICP_CUDA(cudaEventRecord(ctx->evTail[chunk & 1], ctx->stream));
+        NICP_CUDA(cudaStreamWaitEvent(ctx->tailStream, ctx->evTail[chunk & 1], 0));
+        if ((rc = launch_statistics(ctx, ctx->tailStream, base, m))) return rc;
+        tail = ctx->tailStream;
+      }
       NICP_CUDA(cudaMemcpyAsync(ctx->h_results + base, ctx->d_results + base, sizeof(nicp_align_result) * m,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+                                cudaMemcpyDeviceToHost, tail));
       NICP_CUDA(cudaMemcpyAsync(ctx->h_statHb + (size_t)base * 42, ctx->d_statHb + (size_t)base * 42, sizeof(float) * 42 * m,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+                                cudaMemcpyDeviceToHost, tail));
     }
-    NICP_CUDA(cudaEventRecord(ctx->evChunk[chunk & 1], ctx->stream));
+    NICP_CUDA(cudaEventRecord(ctx->evChunk[chunk & 1], tail));
     // while this chunk runs on the GPU, finish the previous one on the host (Aligner::_computeStatistics tail)
     if (chunk > 0) {
       NICP_CUDA(cudaEventSynchronize(ctx->evChunk[(chunk - 1) & 1]));
@@ -1342,6 +1357,7 @@ static int align_common(nicp_context *ctx, int n, const nicp_cloud *const *refs,
     prevM = m;
   }
   NICP_CUDA(cudaStreamSynchronize(ctx->stream));
+  NICP_CUDA(cudaStreamSynchronize(ctx->tailStream));
   collect_timing(ctx);
   finish_results(ctx, prevBase, prevM, results, !single);
   ctx->lastAlignRows = proj->rows;

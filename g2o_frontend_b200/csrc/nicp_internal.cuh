@@ -258,6 +258,8 @@ struct nicp_context {
   uint16_t *d_raw;    // two staging images back to back: frame i+1 is uploaded while frame i is being converted
   size_t rawPixels;   // pixels per staging image
   cudaStream_t copyStream;
+  cudaStream_t tailStream;      // a batch chunk's k_statistics + record copies, beside the next chunk's kernels
+  cudaEvent_t evTail[2];        // chunk's last kernel on `stream` -> tailStream
   cudaEvent_t evRawCopied[2], evRawUsed[2];
   int rawToggle;
   float *d_integral;  // planar [10][rows][cols]
@@ -384,6 +386,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
                     int resultOffset);
 int run_correspond_linearize(nicp_context *ctx, const AlignConsts &ac, bool fromCorrImage, int slot);
 int partial_rows_for(const nicp_context *ctx, size_t pixels);
+int launch_statistics(nicp_context *ctx, cudaStream_t s, int base, int n);
 const PairGroup *device_groups(const nicp_context *ctx);
 PairGroup *host_groups(nicp_context *ctx);
 // map_ops.cu
