@@ -133,7 +133,7 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_corrImage, (size_t)slots * pixels))) return rc;
   ctx->partialRows = partial_rows_for(ctx, pixels);
   if ((rc = dev_alloc(&ctx->d_partials, (size_t)slots * ctx->partialRows * kAccum))) return rc;
-  if ((rc = dev_alloc(&ctx->d_partials2, (size_t)slots * 16 * kAccum))) return rc;
+  if ((rc = dev_alloc(&ctx->d_partials2, (size_t)slots * kRowGroups * kAccum))) return rc;
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   NICP_CUDA(cudaMemset(ctx->d_state, 0, sizeof(PairState) * (size_t)slots));  // the reduction tickets start at 0
   // two sets of: descriptors, one int flag per slot, one pair group per slot
@@ -327,7 +327,7 @@ static void fill_desc(nicp_context *ctx, int slot, int curSlot, const nicp_cloud
   D.curIndex = ctx->d_curIndex + (size_t)curSlot * P;
   D.corrImage = ctx->d_corrImage + (size_t)slot * P;
   D.partials = ctx->d_partials + (size_t)slot * ctx->partialRows * kAccum;
-  D.partials2 = ctx->d_partials2 + (size_t)slot * 16 * kAccum;
+  D.partials2 = ctx->d_partials2 + (size_t)slot * kRowGroups * kAccum;
   D.state = ctx->d_state + slot;
   D.trace = d_trace;
   D.result = d_result;

@@ -32,6 +32,7 @@ void set_error(const char *fmt, ...);
   } while (0)
 
 constexpr int kMaxCams = 8;       // NICP_MAX_CAMERAS
+constexpr int kRowGroups = 16;    // first-level CTAs per pair of k_reduce_solve (align.cu); partials2 holds that many rows per slot
 constexpr int kMaxGroup = 32;     // pairs per group of the grouped fused kernel (corr_lin.cuh)
 constexpr int kMaxPrepBatch = 8;  // frames per frame-preparation launch set (their scratch stays L2 resident)
 constexpr int kAccum = 32;        // accumulator slots per partial (30 used)
