@@ -288,6 +288,44 @@ def test_align_teacher_forced_iterations(ctx, step, seed, dropout):
     print("teacher-forced %dx%d: omega rel %.2e, eigen-ratio rel %.2e" % (s.cols, s.rows, worst_om, worst_ratio))
 
 
+def test_teacher_forced_random_scenes_through_the_grouped_kernel(ctx, monkeypatch):
+    """A sweep instead of three hand-picked cases: 6 random scenes (noise seeds, 0-20 % dropout, with and without a sensor
+    offset) x 4 random guesses within the loop-closure perturbation (5 cm / 3 deg), one iteration each from the SAME guess on
+    both sides, the 4 guesses of a scene in ONE batch that shares the current cloud (forced through the grouped kernel; the
+    single-pair tests above go through the per-pair kernel): correspondence count exact, inliers within 2 (a chi2 that sits
+    on the threshold), summed error within 1e-4, the pose after the step within 1e-4 rad / m of the oracle's."""
+    from g2o_frontend_b200 import capi, synth
+    from oracle import pwn_oracle as O
+    monkeypatch.setenv("NICP_GROUP_MIN_AVG", "0")
+    c = capi.Context(0, verify=ctx.verify)
+    rng = np.random.default_rng(2024)
+    worst_e = worst_t = 0.0
+    worst_inl = 0
+    for seed, dropout, offset in ((11, 0.0, False), (12, 0.05, False), (13, 0.2, False), (14, 0.1, True), (15, 0.0, True),
+                                  (16, 0.05, False)):
+        s = get_scene(4, seed, dropout, offset)
+        ref, cur = upload(c, s.cloudA), upload(c, s.cloudB)
+        guesses = np.stack([synth.perturbed_pose(rng, s.gt.astype(np.float64), 0.05, 3.0) for _ in range(4)]).astype(np.float32)
+        recs = c.align_batch([ref] * 4, [cur] * 4, s.projector(), s.align_params(outer=1), guesses,
+                             ref_offset=s.sensor_offset, cur_offset=s.sensor_offset)
+        for k in range(4):
+            o1 = O.align(s.cloudA, s.cloudB, s.oracle_align_params(outer=1, guess=guesses[k], num_threads=1), accumulate_f64=True)
+            assert int(recs[k]["status"]) == 0
+            assert int(recs[k]["num_correspondences"]) == o1.numCorrespondences, (seed, k)
+            worst_inl = max(worst_inl, abs(int(recs[k]["inliers"]) - o1.inliers))
+            assert abs(int(recs[k]["inliers"]) - o1.inliers) <= 2, (seed, k)
+            e = abs(float(recs[k]["error"]) - o1.error) / abs(o1.error)
+            worst_e = max(worst_e, e)
+            assert e <= H_RTOL, (seed, k, e)
+            T = capi.from_colmajor(recs[k]["T"], 4)
+            dt = max(rot_angle(T[:3, :3], o1.T[:3, :3]), float(np.abs(T[:3, 3] - o1.T[:3, 3]).max()))
+            worst_t = max(worst_t, dt)
+            assert dt <= T_ROT_TOL, (seed, k, dt)
+    print("teacher-forced sweep, 24 pairs through the grouped kernel: worst |dT| %.2e, worst error rel %.2e, worst inlier "
+          "difference %d" % (worst_t, worst_e, worst_inl))
+    c.close()
+
+
 def test_inner_iterations(ctx):
     from g2o_frontend_b200 import capi
     from oracle import pwn_oracle as O
