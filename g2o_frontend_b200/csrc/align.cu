@@ -22,6 +22,8 @@
 #include "nicp_internal.cuh"
 #include "nicp_stats_tail.cuh"
 
+#include <algorithm>
+
 namespace nicp {
 
 // KRt of every camera for the projector pose `pose` (PinholePointProjector::_updateMatrices after
@@ -119,10 +121,12 @@ struct MatsFromParam {
 
 // which: 0/1 = reference cloud into refZ[which] with the pair's KRt; 2 = current cloud into curZ
 // with the (shared) current-sensor KRt, only for the pair that owns that buffer.
+// order (which 0/1, optional): blockIdx.y -> descriptor, pairs that project the same reference cloud adjacent, so that
+// their CTAs run together and all but the first read the cloud's point stream out of L2.
 __global__ void __launch_bounds__(256) k_project(const PairDesc *__restrict__ desc, int which, Affine curKRt, int rows,
                                                  int cols, float minD, float maxD, const int *__restrict__ ownsCur,
-                                                 int epoch) {
-  const PairDesc &D = desc[blockIdx.y];
+                                                 int epoch, const int *__restrict__ order) {
+  const PairDesc &D = desc[order ? order[blockIdx.y] : blockIdx.y];
   const float4 *pts;
   unsigned long long *z;
   int n;
@@ -1069,9 +1073,9 @@ static void launch_tiled(nicp_context *ctx, dim3 grid, int parity, int epoch, in
   k_corr_lin_tiled<MODE, NT, TK, MINB, INPLACE><<<g, NT, smem, ctx->stream>>>(ctx->d_desc, parity, epoch, writeCorr, ac, P, imgStats,
                                                                                imgThr, swap ? 1 : 0, curEpoch);
 }
-// the pair groups live behind the flags in the descriptor staging area, 16-byte aligned
+// the pair groups live behind the flags and the projection order in the descriptor staging area, 16-byte aligned
 static size_t groups_offset(const nicp_context *ctx) {
-  size_t off = sizeof(PairDesc) * (size_t)ctx->slots + sizeof(int) * (size_t)ctx->slots;
+  size_t off = sizeof(PairDesc) * (size_t)ctx->slots + 2 * sizeof(int) * (size_t)ctx->slots;
   return (off + 15) & ~(size_t)15;
 }
 const PairGroup *device_groups(const nicp_context *ctx) {
@@ -1180,6 +1184,19 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
   int *h_flags = reinterpret_cast<int *>(ctx->h_desc + ctx->slots);
   int *d_flags = reinterpret_cast<int *>(ctx->d_desc + ctx->slots);
   for (int i = 0; i < nPairs; i++) h_flags[i] = h_ownsCur ? h_ownsCur[i] : 1;
+  // projection order: descriptors sorted by reference cloud (stable).  A chunk's descriptors are ordered by CURRENT cloud
+  // for the grouped kernel; k_project is DRAM bound and reads the reference's 12-byte point stream, so pairs with the same
+  // reference should be neighbours in ITS grid.
+  int *h_order = h_flags + ctx->slots, *d_order = nullptr;
+  {
+    bool sharedRef = false;
+    for (int i = 0; i < nPairs; i++) h_order[i] = i;
+    std::stable_sort(h_order, h_order + nPairs,
+                     [&](int a, int b) { return (uintptr_t)ctx->h_desc[a].refPoints < (uintptr_t)ctx->h_desc[b].refPoints; });
+    for (int i = 1; i < nPairs && !sharedRef; i++)
+      sharedRef = ctx->h_desc[h_order[i]].refPoints == ctx->h_desc[h_order[i - 1]].refPoints;
+    if (sharedRef && ctx->projByReference) d_order = d_flags + ctx->slots;
+  }
   NICP_CUDA(cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * nPairs, cudaMemcpyHostToDevice, st));
   // flags and the pair groups (staged by the caller behind the flags) in one copy
   NICP_CUDA(cudaMemcpyAsync(d_flags, h_flags, (groups_offset(ctx) - sizeof(PairDesc) * (size_t)ctx->slots) + sizeof(PairGroup) * nGroups,
@@ -1236,7 +1253,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     if (rcm) return rcm;
     k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, 2, geom, d_curMats, ac.rows, ac.cols, d_flags, curEpoch);
   } else {
-    k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, curEpoch);
+    k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, 2, curMats.M[0], ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, curEpoch, nullptr);
   }
   NICP_CHECK_LAUNCH(ctx);
   k_decode_cur<<<dim3((P + 1023) / 1024, nPairs), 256, 0, st>>>(ctx->d_desc, P, d_flags, curEpoch);
@@ -1255,7 +1272,7 @@ int run_align_chunk(nicp_context *ctx, int nPairs, const AlignConsts &ac, const 
     if (cams.multi)
       k_project_multi<<<pg, 256, 0, st>>>(ctx->d_desc, parity, geom, d_curMats, ac.rows, ac.cols, d_flags, epoch);
     else
-      k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, epoch);
+      k_project<<<pg, projThreads, 0, st>>>(ctx->d_desc, parity, dummy, ac.rows, ac.cols, ac.minD, ac.maxD, d_flags, epoch, d_order);
     NICP_TIME_END(evProj, evProjUsed);
     NICP_CHECK_LAUNCH(ctx);
     for (int k = 0; k < innerIters; k++) {

@@ -137,7 +137,8 @@ static int ensure_align(nicp_context *ctx, int slots, size_t pixels) {
   if ((rc = dev_alloc(&ctx->d_state, (size_t)slots))) return rc;
   NICP_CUDA(cudaMemset(ctx->d_state, 0, sizeof(PairState) * (size_t)slots));  // the reduction tickets start at 0
   // two sets of: descriptors, one int flag per slot, one pair group per slot
-  size_t descBytes = sizeof(PairDesc) * slots + sizeof(int) * slots + 16 + sizeof(PairGroup) * slots;
+  // descriptors | ownership flags | projection order | (16-byte aligned) pair groups
+  size_t descBytes = sizeof(PairDesc) * slots + 2 * sizeof(int) * slots + 16 + sizeof(PairGroup) * slots;
   descBytes = (descBytes + 255) & ~(size_t)255;
   void *p = nullptr;
   NICP_CUDA(cudaMalloc(&p, 2 * descBytes));
@@ -461,6 +462,10 @@ int nicp_create(int device, nicp_context **out) {
   ctx->groupSize = env_int("NICP_GROUP", 16);
   ctx->groupMinBlocks = env_int("NICP_GROUP_MINB", 16);
   ctx->groupWarps = env_int("NICP_GROUP_WARPS", 1);
+  {
+    const char *v = getenv("NICP_PROJECT_BY_REFERENCE");
+    ctx->projByReference = (v && *v) ? atoi(v) : 1;
+  }
   {
     const char *v = getenv("NICP_GROUP_MIN_AVG");  // 0 = always the grouped kernel (tests)
     ctx->groupMinAvg = (v && *v) ? atoi(v) : 3;

@@ -290,6 +290,7 @@ struct nicp_context {
   int groupMinBlocks;           // its __launch_bounds__ min-blocks instantiation (16 or 20 warps per SM)
   int groupMinAvg;              // mean pairs per group from which a chunk takes the grouped kernel (else the per-pair one)
   int groupWarps;               // warps per CTA of the grouped kernel (1 or 2; they share the current side of the tile)
+  int projByReference;          // k_project walks the pairs of a chunk grouped by reference cloud (L2 reuse of the point stream)
   int partialRows;              // rows of d_partials per slot
   unsigned long long *d_refZ;   // [slots][2][P]
   unsigned long long *d_curZ;   // [slots][P]
