@@ -1107,16 +1107,19 @@ static void launch_group(nicp_context *ctx, int nGroups, int tiles, int parity, 
                                                                                           curEpoch)
   (void)MINB;
   if (!ac.robust) {
-    NICP_LAUNCH_GROUP(12, false, 0, 1);
+    NICP_LAUNCH_GROUP(12, false, 1, 1);
   } else if (ctx->groupWarps >= 2) {
     if (ctx->groupMinBlocks >= 20) NICP_LAUNCH_GROUP(10, true, 0, 2);  // 10 two-warp CTAs = 20 warps per SM (96 registers)
     else NICP_LAUNCH_GROUP(8, true, 0, 2);                             // 16 warps per SM (128 registers)
   } else {
     switch (var) {
-      // shared memory admits 14 one-warp CTAs per SM, so the kernel may take the 144 registers it wants (measured:
-      // 128 registers 969 us, 144 registers 922 us per 256-pair launch; profiles/r2_summary.md)
-      case 0: NICP_LAUNCH_GROUP(12, true, 0, 1); break;
-      case 1: NICP_LAUNCH_GROUP(16, true, 0, 1); break;   // comparison: capped at 128 registers
+      // registers are handed out 32 per thread at a time, so anything from 129 to 160 leaves 12 resident one-warp CTAs per
+      // SM: with that room the three pixel slots run as ONE straight-line block (every slot executed, weights 0 / 1) and the
+      // compiler interleaves them -- more independent instructions per warp at 3 warps per scheduler.  Measured per
+      // 256-pair launch: 128 registers + slot skipping 969 us, 144 + skipping 905 us, 158 + straight-line 873 us
+      // (profiles/r2_summary.md section 3).
+      case 0: NICP_LAUNCH_GROUP(12, true, 1, 1); break;
+      case 1: NICP_LAUNCH_GROUP(12, true, 0, 1); break;   // comparison: warp-uniform skipping of empty pixel slots
       default: NICP_LAUNCH_GROUP(16, true, 2, 1); break;  // comparison: cross-lane sums through shared memory
     }
   }
